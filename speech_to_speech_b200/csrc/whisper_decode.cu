@@ -1,0 +1,309 @@
+// whisper_decode.cu -- the whole Whisper greedy decode loop as ONE persistent cooperative kernel.
+//
+// Reference path: WhisperGenerationMixin.generate short-form greedy (transformers generation_whisper.py:383-968)
+// over WhisperDecoder (modeling_whisper.py:691-797, layer :449-507) with the tied proj_out (:1081),
+// SuppressTokens / SuppressTokensAtBegin processors (generation_whisper.py:1774-1813) and EOS stop.  The
+// reference launches ~10 tiny kernels per layer per token and syncs with the host every token for the EOS
+// check; here the host launches once per utterance batch and reads the ids at the end.
+//
+// One CTA per SM (148), 512 threads.  A token step is a fixed sequence of phases separated by a grid barrier:
+//   per layer  0: LN1 + QKV GEMV (+ self-KV append)      1: self-attention partials (64-key chunks)
+//              2: combine + out-proj + residual           3: LN2 + cross-q GEMV
+//              4: cross-attention partials over 1500 keys 5: combine + out-proj + residual
+//              6: LN3 + fc1 + GELU                        7: fc2 + residual
+//   then       8L: final LN + tied logits GEMV + suppress masks + per-CTA argmax
+//              8L+1: global argmax, EOS / length bookkeeping, next-token embedding
+// Every phase is a coalesced 16-byte weight/KV stream with fp32 accumulation: the kernel is HBM-bound
+// (decoder weights + per-utterance cross-KV per token).
+#include "whisper_decode.cuh"
+#include "decode_common.cuh"
+
+namespace {
+
+constexpr int HD = 64;
+static_assert(ATT_CHUNK == ATT_CHUNK_KEYS, "chunk size mismatch");
+
+template <typename T, int NB>
+__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, float* xs, float* s_aux) {
+  const int d = p.d, B = p.B, H = p.heads, L = p.layers;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * DEC_WARPS + warp, GW = gridDim.x * DEC_WARPS;
+  const int pos = step;
+  const int rec = PART_STRIDE + HD;
+
+  if (ph < 8 * L) {
+    const int layer = ph >> 3, sub = ph & 7;
+    const WhisperDecLayer& w = p.lw[layer];
+    T* kcache = reinterpret_cast<T*>(p.self_kv);
+    const long long kv_layer_stride = (long long)p.max_pos * d;  // one of K or V for one layer
+    switch (sub) {
+      case 0: {
+        norm_rows_to_smem(p.x, w.ln1_w, w.ln1_b, 1e-5f, B, d, xs);
+        __syncthreads();
+        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_qkv), 3 * d, d, xs, B,
+                            [&](int row, const float* acc, int ln) {
+                              if (ln != 0) return;
+                              const float bias = w.b_qkv[row];
+                              for (int b = 0; b < B; ++b) {
+                                const float v = acc[b] + bias;
+                                if (row < d) {
+                                  p.q[b * d + row] = v;
+                                } else {
+                                  const int which = (row < 2 * d) ? 0 : 1;
+                                  const int c = row - (which + 1) * d;
+                                  kcache[(((long long)b * L + layer) * 2 + which) * kv_layer_stride +
+                                         (long long)pos * d + c] = DT<T>::from_f(v);
+                                }
+                              }
+                            });
+      } break;
+      case 1: {
+        const int n_chunks = pos / ATT_CHUNK + 1;
+        const int n_items = B * H * n_chunks;
+        for (int it = gw; it < n_items; it += GW) {
+          const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
+          const T* Kb = kcache + (((long long)b * L + layer) * 2 + 0) * kv_layer_stride + (long long)c * ATT_CHUNK * d + h * HD;
+          const T* Vb = Kb + kv_layer_stride;
+          const int n_keys = min(ATT_CHUNK, pos + 1 - c * ATT_CHUNK);
+          attend_chunk<T, HD>(p.q + b * d + h * HD, Kb, Vb, d, d, n_keys,
+                              p.part + ((long long)(b * H + h) * p.s_max + c) * rec);
+        }
+      } break;
+      case 2: {
+        combine_partials_to_smem<HD>(p.part, B, H, p.s_max, pos / ATT_CHUNK + 1, xs);
+        __syncthreads();
+        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_o), d, d, xs, B, [&](int row, const float* acc, int ln) {
+          if (ln != 0) return;
+          const float bias = w.b_o[row];
+          for (int b = 0; b < B; ++b) p.x[b * d + row] = __ldcg(p.x + b * d + row) + acc[b] + bias;
+        });
+      } break;
+      case 3: {
+        norm_rows_to_smem(p.x, w.ln2_w, w.ln2_b, 1e-5f, B, d, xs);
+        __syncthreads();
+        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_cq), d, d, xs, B, [&](int row, const float* acc, int ln) {
+          if (ln != 0) return;
+          const float bias = w.b_cq[row];
+          for (int b = 0; b < B; ++b) p.q[b * d + row] = acc[b] + bias;
+        });
+      } break;
+      case 4: {
+        const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK;
+        const int n_items = B * H * n_chunks;
+        const long long ldc = (long long)L * 2 * d;
+        const T* ckv = reinterpret_cast<const T*>(p.cross_kv);
+        for (int it = gw; it < n_items; it += GW) {
+          const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
+          const T* Kb = ckv + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc + (long long)layer * 2 * d + h * HD;
+          const T* Vb = Kb + d;
+          const int n_keys = min(ATT_CHUNK, p.n_ctx - c * ATT_CHUNK);
+          attend_chunk<T, HD>(p.q + b * d + h * HD, Kb, Vb, ldc, ldc, n_keys,
+                              p.part + ((long long)(b * H + h) * p.s_max + c) * rec);
+        }
+      } break;
+      case 5: {
+        combine_partials_to_smem<HD>(p.part, B, H, p.s_max, (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, xs);
+        __syncthreads();
+        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_co), d, d, xs, B, [&](int row, const float* acc, int ln) {
+          if (ln != 0) return;
+          const float bias = w.b_co[row];
+          for (int b = 0; b < B; ++b) p.x[b * d + row] = __ldcg(p.x + b * d + row) + acc[b] + bias;
+        });
+      } break;
+      case 6: {
+        norm_rows_to_smem(p.x, w.ln3_w, w.ln3_b, 1e-5f, B, d, xs);
+        __syncthreads();
+        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_fc1), p.ffn, d, xs, B,
+                            [&](int row, const float* acc, int ln) {
+                              if (ln != 0) return;
+                              const float bias = w.b_fc1[row];
+                              for (int b = 0; b < B; ++b) p.h[b * p.ffn + row] = gelu_erf(acc[b] + bias);
+                            });
+      } break;
+      case 7: {
+        copy_rows_to_smem(p.h, B * p.ffn, xs);
+        __syncthreads();
+        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_fc2), d, p.ffn, xs, B,
+                            [&](int row, const float* acc, int ln) {
+                              if (ln != 0) return;
+                              const float bias = w.b_fc2[row];
+                              for (int b = 0; b < B; ++b) p.x[b * d + row] = __ldcg(p.x + b * d + row) + acc[b] + bias;
+                            });
+      } break;
+    }
+    return;
+  }
+
+  const int g = step - (p.n_prefix - 1);  // index of the token generated at this step
+  if (ph == 8 * L) {
+    if (g < 0) return;
+    norm_rows_to_smem(p.x, p.lnf_w, p.lnf_b, 1e-5f, B, d, xs);
+    __syncthreads();
+    float best_v[NB];
+    int best_i[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { best_v[b] = -INFINITY; best_i[b] = 0x7fffffff; }
+    gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(p.embed), p.vocab, d, xs, B, [&](int row, const float* acc, int ln) {
+      if (ln != 0) return;
+      const unsigned char sm = p.suppress[row];
+      const bool masked = (sm & 1) || (g == 0 && (sm & 2));
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (b < B) {
+          const float v = masked ? -INFINITY : acc[b];
+          if (p.logits_out) p.logits_out[((long long)g * B + b) * p.vocab + row] = v;
+          if (v > best_v[b]) { best_v[b] = v; best_i[b] = row; }
+        }
+      }
+    });
+    // per-CTA argmax: s_aux = [DEC_WARPS][NB] values then indices
+    float* sv = s_aux;
+    int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
+    if (lane == 0) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) { sv[warp * NB + b] = best_v[b]; si[warp * NB + b] = best_i[b]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < B) {
+      const int b = threadIdx.x;
+      float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int wv = 0; wv < DEC_WARPS; ++wv) {
+        const float v = sv[wv * NB + b]; const int i = si[wv * NB + b];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+      p.cand_val[b * gridDim.x + blockIdx.x] = bv;
+      p.cand_idx[b * gridDim.x + blockIdx.x] = bi;
+    }
+    return;
+  }
+
+  // ---- select: global argmax, bookkeeping, next embedding ----
+  int* s_feed = reinterpret_cast<int*>(s_aux);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    if (warp == 0) {
+      int feed;
+      if (g >= 0) {
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int c = lane; c < (int)gridDim.x; c += 32) {
+          const float v = __ldcg(p.cand_val + b * gridDim.x + c); const int i = __ldcg(p.cand_idx + b * gridDim.x + c);
+          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        int tok = bi;
+        if (lane == 0) {
+          const bool was_done = p.done[b] != 0;
+          if (was_done) tok = p.eos;
+          p.out_ids[b * p.max_new + g] = tok;
+          if (!was_done && !p.forced) {
+            if (tok == p.eos) { p.done[b] = 1; p.out_len[b] = g + 1; atomicAdd(p.n_done, 1); }
+            else if (g == p.max_new - 1) { p.out_len[b] = p.max_new; }
+          }
+          if (p.forced && g == p.max_new - 1) p.out_len[b] = p.max_new;
+          feed = p.forced ? p.forced[b * p.max_new + g] : tok;
+          if (pos + 1 < p.max_pos) p.tokens[b * p.max_pos + pos + 1] = feed;
+          *s_feed = feed;
+        }
+      } else if (lane == 0) {
+        *s_feed = p.tokens[b * p.max_pos + pos + 1];
+      }
+    }
+    __syncthreads();
+    const int feed = *s_feed;
+    if (pos + 1 < p.max_pos) {
+      const T* e = reinterpret_cast<const T*>(p.embed) + (long long)feed * d;
+      const float* pe = p.pos + (long long)(pos + 1) * d;
+      for (int i = threadIdx.x; i < d; i += DEC_THREADS) p.x[b * d + i] = DT<T>::to_f(e[i]) + pe[i];
+    }
+  }
+}
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(DEC_THREADS, 1)
+whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, int ph_begin, int ph_end, int coop) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int xs_floats = NB * max(p.d, p.ffn);
+  float* xs = smem_f;
+  float* s_aux = smem_f + xs_floats;
+  unsigned int epoch = 0;
+  const int n_ph = 8 * p.layers + 2;
+  for (int step = step_begin; step < step_end; ++step) {
+    const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
+    for (int ph = pb; ph < pe; ++ph) {
+      // the logits phase is skipped while the forced prompt is still being fed
+      const bool skip = (ph == 8 * p.layers) && (step < p.n_prefix - 1);
+      if (!skip) wd_phase<T, NB>(p, step, ph, xs, s_aux);
+      if (coop && !skip) grid_sync(p.sync_counter, epoch);
+    }
+    if (coop && !p.forced && *reinterpret_cast<volatile int*>(p.n_done) >= p.B) break;
+  }
+}
+
+template <typename T>
+__global__ void whisper_decode_init_kernel(const WhisperDecParams p) {
+  // x = E[first prompt token] + pos[0]; reset flags
+  const int b = blockIdx.x;
+  const int tok = p.tokens[b * p.max_pos];
+  const T* e = reinterpret_cast<const T*>(p.embed) + (long long)tok * p.d;
+  for (int i = threadIdx.x; i < p.d; i += blockDim.x) p.x[b * p.d + i] = DT<T>::to_f(e[i]) + p.pos[i];
+  if (threadIdx.x == 0) {
+    p.done[b] = 0;
+    p.out_len[b] = 0;
+    if (b == 0) { *p.n_done = 0; *p.sync_counter = 0; }
+  }
+  for (int i = threadIdx.x; i < p.max_new; i += blockDim.x) p.out_ids[b * p.max_new + i] = p.eos;
+}
+
+template <typename T, int NB>
+int launch_nb(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStream_t stream) {
+  const size_t smem = ((size_t)NB * (size_t)max(p.d, p.ffn) + 2 * DEC_WARPS * NB + 32) * sizeof(float);
+  auto kern = whisper_decode_kernel<T, NB>;
+  S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  whisper_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(p);
+  S2S_LAUNCH_CHECK();
+  const int total_steps = p.n_prefix - 1 + p.max_new;
+  const int n_ph = 8 * p.layers + 2;
+  const int grid = ctx->num_sms;
+  if (!debug_phases) {
+    int sb = 0, se = total_steps, pb = 0, pe = n_ph, coop = 1;
+    WhisperDecParams pp = p;
+    void* args[] = {&pp, &sb, &se, &pb, &pe, &coop};
+    S2S_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(DEC_THREADS), args, smem, stream));
+    s2s_count_launch();
+  } else {
+    // debug: one ordinary launch per phase (kernel boundaries replace the grid barrier)
+    for (int s = 0; s < total_steps; ++s)
+      for (int ph = 0; ph < n_ph; ++ph) {
+        if (ph == 8 * p.layers && s < p.n_prefix - 1) continue;
+        kern<<<grid, DEC_THREADS, smem, stream>>>(p, s, s + 1, ph, ph + 1, 0);
+        S2S_LAUNCH_CHECK();
+      }
+  }
+  return S2S_OK;
+}
+
+template <typename T>
+int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStream_t stream) {
+  if (p.B <= 1) return launch_nb<T, 1>(ctx, p, debug_phases, stream);
+  if (p.B <= 2) return launch_nb<T, 2>(ctx, p, debug_phases, stream);
+  if (p.B <= 4) return launch_nb<T, 4>(ctx, p, debug_phases, stream);
+  if (p.B <= 8) return launch_nb<T, 8>(ctx, p, debug_phases, stream);
+  s2s_set_error("whisper decode: batch %d > 8 must be split by the caller", p.B);
+  return S2S_ERR_INVALID;
+}
+
+}  // namespace
+
+int whisper_decode_launch(s2s_ctx* ctx, const WhisperDecParams& p, int dtype, int debug_phases, cudaStream_t stream) {
+  S2S_REQUIRE(p.d / p.heads == HD, "whisper decode: head_dim must be 64");
+  S2S_REQUIRE(p.n_prefix >= 1 && p.max_new >= 1 && p.n_prefix + p.max_new <= p.max_pos,
+              "whisper decode: prompt %d + max_new %d exceeds max_target_positions %d", p.n_prefix, p.max_new, p.max_pos);
+  if (dtype == S2S_F16) return launch_t<__half>(ctx, p, debug_phases, stream);
+  if (dtype == S2S_BF16) return launch_t<__nv_bfloat16>(ctx, p, debug_phases, stream);
+  s2s_set_error("whisper decode: unsupported dtype %d", dtype);
+  return S2S_ERR_UNSUPPORTED;
+}

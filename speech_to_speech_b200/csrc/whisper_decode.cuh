@@ -1,0 +1,46 @@
+// whisper_decode.cuh -- parameters of the persistent Whisper greedy-decode kernel.
+#pragma once
+#include "common.cuh"
+
+constexpr int ATT_CHUNK_KEYS = 64;  // keys per attention work item (== ATT_CHUNK in decode_common.cuh)
+
+struct WhisperDecLayer {      // all device pointers; 16-bit weights are [out, in] row-major
+  const void* w_qkv; const float* b_qkv;   // [3d, d]; q rows pre-scaled by head_dim^-0.5, k bias = 0
+  const void* w_o;   const float* b_o;     // [d, d]
+  const void* w_cq;  const float* b_cq;    // cross-attention q [d, d] (pre-scaled)
+  const void* w_co;  const float* b_co;    // cross-attention out [d, d]
+  const void* w_fc1; const float* b_fc1;   // [ffn, d]
+  const void* w_fc2; const float* b_fc2;   // [d, ffn]
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
+};
+
+struct WhisperDecParams {
+  int d, heads, layers, ffn, vocab, B, max_pos, n_ctx;
+  const WhisperDecLayer* lw;   // [layers] device
+  const void* embed;           // [vocab, d] 16-bit (tied output projection)
+  const float* pos;            // [max_pos, d]
+  const float *lnf_w, *lnf_b;
+  // state
+  float* x;                    // [B, d] residual stream
+  float* q;                    // [B, d]
+  float* h;                    // [B, ffn]
+  void* self_kv;               // [B][layers][2][max_pos][d] 16-bit
+  const void* cross_kv;        // [B * n_ctx, layers * 2 * d] 16-bit
+  float* part;                 // [B][heads][s_max][2 + 64]
+  int s_max;
+  // token bookkeeping
+  int* tokens;                 // [B][max_pos]
+  int n_prefix, max_new, eos;
+  const unsigned char* suppress;  // [vocab]: bit0 suppress always, bit1 suppress at the first generated position
+  int* out_ids;                // [B][max_new]
+  int* out_len;                // [B]
+  const int* forced;           // [B][max_new] or null
+  float* logits_out;           // [max_new][B][vocab] or null
+  int* done;                   // [B]
+  int* n_done;                 // [1]
+  float* cand_val;             // [B][grid]
+  int* cand_idx;               // [B][grid]
+  unsigned int* sync_counter;  // [1], zeroed before launch
+};
+
+int whisper_decode_launch(s2s_ctx* ctx, const WhisperDecParams& p, int dtype, int debug_phases, cudaStream_t stream);

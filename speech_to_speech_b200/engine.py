@@ -1,0 +1,214 @@
+"""Thin Python objects over the C ABI.  torch supplies device tensors / streams only; every FLOP on the
+hot path runs in libs2s_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import Mapping, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import S2S_BF16, S2S_F16, S2S_F32, DTYPE_CODES, LlamaConfig, S2SError, WhisperConfig, WhisperDecodeOpts, check
+
+_ctx_lock = threading.Lock()
+_ctx_by_device: dict[int, C.c_void_p] = {}
+
+
+def get_context(device: int = 0) -> C.c_void_p:
+    """One library context per CUDA device (created on first use)."""
+    if not torch.cuda.is_available():
+        raise S2SError("speech_to_speech_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    lib = _lib.load()
+    with _ctx_lock:
+        if device not in _ctx_by_device:
+            h = C.c_void_p()
+            check(lib.s2s_init(device, C.byref(h)), "s2s_init")
+            _ctx_by_device[device] = h
+        return _ctx_by_device[device]
+
+
+def launch_count(device: int = 0, reset: bool = False) -> int:
+    return int(_lib.load().s2s_launch_count(get_context(device), 1 if reset else 0))
+
+
+def _stream_ptr(device: int) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _np_dtype_code(a: np.ndarray) -> int:
+    if a.dtype == np.float32:
+        return S2S_F32
+    if a.dtype == np.float16:
+        return S2S_F16
+    raise TypeError(f"unsupported numpy dtype {a.dtype}")
+
+
+@dataclass
+class WhisperDecodeOptions:
+    """What WhisperGenerationMixin.generate derives from generation_config + the handler's gen_kwargs."""
+
+    prefix: Sequence[int]
+    eos_id: int
+    max_new_tokens: int = 128
+    suppress: Sequence[int] = ()
+    begin_suppress: Sequence[int] = ()
+
+    def to_c(self):
+        pre, n_pre = _lib.i32_array(self.prefix)
+        sup, n_sup = _lib.i32_array(self.suppress)
+        beg, n_beg = _lib.i32_array(self.begin_suppress)
+        o = WhisperDecodeOpts(pre, n_pre, int(self.max_new_tokens), int(self.eos_id), sup, n_sup, beg, n_beg)
+        o._keep = (pre, sup, beg)  # keep the arrays alive
+        return o
+
+
+class WhisperEngine:
+    """Whisper STT on one B200: log-mel -> encoder -> greedy decoder, batched over utterances."""
+
+    def __init__(self, geometry: Mapping[str, int], dtype: str = "float16", max_batch: int = 1, device: int = 0):
+        self.lib = _lib.load()
+        self.device = device
+        self.ctx = get_context(device)
+        self.geometry = dict(geometry)
+        self.dtype = dtype
+        self.max_batch = max_batch
+        g = self.geometry
+        self.cfg = WhisperConfig(
+            g["d_model"], g["heads"], g["enc_layers"], g["dec_layers"], g["ffn"], g["n_mels"], g["vocab"],
+            g.get("max_source_positions", 1500), g.get("max_target_positions", 448), DTYPE_CODES[dtype], max_batch)
+        self.handle = C.c_void_p()
+        check(self.lib.s2s_whisper_create(self.ctx, C.byref(self.cfg), C.byref(self.handle)), "s2s_whisper_create")
+
+    # -- weights -----------------------------------------------------------------------------
+    def load_state_dict(self, weights: Mapping[str, "np.ndarray | torch.Tensor"]) -> None:
+        for name, w in weights.items():
+            if isinstance(w, torch.Tensor):
+                w = w.detach().to("cpu", torch.float32).numpy()
+            a = np.ascontiguousarray(w)
+            if a.dtype not in (np.float32, np.float16):
+                a = a.astype(np.float32)
+            shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+            check(self.lib.s2s_whisper_bind_tensor(self.handle, name.encode(), a.ctypes.data_as(C.c_void_p), shape,
+                                                   a.ndim, _np_dtype_code(a)), f"bind_tensor({name})")
+        check(self.lib.s2s_whisper_finalize(self.handle), "s2s_whisper_finalize")
+
+    def init_random(self, seed: int = 0) -> None:
+        check(self.lib.s2s_whisper_init_random(self.handle, seed), "s2s_whisper_init_random")
+        check(self.lib.s2s_whisper_finalize(self.handle), "s2s_whisper_finalize")
+
+    # -- device-resident API -------------------------------------------------------------------
+    def logmel(self, pcm: torch.Tensor, n_samples: Sequence[int], return_mel: bool = False) -> Optional[torch.Tensor]:
+        """pcm: cuda f32 [B, stride].  Leaves the features inside the engine for encode()."""
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.dim() == 2 and pcm.is_contiguous()
+        B = pcm.shape[0]
+        ns, _ = _lib.i32_array(n_samples)
+        mel = torch.empty((B, self.geometry["n_mels"], 3000), dtype=torch.float32, device=pcm.device) if return_mel else None
+        check(self.lib.s2s_whisper_logmel(self.handle, _ptr(pcm), pcm.shape[1], ns, B, _ptr(mel),
+                                          _stream_ptr(self.device)), "s2s_whisper_logmel")
+        return mel
+
+    def encode(self, B: int, mel: Optional[torch.Tensor] = None, return_output: bool = False) -> Optional[torch.Tensor]:
+        if mel is not None:
+            assert mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous()
+        out = None
+        if return_output:
+            out = torch.empty((B, 1500, self.geometry["d_model"]), dtype=torch.float32, device=f"cuda:{self.device}")
+        check(self.lib.s2s_whisper_encode(self.handle, _ptr(mel), B, _ptr(out), _stream_ptr(self.device)),
+              "s2s_whisper_encode")
+        return out
+
+    def decode(self, B: int, opts: WhisperDecodeOptions, forced: Optional[torch.Tensor] = None,
+               return_logits: bool = False):
+        dev = f"cuda:{self.device}"
+        ids = torch.empty((B, opts.max_new_tokens), dtype=torch.int32, device=dev)
+        lens = torch.empty((B,), dtype=torch.int32, device=dev)
+        logits = None
+        if return_logits:
+            logits = torch.empty((opts.max_new_tokens, B, self.geometry["vocab"]), dtype=torch.float32, device=dev)
+        co = opts.to_c()
+        check(self.lib.s2s_whisper_decode(self.handle, C.byref(co), B, _ptr(ids), _ptr(lens), _ptr(forced), _ptr(logits),
+                                          _stream_ptr(self.device)), "s2s_whisper_decode")
+        return (ids, lens, logits) if return_logits else (ids, lens)
+
+    def detect_language(self, B: int, sot_id: int, lang_ids: Sequence[int]) -> torch.Tensor:
+        out = torch.empty((B,), dtype=torch.int32, device=f"cuda:{self.device}")
+        la, n = _lib.i32_array(lang_ids)
+        check(self.lib.s2s_whisper_detect_language(self.handle, int(sot_id), la, n, B, _ptr(out), _stream_ptr(self.device)),
+              "s2s_whisper_detect_language")
+        return out
+
+    # -- host-buffer API (what the handler calls) --------------------------------------------------
+    def transcribe(self, audio: Sequence[np.ndarray], opts: WhisperDecodeOptions) -> list[list[int]]:
+        """audio: list of f32 mono 16 kHz arrays (host).  H2D + log-mel + encode + greedy decode + D2H."""
+        B = len(audio)
+        n = [min(len(a), 480000) for a in audio]
+        stride = max(max(n), 1)
+        if B == 1 and audio[0].dtype == np.float32 and audio[0].flags.c_contiguous:
+            pcm = audio[0]
+        else:
+            pcm = np.zeros((B, stride), dtype=np.float32)
+            for i, a in enumerate(audio):
+                pcm[i, : n[i]] = a[: n[i]]
+        ns, _ = _lib.i32_array(n)
+        ids = np.empty((B, opts.max_new_tokens), dtype=np.int32)
+        lens = np.empty((B,), dtype=np.int32)
+        co = opts.to_c()
+        check(self.lib.s2s_whisper_transcribe(self.handle, C.byref(co), pcm.ctypes.data_as(C.c_void_p), stride, ns, B,
+                                              ids.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p),
+                                              _stream_ptr(self.device)), "s2s_whisper_transcribe")
+        return [ids[b, : lens[b]].tolist() for b in range(B)]
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.s2s_whisper_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: str = "none",
+         out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """C = A @ W^T (+bias) through the tcgen05 kernel; a [M,K], w [N,K] fp16/bf16 cuda tensors."""
+    assert a.is_cuda and w.is_cuda and a.dtype == w.dtype and a.is_contiguous() and w.is_contiguous()
+    dev = a.device.index or 0
+    M, K = a.shape
+    N = w.shape[0]
+    code = {torch.float16: S2S_F16, torch.bfloat16: S2S_BF16}[a.dtype]
+    out_dtype = out_dtype or a.dtype
+    ocode = S2S_F32 if out_dtype == torch.float32 else code
+    c = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    lib = _lib.load()
+    check(lib.s2s_gemm(get_context(dev), _ptr(a), _ptr(w), _ptr(bias), _ptr(c), M, N, K, code, ocode,
+                       1 if act == "gelu" else 0, _stream_ptr(dev)), "s2s_gemm")
+    return c
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kv_heads: int, scale: float,
+              causal: bool = False) -> torch.Tensor:
+    """q [B,Tq,heads*hd], k/v [B,Tk,kv_heads*hd] (last dim contiguous; row strides taken from the tensors)."""
+    assert q.is_cuda and q.dtype in (torch.float16, torch.bfloat16)
+    B, Tq, dq = q.shape
+    Tk = k.shape[1]
+    hd = dq // heads
+    dev = q.device.index or 0
+    o = torch.empty((B, Tq, dq), dtype=q.dtype, device=q.device)
+    code = {torch.float16: S2S_F16, torch.bfloat16: S2S_BF16}[q.dtype]
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    assert q.stride(0) == Tq * q.stride(1) and k.stride(0) == Tk * k.stride(1) and v.stride(0) == Tk * v.stride(1)
+    lib = _lib.load()
+    check(lib.s2s_attention(get_context(dev), _ptr(q), _ptr(k), _ptr(v), _ptr(o), B, Tq, Tk, heads, kv_heads, hd,
+                            q.stride(1), k.stride(1), v.stride(1), o.stride(1), float(scale), 1 if causal else 0, code,
+                            _stream_ptr(dev)), "s2s_attention")
+    return o
