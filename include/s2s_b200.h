@@ -100,6 +100,10 @@ int s2s_whisper_decode(s2s_whisper* m, const s2s_whisper_decode_opts* opts, int3
 /* One decoder step from <|sot|>, logits restricted to lang_ids -> lang_out_d[B] (detect_language). */
 int s2s_whisper_detect_language(s2s_whisper* m, int32_t sot_id, const int32_t* lang_ids_h, int32_t n_lang,
                                 int32_t B, int32_t* lang_out_d, void* stream);
+/* Profiling aid: when trace_d != NULL the next decode launches record, for CTA 0 and the last CTA, the
+ * %globaltimer (ns) at [phase begin, after staging, -, -, phase body end, barrier exit] of the first
+ * `capacity` phases into trace_d[2][capacity][6] (u64).  NULL disables tracing.                                          */
+int s2s_whisper_set_trace(s2s_whisper* m, uint64_t* trace_d, int32_t capacity);
 /* End-to-end with HOST buffers: H2D of pcm, log-mel, encode, greedy decode, D2H of ids; synchronous.
  * pcm_h: [B, pcm_stride] f32 (pinned or pageable), ids_out_h: [B, max_new_tokens], len_out_h: [B].  */
 int s2s_whisper_transcribe(s2s_whisper* m, const s2s_whisper_decode_opts* opts, const float* pcm_h,

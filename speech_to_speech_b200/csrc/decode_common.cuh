@@ -1,175 +1,343 @@
 // decode_common.cuh -- building blocks of the persistent single-token decode kernels
-// (Whisper decoder, Llama-family decoder).  All of them are HBM-bound weight/KV streaming loops:
-// 16-byte coalesced loads through the read-only no-L1-allocate path, fp32 accumulation, warp-shuffle
-// reductions.  One CTA per SM, DEC_THREADS threads; phases are separated by a grid-wide barrier.
+// (Whisper decoder, Llama-family decoder).
+//
+// A decode step at small batch is a chain of tiny matrix-vector phases; per phase every SM touches only a few
+// KB, so the phase time is (HBM/L2 round trips on its critical path) + (grid barrier), not bytes / bandwidth.
+// Everything here is therefore written for memory-level parallelism: all loads of a phase are independent and
+// issued back to back (explicit register staging, compile-time unrolling) so that each phase costs ONE round
+// trip; work items are interleaved across CTAs so all 148 SMs pull from HBM; buffers produced by other CTAs
+// inside the launch are read with ld.global.cg (L2) so a stale L1 line can never be observed; weights use the
+// read-only no-L1-allocate path.  Reductions are warp shuffles; accumulation is fp32.
 #pragma once
 #include "common.cuh"
 
-constexpr int DEC_THREADS = 512;
+constexpr int DEC_THREADS = 256;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int ATT_CHUNK = 64;   // keys per attention work item
-constexpr int PART_STRIDE = 2;  // partial record = [m, l, o[hd]]
+constexpr int PART_PAD = 4;     // partial record = [o[hd], m, l, pad, pad] (16-byte aligned records)
 
 // ---- grid barrier (all CTAs co-resident: cooperative launch) ------------------------------
 // Monotonic counter: barrier #e completes when counter == e * gridDim.x.  Bounded spin -> trap.
 __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& epoch) {
-  __syncthreads();
+  __syncthreads();  // CTA-scope: every thread's phase results happen-before thread 0's release below
   if (threadIdx.x == 0) {
     epoch += 1;
     const unsigned int target = epoch * gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release-add / acquire-poll at gpu scope (cumulative over the bar.sync above); no MEMBAR.SC, no L1 flush:
+    // all cross-CTA data is read with ld.global.cg / .nc, never through L1.
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int v, spins = 0;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       if (++spins > (1u << 28)) __trap();
     } while (v < target);
-    __threadfence();  // gpu-scope fence: drops stale L1 lines before the CTA reads other CTAs' results
   }
   __syncthreads();
 }
 
-// ---- normalise B rows of x (fp32 [B, d]) into shared memory xs[B][d] -----------------------
-// bias != null: LayerNorm ; bias == null: RMSNorm.  One warp per row.
-__device__ __forceinline__ void norm_rows_to_smem(const float* x, const float* w, const float* bias, float eps, int B,
-                                                  int d, float* xs) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = warp; b < B; b += DEC_WARPS) {
-    const float* xr = x + (long long)b * d;
-    float mean = 0.f;
-    if (bias) {
-      float s = 0.f;
-      for (int i = lane; i < d; i += 32) s += __ldcg(xr + i);
-      mean = warp_sum(s) / (float)d;
-    }
-    float ss = 0.f;
-    for (int i = lane; i < d; i += 32) {
-      const float a = __ldcg(xr + i) - mean;
-      ss += a * a;
-    }
-    const float rstd = rsqrtf(warp_sum(ss) / (float)d + eps);
-    for (int i = lane; i < d; i += 32) {
-      float y = (__ldcg(xr + i) - mean) * rstd * w[i];
-      if (bias) y += bias[i];
-      xs[b * d + i] = y;
-    }
+// Warp w of CTA c takes work items  w * gridDim.x + c, then + total_warps ...: consecutive items land on
+// different SMs, so a phase with few items still spreads over the whole chip.
+__device__ __forceinline__ int dec_first_item() { return (threadIdx.x >> 5) * gridDim.x + blockIdx.x; }
+__device__ __forceinline__ int dec_item_stride() { return gridDim.x * DEC_WARPS; }
+
+// Warm L2 with the weight rows this warp will stream in the NEXT phase (issued before the grid barrier, so the
+// HBM fetch overlaps the barrier latency).  One 128-byte line per lane per instruction.
+template <typename T, int R>
+__device__ __forceinline__ void prefetch_rows_l2(const T* W, int N, int K) {
+  const int lane = threadIdx.x & 31;
+  const int row_bytes = K * (int)sizeof(T);
+  for (int row0 = dec_first_item() * R; row0 < N; row0 += dec_item_stride() * R) {
+    const int nrows = min(R, N - row0);
+    const char* base = reinterpret_cast<const char*>(W + (long long)row0 * K);
+    const int total = nrows * row_bytes;
+    for (int o = lane * 128; o < total; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
   }
 }
 
-__device__ __forceinline__ void copy_rows_to_smem(const float* x, int n, float* xs) {
-  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 4)
-    *reinterpret_cast<float4*>(xs + i) = __ldcg(reinterpret_cast<const float4*>(x + i));
+// Same idea for one attention work item: n_keys rows of `row_bytes` bytes at stride ld_bytes (K and V adjacent).
+__device__ __forceinline__ void prefetch_strided_l2(const void* base, long long ld_bytes, int n_rows, int row_bytes) {
+  const int lane = threadIdx.x & 31;
+  const int lines_per_row = (row_bytes + 127) >> 7;
+  for (int i = lane; i < n_rows * lines_per_row; i += 32) {
+    const char* a = reinterpret_cast<const char*>(base) + (long long)(i / lines_per_row) * ld_bytes + (i % lines_per_row) * 128;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+  }
 }
 
-// ---- skinny GEMV: out[b][row] = sum_k W[row][k] * xs[b][k], rows distributed over every warp of the grid
-// Each warp takes R consecutive rows so that R * (K/256) independent 16-byte loads are in flight per lane.
-template <typename T, int NB, int R, typename Epi>
-__device__ __forceinline__ void gemv_rows(const T* __restrict__ W, int N, int K, const float* xs, int B, Epi epi) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * DEC_WARPS + warp;
-  const int GW = gridDim.x * DEC_WARPS;
-  for (int row0 = gw * R; row0 < N; row0 += GW * R) {
-    float acc[R][NB];
+// ---- stage B rows of x (fp32 [B, d], produced by other CTAs) into shared memory, optionally normalised ----
+// mode 0: plain copy; 1: LayerNorm (w, bias); 2: RMSNorm (w).  Two-pass statistics from shared memory.
+// The norm weights are fetched together with x (one round trip) into wb[2*d].  s_red: >= DEC_WARPS floats.
+// Ends with a __syncthreads().
+__device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs, int mode, const float* w,
+                                           const float* bias, float eps, float* s_red, float* wb) {
+  const int n = B * d;
+  const int n_all = n + (mode == 0 ? 0 : (mode == 1 ? 2 * d : d));
+  for (int i0 = threadIdx.x * 4; i0 < n_all; i0 += DEC_THREADS * 16) {
+    float4 v[4];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * DEC_THREADS * 4;
+      if (i < n) v[u] = __ldcg(reinterpret_cast<const float4*>(x + i));
+      else if (i < n_all && i < n + d) v[u] = __ldg(reinterpret_cast<const float4*>(w + (i - n)));
+      else if (i < n_all) v[u] = __ldg(reinterpret_cast<const float4*>(bias + (i - n - d)));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * DEC_THREADS * 4;
+      if (i < n) *reinterpret_cast<float4*>(xs + i) = v[u];
+      else if (i < n_all) *reinterpret_cast<float4*>(wb + (i - n)) = v[u];
+    }
+  }
+  __syncthreads();
+  if (mode == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int wpr = DEC_WARPS;  // warps per row: largest power of two with wpr * B <= DEC_WARPS (min 1)
+  while (wpr > 1 && wpr * B > DEC_WARPS) wpr >>= 1;
+  const int rows_per_iter = DEC_WARPS / wpr;
+  for (int r0 = 0; r0 < B; r0 += rows_per_iter) {
+    const int row = r0 + warp / wpr, sub = warp % wpr, grp = (warp / wpr) * wpr;
+    const bool valid = row < B;
+    float* xr = xs + row * d;
+    float mean = 0.f;
+    if (mode == 1) {
+      float s = 0.f;
+      if (valid)
+        for (int i = sub * 32 + lane; i < d; i += wpr * 32) s += xr[i];
+      s = warp_sum(s);
+      if (lane == 0) s_red[warp] = s;
+      __syncthreads();
+      for (int k = 0; k < wpr; ++k) mean += s_red[grp + k];
+      mean /= (float)d;
+    }
+    float ss = 0.f;
+    if (valid)
+      for (int i = sub * 32 + lane; i < d; i += wpr * 32) {
+        const float a = xr[i] - mean;
+        ss += a * a;
+      }
+    ss = warp_sum(ss);
+    if (lane == 0) s_red[DEC_WARPS + warp] = ss;  // second half of s_red: no barrier needed before reuse
+    __syncthreads();
+    float var = 0.f;
+    for (int k = 0; k < wpr; ++k) var += s_red[DEC_WARPS + grp + k];
+    const float rstd = rsqrtf(var / (float)d + eps);
+    if (valid)
+      for (int i = sub * 32 + lane; i < d; i += wpr * 32) {
+        float y = (xr[i] - mean) * rstd * wb[i];
+        if (mode == 1) y += wb[d + i];
+        xr[i] = y;
+      }
+    __syncthreads();
+  }
+}
+
+// ---- skinny GEMV: out[b][row] = sum_k W[row][k] * xs[b][k] ---------------------------------------
+// ONE non-inlined routine serves every projection of every layer (runtime shapes and a runtime epilogue
+// mode): the decode step executes each phase once per layer, so per-phase inlined copies (245 KB of SASS)
+// turned the kernel into an instruction-cache streaming problem; sharing the routine keeps the hot loop resident.
+// A warp owns GV_R consecutive rows and keeps GV_R * GV_U independent 16-byte loads in flight per lane; the
+// bias / residual / mask reads are issued BEFORE the weight loads; the NEXT row group of the warp is L2-prefetched
+// while the current one is reduced.  Lane b (< B) applies the epilogue for batch row b.
+constexpr int GV_R = 4, GV_U = 4;
+enum GemvEpi { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_QKV = 3, EPI_LOGITS = 4 };
+struct GemvArgs {
+  const void* W; int N, K;
+  const float* bias;           // [N] or null
+  int mode;
+  float* out; int ldo;         // STORE / GELU / RESID (in-place residual stream) / QKV (q rows)
+  // QKV: rows [d, 2d) -> k cache, [2d, 3d) -> v cache (16-bit), element (b, c) at kv0 + which*kv_which + b*kv_batch + c
+  void* kv0; long long kv_which, kv_batch; int d;
+  // LOGITS
+  const unsigned char* suppress; int first_step; float* logits_out; long long logits_ld;  // logits_out + b*logits_ld + row
+};
+
+template <typename T, int NB>
+__device__ __noinline__ void gemv_generic(const GemvArgs& a, const float* xs, int B, float& best_v, int& best_i) {
+  const int lane = threadIdx.x & 31;
+  const T* __restrict__ W = reinterpret_cast<const T*>(a.W);
+  const int N = a.N, K = a.K, mode = a.mode;
+  const int stride = dec_item_stride() * GV_R;
+  for (int row0 = dec_first_item() * GV_R; row0 < N; row0 += stride) {
+    float bias[GV_R], extra[GV_R];
+#pragma unroll
+    for (int r = 0; r < GV_R; ++r) {
+      const int row = min(row0 + r, N - 1);
+      bias[r] = a.bias ? __ldg(a.bias + row) : 0.f;
+      extra[r] = 0.f;
+      if (mode == EPI_RESID) { if (lane < B) extra[r] = __ldcg(a.out + lane * a.ldo + row); }
+      else if (mode == EPI_LOGITS) {
+        const unsigned char sm = __ldg(a.suppress + row);
+        extra[r] = ((sm & 1) || (a.first_step && (sm & 2))) ? 1.f : 0.f;
+      }
+    }
+    if (row0 + stride < N) {  // warm L2 with this warp's next row group
+      const char* nb = reinterpret_cast<const char*>(W + (long long)(row0 + stride) * K);
+      const int total = min(GV_R, N - row0 - stride) * K * (int)sizeof(T);
+      for (int o = lane * 128; o < total; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
+    }
+    float acc[GV_R][NB];
+#pragma unroll
+    for (int r = 0; r < GV_R; ++r)
 #pragma unroll
       for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
-    for (int k = lane * 8; k < K; k += 256) {
-      uint4 wv[R];
+    for (int k0 = lane * 8; k0 < K; k0 += 256 * GV_U) {
+      uint4 wv[GV_U][GV_R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int row = min(row0 + r, N - 1);
-        wv[r] = ld_stream16(W + (long long)row * K + k);
+      for (int u = 0; u < GV_U; ++u) {
+        const int k = k0 + u * 256;
+#pragma unroll
+        for (int r = 0; r < GV_R; ++r) {
+          const int row = min(row0 + r, N - 1);
+          if (k < K) wv[u][r] = ld_stream16(W + (long long)row * K + k);
+        }
       }
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        if (b < B) {
-          const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + k);
-          const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + k + 4);
+      for (int u = 0; u < GV_U; ++u) {
+        const int k = k0 + u * 256;
+        if (k < K) {
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float2 w0 = DT<T>::to_f2(wv[r].x), w1 = DT<T>::to_f2(wv[r].y);
-            const float2 w2 = DT<T>::to_f2(wv[r].z), w3 = DT<T>::to_f2(wv[r].w);
-            float a = acc[r][b];
-            a = fmaf(w0.x, x0.x, a); a = fmaf(w0.y, x0.y, a);
-            a = fmaf(w1.x, x0.z, a); a = fmaf(w1.y, x0.w, a);
-            a = fmaf(w2.x, x1.x, a); a = fmaf(w2.y, x1.y, a);
-            a = fmaf(w3.x, x1.z, a); a = fmaf(w3.y, x1.w, a);
-            acc[r][b] = a;
+          for (int b = 0; b < NB; ++b) {
+            if (b < B) {
+              const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + k);
+              const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + k + 4);
+#pragma unroll
+              for (int r = 0; r < GV_R; ++r) {
+                const float2 w0 = DT<T>::to_f2(wv[u][r].x), w1 = DT<T>::to_f2(wv[u][r].y);
+                const float2 w2 = DT<T>::to_f2(wv[u][r].z), w3 = DT<T>::to_f2(wv[u][r].w);
+                float c = acc[r][b];
+                c = fmaf(w0.x, x0.x, c); c = fmaf(w0.y, x0.y, c);
+                c = fmaf(w1.x, x0.z, c); c = fmaf(w1.y, x0.w, c);
+                c = fmaf(w2.x, x1.x, c); c = fmaf(w2.y, x1.y, c);
+                c = fmaf(w3.x, x1.z, c); c = fmaf(w3.y, x1.w, c);
+                acc[r][b] = c;
+              }
+            }
           }
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < GV_R; ++r) {
 #pragma unroll
       for (int b = 0; b < NB; ++b) acc[r][b] = warp_sum(acc[r][b]);
-      if (row0 + r < N) epi(row0 + r, acc[r], lane);
+      float v = acc[r][0];
+#pragma unroll
+      for (int b = 1; b < NB; ++b) v = (lane == b) ? acc[r][b] : v;
+      const int row = row0 + r;
+      if (row < N && lane < B) {
+        v += bias[r];
+        if (mode == EPI_STORE) {
+          a.out[lane * a.ldo + row] = v;
+        } else if (mode == EPI_GELU) {
+          a.out[lane * a.ldo + row] = gelu_erf(v);
+        } else if (mode == EPI_RESID) {
+          a.out[lane * a.ldo + row] = extra[r] + v;
+        } else if (mode == EPI_QKV) {
+          if (row < a.d) {
+            a.out[lane * a.ldo + row] = v;
+          } else {
+            const int which = (row < 2 * a.d) ? 0 : 1;
+            reinterpret_cast<T*>(a.kv0)[which * a.kv_which + lane * a.kv_batch + (row - (which + 1) * a.d)] = DT<T>::from_f(v);
+          }
+        } else {  // EPI_LOGITS
+          if (extra[r] != 0.f) v = -INFINITY;
+          if (a.logits_out) a.logits_out[lane * a.logits_ld + row] = v;
+          if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
+        }
+      }
     }
   }
 }
 
 // ---- attention over one chunk of <= 64 keys for one (batch, head): warp-level -----------------
-// 8 lanes cover one key row (HD 16-bit values, HD/8 per lane... for HD=64: 16 B per lane; HD=128: 2 x 16 B),
-// 4 keys per warp step, 16 steps.  Scores are kept in registers so that all K loads (then all V loads)
-// are independent.  q must already carry the softmax scale.  Writes [m, l, o[HD]] (unnormalised).
+// 8 lanes cover one key row (HD/8 values per lane), 4 keys per warp step.  Keys are processed in two halves of
+// 32: the 8 K vectors and 8 V vectors of a half are loaded into registers before any arithmetic, so a half
+// costs one memory round trip.  q must already carry the softmax scale.  Writes [o[HD], m, l] (unnormalised).
 template <typename T, int HD>
-__device__ __forceinline__ void attend_chunk(const float* q /*global fp32 [HD]*/, const T* K, const T* V,
+__device__ __noinline__ void attend_chunk(const float* q /*global fp32 [HD]*/, const T* K, const T* V,
                                              long long ldk, long long ldv, int n_keys, float* part) {
   constexpr int PER = HD / 8;      // elements per lane
   constexpr int NV = PER / 8;      // 16-byte vectors per lane
+  constexpr int KH = 8;            // keys per lane slot per half
   const int lane = threadIdx.x & 31;
   const int g = lane >> 3, j = lane & 7;
   float qr[PER];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) qr[i] = __ldcg(q + j * PER + i);
-  float s[ATT_CHUNK / 4];
-#pragma unroll
-  for (int i = 0; i < ATT_CHUNK / 4; ++i) {
-    const int key = g + 4 * i;
-    float dot = 0.f;
-    if (key < n_keys) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const uint4 kv = __ldcg(reinterpret_cast<const uint4*>(K + (long long)key * ldk + j * PER + v * 8));
-        const float2 a = DT<T>::to_f2(kv.x), b = DT<T>::to_f2(kv.y), c = DT<T>::to_f2(kv.z), d = DT<T>::to_f2(kv.w);
-        dot = fmaf(a.x, qr[v * 8 + 0], dot); dot = fmaf(a.y, qr[v * 8 + 1], dot);
-        dot = fmaf(b.x, qr[v * 8 + 2], dot); dot = fmaf(b.y, qr[v * 8 + 3], dot);
-        dot = fmaf(c.x, qr[v * 8 + 4], dot); dot = fmaf(c.y, qr[v * 8 + 5], dot);
-        dot = fmaf(d.x, qr[v * 8 + 6], dot); dot = fmaf(d.y, qr[v * 8 + 7], dot);
-      }
-    }
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    s[i] = (key < n_keys) ? dot : -INFINITY;
+  for (int i = 0; i < PER; i += 4) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(q + j * PER + i));
+    qr[i] = t.x; qr[i + 1] = t.y; qr[i + 2] = t.z; qr[i + 3] = t.w;
   }
-  float m = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < ATT_CHUNK / 4; ++i) m = fmaxf(m, s[i]);
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-  float l = 0.f;
+  float m = -INFINITY, l = 0.f;
   float o[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) o[i] = 0.f;
+
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int kbase = half * 32;
+    if (kbase >= n_keys) break;
+    uint4 kr[KH][NV], vr[KH][NV];
 #pragma unroll
-  for (int i = 0; i < ATT_CHUNK / 4; ++i) {
-    const int key = g + 4 * i;
-    if (key < n_keys) {
-      const float p = __expf(s[i] - m);
-      l += p;
+    for (int i = 0; i < KH; ++i) {
+      const int key = kbase + g + 4 * i;
+      if (key < n_keys) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const uint4 vv = __ldcg(reinterpret_cast<const uint4*>(V + (long long)key * ldv + j * PER + v * 8));
-        const float2 a = DT<T>::to_f2(vv.x), b = DT<T>::to_f2(vv.y), c = DT<T>::to_f2(vv.z), d = DT<T>::to_f2(vv.w);
-        o[v * 8 + 0] = fmaf(p, a.x, o[v * 8 + 0]); o[v * 8 + 1] = fmaf(p, a.y, o[v * 8 + 1]);
-        o[v * 8 + 2] = fmaf(p, b.x, o[v * 8 + 2]); o[v * 8 + 3] = fmaf(p, b.y, o[v * 8 + 3]);
-        o[v * 8 + 4] = fmaf(p, c.x, o[v * 8 + 4]); o[v * 8 + 5] = fmaf(p, c.y, o[v * 8 + 5]);
-        o[v * 8 + 6] = fmaf(p, d.x, o[v * 8 + 6]); o[v * 8 + 7] = fmaf(p, d.y, o[v * 8 + 7]);
+        for (int v = 0; v < NV; ++v) {
+          kr[i][v] = __ldcg(reinterpret_cast<const uint4*>(K + (long long)key * ldk + j * PER + v * 8));
+          vr[i][v] = __ldcg(reinterpret_cast<const uint4*>(V + (long long)key * ldv + j * PER + v * 8));
+        }
+      }
+    }
+    float s[KH];
+    float mh = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+      const int key = kbase + g + 4 * i;
+      float dot = 0.f;
+      if (key < n_keys) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float2 a = DT<T>::to_f2(kr[i][v].x), b = DT<T>::to_f2(kr[i][v].y);
+          const float2 c = DT<T>::to_f2(kr[i][v].z), d = DT<T>::to_f2(kr[i][v].w);
+          dot = fmaf(a.x, qr[v * 8 + 0], dot); dot = fmaf(a.y, qr[v * 8 + 1], dot);
+          dot = fmaf(b.x, qr[v * 8 + 2], dot); dot = fmaf(b.y, qr[v * 8 + 3], dot);
+          dot = fmaf(c.x, qr[v * 8 + 4], dot); dot = fmaf(c.y, qr[v * 8 + 5], dot);
+          dot = fmaf(d.x, qr[v * 8 + 6], dot); dot = fmaf(d.y, qr[v * 8 + 7], dot);
+        }
+      }
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      s[i] = (key < n_keys) ? dot : -INFINITY;
+      mh = fmaxf(mh, s[i]);
+    }
+    mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 8));
+    mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 16));
+    const float m_new = fmaxf(m, mh);          // finite: the half holds at least one key
+    const float corr = __expf(m - m_new);      // m = -inf on the first half -> 0
+    l *= corr;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) o[i] *= corr;
+    m = m_new;
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+      const int key = kbase + g + 4 * i;
+      if (key < n_keys) {
+        const float p = __expf(s[i] - m);
+        l += p;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float2 a = DT<T>::to_f2(vr[i][v].x), b = DT<T>::to_f2(vr[i][v].y);
+          const float2 c = DT<T>::to_f2(vr[i][v].z), d = DT<T>::to_f2(vr[i][v].w);
+          o[v * 8 + 0] = fmaf(p, a.x, o[v * 8 + 0]); o[v * 8 + 1] = fmaf(p, a.y, o[v * 8 + 1]);
+          o[v * 8 + 2] = fmaf(p, b.x, o[v * 8 + 2]); o[v * 8 + 3] = fmaf(p, b.y, o[v * 8 + 3]);
+          o[v * 8 + 4] = fmaf(p, c.x, o[v * 8 + 4]); o[v * 8 + 5] = fmaf(p, c.y, o[v * 8 + 5]);
+          o[v * 8 + 6] = fmaf(p, d.x, o[v * 8 + 6]); o[v * 8 + 7] = fmaf(p, d.y, o[v * 8 + 7]);
+        }
       }
     }
   }
+  // merge the 4 key slots (lanes differing in bits 3,4): l and o are per-slot partial sums under the common m
   l += __shfl_xor_sync(0xffffffffu, l, 8);
   l += __shfl_xor_sync(0xffffffffu, l, 16);
 #pragma unroll
@@ -179,29 +347,59 @@ __device__ __forceinline__ void attend_chunk(const float* q /*global fp32 [HD]*/
   }
   if (g == 0) {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) part[PART_STRIDE + j * PER + i] = o[i];
+    for (int i = 0; i < PER; i += 4)
+      *reinterpret_cast<float4*>(part + j * PER + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
   }
-  if (lane == 0) { part[0] = m; part[1] = l; }
+  if (lane == 0) { part[HD] = m; part[HD + 1] = l; }
 }
 
 // ---- merge attention partials into shared memory xs[b][h*HD + dd] (normalised) ---------------
-// part layout: [B][H][s_max][2 + HD]; n_chunks valid records per (b, h).
-template <int HD>
-__device__ __forceinline__ void combine_partials_to_smem(const float* part, int B, int H, int s_max, int n_chunks,
+// part layout: [B][H][s_max][HD + 4]; n_chunks valid records per (b, h).  One warp per (b, h): lane c owns record
+// c's (m, l); the o vectors of up to CG records are fetched with independent loads issued together with the
+// (m, l) load, so a pass over <= CG records costs a single L2 round trip.
+template <int HD, int CG>
+__device__ __noinline__ void combine_partials_to_smem(const float* part, int B, int H, int s_max, int n_chunks,
                                                          float* xs) {
-  const int D = H * HD;
-  for (int e = threadIdx.x; e < B * D; e += DEC_THREADS) {
-    const int b = e / D, r = e % D, h = r / HD, dd = r % HD;
-    const float* pp = part + ((long long)(b * H + h) * s_max) * (PART_STRIDE + HD);
-    float M = -INFINITY;
-    for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, __ldcg(pp + c * (PART_STRIDE + HD)));
-    float num = 0.f, den = 0.f;
-    for (int c = 0; c < n_chunks; ++c) {
-      const float* rec = pp + c * (PART_STRIDE + HD);
-      const float wgt = __expf(__ldcg(rec) - M);
-      den = fmaf(__ldcg(rec + 1), wgt, den);
-      num = fmaf(__ldcg(rec + PART_STRIDE + dd), wgt, num);
+  static_assert(CG <= 32, "one lane per record");
+  constexpr int REC = HD + PART_PAD;
+  constexpr int DPL = HD / 32;  // dims per lane
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int bh = warp; bh < B * H; bh += DEC_WARPS) {
+    const float* pp = part + (long long)bh * s_max * REC;
+    float M = -INFINITY, den = 0.f;
+    float num[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) num[i] = 0.f;
+    for (int c0 = 0; c0 < n_chunks; c0 += CG) {
+      const int cnt = min(CG, n_chunks - c0);
+      float mc = -INFINITY, lc = 0.f;
+      if (lane < cnt) {
+        const float2 ml = __ldcg(reinterpret_cast<const float2*>(pp + (long long)(c0 + lane) * REC + HD));
+        mc = ml.x; lc = ml.y;
+      }
+      float ov[CG][DPL];
+#pragma unroll
+      for (int u = 0; u < CG; ++u)
+#pragma unroll
+        for (int i = 0; i < DPL; ++i)
+          ov[u][i] = (u < cnt) ? __ldcg(pp + (long long)(c0 + u) * REC + lane + 32 * i) : 0.f;
+      const float M_new = fmaxf(M, warp_max(mc));
+      const float corr = __expf(M - M_new);
+      const float wc = (lane < cnt) ? __expf(mc - M_new) : 0.f;
+      den = den * corr + warp_sum(lc * wc);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) num[i] *= corr;
+      M = M_new;
+#pragma unroll
+      for (int u = 0; u < CG; ++u) {
+        const float wu = __shfl_sync(0xffffffffu, wc, u);
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) num[i] = fmaf(ov[u][i], wu, num[i]);
+      }
     }
-    xs[e] = num / den;
+    const float inv = 1.f / den;
+    const int b = bh / H, h = bh % H;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) xs[b * (H * HD) + h * HD + lane + 32 * i] = num[i] * inv;
   }
 }

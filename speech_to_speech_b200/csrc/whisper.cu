@@ -71,6 +71,8 @@ struct s2s_whisper {
   int s_max = 0;
   int last_B = 0;
   int debug_phases = 0;
+  unsigned long long* trace = nullptr;
+  int trace_cap = 0;
 };
 
 namespace {
@@ -289,7 +291,7 @@ int alloc_workspace(s2s_whisper* m) {
   S2S_CHECK(dev_alloc(m, &m->dx, (size_t)B * d * 4));
   S2S_CHECK(dev_alloc(m, &m->dq, (size_t)B * d * 4));
   S2S_CHECK(dev_alloc(m, &m->dh, (size_t)B * f * 4));
-  S2S_CHECK(dev_alloc(m, &m->part, (size_t)B * c.heads * m->s_max * 66 * 4));
+  S2S_CHECK(dev_alloc(m, &m->part, (size_t)B * c.heads * m->s_max * 68 * 4));
   S2S_CHECK(dev_alloc(m, &m->self_kv, (size_t)B * c.dec_layers * 2 * c.max_target_positions * d * esz));
   S2S_CHECK(dev_alloc(m, &m->tokens, (size_t)B * c.max_target_positions * 4));
   S2S_CHECK(dev_alloc(m, &m->out_ids, (size_t)B * c.max_target_positions * 4));
@@ -525,7 +527,7 @@ static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, in
     p.x = m->dx + (size_t)b0 * d; p.q = m->dq + (size_t)b0 * d; p.h = m->dh + (size_t)b0 * c.ffn;
     p.self_kv = off(m->self_kv, (int64_t)b0 * c.dec_layers * 2 * c.max_target_positions * d, esz);
     p.cross_kv = off(m->cross_kv, (int64_t)b0 * c.max_source_positions * c.dec_layers * 2 * d, esz);
-    p.part = m->part + (size_t)b0 * c.heads * m->s_max * 66; p.s_max = m->s_max;
+    p.part = m->part + (size_t)b0 * c.heads * m->s_max * 68; p.s_max = m->s_max;
     p.tokens = m->tokens + (size_t)b0 * c.max_target_positions;
     p.n_prefix = n_prefix; p.max_new = max_new; p.eos = eos; p.suppress = suppress_d;
     p.out_ids = ids_out_d + (size_t)b0 * max_new; p.out_len = len_out_d + b0;
@@ -537,6 +539,7 @@ static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, in
     }
     p.done = m->done + b0; p.n_done = m->n_done; p.cand_val = m->cand_val + (size_t)b0 * m->ctx->num_sms;
     p.cand_idx = m->cand_idx + (size_t)b0 * m->ctx->num_sms; p.sync_counter = m->sync_counter;
+    p.trace = m->trace; p.trace_cap = m->trace_cap;
     S2S_CHECK(whisper_decode_launch(m->ctx, p, c.compute_dtype, m->debug_phases, st));
   }
   return S2S_OK;
@@ -566,6 +569,13 @@ int s2s_whisper_decode(s2s_whisper* m, const s2s_whisper_decode_opts* o, int32_t
   S2S_CHECK(upload_suppress(m, m->suppress, o->suppress_h, o->n_suppress, o->begin_suppress_h, o->n_begin_suppress, false, st));
   return decode_impl(m, o->prefix_h, o->n_prefix, o->max_new_tokens, o->eos_id, m->suppress, B, ids_out_d, len_out_d,
                      forced_d, logits_out_d, st);
+}
+
+int s2s_whisper_set_trace(s2s_whisper* m, uint64_t* trace_d, int32_t capacity) {
+  S2S_REQUIRE(m, "set_trace: null model");
+  m->trace = reinterpret_cast<unsigned long long*>(trace_d);
+  m->trace_cap = trace_d ? capacity : 0;
+  return S2S_OK;
 }
 
 int s2s_whisper_detect_language(s2s_whisper* m, int32_t sot_id, const int32_t* lang_ids_h, int32_t n_lang, int32_t B,

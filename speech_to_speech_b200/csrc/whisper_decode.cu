@@ -20,169 +20,95 @@
 
 namespace {
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+
 constexpr int HD = 64;
 static_assert(ATT_CHUNK == ATT_CHUNK_KEYS, "chunk size mismatch");
 
+// L2 prefetch of the weight rows the NEXT phase will stream (called before the grid barrier).
 template <typename T, int NB>
-__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, float* xs, float* s_aux) {
-  const int d = p.d, B = p.B, H = p.heads, L = p.layers;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * DEC_WARPS + warp, GW = gridDim.x * DEC_WARPS;
-  const int pos = step;
-  const int rec = PART_STRIDE + HD;
-
+__device__ __noinline__ void wd_prefetch(const WhisperDecParams& p, int step, int ph) {
+  const int d = p.d, L = p.layers;
+  const T* W = nullptr;
+  int N = 0, K = d;
   if (ph < 8 * L) {
-    const int layer = ph >> 3, sub = ph & 7;
-    const WhisperDecLayer& w = p.lw[layer];
-    T* kcache = reinterpret_cast<T*>(p.self_kv);
-    const long long kv_layer_stride = (long long)p.max_pos * d;  // one of K or V for one layer
-    switch (sub) {
-      case 0: {
-        norm_rows_to_smem(p.x, w.ln1_w, w.ln1_b, 1e-5f, B, d, xs);
-        __syncthreads();
-        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_qkv), 3 * d, d, xs, B,
-                            [&](int row, const float* acc, int ln) {
-                              if (ln != 0) return;
-                              const float bias = w.b_qkv[row];
-                              for (int b = 0; b < B; ++b) {
-                                const float v = acc[b] + bias;
-                                if (row < d) {
-                                  p.q[b * d + row] = v;
-                                } else {
-                                  const int which = (row < 2 * d) ? 0 : 1;
-                                  const int c = row - (which + 1) * d;
-                                  kcache[(((long long)b * L + layer) * 2 + which) * kv_layer_stride +
-                                         (long long)pos * d + c] = DT<T>::from_f(v);
-                                }
-                              }
-                            });
-      } break;
-      case 1: {
-        const int n_chunks = pos / ATT_CHUNK + 1;
-        const int n_items = B * H * n_chunks;
-        for (int it = gw; it < n_items; it += GW) {
-          const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
-          const T* Kb = kcache + (((long long)b * L + layer) * 2 + 0) * kv_layer_stride + (long long)c * ATT_CHUNK * d + h * HD;
-          const T* Vb = Kb + kv_layer_stride;
-          const int n_keys = min(ATT_CHUNK, pos + 1 - c * ATT_CHUNK);
-          attend_chunk<T, HD>(p.q + b * d + h * HD, Kb, Vb, d, d, n_keys,
-                              p.part + ((long long)(b * H + h) * p.s_max + c) * rec);
-        }
-      } break;
-      case 2: {
-        combine_partials_to_smem<HD>(p.part, B, H, p.s_max, pos / ATT_CHUNK + 1, xs);
-        __syncthreads();
-        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_o), d, d, xs, B, [&](int row, const float* acc, int ln) {
-          if (ln != 0) return;
-          const float bias = w.b_o[row];
-          for (int b = 0; b < B; ++b) p.x[b * d + row] = __ldcg(p.x + b * d + row) + acc[b] + bias;
-        });
-      } break;
-      case 3: {
-        norm_rows_to_smem(p.x, w.ln2_w, w.ln2_b, 1e-5f, B, d, xs);
-        __syncthreads();
-        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_cq), d, d, xs, B, [&](int row, const float* acc, int ln) {
-          if (ln != 0) return;
-          const float bias = w.b_cq[row];
-          for (int b = 0; b < B; ++b) p.q[b * d + row] = acc[b] + bias;
-        });
-      } break;
-      case 4: {
-        const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK;
-        const int n_items = B * H * n_chunks;
-        const long long ldc = (long long)L * 2 * d;
-        const T* ckv = reinterpret_cast<const T*>(p.cross_kv);
-        for (int it = gw; it < n_items; it += GW) {
-          const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
-          const T* Kb = ckv + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc + (long long)layer * 2 * d + h * HD;
-          const T* Vb = Kb + d;
+    const WhisperDecLayer& w = p.lw[ph >> 3];
+    switch (ph & 7) {
+      case 0: W = reinterpret_cast<const T*>(w.w_qkv); N = 3 * d; break;
+      case 2: W = reinterpret_cast<const T*>(w.w_o); N = d; break;
+      case 3: W = reinterpret_cast<const T*>(w.w_cq); N = d; break;
+      case 5: W = reinterpret_cast<const T*>(w.w_co); N = d; break;
+      case 6: W = reinterpret_cast<const T*>(w.w_fc1); N = p.ffn; break;
+      case 7: W = reinterpret_cast<const T*>(w.w_fc2); N = d; K = p.ffn; break;
+      case 4: {  // this warp's first cross-attention item: 64 keys x (K | V) = 2 x 128 B per key
+        const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, it = dec_first_item();
+        if (it < p.B * p.heads * n_chunks) {
+          const int c = it % n_chunks, bh = it / n_chunks, h = bh % p.heads, b = bh / p.heads;
+          const long long ldc = (long long)L * 2 * d;
+          const T* Kb = reinterpret_cast<const T*>(p.cross_kv) + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc +
+                        (long long)(ph >> 3) * 2 * d + h * HD;
           const int n_keys = min(ATT_CHUNK, p.n_ctx - c * ATT_CHUNK);
-          attend_chunk<T, HD>(p.q + b * d + h * HD, Kb, Vb, ldc, ldc, n_keys,
-                              p.part + ((long long)(b * H + h) * p.s_max + c) * rec);
+          prefetch_strided_l2(Kb, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
+          prefetch_strided_l2(Kb + d, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
         }
       } break;
-      case 5: {
-        combine_partials_to_smem<HD>(p.part, B, H, p.s_max, (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, xs);
-        __syncthreads();
-        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_co), d, d, xs, B, [&](int row, const float* acc, int ln) {
-          if (ln != 0) return;
-          const float bias = w.b_co[row];
-          for (int b = 0; b < B; ++b) p.x[b * d + row] = __ldcg(p.x + b * d + row) + acc[b] + bias;
-        });
-      } break;
-      case 6: {
-        norm_rows_to_smem(p.x, w.ln3_w, w.ln3_b, 1e-5f, B, d, xs);
-        __syncthreads();
-        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_fc1), p.ffn, d, xs, B,
-                            [&](int row, const float* acc, int ln) {
-                              if (ln != 0) return;
-                              const float bias = w.b_fc1[row];
-                              for (int b = 0; b < B; ++b) p.h[b * p.ffn + row] = gelu_erf(acc[b] + bias);
-                            });
-      } break;
-      case 7: {
-        copy_rows_to_smem(p.h, B * p.ffn, xs);
-        __syncthreads();
-        gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(w.w_fc2), d, p.ffn, xs, B,
-                            [&](int row, const float* acc, int ln) {
-                              if (ln != 0) return;
-                              const float bias = w.b_fc2[row];
-                              for (int b = 0; b < B; ++b) p.x[b * d + row] = __ldcg(p.x + b * d + row) + acc[b] + bias;
-                            });
-      } break;
+      default: break;
     }
-    return;
+  } else if (ph == 8 * L && step >= p.n_prefix - 1) {
+    // first row group of every warp only; later groups are prefetched inside the GEMV loop
+    W = reinterpret_cast<const T*>(p.embed); N = min(p.vocab, dec_item_stride() * GV_R);
   }
+  if (W) prefetch_rows_l2<T, GV_R>(W, N, K);
+}
 
-  const int g = step - (p.n_prefix - 1);  // index of the token generated at this step
-  if (ph == 8 * L) {
-    if (g < 0) return;
-    norm_rows_to_smem(p.x, p.lnf_w, p.lnf_b, 1e-5f, B, d, xs);
-    __syncthreads();
-    float best_v[NB];
-    int best_i[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) { best_v[b] = -INFINITY; best_i[b] = 0x7fffffff; }
-    gemv_rows<T, NB, 4>(reinterpret_cast<const T*>(p.embed), p.vocab, d, xs, B, [&](int row, const float* acc, int ln) {
-      if (ln != 0) return;
-      const unsigned char sm = p.suppress[row];
-      const bool masked = (sm & 1) || (g == 0 && (sm & 2));
-#pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        if (b < B) {
-          const float v = masked ? -INFINITY : acc[b];
-          if (p.logits_out) p.logits_out[((long long)g * B + b) * p.vocab + row] = v;
-          if (v > best_v[b]) { best_v[b] = v; best_i[b] = row; }
-        }
-      }
-    });
-    // per-CTA argmax: s_aux = [DEC_WARPS][NB] values then indices
-    float* sv = s_aux;
-    int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
-    if (lane == 0) {
-#pragma unroll
-      for (int b = 0; b < NB; ++b) { sv[warp * NB + b] = best_v[b]; si[warp * NB + b] = best_i[b]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < B) {
-      const int b = threadIdx.x;
-      float bv = -INFINITY; int bi = 0x7fffffff;
-      for (int wv = 0; wv < DEC_WARPS; ++wv) {
-        const float v = sv[wv * NB + b]; const int i = si[wv * NB + b];
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-      }
-      p.cand_val[b * gridDim.x + blockIdx.x] = bv;
-      p.cand_idx[b * gridDim.x + blockIdx.x] = bi;
-    }
-    return;
+template <typename T, int NB>
+__device__ __noinline__ void wd_self_attn(const WhisperDecParams& p, int layer, int pos) {
+  const int d = p.d, B = p.B, H = p.heads, L = p.layers;
+  const T* kcache = reinterpret_cast<const T*>(p.self_kv);
+  const long long kv_layer_stride = (long long)p.max_pos * d;
+  const int rec = HD + PART_PAD;
+  const int n_chunks = pos / ATT_CHUNK + 1;
+  const int n_items = B * H * n_chunks;
+  for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
+    const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
+    const T* Kb = kcache + (((long long)b * L + layer) * 2 + 0) * kv_layer_stride + (long long)c * ATT_CHUNK * d + h * HD;
+    const T* Vb = Kb + kv_layer_stride;
+    const int n_keys = min(ATT_CHUNK, pos + 1 - c * ATT_CHUNK);
+    attend_chunk<T, HD>(p.q + b * d + h * HD, Kb, Vb, d, d, n_keys, p.part + ((long long)(b * H + h) * p.s_max + c) * rec);
   }
+}
 
-  // ---- select: global argmax, bookkeeping, next embedding ----
+template <typename T, int NB>
+__device__ __noinline__ void wd_cross_attn(const WhisperDecParams& p, int layer) {
+  const int d = p.d, B = p.B, H = p.heads, L = p.layers;
+  const int rec = HD + PART_PAD;
+  const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK;
+  const int n_items = B * H * n_chunks;
+  const long long ldc = (long long)L * 2 * d;
+  const T* ckv = reinterpret_cast<const T*>(p.cross_kv);
+  for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
+    const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
+    const T* Kb = ckv + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc + (long long)layer * 2 * d + h * HD;
+    const T* Vb = Kb + d;
+    const int n_keys = min(ATT_CHUNK, p.n_ctx - c * ATT_CHUNK);
+    attend_chunk<T, HD>(p.q + b * d + h * HD, Kb, Vb, ldc, ldc, n_keys, p.part + ((long long)(b * H + h) * p.s_max + c) * rec);
+  }
+}
+
+// global argmax, EOS / length bookkeeping, next-token embedding
+template <typename T>
+__device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos, float* s_aux) {
+  const int d = p.d, B = p.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* s_feed = reinterpret_cast<int*>(s_aux);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     if (warp == 0) {
-      int feed;
       if (g >= 0) {
         float bv = -INFINITY; int bi = 0x7fffffff;
         for (int c = lane; c < (int)gridDim.x; c += 32) {
@@ -194,8 +120,8 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
           const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
           if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        int tok = bi;
         if (lane == 0) {
+          int tok = bi;
           const bool was_done = p.done[b] != 0;
           if (was_done) tok = p.eos;
           p.out_ids[b * p.max_new + g] = tok;
@@ -204,7 +130,7 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
             else if (g == p.max_new - 1) { p.out_len[b] = p.max_new; }
           }
           if (p.forced && g == p.max_new - 1) p.out_len[b] = p.max_new;
-          feed = p.forced ? p.forced[b * p.max_new + g] : tok;
+          const int feed = p.forced ? p.forced[b * p.max_new + g] : tok;
           if (pos + 1 < p.max_pos) p.tokens[b * p.max_pos + pos + 1] = feed;
           *s_feed = feed;
         }
@@ -222,22 +148,120 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
   }
 }
 
+// One phase = (stage inputs into shared memory) + (one shared routine).  Thin: only argument setup is inlined.
+template <typename T, int NB>
+__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, float* xs, float* s_aux) {
+  float* s_red = s_aux + 2 * DEC_WARPS * NB;
+  float* wb = s_red + 2 * DEC_WARPS;  // LayerNorm weight | bias staged per phase
+  const int L = p.layers, pos = step, d = p.d, B = p.B;
+  float best_v = -INFINITY;
+  int best_i = 0x7fffffff;
+  GemvArgs a;
+  a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
+  a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
+  if (ph < 8 * L) {
+    const int layer = ph >> 3;
+    const WhisperDecLayer& w = p.lw[layer];
+    switch (ph & 7) {
+      case 0: {  // LN1 + QKV (+ self-KV append)
+        stage_rows(p.x, B, d, xs, 1, w.ln1_w, w.ln1_b, 1e-5f, s_red, wb);
+        const long long kvs = (long long)p.max_pos * d;
+        a.W = w.w_qkv; a.N = 3 * d; a.bias = w.b_qkv; a.mode = EPI_QKV; a.out = p.q;
+        a.kv0 = reinterpret_cast<T*>(p.self_kv) + ((long long)layer * 2) * kvs + (long long)pos * d;
+        a.kv_which = kvs; a.kv_batch = (long long)L * 2 * kvs;
+      } break;
+      case 1: wd_self_attn<T, NB>(p, layer, pos); return;
+      case 2:  // combine + out-proj + residual
+        combine_partials_to_smem<HD, 12>(p.part, B, p.heads, p.s_max, pos / ATT_CHUNK + 1, xs);
+        __syncthreads();
+        a.W = w.w_o; a.N = d; a.bias = w.b_o; a.mode = EPI_RESID; a.out = p.x;
+        break;
+      case 3:  // LN2 + cross q
+        stage_rows(p.x, B, d, xs, 1, w.ln2_w, w.ln2_b, 1e-5f, s_red, wb);
+        a.W = w.w_cq; a.N = d; a.bias = w.b_cq; a.mode = EPI_STORE; a.out = p.q;
+        break;
+      case 4: wd_cross_attn<T, NB>(p, layer); return;
+      case 5:
+        combine_partials_to_smem<HD, 12>(p.part, B, p.heads, p.s_max, (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, xs);
+        __syncthreads();
+        a.W = w.w_co; a.N = d; a.bias = w.b_co; a.mode = EPI_RESID; a.out = p.x;
+        break;
+      case 6:  // LN3 + fc1 + GELU
+        stage_rows(p.x, B, d, xs, 1, w.ln3_w, w.ln3_b, 1e-5f, s_red, wb);
+        a.W = w.w_fc1; a.N = p.ffn; a.bias = w.b_fc1; a.mode = EPI_GELU; a.out = p.h; a.ldo = p.ffn;
+        break;
+      default:  // fc2 + residual
+        stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb);
+        a.W = w.w_fc2; a.N = d; a.K = p.ffn; a.bias = w.b_fc2; a.mode = EPI_RESID; a.out = p.x;
+        break;
+    }
+    gemv_generic<T, NB>(a, xs, B, best_v, best_i);
+    return;
+  }
+  const int g = step - (p.n_prefix - 1);  // index of the token generated at this step
+  if (ph == 8 * L) {
+    if (g < 0) return;
+    // final LayerNorm + tied output projection + suppress masks + per-CTA argmax candidates
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    stage_rows(p.x, B, d, xs, 1, p.lnf_w, p.lnf_b, 1e-5f, s_red, wb);
+    a.W = p.embed; a.N = p.vocab; a.mode = EPI_LOGITS; a.suppress = p.suppress; a.first_step = (g == 0);
+    a.logits_out = p.logits_out ? p.logits_out + (long long)g * B * p.vocab : nullptr; a.logits_ld = p.vocab;
+    gemv_generic<T, NB>(a, xs, B, best_v, best_i);
+    float* sv = s_aux;
+    int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
+    if (lane < NB) { sv[warp * NB + lane] = best_v; si[warp * NB + lane] = best_i; }
+    __syncthreads();
+    if (threadIdx.x < B) {
+      const int b = threadIdx.x;
+      float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int wv = 0; wv < DEC_WARPS; ++wv) {
+        const float v = sv[wv * NB + b]; const int i = si[wv * NB + b];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+      p.cand_val[b * gridDim.x + blockIdx.x] = bv;
+      p.cand_idx[b * gridDim.x + blockIdx.x] = bi;
+    }
+  } else {
+    wd_select<T>(p, g, pos, s_aux);
+  }
+}
+
 template <typename T, int NB>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, int ph_begin, int ph_end, int coop) {
   extern __shared__ __align__(16) float smem_f[];
+  __shared__ WhisperDecParams sp;
+  __shared__ WhisperDecLayer s_layers[32];  // per-layer pointer tables: no global pointer chase inside a phase
+  if (threadIdx.x == 0) { sp = p; sp.lw = s_layers; }
+  for (int i = threadIdx.x; i < p.layers; i += DEC_THREADS) s_layers[i] = p.lw[i];
+  __syncthreads();
   const int xs_floats = NB * max(p.d, p.ffn);
   float* xs = smem_f;
   float* s_aux = smem_f + xs_floats;
   unsigned int epoch = 0;
+  int trace_i = 0;
   const int n_ph = 8 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
     for (int ph = pb; ph < pe; ++ph) {
       // the logits phase is skipped while the forced prompt is still being fed
       const bool skip = (ph == 8 * p.layers) && (step < p.n_prefix - 1);
-      if (!skip) wd_phase<T, NB>(p, step, ph, xs, s_aux);
-      if (coop && !skip) grid_sync(p.sync_counter, epoch);
+      const bool tracing = sp.trace && trace_i < sp.trace_cap && threadIdx.x == 0 &&
+                           (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+      unsigned long long* tr = tracing ? sp.trace + ((blockIdx.x == 0 ? 0 : 1) * (long long)sp.trace_cap + trace_i) * 6 : nullptr;
+      if (tracing) tr[0] = globaltimer_ns();
+      if (!skip) wd_phase<T, NB>(sp, step, ph, xs, s_aux);
+      if (tracing) tr[4] = globaltimer_ns();
+      if (coop && !skip) {
+        // warm L2 with the next phase's weight rows while we wait at the barrier
+        int nph = ph + 1, nstep = step;
+        if (nph == n_ph) { nph = 0; nstep = step + 1; }
+        if (nph == 8 * p.layers && nstep < p.n_prefix - 1) nph = n_ph;  // logits phase skipped
+        if (nstep < step_end && nph < n_ph) wd_prefetch<T, NB>(sp, nstep, nph);
+        grid_sync(p.sync_counter, epoch);
+      }
+      if (tracing) tr[5] = globaltimer_ns();
+      if (!skip) ++trace_i;
     }
     if (coop && !p.forced && *reinterpret_cast<volatile int*>(p.n_done) >= p.B) break;
   }
@@ -260,7 +284,7 @@ __global__ void whisper_decode_init_kernel(const WhisperDecParams p) {
 
 template <typename T, int NB>
 int launch_nb(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStream_t stream) {
-  const size_t smem = ((size_t)NB * (size_t)max(p.d, p.ffn) + 2 * DEC_WARPS * NB + 32) * sizeof(float);
+  const size_t smem = ((size_t)NB * (size_t)max(p.d, p.ffn) + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * (size_t)p.d + 32) * sizeof(float);
   auto kern = whisper_decode_kernel<T, NB>;
   S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   whisper_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(p);
@@ -300,6 +324,7 @@ int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStre
 
 int whisper_decode_launch(s2s_ctx* ctx, const WhisperDecParams& p, int dtype, int debug_phases, cudaStream_t stream) {
   S2S_REQUIRE(p.d / p.heads == HD, "whisper decode: head_dim must be 64");
+  S2S_REQUIRE(p.layers <= 32, "whisper decode: at most 32 decoder layers");
   S2S_REQUIRE(p.n_prefix >= 1 && p.max_new >= 1 && p.n_prefix + p.max_new <= p.max_pos,
               "whisper decode: prompt %d + max_new %d exceeds max_target_positions %d", p.n_prefix, p.max_new, p.max_pos);
   if (dtype == S2S_F16) return launch_t<__half>(ctx, p, debug_phases, stream);

@@ -26,7 +26,7 @@ struct WhisperDecParams {
   float* h;                    // [B, ffn]
   void* self_kv;               // [B][layers][2][max_pos][d] 16-bit
   const void* cross_kv;        // [B * n_ctx, layers * 2 * d] 16-bit
-  float* part;                 // [B][heads][s_max][2 + 64]
+  float* part;                 // [B][heads][s_max][64 + 4]
   int s_max;
   // token bookkeeping
   int* tokens;                 // [B][max_pos]
@@ -41,6 +41,8 @@ struct WhisperDecParams {
   float* cand_val;             // [B][grid]
   int* cand_idx;               // [B][grid]
   unsigned int* sync_counter;  // [1], zeroed before launch
+  unsigned long long* trace;   // optional [2][trace_cap][3] globaltimer stamps (profiling aid)
+  int trace_cap;
 };
 
 int whisper_decode_launch(s2s_ctx* ctx, const WhisperDecParams& p, int dtype, int debug_phases, cudaStream_t stream);

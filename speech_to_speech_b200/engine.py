@@ -137,6 +137,11 @@ class WhisperEngine:
                                           _stream_ptr(self.device)), "s2s_whisper_decode")
         return (ids, lens, logits) if return_logits else (ids, lens)
 
+    def set_trace(self, trace: Optional[torch.Tensor]) -> None:
+        """trace: cuda int64 [2, capacity, 6] or None (profiling aid, see include/s2s_b200.h)."""
+        cap = 0 if trace is None else trace.shape[1]
+        check(self.lib.s2s_whisper_set_trace(self.handle, _ptr(trace), cap), "s2s_whisper_set_trace")
+
     def detect_language(self, B: int, sot_id: int, lang_ids: Sequence[int]) -> torch.Tensor:
         out = torch.empty((B,), dtype=torch.int32, device=f"cuda:{self.device}")
         la, n = _lib.i32_array(lang_ids)
