@@ -145,13 +145,15 @@ int s2s_llama_session_reset(s2s_llama* m, int32_t slot);
  * next_id_d optional [1] i32 = argmax of the last position.                                 */
 int s2s_llama_prefill(s2s_llama* m, int32_t slot, const int32_t* ids_h, int32_t n, float* logits_out_d,
                       int32_t* next_id_d, void* stream);
-/* Greedy decode n_steps tokens for B sessions in one persistent launch.  slots_h[B]; first_ids_d[B]
- * are the tokens to feed first (the prefill argmax); ids_out_d [B, n_steps]; eos stops a row
- * (eos_id < 0 disables); forced_d optional [B, n_steps]; logits_out_d optional [n_steps, B, vocab]. */
+/* Greedy decode for B (<= 4) sessions in one persistent launch.  slots_h[B]; first_ids_d[B] are the tokens to
+ * feed first (the prefill argmax); ids_out_d [B, n_steps] receives the n_steps tokens generated AFTER them; eos stops
+ * a row (eos_id < 0 disables); forced_d optional [B, n_steps] teacher-forced feedback; logits_out_d optional
+ * [n_steps, B, vocab].                                                                              */
 int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int32_t* first_ids_d,
                      int32_t n_steps, int32_t eos_id, int32_t* ids_out_d, int32_t* len_out_d,
                      const int32_t* forced_d, float* logits_out_d, void* stream);
-/* End-to-end with HOST buffers: prefill + n_steps greedy tokens, synchronous. */
+/* End-to-end with HOST buffers: (chunked) prefill + greedy decode, synchronous.  ids_out_h[0] is the argmax of the
+ * prompt's last position, n_steps tokens in total (generate() semantics of the reference's pipeline call). */
 int s2s_llama_generate(s2s_llama* m, int32_t slot, const int32_t* prompt_h, int32_t n_prompt, int32_t n_steps,
                        int32_t eos_id, int32_t* ids_out_h, int32_t* len_out_h, void* stream);
 

@@ -46,10 +46,12 @@ template <typename T, int R>
 __device__ __forceinline__ void prefetch_rows_l2(const T* W, int N, int K) {
   const int lane = threadIdx.x & 31;
   const int row_bytes = K * (int)sizeof(T);
+#pragma unroll 1
   for (int row0 = dec_first_item() * R; row0 < N; row0 += dec_item_stride() * R) {
     const int nrows = min(R, N - row0);
     const char* base = reinterpret_cast<const char*>(W + (long long)row0 * K);
     const int total = nrows * row_bytes;
+#pragma unroll 1
     for (int o = lane * 128; o < total; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
   }
 }
@@ -58,6 +60,7 @@ __device__ __forceinline__ void prefetch_rows_l2(const T* W, int N, int K) {
 __device__ __forceinline__ void prefetch_strided_l2(const void* base, long long ld_bytes, int n_rows, int row_bytes) {
   const int lane = threadIdx.x & 31;
   const int lines_per_row = (row_bytes + 127) >> 7;
+#pragma unroll 1
   for (int i = lane; i < n_rows * lines_per_row; i += 32) {
     const char* a = reinterpret_cast<const char*>(base) + (long long)(i / lines_per_row) * ld_bytes + (i % lines_per_row) * 128;
     asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
@@ -68,24 +71,27 @@ __device__ __forceinline__ void prefetch_strided_l2(const void* base, long long 
 // mode 0: plain copy; 1: LayerNorm (w, bias); 2: RMSNorm (w).  Two-pass statistics from shared memory.
 // The norm weights are fetched together with x (one round trip) into wb[2*d].  s_red: >= DEC_WARPS floats.
 // Ends with a __syncthreads().
-__device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs, int mode, const float* w,
+static __device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs, int mode, const float* w,
                                            const float* bias, float eps, float* s_red, float* wb) {
   const int n = B * d;
-  const int n_all = n + (mode == 0 ? 0 : (mode == 1 ? 2 * d : d));
-  for (int i0 = threadIdx.x * 4; i0 < n_all; i0 += DEC_THREADS * 16) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * DEC_THREADS * 4;
-      if (i < n) v[u] = __ldcg(reinterpret_cast<const float4*>(x + i));
-      else if (i < n_all && i < n + d) v[u] = __ldg(reinterpret_cast<const float4*>(w + (i - n)));
-      else if (i < n_all) v[u] = __ldg(reinterpret_cast<const float4*>(bias + (i - n - d)));
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * DEC_THREADS * 4;
-      if (i < n) *reinterpret_cast<float4*>(xs + i) = v[u];
-      else if (i < n_all) *reinterpret_cast<float4*>(wb + (i - n)) = v[u];
+  // x rows: two independent 16-byte loads per thread per trip (one trip for B*d <= 2048)
+#pragma unroll 1
+  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 8) {
+    const int j = i + DEC_THREADS * 4;
+    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(x + i));
+    float4 v1;
+    if (j < n) v1 = __ldcg(reinterpret_cast<const float4*>(x + j));
+    *reinterpret_cast<float4*>(xs + i) = v0;
+    if (j < n) *reinterpret_cast<float4*>(xs + j) = v1;
+  }
+  if (mode != 0) {
+#pragma unroll 1
+    for (int i = threadIdx.x * 4; i < d; i += DEC_THREADS * 4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w + i));
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mode == 1) bb = __ldg(reinterpret_cast<const float4*>(bias + i));
+      *reinterpret_cast<float4*>(wb + i) = g;
+      *reinterpret_cast<float4*>(wb + d + i) = bb;
     }
   }
   __syncthreads();
@@ -94,6 +100,7 @@ __device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs,
   int wpr = DEC_WARPS;  // warps per row: largest power of two with wpr * B <= DEC_WARPS (min 1)
   while (wpr > 1 && wpr * B > DEC_WARPS) wpr >>= 1;
   const int rows_per_iter = DEC_WARPS / wpr;
+#pragma unroll 1
   for (int r0 = 0; r0 < B; r0 += rows_per_iter) {
     const int row = r0 + warp / wpr, sub = warp % wpr, grp = (warp / wpr) * wpr;
     const bool valid = row < B;
@@ -101,8 +108,10 @@ __device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs,
     float mean = 0.f;
     if (mode == 1) {
       float s = 0.f;
-      if (valid)
+      if (valid) {
+#pragma unroll 2
         for (int i = sub * 32 + lane; i < d; i += wpr * 32) s += xr[i];
+      }
       s = warp_sum(s);
       if (lane == 0) s_red[warp] = s;
       __syncthreads();
@@ -110,23 +119,27 @@ __device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs,
       mean /= (float)d;
     }
     float ss = 0.f;
-    if (valid)
+    if (valid) {
+#pragma unroll 2
       for (int i = sub * 32 + lane; i < d; i += wpr * 32) {
         const float a = xr[i] - mean;
         ss += a * a;
       }
+    }
     ss = warp_sum(ss);
     if (lane == 0) s_red[DEC_WARPS + warp] = ss;  // second half of s_red: no barrier needed before reuse
     __syncthreads();
     float var = 0.f;
     for (int k = 0; k < wpr; ++k) var += s_red[DEC_WARPS + grp + k];
     const float rstd = rsqrtf(var / (float)d + eps);
-    if (valid)
+    if (valid) {
+#pragma unroll 2
       for (int i = sub * 32 + lane; i < d; i += wpr * 32) {
         float y = (xr[i] - mean) * rstd * wb[i];
-        if (mode == 1) y += wb[d + i];
+        y += wb[d + i];
         xr[i] = y;
       }
+    }
     __syncthreads();
   }
 }
@@ -138,8 +151,9 @@ __device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs,
 // A warp owns GV_R consecutive rows and keeps GV_R * GV_U independent 16-byte loads in flight per lane; the
 // bias / residual / mask reads are issued BEFORE the weight loads; the NEXT row group of the warp is L2-prefetched
 // while the current one is reduced.  Lane b (< B) applies the epilogue for batch row b.
-constexpr int GV_R = 4, GV_U = 4;
-enum GemvEpi { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_QKV = 3, EPI_LOGITS = 4 };
+constexpr int GV_R = 2, GV_U = 4, GV_PF = 3;
+enum GemvEpi { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_QKV = 3, EPI_LOGITS = 4,
+               EPI_QKV_ROPE = 5 /* row pairs */, EPI_SWIGLU = 6 /* row pairs */ };
 struct GemvArgs {
   const void* W; int N, K;
   const float* bias;           // [N] or null
@@ -149,7 +163,120 @@ struct GemvArgs {
   void* kv0; long long kv_which, kv_batch; int d;
   // LOGITS
   const unsigned char* suppress; int first_step; float* logits_out; long long logits_ld;  // logits_out + b*logits_ld + row
+  // QKV_ROPE (Llama family): rows are stored so that rotate_half partners (j, j + hd/2) are adjacent (2j, 2j+1).
+  // rows [0, q_rows) -> out (fp32 q, rotated); [q_rows, q_rows + k_rows) -> K cache (rotated); rest -> V cache.
+  // cache element (b, c): kv0 + which*kv_which + slot[b]*kv_slot + pos[b]*kv_ld + c ; rope[pos][j] = (cos, sin)
+  const int* pos; const int* slot; long long kv_slot; int kv_ld; const float2* rope; int hd, q_rows, k_rows;
+  float q_scale;               // softmax scale folded into the stored q (head_dim^-0.5)
 };
+
+// epilogue of one reduced row for batch row `lane`
+template <typename T>
+__device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, int mode, int row, int lane, float v, float bias,
+                                              float resid, int sup, float& best_v, int& best_i) {
+  v += bias;
+  if (mode == EPI_STORE) {
+    a.out[lane * a.ldo + row] = v;
+  } else if (mode == EPI_GELU) {
+    a.out[lane * a.ldo + row] = gelu_erf(v);
+  } else if (mode == EPI_RESID) {
+    a.out[lane * a.ldo + row] = resid + v;
+  } else if (mode == EPI_QKV) {
+    if (row < a.d) {
+      a.out[lane * a.ldo + row] = v;
+    } else {
+      const int which = (row < 2 * a.d) ? 0 : 1;
+      reinterpret_cast<T*>(a.kv0)[which * a.kv_which + lane * a.kv_batch + (row - (which + 1) * a.d)] = DT<T>::from_f(v);
+    }
+  } else {  // EPI_LOGITS
+    if ((sup & 1) || (a.first_step && (sup & 2))) v = -INFINITY;
+    if (a.logits_out) a.logits_out[lane * a.logits_ld + row] = v;
+    if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
+  }
+}
+
+// epilogue of one reduced ROW PAIR (rows row0, row0 + 1) for batch row `lane`
+template <typename T>
+__device__ __forceinline__ void gemv_pair_epilogue(const GemvArgs& a, int mode, int row0, int lane, float v0, float v1) {
+  if (mode == EPI_SWIGLU) {
+    a.out[lane * a.ldo + (row0 >> 1)] = (v0 / (1.0f + __expf(-v0))) * v1;
+    return;
+  }
+  // EPI_QKV_ROPE
+  const int kv_end = a.q_rows + a.k_rows;
+  if (row0 < kv_end) {
+    const int p = __ldcg(a.pos + lane);
+    const float2 cs = a.rope[(long long)p * (a.hd >> 1) + ((row0 % a.hd) >> 1)];
+    const float r0 = v0 * cs.x - v1 * cs.y, r1 = v1 * cs.x + v0 * cs.y;
+    v0 = r0; v1 = r1;
+  }
+  if (row0 < a.q_rows) {
+    *reinterpret_cast<float2*>(a.out + lane * a.ldo + row0) = make_float2(v0 * a.q_scale, v1 * a.q_scale);
+  } else {
+    const int which = (row0 < kv_end) ? 0 : 1;
+    const int c = row0 - (which ? kv_end : a.q_rows);
+    T* dst = reinterpret_cast<T*>(a.kv0) + which * a.kv_which + (long long)a.slot[lane] * a.kv_slot +
+             (long long)__ldcg(a.pos + lane) * a.kv_ld + c;
+    *reinterpret_cast<uint32_t*>(dst) = DT<T>::pack2(v0, v1);
+  }
+}
+
+// all loads of one row group (nothing is consumed here, so they are issued back to back)
+template <typename T>
+__device__ __forceinline__ void gemv_load_group(const GemvArgs& a, const T* __restrict__ W, int row0, int k0, int B,
+                                                int lane, bool first_k, uint4 (&wv)[GV_U][GV_R], float (&bias)[GV_R],
+                                                float (&resid)[GV_R], int (&sup)[GV_R]) {
+  const int N = a.N, K = a.K;
+  if (first_k) {
+#pragma unroll
+    for (int r = 0; r < GV_R; ++r) {
+      const int row = min(row0 + r, N - 1);
+      bias[r] = a.bias ? __ldg(a.bias + row) : 0.f;
+      resid[r] = 0.f;
+      sup[r] = 0;
+      if (a.mode == EPI_RESID) { if (lane < B) resid[r] = __ldcg(a.out + lane * a.ldo + row); }
+      else if (a.mode == EPI_LOGITS && a.suppress) sup[r] = __ldg(a.suppress + row);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < GV_U; ++u) {
+    const int k = k0 + u * 256;
+#pragma unroll
+    for (int r = 0; r < GV_R; ++r) {
+      const int row = min(row0 + r, N - 1);
+      if (k < K) wv[u][r] = ld_stream16(W + (long long)row * K + k);
+    }
+  }
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void gemv_fma_group(const uint4 (&wv)[GV_U][GV_R], const float* xs, int K, int k0, int B,
+                                               float (&acc)[GV_R][NB]) {
+#pragma unroll
+  for (int u = 0; u < GV_U; ++u) {
+    const int k = k0 + u * 256;
+    if (k < K) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (b < B) {
+          const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + k);
+          const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + k + 4);
+#pragma unroll
+          for (int r = 0; r < GV_R; ++r) {
+            const float2 w0 = DT<T>::to_f2(wv[u][r].x), w1 = DT<T>::to_f2(wv[u][r].y);
+            const float2 w2 = DT<T>::to_f2(wv[u][r].z), w3 = DT<T>::to_f2(wv[u][r].w);
+            float c = acc[r][b];
+            c = fmaf(w0.x, x0.x, c); c = fmaf(w0.y, x0.y, c);
+            c = fmaf(w1.x, x0.z, c); c = fmaf(w1.y, x0.w, c);
+            c = fmaf(w2.x, x1.x, c); c = fmaf(w2.y, x1.y, c);
+            c = fmaf(w3.x, x1.z, c); c = fmaf(w3.y, x1.w, c);
+            acc[r][b] = c;
+          }
+        }
+      }
+    }
+  }
+}
 
 template <typename T, int NB>
 __device__ __noinline__ void gemv_generic(const GemvArgs& a, const float* xs, int B, float& best_v, int& best_i) {
@@ -157,22 +284,14 @@ __device__ __noinline__ void gemv_generic(const GemvArgs& a, const float* xs, in
   const T* __restrict__ W = reinterpret_cast<const T*>(a.W);
   const int N = a.N, K = a.K, mode = a.mode;
   const int stride = dec_item_stride() * GV_R;
+  const int kl = lane * 8;
+#pragma unroll 1
   for (int row0 = dec_first_item() * GV_R; row0 < N; row0 += stride) {
-    float bias[GV_R], extra[GV_R];
-#pragma unroll
-    for (int r = 0; r < GV_R; ++r) {
-      const int row = min(row0 + r, N - 1);
-      bias[r] = a.bias ? __ldg(a.bias + row) : 0.f;
-      extra[r] = 0.f;
-      if (mode == EPI_RESID) { if (lane < B) extra[r] = __ldcg(a.out + lane * a.ldo + row); }
-      else if (mode == EPI_LOGITS) {
-        const unsigned char sm = __ldg(a.suppress + row);
-        extra[r] = ((sm & 1) || (a.first_step && (sm & 2))) ? 1.f : 0.f;
-      }
-    }
-    if (row0 + stride < N) {  // warm L2 with this warp's next row group
-      const char* nb = reinterpret_cast<const char*>(W + (long long)(row0 + stride) * K);
-      const int total = min(GV_R, N - row0 - stride) * K * (int)sizeof(T);
+    const int pf_row = row0 + GV_PF * stride;
+    if (pf_row < N) {  // warm L2 GV_PF row groups ahead: HBM latency is hidden behind the groups in between
+      const char* nb = reinterpret_cast<const char*>(W + (long long)pf_row * K);
+      const int total = min(GV_R, N - pf_row) * K * (int)sizeof(T);
+#pragma unroll 1
       for (int o = lane * 128; o < total; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
     }
     float acc[GV_R][NB];
@@ -180,42 +299,15 @@ __device__ __noinline__ void gemv_generic(const GemvArgs& a, const float* xs, in
     for (int r = 0; r < GV_R; ++r)
 #pragma unroll
       for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
-    for (int k0 = lane * 8; k0 < K; k0 += 256 * GV_U) {
+    float bias[GV_R], resid[GV_R];
+    int sup[GV_R];
+#pragma unroll 1
+    for (int k0 = kl; k0 < K; k0 += 256 * GV_U) {
       uint4 wv[GV_U][GV_R];
-#pragma unroll
-      for (int u = 0; u < GV_U; ++u) {
-        const int k = k0 + u * 256;
-#pragma unroll
-        for (int r = 0; r < GV_R; ++r) {
-          const int row = min(row0 + r, N - 1);
-          if (k < K) wv[u][r] = ld_stream16(W + (long long)row * K + k);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < GV_U; ++u) {
-        const int k = k0 + u * 256;
-        if (k < K) {
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            if (b < B) {
-              const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + k);
-              const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + k + 4);
-#pragma unroll
-              for (int r = 0; r < GV_R; ++r) {
-                const float2 w0 = DT<T>::to_f2(wv[u][r].x), w1 = DT<T>::to_f2(wv[u][r].y);
-                const float2 w2 = DT<T>::to_f2(wv[u][r].z), w3 = DT<T>::to_f2(wv[u][r].w);
-                float c = acc[r][b];
-                c = fmaf(w0.x, x0.x, c); c = fmaf(w0.y, x0.y, c);
-                c = fmaf(w1.x, x0.z, c); c = fmaf(w1.y, x0.w, c);
-                c = fmaf(w2.x, x1.x, c); c = fmaf(w2.y, x1.y, c);
-                c = fmaf(w3.x, x1.z, c); c = fmaf(w3.y, x1.w, c);
-                acc[r][b] = c;
-              }
-            }
-          }
-        }
-      }
+      gemv_load_group<T>(a, W, row0, k0, B, lane, k0 == kl, wv, bias, resid, sup);
+      gemv_fma_group<T, NB>(wv, xs, K, k0, B, acc);
     }
+    float vr[GV_R];
 #pragma unroll
     for (int r = 0; r < GV_R; ++r) {
 #pragma unroll
@@ -223,28 +315,16 @@ __device__ __noinline__ void gemv_generic(const GemvArgs& a, const float* xs, in
       float v = acc[r][0];
 #pragma unroll
       for (int b = 1; b < NB; ++b) v = (lane == b) ? acc[r][b] : v;
-      const int row = row0 + r;
-      if (row < N && lane < B) {
-        v += bias[r];
-        if (mode == EPI_STORE) {
-          a.out[lane * a.ldo + row] = v;
-        } else if (mode == EPI_GELU) {
-          a.out[lane * a.ldo + row] = gelu_erf(v);
-        } else if (mode == EPI_RESID) {
-          a.out[lane * a.ldo + row] = extra[r] + v;
-        } else if (mode == EPI_QKV) {
-          if (row < a.d) {
-            a.out[lane * a.ldo + row] = v;
-          } else {
-            const int which = (row < 2 * a.d) ? 0 : 1;
-            reinterpret_cast<T*>(a.kv0)[which * a.kv_which + lane * a.kv_batch + (row - (which + 1) * a.d)] = DT<T>::from_f(v);
-          }
-        } else {  // EPI_LOGITS
-          if (extra[r] != 0.f) v = -INFINITY;
-          if (a.logits_out) a.logits_out[lane * a.logits_ld + row] = v;
-          if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
-        }
-      }
+      vr[r] = v;
+    }
+    if (mode >= EPI_QKV_ROPE) {
+      static_assert(GV_R == 2, "pair epilogues need two rows per group");
+      if (lane < B) gemv_pair_epilogue<T>(a, mode, row0, lane, vr[0] + bias[0], vr[1] + bias[1]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < GV_R; ++r)
+        if (row0 + r < N && lane < B)
+          gemv_epilogue<T>(a, mode, row0 + r, lane, vr[r], bias[r], resid[r], sup[r], best_v, best_i);
     }
   }
 }
@@ -364,12 +444,14 @@ __device__ __noinline__ void combine_partials_to_smem(const float* part, int B, 
   constexpr int REC = HD + PART_PAD;
   constexpr int DPL = HD / 32;  // dims per lane
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
   for (int bh = warp; bh < B * H; bh += DEC_WARPS) {
     const float* pp = part + (long long)bh * s_max * REC;
     float M = -INFINITY, den = 0.f;
     float num[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) num[i] = 0.f;
+#pragma unroll 1
     for (int c0 = 0; c0 < n_chunks; c0 += CG) {
       const int cnt = min(CG, n_chunks - c0);
       float mc = -INFINITY, lc = 0.f;

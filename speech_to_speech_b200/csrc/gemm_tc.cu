@@ -148,6 +148,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
+        if (ep.act == 2) {
+          // SwiGLU over interleaved (gate, up) columns: out[n/2] = silu(v[2i]) * v[2i+1]; 16-bit output, ld = N/2
+          T* dst = reinterpret_cast<T*>(ep.out_h) + orow * ep.ldo_h + (n0 >> 1);
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float gte = v[2 * j];
+            o[j] = (gte / (1.0f + __expf(-gte))) * v[2 * j + 1];
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            uint4 q;
+            q.x = DT<T>::pack2(o[j], o[j + 1]);
+            q.y = DT<T>::pack2(o[j + 2], o[j + 3]);
+            q.z = DT<T>::pack2(o[j + 4], o[j + 5]);
+            q.w = DT<T>::pack2(o[j + 6], o[j + 7]);
+            *reinterpret_cast<uint4*>(dst + j) = q;
+          }
+          continue;
+        }
         if (ep.out_f) {
           float* dst = ep.out_f + orow * ep.ldo_f + n0;
           if (ep.resid) {

@@ -17,7 +17,7 @@ struct GemmProblem {
   int32_t batch;
   // epilogue
   const float* bias;    // [N] or null
-  int32_t act;          // 0 none, 1 exact GELU
+  int32_t act;          // 0 none, 1 exact GELU, 2 SwiGLU over interleaved (gate, up) columns -> out_h [.., N/2]
   void* out_h;          // 16-bit output or null
   int64_t ldo_h;
   float* out_f;         // fp32 output or null:  out_f = v (+ resid)

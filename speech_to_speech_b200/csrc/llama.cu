@@ -1,15 +1,509 @@
-// llama.cu -- Llama-family LLM model object behind the C ABI (placeholder until the decode path lands).
+// llama.cu -- Llama-family LLM model object behind the C ABI: weight arena (transformers state-dict names ->
+// kernel layouts), per-session KV cache, prefill launch sequence (tcgen05 GEMMs + causal GQA attention) and
+// the persistent greedy decode.  Replaces the device work of LanguageModelHandler._generate
+// (reference S/LLM/language_model.py:832-892: tokenizer -> pipeline("text-generation") -> streamer).
+//
+// Layout choices:
+//   * q_proj / k_proj rows are permuted so that the rotate_half partners (j, j + hd/2) of every head are stored
+//     adjacently (2j, 2j+1): RoPE becomes a 2-element rotation inside one thread both in the decode GEMV epilogue
+//     and in the prefill RoPE kernel; q.k dot products are invariant under the common permutation.
+//   * gate_proj / up_proj rows are interleaved (gate_i, up_i): SwiGLU is fused into the producing GEMM / GEMV epilogue.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
 #include "common.cuh"
-extern "C" {
-#define NOT_YET(name) s2s_set_error(name ": not implemented yet"); return S2S_ERR_UNSUPPORTED
-int s2s_llama_create(s2s_ctx*, const s2s_llama_config*, s2s_llama**) { NOT_YET("s2s_llama_create"); }
-int s2s_llama_destroy(s2s_llama*) { return S2S_OK; }
-int s2s_llama_bind_tensor(s2s_llama*, const char*, const void*, const int64_t*, int32_t, int32_t) { NOT_YET("s2s_llama_bind_tensor"); }
-int s2s_llama_init_random(s2s_llama*, uint64_t) { NOT_YET("s2s_llama_init_random"); }
-int s2s_llama_finalize(s2s_llama*) { NOT_YET("s2s_llama_finalize"); }
-int s2s_llama_session_reset(s2s_llama*, int32_t) { NOT_YET("s2s_llama_session_reset"); }
-int s2s_llama_prefill(s2s_llama*, int32_t, const int32_t*, int32_t, float*, int32_t*, void*) { NOT_YET("s2s_llama_prefill"); }
-int s2s_llama_decode(s2s_llama*, const int32_t*, int32_t, const int32_t*, int32_t, int32_t, int32_t*, int32_t*,
-                     const int32_t*, float*, void*) { NOT_YET("s2s_llama_decode"); }
-int s2s_llama_generate(s2s_llama*, int32_t, const int32_t*, int32_t, int32_t, int32_t, int32_t*, int32_t*, void*) { NOT_YET("s2s_llama_generate"); }
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include "llama_decode.cuh"
+
+namespace {
+
+enum LSlotKind { L_PLAIN = 0, L_ROPE_PERM = 1, L_INTERLEAVE = 2 };
+struct LSlot {
+  void* dst = nullptr;
+  bool half = false;
+  int64_t rows = 0, cols = 0;
+  int kind = L_PLAIN;
+  int hd = 0;          // ROPE_PERM
+  int parity = 0;      // INTERLEAVE: 0 gate, 1 up
+  bool bound = false;
+  float rnd_scale = 0.02f, rnd_offset = 0.f;
+};
+
+template <typename T>
+__global__ void embed_gather_kernel(const int* __restrict__ ids, const T* __restrict__ embed, float* __restrict__ x, int d) {
+  const int t = blockIdx.x;
+  const T* e = embed + (long long)ids[t] * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) x[(long long)t * d + i] = DT<T>::to_f(e[i]);
 }
+
+// qkv [n, qd + 2*kvd] (q,k pair-adjacent layout): rotate q in place, rotate k -> cache, copy v -> cache.
+template <typename T>
+__global__ void rope_prefill_kernel(T* __restrict__ qkv, int n, int qd, int kvd, int hd, int past,
+                                    const float2* __restrict__ rope, T* __restrict__ kcache, T* __restrict__ vcache) {
+  const int t = blockIdx.x;
+  const int ld = qd + 2 * kvd;
+  T* row = qkv + (long long)t * ld;
+  const float2* cs = rope + (long long)(past + t) * (hd >> 1);
+  for (int i = threadIdx.x * 2; i < ld; i += blockDim.x * 2) {
+    uint32_t u = *reinterpret_cast<uint32_t*>(row + i);
+    if (i < qd + kvd) {
+      const float2 v = DT<T>::to_f2(u);
+      const float2 c = cs[(i % hd) >> 1];
+      u = DT<T>::pack2(v.x * c.x - v.y * c.y, v.y * c.x + v.x * c.y);
+    }
+    if (i < qd) *reinterpret_cast<uint32_t*>(row + i) = u;
+    else if (i < qd + kvd) *reinterpret_cast<uint32_t*>(kcache + (long long)(past + t) * kvd + (i - qd)) = u;
+    else *reinterpret_cast<uint32_t*>(vcache + (long long)(past + t) * kvd + (i - qd - kvd)) = u;
+  }
+}
+
+__global__ void argmax_row_kernel(const float* __restrict__ logits, int n, int* __restrict__ out) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = logits[i];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+    *out = bi;
+  }
+}
+
+inline uint16_t f2h(float f) { __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+inline uint16_t f2bf(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float src_f32(const void* data, int64_t i, int dtype) {
+  if (dtype == S2S_F32) return reinterpret_cast<const float*>(data)[i];
+  uint16_t u = reinterpret_cast<const uint16_t*>(data)[i];
+  if (dtype == S2S_BF16) { uint32_t w = (uint32_t)u << 16; float f; memcpy(&f, &w, 4); return f; }
+  __half h; memcpy(&h, &u, 2); return __half2float(h);
+}
+
+}  // namespace
+
+struct s2s_llama {
+  s2s_ctx* ctx = nullptr;
+  s2s_llama_config cfg{};
+  bool finalized = false;
+  int debug_phases = 0;
+  std::vector<void*> allocs;
+  std::unordered_map<std::string, LSlot> slots;
+  bool lm_head_bound = false;
+  // weights
+  void *embed = nullptr, *lm_head = nullptr;
+  float* norm_f = nullptr;
+  std::vector<LlamaDecLayer> layers_h;
+  LlamaDecLayer* layers_d = nullptr;
+  float2* rope = nullptr;
+  // KV + sessions
+  void* kv = nullptr;
+  long long kv_slot_stride = 0, kv_layer_stride = 0, kv_which_stride = 0;
+  std::vector<int> len;  // tokens in each slot
+  // prefill workspace
+  int* ids_d = nullptr;
+  float *x = nullptr, *last_logits = nullptr;
+  void *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr;
+  // decode state
+  float *dx = nullptr, *dq = nullptr, *dh = nullptr, *part = nullptr, *cand_val = nullptr;
+  int *slot_d = nullptr, *pos_d = nullptr, *done = nullptr, *n_done = nullptr, *cand_idx = nullptr, *out_ids = nullptr,
+      *out_len = nullptr, *next_id = nullptr;
+  unsigned int* sync_counter = nullptr;
+  int s_max = 0;
+};
+
+namespace {
+
+constexpr int MAX_DEC_B = 4;
+
+template <typename P> int lalloc(s2s_llama* m, P** out, size_t bytes, bool zero = true) {
+  void* p = nullptr;
+  S2S_CHECK_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+  if (zero) S2S_CHECK_CUDA(cudaMemset(p, 0, bytes ? bytes : 16));
+  m->allocs.push_back(p);
+  *out = reinterpret_cast<P*>(p);
+  return S2S_OK;
+}
+
+void lslot(s2s_llama* m, const std::string& name, void* dst, bool half, int64_t rows, int64_t cols, float rnd_scale,
+           float rnd_offset = 0.f, int kind = L_PLAIN, int hd = 0, int parity = 0) {
+  LSlot s;
+  s.dst = dst; s.half = half; s.rows = rows; s.cols = cols; s.kind = kind; s.hd = hd; s.parity = parity;
+  s.rnd_scale = rnd_scale; s.rnd_offset = rnd_offset;
+  m->slots[name] = s;
+}
+
+int build(s2s_llama* m) {
+  const auto& c = m->cfg;
+  const int d = c.d_model, f = c.ffn, hd = c.head_dim, qd = c.heads * hd, kvd = c.kv_heads * hd;
+  const int esz = 2;
+  auto off = [&](void* base, int64_t elems) { return reinterpret_cast<char*>(base) + elems * esz; };
+  S2S_CHECK(lalloc(m, &m->embed, (size_t)c.vocab * d * esz));
+  S2S_CHECK(lalloc(m, &m->lm_head, (size_t)c.vocab * d * esz));
+  S2S_CHECK(lalloc(m, &m->norm_f, d * 4));
+  lslot(m, "model.embed_tokens.weight", m->embed, true, c.vocab, d, 0.02f);
+  lslot(m, "lm_head.weight", m->lm_head, true, c.vocab, d, 0.02f);
+  lslot(m, "model.norm.weight", m->norm_f, false, d, 1, 0.1f, 1.0f);
+  m->layers_h.resize(c.layers);
+  const float sd = 1.0f / sqrtf((float)d);
+  for (int i = 0; i < c.layers; ++i) {
+    const std::string p = "model.layers." + std::to_string(i) + ".";
+    void *w_qkv, *w_o, *w_gu, *w_down;
+    float *n1, *n2;
+    S2S_CHECK(lalloc(m, &w_qkv, (size_t)(qd + 2 * kvd) * d * esz));
+    S2S_CHECK(lalloc(m, &w_o, (size_t)d * qd * esz));
+    S2S_CHECK(lalloc(m, &w_gu, (size_t)2 * f * d * esz));
+    S2S_CHECK(lalloc(m, &w_down, (size_t)d * f * esz));
+    S2S_CHECK(lalloc(m, &n1, d * 4));
+    S2S_CHECK(lalloc(m, &n2, d * 4));
+    lslot(m, p + "self_attn.q_proj.weight", w_qkv, true, qd, d, 2.0f * sd, 0.f, L_ROPE_PERM, hd);
+    lslot(m, p + "self_attn.k_proj.weight", off(w_qkv, (int64_t)qd * d), true, kvd, d, 2.0f * sd, 0.f, L_ROPE_PERM, hd);
+    lslot(m, p + "self_attn.v_proj.weight", off(w_qkv, (int64_t)(qd + kvd) * d), true, kvd, d, 0.8f * sd);
+    lslot(m, p + "self_attn.o_proj.weight", w_o, true, d, qd, 1.0f * sd);
+    lslot(m, p + "mlp.gate_proj.weight", w_gu, true, f, d, 1.0f * sd, 0.f, L_INTERLEAVE, 0, 0);
+    lslot(m, p + "mlp.up_proj.weight", w_gu, true, f, d, 1.0f * sd, 0.f, L_INTERLEAVE, 0, 1);
+    lslot(m, p + "mlp.down_proj.weight", w_down, true, d, f, 0.7f / sqrtf((float)f));
+    lslot(m, p + "input_layernorm.weight", n1, false, d, 1, 0.1f, 1.0f);
+    lslot(m, p + "post_attention_layernorm.weight", n2, false, d, 1, 0.1f, 1.0f);
+    LlamaDecLayer& L = m->layers_h[i];
+    L.w_qkv = w_qkv; L.w_o = w_o; L.w_gu = w_gu; L.w_down = w_down; L.norm1 = n1; L.norm2 = n2;
+  }
+  S2S_CHECK(lalloc(m, &m->layers_d, sizeof(LlamaDecLayer) * c.layers));
+  S2S_CHECK_CUDA(cudaMemcpy(m->layers_d, m->layers_h.data(), sizeof(LlamaDecLayer) * c.layers, cudaMemcpyHostToDevice));
+
+  // RoPE table, float32 arithmetic like LlamaRotaryEmbedding (modeling_llama.py:73-137)
+  {
+    std::vector<float2> tab((size_t)c.max_positions * (hd / 2));
+    for (int j = 0; j < hd / 2; ++j) {
+      const float inv = 1.0f / powf(c.rope_theta, (float)(2 * j) / (float)hd);
+      for (int p = 0; p < c.max_positions; ++p) {
+        const float ang = (float)p * inv;
+        tab[(size_t)p * (hd / 2) + j] = make_float2(cosf(ang), sinf(ang));
+      }
+    }
+    S2S_CHECK(lalloc(m, &m->rope, tab.size() * sizeof(float2)));
+    S2S_CHECK_CUDA(cudaMemcpy(m->rope, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  // KV cache [slot][layer][2][max_pos][kvd]
+  m->kv_which_stride = (long long)c.max_positions * kvd;
+  m->kv_layer_stride = 2 * m->kv_which_stride;
+  m->kv_slot_stride = (long long)c.layers * m->kv_layer_stride;
+  S2S_CHECK(lalloc(m, &m->kv, (size_t)c.max_sessions * m->kv_slot_stride * esz));
+  m->len.assign(c.max_sessions, 0);
+  // prefill workspace
+  const int P = c.max_prefill;
+  S2S_CHECK(lalloc(m, &m->ids_d, (size_t)P * 4));
+  S2S_CHECK(lalloc(m, &m->x, (size_t)P * d * 4));
+  S2S_CHECK(lalloc(m, &m->xn, (size_t)P * d * esz));
+  S2S_CHECK(lalloc(m, &m->qkv, (size_t)P * (qd + 2 * kvd) * esz));
+  S2S_CHECK(lalloc(m, &m->attn, (size_t)P * qd * esz));
+  S2S_CHECK(lalloc(m, &m->hbuf, (size_t)P * f * esz));
+  S2S_CHECK(lalloc(m, &m->last_logits, (size_t)c.vocab * 4));
+  // decode state
+  m->s_max = (c.max_positions + 63) / 64;
+  const int grid = m->ctx->num_sms;
+  S2S_CHECK(lalloc(m, &m->dx, (size_t)MAX_DEC_B * d * 4));
+  S2S_CHECK(lalloc(m, &m->dq, (size_t)MAX_DEC_B * qd * 4));
+  S2S_CHECK(lalloc(m, &m->dh, (size_t)MAX_DEC_B * f * 4));
+  S2S_CHECK(lalloc(m, &m->part, (size_t)MAX_DEC_B * c.heads * m->s_max * (hd + 4) * 4));
+  S2S_CHECK(lalloc(m, &m->slot_d, MAX_DEC_B * 4));
+  S2S_CHECK(lalloc(m, &m->pos_d, MAX_DEC_B * 4));
+  S2S_CHECK(lalloc(m, &m->done, MAX_DEC_B * 4));
+  S2S_CHECK(lalloc(m, &m->n_done, 16));
+  S2S_CHECK(lalloc(m, &m->cand_val, (size_t)MAX_DEC_B * grid * 4));
+  S2S_CHECK(lalloc(m, &m->cand_idx, (size_t)MAX_DEC_B * grid * 4));
+  S2S_CHECK(lalloc(m, &m->out_ids, (size_t)MAX_DEC_B * c.max_positions * 4));
+  S2S_CHECK(lalloc(m, &m->out_len, MAX_DEC_B * 4));
+  S2S_CHECK(lalloc(m, &m->next_id, 16));
+  S2S_CHECK(lalloc(m, &m->sync_counter, 16));
+  return S2S_OK;
+}
+
+GemmProblem lgemm(const void* a, int64_t lda, const void* w, int64_t ldw, int64_t M, int N, int K) {
+  GemmProblem p{};
+  p.a = a; p.a_row_stride = lda; p.a_batch_stride = lda * M; p.w = w; p.ldw = ldw;
+  p.M = (int32_t)M; p.N = N; p.K = K; p.batch = 1;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int s2s_llama_create(s2s_ctx* ctx, const s2s_llama_config* cfg, s2s_llama** out) {
+  S2S_REQUIRE(ctx && cfg && out, "llama_create: null argument");
+  S2S_REQUIRE(cfg->head_dim == 64 || cfg->head_dim == 128, "llama: head_dim must be 64 or 128");
+  S2S_REQUIRE(cfg->heads % cfg->kv_heads == 0, "llama: heads %% kv_heads != 0");
+  S2S_REQUIRE(cfg->d_model % 64 == 0 && cfg->ffn % 64 == 0 && cfg->vocab % 64 == 0, "llama: d_model, ffn, vocab must be multiples of 64");
+  S2S_REQUIRE(cfg->compute_dtype == S2S_BF16 || cfg->compute_dtype == S2S_F16, "llama: compute_dtype must be bf16/f16");
+  S2S_REQUIRE(cfg->qk_norm == 0, "llama: qk_norm (Qwen3-style) is not implemented yet");
+  S2S_REQUIRE(cfg->max_sessions >= 1 && cfg->max_positions >= 64 && cfg->max_prefill >= 1, "llama: bad capacity");
+  S2S_REQUIRE(cfg->layers >= 1 && cfg->layers <= 64, "llama: layers in [1,64]");
+  S2S_CHECK_CUDA(cudaSetDevice(ctx->device));
+  s2s_llama* m = new s2s_llama();
+  m->ctx = ctx;
+  m->cfg = *cfg;
+  int r = build(m);
+  if (r != S2S_OK) { s2s_llama_destroy(m); return r; }
+  const char* dbg = getenv("S2S_DEBUG_PHASES");
+  m->debug_phases = (dbg && dbg[0] == '1') ? 1 : 0;
+  *out = m;
+  return S2S_OK;
+}
+
+int s2s_llama_destroy(s2s_llama* m) {
+  if (!m) return S2S_OK;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return S2S_OK;
+}
+
+int s2s_llama_bind_tensor(s2s_llama* m, const char* name, const void* data_h, const int64_t* shape, int32_t ndim,
+                          int32_t dtype) {
+  S2S_REQUIRE(m && name && data_h && shape, "llama bind_tensor: null argument");
+  auto it = m->slots.find(name);
+  if (it == m->slots.end()) {
+    s2s_set_error("llama bind_tensor: unknown tensor '%s'", name);
+    return S2S_ERR_NOT_FOUND;
+  }
+  LSlot& s = it->second;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  S2S_REQUIRE(n == s.rows * s.cols, "llama bind_tensor: '%s' has %lld elements, expected %lld", name, (long long)n,
+              (long long)(s.rows * s.cols));
+  S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+  const bool bf = m->cfg.compute_dtype == S2S_BF16;
+  if (!s.half) {
+    std::vector<float> tmp((size_t)n);
+    for (int64_t i = 0; i < n; ++i) tmp[(size_t)i] = src_f32(data_h, i, dtype);
+    S2S_CHECK_CUDA(cudaMemcpy(s.dst, tmp.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+  } else {
+    // row-wise conversion + placement
+    std::vector<uint16_t> rowbuf((size_t)s.cols);
+    for (int64_t r = 0; r < s.rows; ++r) {
+      for (int64_t c = 0; c < s.cols; ++c) {
+        const float v = src_f32(data_h, r * s.cols + c, dtype);
+        rowbuf[(size_t)c] = bf ? f2bf(v) : f2h(v);
+      }
+      int64_t dr = r;
+      if (s.kind == L_ROPE_PERM) {
+        const int64_t h = r / s.hd, j = r % s.hd, half = s.hd / 2;
+        dr = h * s.hd + (j < half ? 2 * j : 2 * (j - half) + 1);
+      } else if (s.kind == L_INTERLEAVE) {
+        dr = 2 * r + s.parity;
+      }
+      S2S_CHECK_CUDA(cudaMemcpy(reinterpret_cast<char*>(s.dst) + dr * s.cols * 2, rowbuf.data(), (size_t)s.cols * 2,
+                                cudaMemcpyHostToDevice));
+    }
+  }
+  s.bound = true;
+  if (strcmp(name, "lm_head.weight") == 0) m->lm_head_bound = true;
+  return S2S_OK;
+}
+
+int s2s_llama_init_random(s2s_llama* m, uint64_t seed) {
+  S2S_REQUIRE(m, "llama init_random: null model");
+  S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+  for (auto& kv : m->slots) {
+    LSlot& s = kv.second;
+    uint64_t hsh = 1469598103934665603ull;
+    for (char ch : kv.first) hsh = (hsh ^ (uint64_t)(unsigned char)ch) * 1099511628211ull;
+    if (s.kind == L_INTERLEAVE) {
+      if (s.parity == 1) { s.bound = true; continue; }  // gate slot fills the whole interleaved [2*ffn, d] block
+      S2S_CHECK(fill_random_launch(s.dst, 2 * s.rows * s.cols, m->cfg.compute_dtype, s.rnd_scale, 0.f, seed ^ hsh, 0));
+    } else {
+      S2S_CHECK(fill_random_launch(s.dst, s.rows * s.cols, s.half ? m->cfg.compute_dtype : S2S_F32, s.rnd_scale,
+                                   s.rnd_offset, seed ^ hsh, 0));
+    }
+    s.bound = true;
+  }
+  m->lm_head_bound = true;
+  S2S_CHECK_CUDA(cudaDeviceSynchronize());
+  return S2S_OK;
+}
+
+int s2s_llama_finalize(s2s_llama* m) {
+  S2S_REQUIRE(m, "llama finalize: null model");
+  if (!m->lm_head_bound && m->slots["model.embed_tokens.weight"].bound) {
+    // tied embeddings (tie_word_embeddings=True): lm_head shares embed_tokens
+    S2S_CHECK_CUDA(cudaMemcpy(m->lm_head, m->embed, (size_t)m->cfg.vocab * m->cfg.d_model * 2, cudaMemcpyDeviceToDevice));
+    m->slots["lm_head.weight"].bound = true;
+  }
+  for (auto& kv : m->slots)
+    if (!kv.second.bound) {
+      s2s_set_error("llama finalize: tensor '%s' was never bound", kv.first.c_str());
+      return S2S_ERR_INVALID;
+    }
+  m->finalized = true;
+  return S2S_OK;
+}
+
+int s2s_llama_session_reset(s2s_llama* m, int32_t slot) {
+  S2S_REQUIRE(m && slot >= 0 && slot < m->cfg.max_sessions, "llama session_reset: bad slot %d", slot);
+  m->len[slot] = 0;
+  return S2S_OK;
+}
+
+int s2s_llama_prefill(s2s_llama* m, int32_t slot, const int32_t* ids_h, int32_t n, float* logits_out_d,
+                      int32_t* next_id_d, void* stream) {
+  S2S_REQUIRE(m && m->finalized && ids_h, "llama prefill: null argument / not finalized");
+  const auto& c = m->cfg;
+  S2S_REQUIRE(slot >= 0 && slot < c.max_sessions, "llama prefill: bad slot %d", slot);
+  S2S_REQUIRE(n >= 1 && n <= c.max_prefill, "llama prefill: n=%d outside [1,%d]", n, c.max_prefill);
+  const int past = m->len[slot];
+  S2S_REQUIRE(past + n <= c.max_positions, "llama prefill: %d + %d tokens exceed max_positions %d", past, n, c.max_positions);
+  for (int i = 0; i < n; ++i) S2S_REQUIRE(ids_h[i] >= 0 && ids_h[i] < c.vocab, "llama prefill: token %d out of range", ids_h[i]);
+  cudaStream_t st = (cudaStream_t)stream;
+  S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+  const int d = c.d_model, f = c.ffn, hd = c.head_dim, qd = c.heads * hd, kvd = c.kv_heads * hd, dt = c.compute_dtype;
+  const int ldq = qd + 2 * kvd;
+  S2S_CHECK_CUDA(cudaMemcpyAsync(m->ids_d, ids_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  S2S_CHECK_CUDA(cudaStreamSynchronize(st));  // ids_h may be a temporary of the caller
+  const bool bf = dt == S2S_BF16;
+  if (bf) embed_gather_kernel<__nv_bfloat16><<<n, 256, 0, st>>>(m->ids_d, (const __nv_bfloat16*)m->embed, m->x, d);
+  else embed_gather_kernel<__half><<<n, 256, 0, st>>>(m->ids_d, (const __half*)m->embed, m->x, d);
+  S2S_LAUNCH_CHECK();
+  char* kvb = reinterpret_cast<char*>(m->kv) + (size_t)slot * m->kv_slot_stride * 2;
+  for (int i = 0; i < c.layers; ++i) {
+    const LlamaDecLayer& L = m->layers_h[i];
+    char* kc = kvb + (size_t)i * m->kv_layer_stride * 2;
+    char* vc = kc + (size_t)m->kv_which_stride * 2;
+    S2S_CHECK(norm_rows_launch(m->x, L.norm1, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
+    {
+      GemmProblem p = lgemm(m->xn, d, L.w_qkv, d, n, ldq, d);
+      p.out_h = m->qkv; p.ldo_h = ldq;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    if (bf) rope_prefill_kernel<__nv_bfloat16><<<n, 256, 0, st>>>((__nv_bfloat16*)m->qkv, n, qd, kvd, hd, past, m->rope,
+                                                                 (__nv_bfloat16*)kc, (__nv_bfloat16*)vc);
+    else rope_prefill_kernel<__half><<<n, 256, 0, st>>>((__half*)m->qkv, n, qd, kvd, hd, past, m->rope, (__half*)kc, (__half*)vc);
+    S2S_LAUNCH_CHECK();
+    S2S_CHECK(attention_launch(m->qkv, kc, vc, m->attn, 1, n, past + n, c.heads, c.kv_heads, hd, ldq, kvd, kvd, qd,
+                               1.0f / sqrtf((float)hd), 1, dt, st));
+    {
+      GemmProblem p = lgemm(m->attn, qd, L.w_o, qd, n, d, qd);
+      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    S2S_CHECK(norm_rows_launch(m->x, L.norm2, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
+    {
+      GemmProblem p = lgemm(m->xn, d, L.w_gu, d, n, 2 * f, d);
+      p.act = 2; p.out_h = m->hbuf; p.ldo_h = f;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    {
+      GemmProblem p = lgemm(m->hbuf, f, L.w_down, f, n, d, f);
+      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+  }
+  S2S_CHECK(norm_rows_launch(m->x, m->norm_f, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
+  if (logits_out_d) {
+    GemmProblem p = lgemm(m->xn, d, m->lm_head, d, n, c.vocab, d);
+    p.out_f = logits_out_d; p.ldo_f = c.vocab;
+    S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+  }
+  if (next_id_d) {
+    const float* last = nullptr;
+    if (logits_out_d) {
+      last = logits_out_d + (size_t)(n - 1) * c.vocab;
+    } else {
+      GemmProblem p = lgemm(reinterpret_cast<char*>(m->xn) + (size_t)(n - 1) * d * 2, d, m->lm_head, d, 1, c.vocab, d);
+      p.out_f = m->last_logits; p.ldo_f = c.vocab;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+      last = m->last_logits;
+    }
+    argmax_row_kernel<<<1, 1024, 0, st>>>(last, c.vocab, next_id_d);
+    S2S_LAUNCH_CHECK();
+  }
+  m->len[slot] = past + n;
+  return S2S_OK;
+}
+
+int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int32_t* first_ids_d, int32_t n_steps,
+                     int32_t eos_id, int32_t* ids_out_d, int32_t* len_out_d, const int32_t* forced_d,
+                     float* logits_out_d, void* stream) {
+  S2S_REQUIRE(m && m->finalized && slots_h && first_ids_d && ids_out_d && len_out_d, "llama decode: null argument");
+  const auto& c = m->cfg;
+  S2S_REQUIRE(B >= 1 && B <= MAX_DEC_B, "llama decode: B=%d outside [1,%d]", B, MAX_DEC_B);
+  S2S_REQUIRE(n_steps >= 1, "llama decode: n_steps must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+  int pos_h[MAX_DEC_B], max_len = 0;
+  for (int b = 0; b < B; ++b) {
+    const int s = slots_h[b];
+    S2S_REQUIRE(s >= 0 && s < c.max_sessions, "llama decode: bad slot %d", s);
+    for (int b2 = 0; b2 < b; ++b2) S2S_REQUIRE(slots_h[b2] != s, "llama decode: slot %d listed twice", s);
+    S2S_REQUIRE(m->len[s] + n_steps <= c.max_positions, "llama decode: slot %d would exceed max_positions", s);
+    pos_h[b] = m->len[s];
+    max_len = pos_h[b] + 1 > max_len ? pos_h[b] + 1 : max_len;
+  }
+  S2S_CHECK_CUDA(cudaMemcpyAsync(m->slot_d, slots_h, B * 4, cudaMemcpyHostToDevice, st));
+  S2S_CHECK_CUDA(cudaMemcpyAsync(m->pos_d, pos_h, B * 4, cudaMemcpyHostToDevice, st));
+  S2S_CHECK_CUDA(cudaStreamSynchronize(st));
+  LlamaDecParams p{};
+  p.d = c.d_model; p.heads = c.heads; p.kv_heads = c.kv_heads; p.hd = c.head_dim; p.layers = c.layers; p.ffn = c.ffn;
+  p.vocab = c.vocab; p.B = B; p.max_pos = c.max_positions; p.eps = c.rms_eps;
+  p.lw = m->layers_d; p.embed = m->embed; p.lm_head = m->lm_head; p.norm_f = m->norm_f; p.rope = m->rope;
+  p.x = m->dx; p.q = m->dq; p.h = m->dh; p.kv = m->kv;
+  p.kv_slot_stride = m->kv_slot_stride; p.kv_layer_stride = m->kv_layer_stride; p.kv_which_stride = m->kv_which_stride;
+  p.part = m->part; p.s_max = m->s_max; p.slot = m->slot_d; p.pos = m->pos_d; p.max_len = max_len;
+  p.first_ids = first_ids_d; p.n_steps = n_steps; p.eos = eos_id; p.out_ids = ids_out_d; p.out_len = len_out_d;
+  p.forced = forced_d; p.logits_out = logits_out_d; p.done = m->done; p.n_done = m->n_done;
+  p.cand_val = m->cand_val; p.cand_idx = m->cand_idx; p.sync_counter = m->sync_counter;
+  S2S_CHECK(llama_decode_launch(m->ctx, p, c.compute_dtype, m->debug_phases, st));
+  for (int b = 0; b < B; ++b) m->len[slots_h[b]] += n_steps;
+  return S2S_OK;
+}
+
+int s2s_llama_generate(s2s_llama* m, int32_t slot, const int32_t* prompt_h, int32_t n_prompt, int32_t n_steps,
+                       int32_t eos_id, int32_t* ids_out_h, int32_t* len_out_h, void* stream) {
+  S2S_REQUIRE(m && prompt_h && ids_out_h && len_out_h, "llama generate: null argument");
+  S2S_REQUIRE(n_steps >= 1 && n_steps <= m->cfg.max_positions, "llama generate: bad n_steps");
+  cudaStream_t st = (cudaStream_t)stream;
+  S2S_CHECK(s2s_llama_session_reset(m, slot));
+  // chunked prefill
+  for (int o = 0; o < n_prompt; o += m->cfg.max_prefill) {
+    const int n = (n_prompt - o) < m->cfg.max_prefill ? (n_prompt - o) : m->cfg.max_prefill;
+    const bool last = o + n >= n_prompt;
+    S2S_CHECK(s2s_llama_prefill(m, slot, prompt_h + o, n, nullptr, last ? m->next_id : nullptr, stream));
+  }
+  // ids_out[0] = argmax of the prompt's last position; the decode kernel then feeds it and produces the rest
+  int first = 0;
+  S2S_CHECK_CUDA(cudaMemcpyAsync(&first, m->next_id, 4, cudaMemcpyDeviceToHost, st));
+  int n_dec = 0;
+  if (n_steps > 1) {
+    S2S_CHECK(s2s_llama_decode(m, &slot, 1, m->next_id, n_steps - 1, eos_id, m->out_ids, m->out_len, nullptr, nullptr, stream));
+    S2S_CHECK_CUDA(cudaMemcpyAsync(ids_out_h + 1, m->out_ids, (size_t)(n_steps - 1) * 4, cudaMemcpyDeviceToHost, st));
+    S2S_CHECK_CUDA(cudaMemcpyAsync(&n_dec, m->out_len, 4, cudaMemcpyDeviceToHost, st));
+  }
+  S2S_CHECK_CUDA(cudaStreamSynchronize(st));
+  ids_out_h[0] = first;
+  if (first == eos_id) {
+    *len_out_h = 1;
+    for (int i = 1; i < n_steps; ++i) ids_out_h[i] = eos_id;
+  } else {
+    *len_out_h = 1 + n_dec;
+  }
+  return S2S_OK;
+}
+
+}  // extern "C"

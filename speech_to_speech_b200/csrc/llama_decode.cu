@@ -1,2 +1,264 @@
-// llama_decode.cu -- persistent Llama-family decode kernel (lands after the Whisper path is parity-green).
-#include "common.cuh"
+// llama_decode.cu -- greedy decode of a Llama-family LLM as ONE persistent cooperative kernel.
+//
+// Reference path: LanguageModelHandler._generate -> pipeline("text-generation") -> model.generate greedy
+// (S/LLM/language_model.py:832-892) over LlamaForCausalLM (transformers modeling_llama.py:292-333 layer,
+// :225-289 attention, :171-184 MLP, :53-71 RMSNorm, :140-168 RoPE).  The reference streams the 16 GB of bf16
+// weights once per token through ~10 library kernels per layer and synchronises with the host every token
+// (TextIteratorStreamer); here a token step is 5 phases per layer inside one launch:
+//   0: RMSNorm + QKV GEMV + RoPE + KV append     1: attention partials (GQA, 64-key chunks)
+//   2: combine + o_proj + residual               3: RMSNorm + gate/up GEMV + SwiGLU      4: down + residual
+//   then 5L: final RMSNorm + lm_head + per-CTA argmax      5L+1: global argmax, EOS bookkeeping, next embedding
+// Every phase streams its weights with 16-byte coalesced read-only loads (decode_common.cuh); HBM-bound:
+// 16.06 GB / token for Llama-3-8B.
+#include "llama_decode.cuh"
+#include "decode_common.cuh"
+
+namespace {
+
+template <typename T, int NB>
+__device__ __noinline__ void ld_prefetch(const LlamaDecParams& p, int ph) {
+  const int L = p.layers;
+  const T* W = nullptr;
+  int N = 0, K = p.d;
+  if (ph < 5 * L) {
+    const LlamaDecLayer& w = p.lw[ph / 5];
+    switch (ph % 5) {
+      case 0: W = reinterpret_cast<const T*>(w.w_qkv); N = (p.heads + 2 * p.kv_heads) * p.hd; break;
+      case 2: W = reinterpret_cast<const T*>(w.w_o); N = p.d; K = p.heads * p.hd; break;
+      case 3: W = reinterpret_cast<const T*>(w.w_gu); N = 2 * p.ffn; break;
+      case 4: W = reinterpret_cast<const T*>(w.w_down); N = p.d; K = p.ffn; break;
+      default: break;
+    }
+  } else if (ph == 5 * L) {
+    W = reinterpret_cast<const T*>(p.lm_head); N = p.vocab;
+  }
+  // only the first GV_PF row groups of every warp; the GEMV loop prefetches the rest as it goes
+  if (W) prefetch_rows_l2<T, GV_R>(W, min(N, GV_PF * dec_item_stride() * GV_R), K);
+}
+
+template <typename T, int HD>
+__device__ __noinline__ void ld_attn(const LlamaDecParams& p, int layer, int step) {
+  const int B = p.B, H = p.heads, grp = p.heads / p.kv_heads;
+  const int kvd = p.kv_heads * HD;
+  const int rec = HD + PART_PAD;
+  const int n_chunks = (p.max_len + step + ATT_CHUNK - 1) / ATT_CHUNK;
+  const int n_items = B * H * n_chunks;
+  const T* kv = reinterpret_cast<const T*>(p.kv);
+#pragma unroll 1
+  for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
+    const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
+    const int len = __ldcg(p.pos + b) + 1;
+    float* rec_out = p.part + ((long long)(b * H + h) * p.s_max + c) * rec;
+    const int n_keys = min(ATT_CHUNK, len - c * ATT_CHUNK);
+    if (n_keys <= 0) {  // this session is shorter: mark the record empty (weight exp(-inf) = 0 in the combine)
+      if ((threadIdx.x & 31) == 0) { rec_out[HD] = -INFINITY; rec_out[HD + 1] = 0.f; }
+      continue;
+    }
+    const T* Kb = kv + (long long)__ldg(p.slot + b) * p.kv_slot_stride + (long long)layer * p.kv_layer_stride +
+                  (long long)c * ATT_CHUNK * kvd + (h / grp) * HD;
+    const T* Vb = Kb + p.kv_which_stride;
+    attend_chunk<T, HD>(p.q + (long long)b * H * HD + h * HD, Kb, Vb, kvd, kvd, n_keys, rec_out);
+  }
+}
+
+template <typename T>
+__device__ __noinline__ void ld_select(const LlamaDecParams& p, int step, float* s_aux) {
+  const int d = p.d, B = p.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* s_feed = reinterpret_cast<int*>(s_aux);
+#pragma unroll 1
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    if (warp == 0) {
+      float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 1
+      for (int c = lane; c < (int)gridDim.x; c += 32) {
+        const float v = __ldcg(p.cand_val + b * gridDim.x + c); const int i = __ldcg(p.cand_idx + b * gridDim.x + c);
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        int tok = bi;
+        const bool was_done = p.done[b] != 0;
+        if (was_done) tok = p.eos;
+        p.out_ids[b * p.n_steps + step] = tok;
+        if (!was_done && !p.forced) {
+          if (tok == p.eos) { p.done[b] = 1; p.out_len[b] = step + 1; atomicAdd(p.n_done, 1); }
+          else if (step == p.n_steps - 1) { p.out_len[b] = p.n_steps; }
+        }
+        if (p.forced && step == p.n_steps - 1) p.out_len[b] = p.n_steps;
+        *s_feed = p.forced ? p.forced[b * p.n_steps + step] : tok;
+        p.pos[b] = p.pos[b] + 1;  // the fed token sits at the next position
+      }
+    }
+    __syncthreads();
+    const int feed = *s_feed;
+    const T* e = reinterpret_cast<const T*>(p.embed) + (long long)feed * d;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < d; i += DEC_THREADS) p.x[(long long)b * d + i] = DT<T>::to_f(e[i]);
+  }
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, float* xs, float* s_aux) {
+  float* s_red = s_aux + 2 * DEC_WARPS * NB;
+  float* wb = s_red + 2 * DEC_WARPS;
+  const int L = p.layers, d = p.d, B = p.B, qd = p.heads * p.hd, kvd = p.kv_heads * p.hd;
+  float best_v = -INFINITY;
+  int best_i = 0x7fffffff;
+  GemvArgs a;
+  a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = qd; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
+  a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
+  a.pos = p.pos; a.slot = p.slot; a.kv_slot = p.kv_slot_stride; a.kv_ld = kvd; a.rope = p.rope; a.hd = p.hd;
+  a.q_rows = qd; a.k_rows = kvd; a.q_scale = rsqrtf((float)p.hd);
+  if (ph < 5 * L) {
+    const int layer = ph / 5;
+    const LlamaDecLayer& w = p.lw[layer];
+    switch (ph % 5) {
+      case 0:
+        stage_rows(p.x, B, d, xs, 2, w.norm1, nullptr, p.eps, s_red, wb);
+        a.W = w.w_qkv; a.N = qd + 2 * kvd; a.mode = EPI_QKV_ROPE; a.out = p.q; a.ldo = qd;
+        a.kv0 = reinterpret_cast<T*>(p.kv) + (long long)layer * p.kv_layer_stride; a.kv_which = p.kv_which_stride;
+        break;
+      case 1:
+        if (p.hd == 128) ld_attn<T, 128>(p, layer, step); else ld_attn<T, 64>(p, layer, step);
+        return;
+      case 2: {
+        const int n_chunks = (p.max_len + step + ATT_CHUNK - 1) / ATT_CHUNK;
+        if (p.hd == 128) combine_partials_to_smem<128, 8>(p.part, B, p.heads, p.s_max, n_chunks, xs);
+        else combine_partials_to_smem<64, 8>(p.part, B, p.heads, p.s_max, n_chunks, xs);
+        __syncthreads();
+        a.W = w.w_o; a.N = d; a.K = qd; a.mode = EPI_RESID; a.out = p.x; a.ldo = d;
+      } break;
+      case 3:
+        stage_rows(p.x, B, d, xs, 2, w.norm2, nullptr, p.eps, s_red, wb);
+        a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out = p.h; a.ldo = p.ffn;
+        break;
+      default:
+        stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb);
+        a.W = w.w_down; a.N = d; a.K = p.ffn; a.mode = EPI_RESID; a.out = p.x; a.ldo = d;
+        break;
+    }
+    gemv_generic<T, NB>(a, xs, B, best_v, best_i);
+    return;
+  }
+  if (ph == 5 * L) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    stage_rows(p.x, B, d, xs, 2, p.norm_f, nullptr, p.eps, s_red, wb);
+    a.W = p.lm_head; a.N = p.vocab; a.mode = EPI_LOGITS;
+    a.logits_out = p.logits_out ? p.logits_out + (long long)step * B * p.vocab : nullptr; a.logits_ld = p.vocab;
+    gemv_generic<T, NB>(a, xs, B, best_v, best_i);
+    float* sv = s_aux;
+    int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
+    if (lane < NB) { sv[warp * NB + lane] = best_v; si[warp * NB + lane] = best_i; }
+    __syncthreads();
+    if (threadIdx.x < B) {
+      const int b = threadIdx.x;
+      float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 1
+      for (int wv = 0; wv < DEC_WARPS; ++wv) {
+        const float v = sv[wv * NB + b]; const int i = si[wv * NB + b];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+      p.cand_val[b * gridDim.x + blockIdx.x] = bv;
+      p.cand_idx[b * gridDim.x + blockIdx.x] = bi;
+    }
+  } else {
+    ld_select<T>(p, step, s_aux);
+  }
+}
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(DEC_THREADS, 1)
+llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph_begin, int ph_end, int coop) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ LlamaDecParams sp;
+  __shared__ LlamaDecLayer s_layers[64];
+  if (threadIdx.x == 0) { sp = p; sp.lw = s_layers; }
+  for (int i = threadIdx.x; i < p.layers; i += DEC_THREADS) s_layers[i] = p.lw[i];
+  __syncthreads();
+  const int kmax = max(max(p.d, p.ffn), p.heads * p.hd);
+  float* xs = smem_f;
+  float* s_aux = smem_f + NB * kmax;
+  unsigned int epoch = 0;
+  const int n_ph = 5 * p.layers + 2;
+  for (int step = step_begin; step < step_end; ++step) {
+    const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
+    for (int ph = pb; ph < pe; ++ph) {
+      ld_phase<T, NB>(sp, step, ph, xs, s_aux);
+      if (coop) {
+        int nph = ph + 1, nstep = step;
+        if (nph == n_ph) { nph = 0; nstep = step + 1; }
+        if (nstep < step_end) ld_prefetch<T, NB>(sp, nph);
+        grid_sync(p.sync_counter, epoch);
+      }
+    }
+    if (coop && !p.forced && *reinterpret_cast<volatile int*>(p.n_done) >= p.B) break;
+  }
+}
+
+template <typename T>
+__global__ void llama_decode_init_kernel(const LlamaDecParams p) {
+  const int b = blockIdx.x;
+  const int tok = p.first_ids[b];
+  const T* e = reinterpret_cast<const T*>(p.embed) + (long long)tok * p.d;
+  for (int i = threadIdx.x; i < p.d; i += blockDim.x) p.x[(long long)b * p.d + i] = DT<T>::to_f(e[i]);
+  if (threadIdx.x == 0) {
+    p.done[b] = 0;
+    p.out_len[b] = 0;
+    if (b == 0) { *p.n_done = 0; *p.sync_counter = 0; }
+  }
+  for (int i = threadIdx.x; i < p.n_steps; i += blockDim.x) p.out_ids[b * p.n_steps + i] = p.eos;
+}
+
+template <typename T, int NB>
+int launch_nb(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
+  const int kmax = max(max(p.d, p.ffn), p.heads * p.hd);
+  const size_t smem = ((size_t)NB * kmax + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * (size_t)p.d + 32) * sizeof(float);
+  S2S_REQUIRE(smem <= 220 * 1024, "llama decode: batch %d x K %d does not fit shared memory", NB, kmax);
+  auto kern = llama_decode_kernel<T, NB>;
+  S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  llama_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(p);
+  S2S_LAUNCH_CHECK();
+  const int n_ph = 5 * p.layers + 2;
+  const int grid = ctx->num_sms;
+  if (!debug_phases) {
+    int sb = 0, se = p.n_steps, pb = 0, pe = n_ph, coop = 1;
+    LlamaDecParams pp = p;
+    void* args[] = {&pp, &sb, &se, &pb, &pe, &coop};
+    S2S_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(DEC_THREADS), args, smem, stream));
+    s2s_count_launch();
+  } else {
+    for (int s = 0; s < p.n_steps; ++s)
+      for (int ph = 0; ph < n_ph; ++ph) {
+        kern<<<grid, DEC_THREADS, smem, stream>>>(p, s, s + 1, ph, ph + 1, 0);
+        S2S_LAUNCH_CHECK();
+      }
+  }
+  return S2S_OK;
+}
+
+template <typename T>
+int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
+  if (p.B <= 1) return launch_nb<T, 1>(ctx, p, debug_phases, stream);
+  if (p.B <= 2) return launch_nb<T, 2>(ctx, p, debug_phases, stream);
+  if (p.B <= 4) return launch_nb<T, 4>(ctx, p, debug_phases, stream);
+  s2s_set_error("llama decode: batch %d > 4 must be split by the caller", p.B);
+  return S2S_ERR_INVALID;
+}
+
+}  // namespace
+
+int llama_decode_launch(s2s_ctx* ctx, const LlamaDecParams& p, int dtype, int debug_phases, cudaStream_t stream) {
+  S2S_REQUIRE(p.hd == 64 || p.hd == 128, "llama decode: head_dim must be 64 or 128");
+  S2S_REQUIRE(p.layers <= 64, "llama decode: at most 64 layers");
+  S2S_REQUIRE(p.n_steps >= 1, "llama decode: n_steps must be >= 1");
+  if (dtype == S2S_BF16) return launch_t<__nv_bfloat16>(ctx, p, debug_phases, stream);
+  if (dtype == S2S_F16) return launch_t<__half>(ctx, p, debug_phases, stream);
+  s2s_set_error("llama decode: unsupported dtype %d", dtype);
+  return S2S_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,44 @@
+// llama_decode.cuh -- parameters of the persistent Llama-family greedy-decode kernel.
+#pragma once
+#include "common.cuh"
+
+struct LlamaDecLayer {          // device pointers; 16-bit weights [out, in] row-major
+  const void* w_qkv;            // [(H + 2 KV) * hd, d]; q and k rows stored pair-adjacent for RoPE (see llama.cu)
+  const void* w_o;              // [d, H * hd]
+  const void* w_gu;             // [2 * ffn, d], rows interleaved (gate_i, up_i)
+  const void* w_down;           // [d, ffn]
+  const float *norm1, *norm2;   // RMSNorm weights [d]
+};
+
+struct LlamaDecParams {
+  int d, heads, kv_heads, hd, layers, ffn, vocab, B, max_pos;
+  float eps;
+  const LlamaDecLayer* lw;      // [layers] device
+  const void* embed;            // [vocab, d] 16-bit
+  const void* lm_head;          // [vocab, d] 16-bit
+  const float* norm_f;          // [d]
+  const float2* rope;           // [max_pos][hd/2] (cos, sin)
+  // state
+  float* x;                     // [B, d] residual stream
+  float* q;                     // [B, H*hd]
+  float* h;                     // [B, ffn]
+  void* kv;                     // [slots][layers][2][max_pos][KV*hd] 16-bit
+  long long kv_slot_stride, kv_layer_stride, kv_which_stride;
+  float* part;                  // [B][H][s_max][hd + 4]
+  int s_max;
+  const int* slot;              // [B]
+  int* pos;                     // [B] position of the token being processed (advanced by the kernel)
+  int max_len;                  // max over b of (pos[b] + 1) at step 0
+  // token bookkeeping
+  const int* first_ids;         // [B]
+  int n_steps, eos;
+  int* out_ids;                 // [B][n_steps]
+  int* out_len;                 // [B]
+  const int* forced;            // [B][n_steps] or null
+  float* logits_out;            // [n_steps][B][vocab] or null
+  int* done; int* n_done;
+  float* cand_val; int* cand_idx;   // [B][grid]
+  unsigned int* sync_counter;
+};
+
+int llama_decode_launch(s2s_ctx* ctx, const LlamaDecParams& p, int dtype, int debug_phases, cudaStream_t stream);

@@ -60,8 +60,8 @@ __device__ __noinline__ void wd_prefetch(const WhisperDecParams& p, int step, in
       default: break;
     }
   } else if (ph == 8 * L && step >= p.n_prefix - 1) {
-    // first row group of every warp only; later groups are prefetched inside the GEMV loop
-    W = reinterpret_cast<const T*>(p.embed); N = min(p.vocab, dec_item_stride() * GV_R);
+    // the first GV_PF row groups of every warp; later groups are prefetched inside the GEMV loop
+    W = reinterpret_cast<const T*>(p.embed); N = min(p.vocab, GV_PF * dec_item_stride() * GV_R);
   }
   if (W) prefetch_rows_l2<T, GV_R>(W, N, K);
 }
@@ -74,6 +74,7 @@ __device__ __noinline__ void wd_self_attn(const WhisperDecParams& p, int layer, 
   const int rec = HD + PART_PAD;
   const int n_chunks = pos / ATT_CHUNK + 1;
   const int n_items = B * H * n_chunks;
+#pragma unroll 1
   for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
     const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
     const T* Kb = kcache + (((long long)b * L + layer) * 2 + 0) * kv_layer_stride + (long long)c * ATT_CHUNK * d + h * HD;
@@ -91,6 +92,7 @@ __device__ __noinline__ void wd_cross_attn(const WhisperDecParams& p, int layer)
   const int n_items = B * H * n_chunks;
   const long long ldc = (long long)L * 2 * d;
   const T* ckv = reinterpret_cast<const T*>(p.cross_kv);
+#pragma unroll 1
   for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
     const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
     const T* Kb = ckv + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc + (long long)layer * 2 * d + h * HD;
@@ -106,11 +108,13 @@ __device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos
   const int d = p.d, B = p.B;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* s_feed = reinterpret_cast<int*>(s_aux);
+#pragma unroll 1
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     if (warp == 0) {
       if (g >= 0) {
         float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 1
         for (int c = lane; c < (int)gridDim.x; c += 32) {
           const float v = __ldcg(p.cand_val + b * gridDim.x + c); const int i = __ldcg(p.cand_idx + b * gridDim.x + c);
           if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
@@ -143,6 +147,7 @@ __device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos
     if (pos + 1 < p.max_pos) {
       const T* e = reinterpret_cast<const T*>(p.embed) + (long long)feed * d;
       const float* pe = p.pos + (long long)(pos + 1) * d;
+#pragma unroll 2
       for (int i = threadIdx.x; i < d; i += DEC_THREADS) p.x[b * d + i] = DT<T>::to_f(e[i]) + pe[i];
     }
   }
@@ -159,6 +164,7 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
   GemvArgs a;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
+  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f;
   if (ph < 8 * L) {
     const int layer = ph >> 3;
     const WhisperDecLayer& w = p.lw[layer];
@@ -214,6 +220,7 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
     if (threadIdx.x < B) {
       const int b = threadIdx.x;
       float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 1
       for (int wv = 0; wv < DEC_WARPS; ++wv) {
         const float v = sv[wv * NB + b]; const int i = si[wv * NB + b];
         if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }

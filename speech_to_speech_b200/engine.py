@@ -217,3 +217,83 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kv_
                             q.stride(1), k.stride(1), v.stride(1), o.stride(1), float(scale), 1 if causal else 0, code,
                             _stream_ptr(dev)), "s2s_attention")
     return o
+
+
+class LlamaEngine:
+    """Llama-family LLM on one B200: tcgen05 prefill + persistent greedy decode with a per-session KV cache."""
+
+    def __init__(self, geometry: Mapping[str, float], dtype: str = "bfloat16", max_sessions: int = 1,
+                 max_positions: int = 2048, max_prefill: int = 512, device: int = 0):
+        self.lib = _lib.load()
+        self.device = device
+        self.ctx = get_context(device)
+        self.geometry = dict(geometry)
+        g = self.geometry
+        self.cfg = LlamaConfig(
+            int(g["d_model"]), int(g["layers"]), int(g["heads"]), int(g["kv_heads"]), int(g["head_dim"]), int(g["ffn"]),
+            int(g["vocab"]), float(g.get("rope_theta", 500000.0)), float(g.get("rms_eps", 1e-5)), DTYPE_CODES[dtype],
+            max_sessions, min(max_positions, int(g.get("max_positions", max_positions))), max_prefill, 0)
+        self.max_positions = self.cfg.max_positions
+        self.handle = C.c_void_p()
+        check(self.lib.s2s_llama_create(self.ctx, C.byref(self.cfg), C.byref(self.handle)), "s2s_llama_create")
+
+    def load_state_dict(self, weights: Mapping[str, "np.ndarray | torch.Tensor"]) -> None:
+        for name, w in weights.items():
+            if isinstance(w, torch.Tensor):
+                w = w.detach().to("cpu", torch.float32).numpy()
+            a = np.ascontiguousarray(w)
+            if a.dtype not in (np.float32, np.float16):
+                a = a.astype(np.float32)
+            shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+            check(self.lib.s2s_llama_bind_tensor(self.handle, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim,
+                                                 _np_dtype_code(a)), f"llama bind_tensor({name})")
+        check(self.lib.s2s_llama_finalize(self.handle), "s2s_llama_finalize")
+
+    def init_random(self, seed: int = 0) -> None:
+        check(self.lib.s2s_llama_init_random(self.handle, seed), "s2s_llama_init_random")
+        check(self.lib.s2s_llama_finalize(self.handle), "s2s_llama_finalize")
+
+    def reset(self, slot: int = 0) -> None:
+        check(self.lib.s2s_llama_session_reset(self.handle, slot), "s2s_llama_session_reset")
+
+    def prefill(self, slot: int, ids: Sequence[int], return_logits: bool = False):
+        """Append `ids` to the session.  Returns (next_id cuda int32[1], logits cuda f32[n, vocab] or None)."""
+        arr, n = _lib.i32_array(ids)
+        dev = f"cuda:{self.device}"
+        nxt = torch.empty((1,), dtype=torch.int32, device=dev)
+        logits = torch.empty((n, self.geometry["vocab"]), dtype=torch.float32, device=dev) if return_logits else None
+        check(self.lib.s2s_llama_prefill(self.handle, slot, arr, n, _ptr(logits), _ptr(nxt), _stream_ptr(self.device)),
+              "s2s_llama_prefill")
+        return nxt, logits
+
+    def decode(self, slots: Sequence[int], first_ids: torch.Tensor, n_steps: int, eos_id: int = -1,
+               forced: Optional[torch.Tensor] = None, return_logits: bool = False):
+        B = len(slots)
+        dev = f"cuda:{self.device}"
+        sl, _ = _lib.i32_array(slots)
+        ids = torch.empty((B, n_steps), dtype=torch.int32, device=dev)
+        lens = torch.empty((B,), dtype=torch.int32, device=dev)
+        logits = torch.empty((n_steps, B, self.geometry["vocab"]), dtype=torch.float32, device=dev) if return_logits else None
+        check(self.lib.s2s_llama_decode(self.handle, sl, B, _ptr(first_ids), n_steps, eos_id, _ptr(ids), _ptr(lens),
+                                        _ptr(forced), _ptr(logits), _stream_ptr(self.device)), "s2s_llama_decode")
+        return (ids, lens, logits) if return_logits else (ids, lens)
+
+    def generate(self, prompt: Sequence[int], max_new_tokens: int, eos_id: int = -1, slot: int = 0) -> list[int]:
+        """Host ids in, host ids out: (chunked) prefill + greedy decode.  generate() semantics of the reference."""
+        arr, n = _lib.i32_array(prompt)
+        out = np.empty((max_new_tokens,), dtype=np.int32)
+        ln = np.zeros((1,), dtype=np.int32)
+        check(self.lib.s2s_llama_generate(self.handle, slot, arr, n, max_new_tokens, eos_id, out.ctypes.data_as(C.c_void_p),
+                                          ln.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)), "s2s_llama_generate")
+        return out[: int(ln[0])].tolist()
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.s2s_llama_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
