@@ -149,6 +149,13 @@ class WhisperEngine:
               "s2s_whisper_detect_language")
         return out
 
+    def detect_language_host(self, audio: np.ndarray, sot_id: int, lang_ids: Sequence[int]) -> int:
+        """Host PCM in: H2D + log-mel + encoder + one masked decoder step -> language token id."""
+        pcm = torch.from_numpy(audio)[None].to(f"cuda:{self.device}")
+        self.logmel(pcm, [pcm.shape[1]])
+        self.encode(1)
+        return int(self.detect_language(1, sot_id, lang_ids)[0])
+
     # -- host-buffer API (what the handler calls) --------------------------------------------------
     def transcribe(self, audio: Sequence[np.ndarray], opts: WhisperDecodeOptions) -> list[list[int]]:
         """audio: list of f32 mono 16 kHz arrays (host).  H2D + log-mel + encode + greedy decode + D2H."""

@@ -1,0 +1,176 @@
+"""B200LanguageModelHandler -- the reference's `transformers` LLM slot with prefill + decode on libs2s_b200.so.
+
+Mirrors LanguageModelHandler (/root/reference/src/speech_to_speech/LLM/language_model.py:785-972): it implements the
+two hooks the reference's BaseLanguageModelHandler leaves abstract, `_load_model(model_name, device, torch_dtype,
+gen_kwargs)` (:217-224) and `_generate(chat, language_code, gen, ctx, runtime_config, response)` (:238-247), and
+reuses the reference's own `_stream_tokens` / sentence batching / cancel logic unchanged (:309-560).  Where the
+reference spawns a thread running `pipeline("text-generation")` with a TextIteratorStreamer (:883-888), we run
+`s2s_llama_prefill` once and then `s2s_llama_decode` in short persistent launches, detokenising on the host between
+launches, so cancellation is polled every `stream_chunk_tokens` tokens.  No CPU fallback."""
+from __future__ import annotations
+
+import logging
+from typing import Any, Callable, Iterator, Optional, Sequence
+
+from ..host import _stub_optional
+
+logger = logging.getLogger(__name__)
+
+LLAMA_GEOMETRIES = {
+    "micro": dict(d_model=256, layers=2, heads=2, kv_heads=1, head_dim=128, ffn=512, vocab=2048),
+    "mini": dict(d_model=1024, layers=4, heads=8, kv_heads=2, head_dim=128, ffn=3584, vocab=32064),
+    "llama-3-8b": dict(d_model=4096, layers=32, heads=32, kv_heads=8, head_dim=128, ffn=14336, vocab=128256,
+                       rope_theta=500000.0, rms_eps=1e-5),
+}
+
+
+class TokenStreamer:
+    """Greedy generation as an iterator of text fragments (the role TextIteratorStreamer plays in the reference)."""
+
+    def __init__(self, engine: Any, decode_text: Callable[[Sequence[int]], str], eos_ids: Sequence[int], chunk: int = 8, slot: int = 0):
+        self.engine, self.decode_text, self.eos_ids, self.chunk, self.slot = engine, decode_text, set(int(e) for e in eos_ids), max(1, chunk), slot
+        self.generated: list[int] = []
+
+    def stream(self, prompt_ids: Sequence[int], max_new_tokens: int, should_stop: Callable[[], bool] = lambda: False) -> Iterator[str]:
+        import torch
+        eng = self.engine
+        eng.reset(self.slot)
+        max_prefill = eng.cfg.max_prefill
+        nxt = None
+        for o in range(0, len(prompt_ids), max_prefill):
+            nxt, _ = eng.prefill(self.slot, list(prompt_ids[o:o + max_prefill]))
+        self.generated = []
+        emitted = ""
+        tok = int(nxt[0])
+        eos_for_kernel = next(iter(self.eos_ids)) if len(self.eos_ids) == 1 else -1
+        while len(self.generated) < max_new_tokens:
+            if tok in self.eos_ids:
+                break
+            self.generated.append(tok)
+            text = self.decode_text(self.generated)
+            if len(text) > len(emitted) and not text.endswith("�"):
+                yield text[len(emitted):]
+                emitted = text
+            if should_stop() or len(self.generated) >= max_new_tokens:
+                break
+            n = min(self.chunk, max_new_tokens - len(self.generated))
+            first = torch.tensor([tok], dtype=torch.int32, device=f"cuda:{eng.device}")
+            ids, lens = eng.decode([self.slot], first, n, eos_id=eos_for_kernel)
+            out = ids[0, : int(lens[0]) if int(lens[0]) > 0 else n].tolist()
+            stop = False
+            for t in out[:-1]:
+                if t in self.eos_ids:
+                    stop = True
+                    break
+                self.generated.append(t)
+            if stop or not out:
+                break
+            tok = out[-1]
+        text = self.decode_text(self.generated) if self.generated else ""
+        if len(text) > len(emitted):  # flush the tail (tokens appended by the last launch before EOS / budget end)
+            yield text[len(emitted):]
+
+
+def _reference_base():
+    """The reference's BaseLanguageModelHandler when importable (nltk stubbed like the reference's own tests do)."""
+    try:
+        _stub_optional("nltk")
+        from speech_to_speech.LLM.language_model import BaseLanguageModelHandler
+        return BaseLanguageModelHandler
+    except Exception:
+        return None
+
+
+_Base = _reference_base()
+
+
+class _StandaloneBase:
+    """Used only where the reference package is absent (e.g. the GPU test box): owns the load hook and exposes
+    `generate_text_stream`; the reference-side request lifecycle (Chat, LLMResponseChunk, cancel scopes) needs the
+    reference package and is exercised by tests/test_handlers.py with it present."""
+
+    def __init__(self, model_name: str, device: str = "cuda", torch_dtype: str = "bfloat16", gen_kwargs: Optional[dict] = None):
+        self.device = device
+        self._load_model(model_name, device, torch_dtype, dict(gen_kwargs or {}))
+
+
+class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):  # type: ignore[misc]
+    backend = "transformers"
+
+    def _load_model(self, model_name: str, device: str, torch_dtype: str, gen_kwargs: dict[str, Any]) -> None:
+        if not str(device).startswith("cuda"):
+            raise ValueError(f"B200LanguageModelHandler runs on CUDA (sm_100a) only, got device={device!r}; there is no CPU fallback")
+        from .. import engine as E
+        dev = int(device.split(":")[1]) if ":" in device else 0
+        self.gen_kwargs = dict(gen_kwargs)
+        self.stream_chunk_tokens = int(self.gen_kwargs.pop("stream_chunk_tokens", 8))
+        max_pos = int(self.gen_kwargs.pop("max_positions", 4096))
+        if model_name.startswith("random:"):
+            parts = model_name.split(":")
+            geom = LLAMA_GEOMETRIES[parts[1]]
+            self.engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=1, max_positions=max_pos, max_prefill=512, device=dev)
+            self.engine.init_random(int(parts[2]) if len(parts) > 2 else 0)
+            self.tokenizer = _IdTokenizer(geom["vocab"])
+            self.eos_ids = [geom["vocab"] - 1]
+        else:
+            from transformers import AutoModelForCausalLM, AutoTokenizer
+            self.tokenizer = AutoTokenizer.from_pretrained(model_name)
+            hf = AutoModelForCausalLM.from_pretrained(model_name)
+            c = hf.config
+            if c.model_type not in ("llama", "mistral"):
+                raise ValueError(f"B200LanguageModelHandler supports Llama-family checkpoints (got model_type={c.model_type!r})")
+            geom = dict(d_model=c.hidden_size, layers=c.num_hidden_layers, heads=c.num_attention_heads, kv_heads=c.num_key_value_heads,
+                        head_dim=getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads, ffn=c.intermediate_size,
+                        vocab=c.vocab_size, rope_theta=float(getattr(c, "rope_theta", 10000.0)), rms_eps=float(c.rms_norm_eps))
+            self.engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=1, max_positions=max_pos, max_prefill=512, device=dev)
+            self.engine.load_state_dict(hf.state_dict())
+            eos = hf.generation_config.eos_token_id
+            self.eos_ids = list(eos) if isinstance(eos, (list, tuple)) else [int(eos)]
+            del hf
+        self.streamer = TokenStreamer(self.engine, lambda ids: self.tokenizer.decode(list(ids), skip_special_tokens=True),
+                                      self.eos_ids, self.stream_chunk_tokens)
+
+    def generate_text_stream(self, prompt_ids: Sequence[int], max_new_tokens: Optional[int] = None,
+                             should_stop: Callable[[], bool] = lambda: False) -> Iterator[str]:
+        n = int(max_new_tokens or self.gen_kwargs.get("max_new_tokens", 1024))
+        return self.streamer.stream(prompt_ids, n, should_stop)
+
+    # -- reference hook (S/LLM/language_model.py:832-892) -----------------------------------------
+    def _generate(self, chat: Any, language_code: Optional[str], gen: Optional[int], ctx: Any, runtime_config: Any = None,
+                  response: Any = None) -> Iterator[Any]:
+        chat_messages = chat.to_transformers_chat()
+        prompt_ids = self.tokenizer.apply_chat_template(chat_messages, tokenize=True, add_generation_prompt=True)
+        if isinstance(prompt_ids, dict):
+            prompt_ids = prompt_ids["input_ids"]
+        ctx.input_tokens += len(prompt_ids)
+        stop = (lambda: self._check_stop(gen, ctx)) if hasattr(self, "_check_stop") else (lambda: False)
+        token_iter = self.generate_text_stream(prompt_ids, should_stop=stop)
+        yield from self._stream_tokens(token_iter, gen, language_code, ctx, runtime_config, response)
+
+    def warmup(self) -> None:
+        for _ in self.generate_text_stream([1, 2, 3, 4], max_new_tokens=4):
+            pass
+
+    def cleanup(self) -> None:
+        eng = getattr(self, "engine", None)
+        if eng is not None:
+            eng.close()
+
+
+class _IdTokenizer:
+    """Stand-in tokenizer for random-init models: token i <-> the text "<i> "."""
+
+    def __init__(self, vocab: int):
+        self.vocab = vocab
+
+    def decode(self, ids: Sequence[int], skip_special_tokens: bool = True) -> str:
+        return "".join(f"<{int(i)}> " for i in ids)
+
+    def encode(self, text: str) -> list[int]:
+        return [int(t.strip("<> ")) % self.vocab for t in text.split() if t.strip("<> ").isdigit()]
+
+    def apply_chat_template(self, messages: Any, tokenize: bool = True, add_generation_prompt: bool = True, **kw: Any):
+        ids: list[int] = []
+        for m in messages:
+            ids += self.encode(str(m.get("content", ""))) or [1]
+        return ids if tokenize else " ".join(f"<{i}>" for i in ids)

@@ -1,0 +1,182 @@
+"""B200WhisperSTTHandler -- the reference's WhisperSTTHandler slot with the forward pass on libs2s_b200.so.
+
+Mirrors /root/reference/src/speech_to_speech/STT/whisper_stt_handler.py: same `setup()` kwargs (:53-61), same
+`process(VADAudio) -> Iterator[PartialTranscription | Transcription]` contract (:225-282) including the
+language bookkeeping ("-auto" suffix, sticky last_language restricted to SUPPORTED_LANGUAGES, progressive mode).
+What changes is what the handler calls: `processor(...)` + `model.generate(...)` become ONE call into the C ABI
+(`s2s_whisper_transcribe`: H2D PCM, log-mel, encoder, greedy decode, D2H ids); only the BPE detokenisation
+(`processor.batch_decode`, CPU, :259) stays in Python.  No CPU fallback: a non-CUDA `device` raises."""
+from __future__ import annotations
+
+import logging
+import re
+from typing import Any, Iterator, Optional
+
+import numpy as np
+
+from ..host import resolve
+
+logger = logging.getLogger(__name__)
+_api = resolve()
+
+SUPPORTED_LANGUAGES = ["en", "fr", "es", "zh", "ja", "ko", "hi", "de", "pt", "pl", "it", "nl"]
+DEFAULT_LANGUAGE = "en"
+_LANGUAGE_TOKEN_RE = re.compile(r"^<\|([a-z]{2,3})\|>$")
+
+
+class TokenTable:
+    """Special-token ids the decoder prompt and logit processors need; from a checkpoint's generation_config
+    (transformers generation_whisper.py:1455-1608 `_retrieve_init_tokens`) or synthetic for random-init models."""
+
+    def __init__(self, sot: int, eos: int, transcribe: int, translate: int, no_timestamps: int, lang_to_id: dict[str, int],
+                 suppress: list[int], begin_suppress: list[int]):
+        self.sot, self.eos, self.transcribe, self.translate, self.no_timestamps = sot, eos, transcribe, translate, no_timestamps
+        self.lang_to_id = dict(lang_to_id)
+        self.id_to_lang = {v: k for k, v in lang_to_id.items()}
+        self.suppress, self.begin_suppress = list(suppress), list(begin_suppress)
+
+    @classmethod
+    def from_generation_config(cls, gc: Any) -> "TokenTable":
+        lang = {}
+        for tok, idx in (getattr(gc, "lang_to_id", None) or {}).items():
+            m = _LANGUAGE_TOKEN_RE.match(tok)
+            if m:
+                lang[m.group(1)] = int(idx)
+        task = getattr(gc, "task_to_id", None) or {}
+        eos = gc.eos_token_id if isinstance(gc.eos_token_id, int) else gc.eos_token_id[0]
+        return cls(int(gc.decoder_start_token_id), int(eos), int(task.get("transcribe", 50359)), int(task.get("translate", 50358)),
+                   int(getattr(gc, "no_timestamps_token_id", 50363)), lang, list(getattr(gc, "suppress_tokens", None) or []),
+                   list(getattr(gc, "begin_suppress_tokens", None) or []))
+
+    @classmethod
+    def synthetic(cls, vocab: int) -> "TokenTable":
+        if vocab >= 51865:  # multilingual Whisper layout
+            langs = {c: 50259 + i for i, c in enumerate(["en", "zh", "de", "es", "ru", "ko", "fr", "ja", "pt", "tr", "pl", "ca", "nl", "ar", "sv", "it", "id", "hi"])}
+            return cls(50258, 50257, 50359, 50358, 50363, langs, [1, 2, 7, 8, 9, 10, 14, 25, 50258, 50358, 50359, 50360, 50361, 50362], [220, 50257])
+        base = vocab - 96
+        langs = {c: base + 1 + i for i, c in enumerate(["en", "zh", "de", "es", "fr", "ja"])}
+        return cls(base, vocab - 1, base + 10, base + 11, base + 12, langs, [1, 2, 7, base, base + 10, base + 11], [220, vocab - 1])
+
+
+class B200WhisperSTTHandler(_api.BaseSTTHandler):
+    """Speech-to-text on the B200 engine.  `model_name`: a local transformers Whisper checkpoint directory / hub id
+    (weights are read once on the CPU and copied into the engine), or "random:<geometry>[:seed]" for seeded
+    random-init weights at a reference geometry (tiny/small/large-v3) -- used by the tests and benches because no
+    checkpoints exist offline."""
+
+    _language_token_id_map: Optional[dict[int, str]] = None
+
+    def setup(self, model_name: str = "distil-whisper/distil-large-v3", device: str = "cuda", torch_dtype: str = "float16",
+              compile_mode: Optional[str] = None, language: Optional[str] = None, gen_kwargs: dict[str, Any] = {},
+              max_batch: int = 1) -> None:
+        if not str(device).startswith("cuda"):
+            raise ValueError(f"B200WhisperSTTHandler runs on CUDA (sm_100a) only, got device={device!r}; there is no CPU fallback")
+        from .. import engine as E  # raises ImportError if libs2s_b200.so is not built
+
+        self.device = device
+        self.device_index = int(device.split(":")[1]) if ":" in device else 0
+        self.torch_dtype = torch_dtype
+        self.compile_mode = compile_mode  # accepted for config compatibility; the engine has no tracing compiler
+        self.gen_kwargs = dict(gen_kwargs)
+        self.start_language = language
+        self.last_language = language if language != "auto" else None
+        if self.last_language is not None:
+            self.gen_kwargs["language"] = self.last_language
+        self._E = E
+        self.processor = None
+        self._load(model_name)
+        self.warmup()
+
+    # -- loading ---------------------------------------------------------------------------------
+    def _load(self, model_name: str) -> None:
+        E = self._E
+        if model_name.startswith("random:"):
+            parts = model_name.split(":")
+            geom = GEOMETRIES[parts[1]]
+            seed = int(parts[2]) if len(parts) > 2 else 0
+            self.engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=1, device=self.device_index)
+            self.engine.init_random(seed)
+            self.tokens = TokenTable.synthetic(geom["vocab"])
+            self._decode_text = lambda ids: " ".join(f"<{i}>" for i in ids)
+            return
+        from transformers import AutoModelForSpeechSeq2Seq, AutoProcessor
+        self.processor = AutoProcessor.from_pretrained(model_name)
+        hf = AutoModelForSpeechSeq2Seq.from_pretrained(model_name)
+        c = hf.config
+        geom = dict(d_model=c.d_model, heads=c.encoder_attention_heads, enc_layers=c.encoder_layers, dec_layers=c.decoder_layers,
+                    ffn=c.encoder_ffn_dim, n_mels=c.num_mel_bins, vocab=c.vocab_size,
+                    max_source_positions=c.max_source_positions, max_target_positions=c.max_target_positions)
+        self.engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=1, device=self.device_index)
+        self.engine.load_state_dict({k: v for k, v in hf.state_dict().items() if not k.startswith("proj_out")})
+        self.tokens = TokenTable.from_generation_config(hf.generation_config)
+        del hf
+        self._decode_text = lambda ids: self.processor.batch_decode([ids], skip_special_tokens=True, decode_with_timestamps=False)[0]
+
+    def warmup(self) -> None:
+        logger.info("Warming up %s", type(self).__name__)
+        dummy = np.zeros(16000, dtype=np.float32)
+        for _ in range(2):
+            self._transcribe(dummy, self._forced_language() or DEFAULT_LANGUAGE)
+
+    # -- decoding controls ------------------------------------------------------------------------
+    def _forced_language(self) -> Optional[str]:
+        forced = self.gen_kwargs.get("language")
+        return forced if isinstance(forced, str) and forced and forced != "auto" else None
+
+    def _options(self, language: str):
+        t = self.tokens
+        lang_id = t.lang_to_id.get(language, t.lang_to_id.get(DEFAULT_LANGUAGE, t.sot + 1))
+        task = t.translate if self.gen_kwargs.get("task") == "translate" else t.transcribe
+        prefix = [t.sot, lang_id, task] + ([] if self.gen_kwargs.get("return_timestamps") else [t.no_timestamps])
+        return self._E.WhisperDecodeOptions(prefix=prefix, eos_id=t.eos, max_new_tokens=int(self.gen_kwargs.get("max_new_tokens", 128)),
+                                            suppress=t.suppress, begin_suppress=t.begin_suppress)
+
+    def _detect_language(self, audio: np.ndarray) -> Optional[str]:
+        """Encoder + one decoder step restricted to the language tokens (reference :166-197)."""
+        t = self.tokens
+        if not t.lang_to_id:
+            return None
+        tok = self.engine.detect_language_host(np.ascontiguousarray(audio[:480000], dtype=np.float32), t.sot,
+                                               list(t.lang_to_id.values()))
+        return t.id_to_lang.get(int(tok))
+
+    def _transcribe(self, audio: np.ndarray, language: str) -> list[int]:
+        ids = self.engine.transcribe([np.ascontiguousarray(audio, dtype=np.float32)], self._options(language))[0]
+        return [i for i in ids if i != self.tokens.eos]
+
+    # -- the slot -----------------------------------------------------------------------------------
+    def process(self, vad_audio: Any) -> Iterator[Any]:
+        logger.debug("infering whisper (b200)...")
+        audio = np.asarray(vad_audio.audio, dtype=np.float32)
+        forced = self._forced_language()
+        language_code = forced
+        if forced is None:
+            language_code = self._detect_language(audio) or self.last_language or DEFAULT_LANGUAGE
+        ids = self._transcribe(audio, language_code)
+        if language_code in SUPPORTED_LANGUAGES:
+            self.last_language = language_code
+        else:
+            logger.warning("Whisper detected unsupported language: %s", language_code)
+        pred_text = self._decode_text(ids)
+        logger.debug("finished whisper inference")
+        if self.start_language == "auto":
+            language_code += "-auto"
+        if getattr(vad_audio, "mode", None) == "progressive":
+            yield _api.PartialTranscription(text=pred_text, turn_id=vad_audio.turn_id, turn_revision=vad_audio.turn_revision)
+            return
+        yield _api.Transcription(text=pred_text, language_code=language_code, turn_id=vad_audio.turn_id,
+                                 turn_revision=vad_audio.turn_revision, speech_stopped_at_s=vad_audio.created_at_s)
+
+    def cleanup(self) -> None:
+        eng = getattr(self, "engine", None)
+        if eng is not None:
+            eng.close()
+
+
+# Whisper geometries (transformers WhisperConfig values of the public checkpoints)
+GEOMETRIES = {
+    "micro": dict(d_model=128, heads=2, enc_layers=2, dec_layers=2, ffn=512, n_mels=80, vocab=4096),
+    "tiny": dict(d_model=384, heads=6, enc_layers=4, dec_layers=4, ffn=1536, n_mels=80, vocab=51865),
+    "small": dict(d_model=768, heads=12, enc_layers=12, dec_layers=12, ffn=3072, n_mels=80, vocab=51865),
+    "large-v3": dict(d_model=1280, heads=20, enc_layers=32, dec_layers=32, ffn=5120, n_mels=128, vocab=51866),
+}
