@@ -192,7 +192,7 @@ def main():
     import torch
     import torch.distributed as dist
     from oracle import weights as W
-    from speech_to_speech_b200 import engine as E
+    from speech_to_speech_b200 import engine as E, shard
 
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     torch.cuda.set_device(local_rank)
@@ -206,7 +206,8 @@ def main():
     dev = f"cuda:{local_rank}"
     n_in = args.warmup + args.steps
     # every step gets its own utterance; each rank a disjoint shard of the session stream (weak scaling, no collective)
-    auds = [W.synthetic_audio(rank * 1000 + i, N_SAMPLES) for i in range(min(n_in, 8))]
+    sessions = shard.local_sessions(rank, world, world * min(n_in, 8))  # global session ids owned by this rank
+    auds = [W.synthetic_audio(sid, N_SAMPLES) for sid in sessions]
     pcm_dev = [torch.from_numpy(a)[None].to(dev).contiguous() for a in auds]
     pinned = [torch.from_numpy(a).pin_memory() for a in auds]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -266,15 +267,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     e2e_total = sum(e2e_t)
 
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_total = float(t[0]), float(t[1])
+    total_ms, e2e_total = shard.max_over_ranks([total_ms, e2e_total], device=dev)  # slowest rank defines the job
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
-        value = world * AUDIO_S / (ms_per_step / 1e3)
-        e2e_value = world * AUDIO_S / (e2e_total / args.steps)
+        value = shard.whole_job_sessions(world, AUDIO_S, ms_per_step)
+        e2e_value = shard.whole_job_sessions(world, AUDIO_S, 1e3 * e2e_total / args.steps)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
