@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--cpu-baseline-utts", type=int, default=2, help="utterances timed on the host CPU (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--profile-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the device-timed region (use with ncu --profile-from-start off)")
+    ap.add_argument("--batch", type=int, default=8, help="sessions per launch for the secondary 'batched' figure (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -199,7 +202,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     g = W.WHISPER_GEOMETRIES[args.model]
-    eng = E.WhisperEngine(g.to_dict(), dtype="float16", max_batch=1, device=local_rank)
+    eng = E.WhisperEngine(g.to_dict(), dtype="float16", max_batch=max(1, args.batch), device=local_rank)
     eng.init_random(seed=1234)
     opts = E.WhisperDecodeOptions(prefix=PREFIX, eos_id=-1, max_new_tokens=MAX_NEW, suppress=SUPPRESS,
                                   begin_suppress=BEGIN_SUPPRESS)
@@ -234,6 +237,8 @@ def main():
           for _ in range(args.steps)]
     E.launch_count(local_rank, reset=True)
     barrier()
+    if args.profile_region:
+        torch.cuda.cudart().cudaProfilerStart()
     t_wall = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)          # L2 flush (not timed)
@@ -245,6 +250,8 @@ def main():
         eng.decode(1, opts)
         e.record()
     barrier()
+    if args.profile_region:
+        torch.cuda.cudart().cudaProfilerStop()
     wall_s = time.perf_counter() - t_wall
     launches = E.launch_count(local_rank, reset=True)
     step_ms = [s.elapsed_time(e) for s, _, e in ev]
@@ -264,8 +271,37 @@ def main():
         ids = eng.transcribe([pinned[i % len(pinned)].numpy()], opts)
         e2e_t.append(time.perf_counter() - t)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     e2e_total = sum(e2e_t)
+
+    # ---- secondary figure: B concurrent sessions per launch (the weight stream is shared by the batch) ----
+    batched = None
+    if args.batch > 1:
+        Bn = args.batch
+        pcm_b = torch.stack([pcm_dev[i % len(pcm_dev)][0] for i in range(Bn)]).contiguous()
+        host_b = [pinned[i % len(pinned)].numpy() for i in range(Bn)]
+        for _ in range(2):
+            eng.logmel(pcm_b, [N_SAMPLES] * Bn); eng.encode(Bn); eng.decode(Bn, opts)
+        torch.cuda.synchronize()
+        nb_steps = max(3, args.steps // 4)
+        evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nb_steps)]
+        barrier()
+        for i in range(nb_steps):
+            flush.fill_(i & 0xFF)
+            evb[i][0].record()
+            eng.logmel(pcm_b, [N_SAMPLES] * Bn); eng.encode(Bn); eng.decode(Bn, opts)
+            evb[i][1].record()
+        barrier()
+        b_ms = [a.elapsed_time(b) for a, b in evb]
+        tb = []
+        for i in range(nb_steps):
+            t = time.perf_counter(); eng.transcribe(host_b, opts); tb.append(time.perf_counter() - t)
+        barrier()
+        b_tot, b_e2e = shard.max_over_ranks([sum(b_ms), sum(tb)], device=dev)
+        batched = {"batch_per_gpu": Bn, "steps": nb_steps, "ms_per_step": b_tot / nb_steps,
+                   "value": world * Bn * AUDIO_S / (b_tot / nb_steps / 1e3),
+                   "e2e_value": world * Bn * AUDIO_S / (b_e2e / nb_steps), "latency_ms_p50": statistics.median(b_ms),
+                   "note": "same kernels, Bn utterances per launch; every session still gets its full 128-token decode"}
+    clocks = sampler.stop() if rank == 0 else None
 
     total_ms, e2e_total = shard.max_over_ranks([total_ms, e2e_total], device=dev)  # slowest rank defines the job
 
@@ -300,6 +336,7 @@ def main():
                          "traffic": None, "algorithmic_bytes_per_launch": nb["per_launch"], "peak_source": peak_src,
                          "share_of_step": dec_avg_ms / ms_per_step},
             "clocks": clocks,
+            "batched": batched,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(g, args.cpu_baseline_utts)
