@@ -152,6 +152,8 @@ int s2s_llama_prefill(s2s_llama* m, int32_t slot, const int32_t* ids_h, int32_t 
 int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int32_t* first_ids_d,
                      int32_t n_steps, int32_t eos_id, int32_t* ids_out_d, int32_t* len_out_d,
                      const int32_t* forced_d, float* logits_out_d, void* stream);
+/* Profiling aid (see s2s_whisper_set_trace): CTA 0's [phase begin, body end, barrier exit] stamps, trace_d[capacity][3]. */
+int s2s_llama_set_trace(s2s_llama* m, uint64_t* trace_d, int32_t capacity);
 /* End-to-end with HOST buffers: (chunked) prefill + greedy decode, synchronous.  ids_out_h[0] is the argmax of the
  * prompt's last position, n_steps tokens in total (generate() semantics of the reference's pipeline call). */
 int s2s_llama_generate(s2s_llama* m, int32_t slot, const int32_t* prompt_h, int32_t n_prompt, int32_t n_steps,

@@ -18,7 +18,7 @@ EXPORTED = [
     "s2s_whisper_detect_language", "s2s_whisper_transcribe", "s2s_whisper_set_trace",
     "s2s_gemm", "s2s_attention",
     "s2s_llama_create", "s2s_llama_destroy", "s2s_llama_bind_tensor", "s2s_llama_init_random",
-    "s2s_llama_finalize", "s2s_llama_session_reset", "s2s_llama_prefill", "s2s_llama_decode", "s2s_llama_generate",
+    "s2s_llama_finalize", "s2s_llama_session_reset", "s2s_llama_prefill", "s2s_llama_decode", "s2s_llama_generate", "s2s_llama_set_trace",
     "s2s_tts_postproc",
 ]
 
@@ -94,6 +94,7 @@ def load() -> C.CDLL:
     lib.s2s_llama_prefill.argtypes = [vp, i32, C.POINTER(i32), i32, vp, vp, vp]
     lib.s2s_llama_decode.argtypes = [vp, C.POINTER(i32), i32, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.s2s_llama_generate.argtypes = [vp, i32, C.POINTER(i32), i32, i32, i32, vp, vp, vp]
+    lib.s2s_llama_set_trace.argtypes = [vp, vp, i32]
     lib.s2s_tts_postproc.argtypes = [vp, vp, i32, vp, i32, vp, C.POINTER(i32), vp]
     _lib = lib
     return lib

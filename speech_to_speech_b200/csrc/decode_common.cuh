@@ -151,7 +151,7 @@ static __device__ __noinline__ void stage_rows(const float* x, int B, int d, flo
 // A warp owns GV_R consecutive rows and keeps GV_R * GV_U independent 16-byte loads in flight per lane; the
 // bias / residual / mask reads are issued BEFORE the weight loads; the NEXT row group of the warp is L2-prefetched
 // while the current one is reduced.  Lane b (< B) applies the epilogue for batch row b.
-constexpr int GV_R = 2, GV_U = 4, GV_PF = 3;
+constexpr int GV_R = 2, GV_PF = 3;
 enum GemvEpi { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_QKV = 3, EPI_LOGITS = 4,
                EPI_QKV_ROPE = 5 /* row pairs */, EPI_SWIGLU = 6 /* row pairs */ };
 struct GemvArgs {
@@ -221,112 +221,194 @@ __device__ __forceinline__ void gemv_pair_epilogue(const GemvArgs& a, int mode, 
   }
 }
 
-// all loads of one row group (nothing is consumed here, so they are issued back to back)
+// ---- weight streaming through a per-warp shared-memory ring filled by the bulk-copy engine ---------------
+// Each warp owns `ring_slots` slots of GV_R rows x GV_CH 16-bit weights.  Lane 0 issues cp.async.bulk
+// (global -> shared, completion on the slot's mbarrier); the warp then multiplies from shared memory.  Bytes in
+// flight are bounded by shared memory (128 KB per SM), not by registers, and the copies are not droppable hints.
+// The warp is its own producer and consumer, so no cross-warp synchronisation is needed: slot reuse is ordered
+// by program order + __syncwarp + fence.proxy.async.
+constexpr int GV_CH = 1024;                       // weights per row chunk (2 KB)
+constexpr int GV_SLOT_BYTES = GV_R * GV_CH * 2;   // one slot: GV_R row chunks
+
+struct GemvRing {
+  uint32_t base_s;       // this warp's ring: 32-bit shared-space address (16-byte aligned)
+  uint32_t bars_s;       // this warp's mbarriers [slots], shared-space address
+  int slots;
+  unsigned int slot;     // next slot to consume and its phase parity; persist across phases (all lanes identical)
+  unsigned int parity;
+  // units of the NEXT gemv already issued into the ring by gemv_prefetch() (weights do not depend on the barrier)
+  int pre_valid, pre_pg, pre_pc;
+  const void* pre_W;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float4 lds16f(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();
+  } while (!ok);
+}
+
+// producer side of one unit = chunk c of the GV_R rows starting at row0 (lane 0 only)
 template <typename T>
-__device__ __forceinline__ void gemv_load_group(const GemvArgs& a, const T* __restrict__ W, int row0, int k0, int B,
-                                                int lane, bool first_k, uint4 (&wv)[GV_U][GV_R], float (&bias)[GV_R],
-                                                float (&resid)[GV_R], int (&sup)[GV_R]) {
+__device__ __forceinline__ void gemv_issue_unit(const T* __restrict__ W, int N, int K, int row0, int c, uint32_t dst,
+                                                uint32_t bar) {
+  const int nrows = min(GV_R, N - row0);
+  const int len = min(GV_CH, K - c * GV_CH);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of the slot are done
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(nrows * len * 2)) : "memory");
+  const T* src = W + (long long)row0 * K + c * GV_CH;
+  bulk_g2s(dst, src, (uint32_t)(len * 2), bar);
+  if (nrows > 1) bulk_g2s(dst + GV_CH * 2, src + K, (uint32_t)(len * 2), bar);
+}
+
+// Issue the first `slots` units of a gemv into the (empty) ring.  Called right after the previous gemv finished,
+// i.e. BEFORE the grid barrier and the input staging of the phase that will consume them: the weight stream of the
+// next projection is already landing in shared memory while the chip synchronises.
+template <typename T>
+__device__ __forceinline__ void gemv_prefetch(const GemvArgs& a, GemvRing& ring) {
+  const int lane = threadIdx.x & 31;
+  const T* __restrict__ W = reinterpret_cast<const T*>(a.W);
   const int N = a.N, K = a.K;
-  if (first_k) {
-#pragma unroll
-    for (int r = 0; r < GV_R; ++r) {
-      const int row = min(row0 + r, N - 1);
-      bias[r] = a.bias ? __ldg(a.bias + row) : 0.f;
-      resid[r] = 0.f;
-      sup[r] = 0;
-      if (a.mode == EPI_RESID) { if (lane < B) resid[r] = __ldcg(a.out + lane * a.ldo + row); }
-      else if (a.mode == EPI_LOGITS && a.suppress) sup[r] = __ldg(a.suppress + row);
+  const int first = dec_first_item(), istride = dec_item_stride();
+  ring.pre_valid = 1; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = a.W;
+  if (first * GV_R >= N) return;
+  const int n_groups = ((N + GV_R - 1) / GV_R - first + istride - 1) / istride;
+  const int cpr = (K + GV_CH - 1) / GV_CH;
+  if (lane == 0) {
+    int pg = 0, pc = 0, n_ahead = 0;
+    unsigned int pslot = ring.slot;
+#pragma unroll 1
+    while (n_ahead < ring.slots && pg < n_groups) {
+      gemv_issue_unit<T>(W, N, K, (first + pg * istride) * GV_R, pc, ring.base_s + pslot * GV_SLOT_BYTES, ring.bars_s + pslot * 8);
+      if (++pc == cpr) { pc = 0; ++pg; }
+      if (++pslot == (unsigned)ring.slots) pslot = 0;
+      ++n_ahead;
     }
-  }
-#pragma unroll
-  for (int u = 0; u < GV_U; ++u) {
-    const int k = k0 + u * 256;
-#pragma unroll
-    for (int r = 0; r < GV_R; ++r) {
-      const int row = min(row0 + r, N - 1);
-      if (k < K) wv[u][r] = ld_stream16(W + (long long)row * K + k);
-    }
+    ring.pre_pg = pg; ring.pre_pc = pc;
   }
 }
 
-template <typename T, int NB>
-__device__ __forceinline__ void gemv_fma_group(const uint4 (&wv)[GV_U][GV_R], const float* xs, int K, int k0, int B,
-                                               float (&acc)[GV_R][NB]) {
-#pragma unroll
-  for (int u = 0; u < GV_U; ++u) {
-    const int k = k0 + u * 256;
-    if (k < K) {
-#pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        if (b < B) {
-          const float4 x0 = *reinterpret_cast<const float4*>(xs + b * K + k);
-          const float4 x1 = *reinterpret_cast<const float4*>(xs + b * K + k + 4);
-#pragma unroll
-          for (int r = 0; r < GV_R; ++r) {
-            const float2 w0 = DT<T>::to_f2(wv[u][r].x), w1 = DT<T>::to_f2(wv[u][r].y);
-            const float2 w2 = DT<T>::to_f2(wv[u][r].z), w3 = DT<T>::to_f2(wv[u][r].w);
-            float c = acc[r][b];
-            c = fmaf(w0.x, x0.x, c); c = fmaf(w0.y, x0.y, c);
-            c = fmaf(w1.x, x0.z, c); c = fmaf(w1.y, x0.w, c);
-            c = fmaf(w2.x, x1.x, c); c = fmaf(w2.y, x1.y, c);
-            c = fmaf(w3.x, x1.z, c); c = fmaf(w3.y, x1.w, c);
-            acc[r][b] = c;
-          }
-        }
-      }
-    }
+// Wait for prefetched units that will never be consumed (early exit) so no bulk copy is in flight at CTA exit.
+template <typename T>
+__device__ __forceinline__ void gemv_drain(const GemvArgs& a, GemvRing& ring) {
+  if (!ring.pre_valid) return;
+  const int first = dec_first_item(), istride = dec_item_stride();
+  ring.pre_valid = 0;
+  if (first * GV_R >= a.N) return;
+  const int n_groups = ((a.N + GV_R - 1) / GV_R - first + istride - 1) / istride;
+  const int n_units = min(ring.slots, n_groups * ((a.K + GV_CH - 1) / GV_CH));
+  unsigned int cslot = ring.slot, cpar = ring.parity;
+  for (int u = 0; u < n_units; ++u) {
+    mbar_wait_s(ring.bars_s + cslot * 8, cpar);
+    if (++cslot == (unsigned)ring.slots) { cslot = 0; cpar ^= 1u; }
   }
+  ring.slot = cslot; ring.parity = cpar;
 }
 
+// The unit stream of a warp: row groups first + j*istride (j = 0..n_groups-1), each split into cpr chunks.
+// Producer cursor (pg, pc) runs `slots` units ahead of the consumer cursor (g, c); no divisions in the loop.
 template <typename T, int NB>
-__device__ __noinline__ void gemv_generic(const GemvArgs& a, const float* xs, int B, float& best_v, int& best_i) {
+__device__ __noinline__ void gemv_generic(const GemvArgs& a, uint32_t xs_s, int B, float& best_v, int& best_i,
+                                          GemvRing& ring) {
+  static_assert(GV_R == 2, "two rows per group");
   const int lane = threadIdx.x & 31;
   const T* __restrict__ W = reinterpret_cast<const T*>(a.W);
   const int N = a.N, K = a.K, mode = a.mode;
-  const int stride = dec_item_stride() * GV_R;
-  const int kl = lane * 8;
+  const int first = dec_first_item(), istride = dec_item_stride();
+  if (first * GV_R >= N) { ring.pre_valid = 0; return; }
+  const int n_groups = ((N + GV_R - 1) / GV_R - first + istride - 1) / istride;
+  const int cpr = (K + GV_CH - 1) / GV_CH;
+  const int slots = ring.slots;
+  // ---- producer prologue (normally already done by gemv_prefetch before the barrier) ----
+  if (ring.pre_valid && ring.pre_W != a.W) __trap();  // prefetch bookkeeping bug: the ring holds another matrix
+  if (!ring.pre_valid) gemv_prefetch<T>(a, ring);
+  int pg = ring.pre_pg, pc = ring.pre_pc;  // lane 0's cursor
+  ring.pre_valid = 0;
+  unsigned int cslot = ring.slot, cpar = ring.parity;
+  const uint32_t lane_off = lane * 16;
 #pragma unroll 1
-  for (int row0 = dec_first_item() * GV_R; row0 < N; row0 += stride) {
-    const int pf_row = row0 + GV_PF * stride;
-    if (pf_row < N) {  // warm L2 GV_PF row groups ahead: HBM latency is hidden behind the groups in between
-      const char* nb = reinterpret_cast<const char*>(W + (long long)pf_row * K);
-      const int total = min(GV_R, N - pf_row) * K * (int)sizeof(T);
+  for (int g = 0; g < n_groups; ++g) {
+    const int row0 = (first + g * istride) * GV_R;
+    const int r1 = min(row0 + 1, N - 1);
+    const float bias0 = a.bias ? __ldg(a.bias + row0) : 0.f;
+    const float bias1 = a.bias ? __ldg(a.bias + r1) : 0.f;
+    float resid0 = 0.f, resid1 = 0.f;
+    int sup0 = 0, sup1 = 0;
+    if (mode == EPI_RESID) {
+      if (lane < B) { resid0 = __ldcg(a.out + lane * a.ldo + row0); resid1 = __ldcg(a.out + lane * a.ldo + r1); }
+    } else if (mode == EPI_LOGITS && a.suppress) {
+      sup0 = __ldg(a.suppress + row0); sup1 = __ldg(a.suppress + r1);
+    }
+    float acc0[NB], acc1[NB], acc2[NB], acc3[NB];  // rows 0/1 x even/odd element pairs: four independent chains
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc0[b] = acc1[b] = acc2[b] = acc3[b] = 0.f;
 #pragma unroll 1
-      for (int o = lane * 128; o < total; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
+    for (int c = 0; c < cpr; ++c) {
+      mbar_wait_s(ring.bars_s + cslot * 8, cpar);
+      const uint32_t src = ring.base_s + cslot * GV_SLOT_BYTES + lane_off;
+      const int len = min(GV_CH, K - c * GV_CH);
+      const uint32_t xk = xs_s + (uint32_t)(c * GV_CH + lane * 8) * 4;
+#pragma unroll 2
+      for (int e = lane * 8; e < len; e += 256) {
+        const uint32_t eo = (uint32_t)(e - lane * 8);
+        const uint4 w0 = lds16(src + eo * 2), w1 = lds16(src + GV_CH * 2 + eo * 2);
+        const float2 a0 = DT<T>::to_f2(w0.x), a1 = DT<T>::to_f2(w0.y), a2 = DT<T>::to_f2(w0.z), a3 = DT<T>::to_f2(w0.w);
+        const float2 c0 = DT<T>::to_f2(w1.x), c1 = DT<T>::to_f2(w1.y), c2 = DT<T>::to_f2(w1.z), c3 = DT<T>::to_f2(w1.w);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          if (b < B) {
+            const float4 x0 = lds16f(xk + (uint32_t)(b * K) * 4 + eo * 4), x1 = lds16f(xk + (uint32_t)(b * K) * 4 + eo * 4 + 16);
+            acc0[b] = fmaf(a0.x, x0.x, acc0[b]); acc1[b] = fmaf(a0.y, x0.y, acc1[b]);
+            acc0[b] = fmaf(a1.x, x0.z, acc0[b]); acc1[b] = fmaf(a1.y, x0.w, acc1[b]);
+            acc0[b] = fmaf(a2.x, x1.x, acc0[b]); acc1[b] = fmaf(a2.y, x1.y, acc1[b]);
+            acc0[b] = fmaf(a3.x, x1.z, acc0[b]); acc1[b] = fmaf(a3.y, x1.w, acc1[b]);
+            acc2[b] = fmaf(c0.x, x0.x, acc2[b]); acc3[b] = fmaf(c0.y, x0.y, acc3[b]);
+            acc2[b] = fmaf(c1.x, x0.z, acc2[b]); acc3[b] = fmaf(c1.y, x0.w, acc3[b]);
+            acc2[b] = fmaf(c2.x, x1.x, acc2[b]); acc3[b] = fmaf(c2.y, x1.y, acc3[b]);
+            acc2[b] = fmaf(c3.x, x1.z, acc2[b]); acc3[b] = fmaf(c3.y, x1.w, acc3[b]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0 && pg < n_groups) {  // refill the slot just drained
+        gemv_issue_unit<T>(W, N, K, (first + pg * istride) * GV_R, pc, ring.base_s + cslot * GV_SLOT_BYTES, ring.bars_s + cslot * 8);
+        if (++pc == cpr) { pc = 0; ++pg; }
+      }
+      if (++cslot == (unsigned)slots) { cslot = 0; cpar ^= 1u; }
     }
-    float acc[GV_R][NB];
+    float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-    for (int r = 0; r < GV_R; ++r)
-#pragma unroll
-      for (int b = 0; b < NB; ++b) acc[r][b] = 0.f;
-    float bias[GV_R], resid[GV_R];
-    int sup[GV_R];
-#pragma unroll 1
-    for (int k0 = kl; k0 < K; k0 += 256 * GV_U) {
-      uint4 wv[GV_U][GV_R];
-      gemv_load_group<T>(a, W, row0, k0, B, lane, k0 == kl, wv, bias, resid, sup);
-      gemv_fma_group<T, NB>(wv, xs, K, k0, B, acc);
+    for (int b = 0; b < NB; ++b) {
+      const float s0 = warp_sum(acc0[b] + acc1[b]), s1 = warp_sum(acc2[b] + acc3[b]);
+      if (b == 0 || lane == b) { v0 = s0; v1 = s1; }
     }
-    float vr[GV_R];
-#pragma unroll
-    for (int r = 0; r < GV_R; ++r) {
-#pragma unroll
-      for (int b = 0; b < NB; ++b) acc[r][b] = warp_sum(acc[r][b]);
-      float v = acc[r][0];
-#pragma unroll
-      for (int b = 1; b < NB; ++b) v = (lane == b) ? acc[r][b] : v;
-      vr[r] = v;
-    }
-    if (mode >= EPI_QKV_ROPE) {
-      static_assert(GV_R == 2, "pair epilogues need two rows per group");
-      if (lane < B) gemv_pair_epilogue<T>(a, mode, row0, lane, vr[0] + bias[0], vr[1] + bias[1]);
-    } else {
-#pragma unroll
-      for (int r = 0; r < GV_R; ++r)
-        if (row0 + r < N && lane < B)
-          gemv_epilogue<T>(a, mode, row0 + r, lane, vr[r], bias[r], resid[r], sup[r], best_v, best_i);
+    if (lane < B) {
+      if (mode >= EPI_QKV_ROPE) {
+        gemv_pair_epilogue<T>(a, mode, row0, lane, v0 + bias0, v1 + bias1);
+      } else {
+        gemv_epilogue<T>(a, mode, row0, lane, v0, bias0, resid0, sup0, best_v, best_i);
+        if (row0 + 1 < N) gemv_epilogue<T>(a, mode, row0 + 1, lane, v1, bias1, resid1, sup1, best_v, best_i);
+      }
     }
   }
+  ring.slot = cslot;
+  ring.parity = cpar;
 }
 
 // ---- attention over one chunk of <= 64 keys for one (batch, head): warp-level -----------------

@@ -128,6 +128,8 @@ struct s2s_llama {
       *out_len = nullptr, *next_id = nullptr;
   unsigned int* sync_counter = nullptr;
   int s_max = 0;
+  unsigned long long* trace = nullptr;
+  int trace_cap = 0;
 };
 
 namespace {
@@ -469,8 +471,16 @@ int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int3
   p.first_ids = first_ids_d; p.n_steps = n_steps; p.eos = eos_id; p.out_ids = ids_out_d; p.out_len = len_out_d;
   p.forced = forced_d; p.logits_out = logits_out_d; p.done = m->done; p.n_done = m->n_done;
   p.cand_val = m->cand_val; p.cand_idx = m->cand_idx; p.sync_counter = m->sync_counter;
+  p.trace = m->trace; p.trace_cap = m->trace_cap;
   S2S_CHECK(llama_decode_launch(m->ctx, p, c.compute_dtype, m->debug_phases, st));
   for (int b = 0; b < B; ++b) m->len[slots_h[b]] += n_steps;
+  return S2S_OK;
+}
+
+int s2s_llama_set_trace(s2s_llama* m, uint64_t* trace_d, int32_t capacity) {
+  S2S_REQUIRE(m, "llama set_trace: null model");
+  m->trace = reinterpret_cast<unsigned long long*>(trace_d);
+  m->trace_cap = trace_d ? capacity : 0;
   return S2S_OK;
 }
 

@@ -10,30 +10,17 @@
 //   then 5L: final RMSNorm + lm_head + per-CTA argmax      5L+1: global argmax, EOS bookkeeping, next embedding
 // Every phase streams its weights with 16-byte coalesced read-only loads (decode_common.cuh); HBM-bound:
 // 16.06 GB / token for Llama-3-8B.
+#include <algorithm>
+
 #include "llama_decode.cuh"
 #include "decode_common.cuh"
 
 namespace {
 
-template <typename T, int NB>
-__device__ __noinline__ void ld_prefetch(const LlamaDecParams& p, int ph) {
-  const int L = p.layers;
-  const T* W = nullptr;
-  int N = 0, K = p.d;
-  if (ph < 5 * L) {
-    const LlamaDecLayer& w = p.lw[ph / 5];
-    switch (ph % 5) {
-      case 0: W = reinterpret_cast<const T*>(w.w_qkv); N = (p.heads + 2 * p.kv_heads) * p.hd; break;
-      case 2: W = reinterpret_cast<const T*>(w.w_o); N = p.d; K = p.heads * p.hd; break;
-      case 3: W = reinterpret_cast<const T*>(w.w_gu); N = 2 * p.ffn; break;
-      case 4: W = reinterpret_cast<const T*>(w.w_down); N = p.d; K = p.ffn; break;
-      default: break;
-    }
-  } else if (ph == 5 * L) {
-    W = reinterpret_cast<const T*>(p.lm_head); N = p.vocab;
-  }
-  // only the first GV_PF row groups of every warp; the GEMV loop prefetches the rest as it goes
-  if (W) prefetch_rows_l2<T, GV_R>(W, min(N, GV_PF * dec_item_stride() * GV_R), K);
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 template <typename T, int HD>
@@ -103,14 +90,9 @@ __device__ __noinline__ void ld_select(const LlamaDecParams& p, int step, float*
   }
 }
 
-template <typename T, int NB>
-__device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, float* xs, float* s_aux) {
-  float* s_red = s_aux + 2 * DEC_WARPS * NB;
-  float* wb = s_red + 2 * DEC_WARPS;
+template <typename T>
+__device__ __noinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, int ph, GemvArgs& a) {
   const int L = p.layers, d = p.d, B = p.B, qd = p.heads * p.hd, kvd = p.kv_heads * p.hd;
-  float best_v = -INFINITY;
-  int best_i = 0x7fffffff;
-  GemvArgs a;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = qd; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
   a.pos = p.pos; a.slot = p.slot; a.kv_slot = p.kv_slot_stride; a.kv_ld = kvd; a.rope = p.rope; a.hd = p.hd;
@@ -120,10 +102,37 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
     const LlamaDecLayer& w = p.lw[layer];
     switch (ph % 5) {
       case 0:
-        stage_rows(p.x, B, d, xs, 2, w.norm1, nullptr, p.eps, s_red, wb);
         a.W = w.w_qkv; a.N = qd + 2 * kvd; a.mode = EPI_QKV_ROPE; a.out = p.q; a.ldo = qd;
         a.kv0 = reinterpret_cast<T*>(p.kv) + (long long)layer * p.kv_layer_stride; a.kv_which = p.kv_which_stride;
-        break;
+        return true;
+      case 2: a.W = w.w_o; a.N = d; a.K = qd; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; return true;
+      case 3: a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out = p.h; a.ldo = p.ffn; return true;
+      case 4: a.W = w.w_down; a.N = d; a.K = p.ffn; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; return true;
+      default: return false;
+    }
+  }
+  if (ph == 5 * L) {
+    a.W = p.lm_head; a.N = p.vocab; a.mode = EPI_LOGITS;
+    a.logits_out = p.logits_out ? p.logits_out + (long long)step * B * p.vocab : nullptr; a.logits_ld = p.vocab;
+    return true;
+  }
+  return false;
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, float* xs, float* s_aux, GemvRing& ring) {
+  float* s_red = s_aux + 2 * DEC_WARPS * NB;
+  float* wb = s_red + 2 * DEC_WARPS;
+  const int L = p.layers, d = p.d, B = p.B;
+  float best_v = -INFINITY;
+  int best_i = 0x7fffffff;
+  GemvArgs a;
+  ld_gemv_args<T>(p, step, ph, a);
+  if (ph < 5 * L) {
+    const int layer = ph / 5;
+    const LlamaDecLayer& w = p.lw[layer];
+    switch (ph % 5) {
+      case 0: stage_rows(p.x, B, d, xs, 2, w.norm1, nullptr, p.eps, s_red, wb); break;
       case 1:
         if (p.hd == 128) ld_attn<T, 128>(p, layer, step); else ld_attn<T, 64>(p, layer, step);
         return;
@@ -132,26 +141,17 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
         if (p.hd == 128) combine_partials_to_smem<128, 8>(p.part, B, p.heads, p.s_max, n_chunks, xs);
         else combine_partials_to_smem<64, 8>(p.part, B, p.heads, p.s_max, n_chunks, xs);
         __syncthreads();
-        a.W = w.w_o; a.N = d; a.K = qd; a.mode = EPI_RESID; a.out = p.x; a.ldo = d;
       } break;
-      case 3:
-        stage_rows(p.x, B, d, xs, 2, w.norm2, nullptr, p.eps, s_red, wb);
-        a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out = p.h; a.ldo = p.ffn;
-        break;
-      default:
-        stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb);
-        a.W = w.w_down; a.N = d; a.K = p.ffn; a.mode = EPI_RESID; a.out = p.x; a.ldo = d;
-        break;
+      case 3: stage_rows(p.x, B, d, xs, 2, w.norm2, nullptr, p.eps, s_red, wb); break;
+      default: stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb); break;
     }
-    gemv_generic<T, NB>(a, xs, B, best_v, best_i);
+    gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
     return;
   }
   if (ph == 5 * L) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     stage_rows(p.x, B, d, xs, 2, p.norm_f, nullptr, p.eps, s_red, wb);
-    a.W = p.lm_head; a.N = p.vocab; a.mode = EPI_LOGITS;
-    a.logits_out = p.logits_out ? p.logits_out + (long long)step * B * p.vocab : nullptr; a.logits_ld = p.vocab;
-    gemv_generic<T, NB>(a, xs, B, best_v, best_i);
+    gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
     float* sv = s_aux;
     int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
     if (lane < NB) { sv[warp * NB + lane] = best_v; si[warp * NB + lane] = best_i; }
@@ -184,21 +184,54 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   const int kmax = max(max(p.d, p.ffn), p.heads * p.hd);
   float* xs = smem_f;
   float* s_aux = smem_f + NB * kmax;
+  GemvRing ring;
+  {
+    const int fixed_floats = NB * kmax + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * p.d;
+    unsigned char* rb = reinterpret_cast<unsigned char*>(smem_f) + (((size_t)fixed_floats * 4 + 127) & ~(size_t)127);
+    const int warp = threadIdx.x >> 5;
+    ring.slots = p.ring_slots;
+    ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rb + (size_t)DEC_WARPS * p.ring_slots * GV_SLOT_BYTES) + warp * p.ring_slots;
+    ring.bars_s = smem_u32(bars);
+    ring.slot = 0;
+    ring.parity = 0;
+    if ((threadIdx.x & 31) == 0) {
+      for (int i = 0; i < p.ring_slots; ++i) mbar_init(bars + i, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+  }
   unsigned int epoch = 0;
+  int trace_i = 0;
+  GemvArgs pre_args;
+  ring.pre_valid = 0; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = nullptr;
   const int n_ph = 5 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
     for (int ph = pb; ph < pe; ++ph) {
-      ld_phase<T, NB>(sp, step, ph, xs, s_aux);
+      const bool tracing = sp.trace && trace_i < sp.trace_cap && threadIdx.x == 0 && blockIdx.x == 0;
+      unsigned long long* tr = tracing ? sp.trace + (long long)trace_i * 3 : nullptr;
+      if (tracing) tr[0] = gtimer_ns();
+      ld_phase<T, NB>(sp, step, ph, xs, s_aux, ring);
+      if (tracing) tr[1] = gtimer_ns();
       if (coop) {
-        int nph = ph + 1, nstep = step;
-        if (nph == n_ph) { nph = 0; nstep = step + 1; }
-        if (nstep < step_end) ld_prefetch<T, NB>(sp, nph);
+        if (!ring.pre_valid) {
+          int nph = ph + 1, nstep = step;
+          if (nph == n_ph) { nph = 0; nstep = step + 1; }
+#pragma unroll 1
+          for (int look = 0; look < 3 && nstep < step_end; ++look) {
+            if (ld_gemv_args<T>(sp, nstep, nph, pre_args)) { gemv_prefetch<T>(pre_args, ring); break; }
+            if (++nph == n_ph) { nph = 0; ++nstep; }
+          }
+        }
         grid_sync(p.sync_counter, epoch);
       }
+      if (tracing) tr[2] = gtimer_ns();
+      ++trace_i;
     }
     if (coop && !p.forced && *reinterpret_cast<volatile int*>(p.n_done) >= p.B) break;
   }
+  gemv_drain<T>(pre_args, ring);
 }
 
 template <typename T>
@@ -218,24 +251,27 @@ __global__ void llama_decode_init_kernel(const LlamaDecParams p) {
 template <typename T, int NB>
 int launch_nb(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
   const int kmax = max(max(p.d, p.ffn), p.heads * p.hd);
-  const size_t smem = ((size_t)NB * kmax + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * (size_t)p.d + 32) * sizeof(float);
-  S2S_REQUIRE(smem <= 220 * 1024, "llama decode: batch %d x K %d does not fit shared memory", NB, kmax);
+  const size_t fixed = (((size_t)NB * kmax + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * (size_t)p.d) * sizeof(float) + 127) & ~(size_t)127;
+  S2S_REQUIRE(fixed + (size_t)DEC_WARPS * GV_SLOT_BYTES + 2048 <= 220 * 1024, "llama decode: batch %d x K %d does not fit shared memory", NB, kmax);
+  LlamaDecParams pr = p;
+  pr.ring_slots = (int)std::min<size_t>(4, (220 * 1024 - fixed - 1024) / ((size_t)DEC_WARPS * GV_SLOT_BYTES));
+  const size_t smem = fixed + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
   auto kern = llama_decode_kernel<T, NB>;
   S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  llama_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(p);
+  llama_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
   S2S_LAUNCH_CHECK();
   const int n_ph = 5 * p.layers + 2;
   const int grid = ctx->num_sms;
   if (!debug_phases) {
     int sb = 0, se = p.n_steps, pb = 0, pe = n_ph, coop = 1;
-    LlamaDecParams pp = p;
+    LlamaDecParams pp = pr;
     void* args[] = {&pp, &sb, &se, &pb, &pe, &coop};
     S2S_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(DEC_THREADS), args, smem, stream));
     s2s_count_launch();
   } else {
     for (int s = 0; s < p.n_steps; ++s)
       for (int ph = 0; ph < n_ph; ++ph) {
-        kern<<<grid, DEC_THREADS, smem, stream>>>(p, s, s + 1, ph, ph + 1, 0);
+        kern<<<grid, DEC_THREADS, smem, stream>>>(pr, s, s + 1, ph, ph + 1, 0);
         S2S_LAUNCH_CHECK();
       }
   }

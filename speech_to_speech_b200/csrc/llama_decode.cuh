@@ -39,6 +39,9 @@ struct LlamaDecParams {
   int* done; int* n_done;
   float* cand_val; int* cand_idx;   // [B][grid]
   unsigned int* sync_counter;
+  int ring_slots;               // weight-ring slots per warp (set by the launcher)
+  unsigned long long* trace;    // optional [cap][3] globaltimer stamps of CTA 0 (phase begin, body end, barrier exit)
+  int trace_cap;
 };
 
 int llama_decode_launch(s2s_ctx* ctx, const LlamaDecParams& p, int dtype, int debug_phases, cudaStream_t stream);

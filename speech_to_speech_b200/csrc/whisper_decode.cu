@@ -15,6 +15,8 @@
 //              8L+1: global argmax, EOS / length bookkeeping, next-token embedding
 // Every phase is a coalesced 16-byte weight/KV stream with fp32 accumulation: the kernel is HBM-bound
 // (decoder weights + per-utterance cross-KV per token).
+#include <algorithm>
+
 #include "whisper_decode.cuh"
 #include "decode_common.cuh"
 
@@ -30,7 +32,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 constexpr int HD = 64;
 static_assert(ATT_CHUNK == ATT_CHUNK_KEYS, "chunk size mismatch");
 
-// L2 prefetch of the weight rows the NEXT phase will stream (called before the grid barrier).
+// L2 prefetch of what this warp will read first in the NEXT phase: weight rows of the projection, or its
+// cross-attention K/V chunk (called before the barrier).
 template <typename T, int NB>
 __device__ __noinline__ void wd_prefetch(const WhisperDecParams& p, int step, int ph) {
   const int d = p.d, L = p.layers;
@@ -45,25 +48,24 @@ __device__ __noinline__ void wd_prefetch(const WhisperDecParams& p, int step, in
       case 5: W = reinterpret_cast<const T*>(w.w_co); N = d; break;
       case 6: W = reinterpret_cast<const T*>(w.w_fc1); N = p.ffn; break;
       case 7: W = reinterpret_cast<const T*>(w.w_fc2); N = d; K = p.ffn; break;
-      case 4: {  // this warp's first cross-attention item: 64 keys x (K | V) = 2 x 128 B per key
-        const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, it = dec_first_item();
-        if (it < p.B * p.heads * n_chunks) {
-          const int c = it % n_chunks, bh = it / n_chunks, h = bh % p.heads, b = bh / p.heads;
-          const long long ldc = (long long)L * 2 * d;
-          const T* Kb = reinterpret_cast<const T*>(p.cross_kv) + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc +
-                        (long long)(ph >> 3) * 2 * d + h * HD;
-          const int n_keys = min(ATT_CHUNK, p.n_ctx - c * ATT_CHUNK);
-          prefetch_strided_l2(Kb, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
-          prefetch_strided_l2(Kb + d, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
-        }
-      } break;
       default: break;
     }
   } else if (ph == 8 * L && step >= p.n_prefix - 1) {
-    // the first GV_PF row groups of every warp; later groups are prefetched inside the GEMV loop
     W = reinterpret_cast<const T*>(p.embed); N = min(p.vocab, GV_PF * dec_item_stride() * GV_R);
   }
   if (W) prefetch_rows_l2<T, GV_R>(W, N, K);
+  if (ph < 8 * L && (ph & 7) == 4) {  // this warp's first cross-attention item: 64 keys x (K | V) = 2 x 128 B per key
+    const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, it = dec_first_item();
+    if (it < p.B * p.heads * n_chunks) {
+      const int c = it % n_chunks, bh = it / n_chunks, h = bh % p.heads, b = bh / p.heads;
+      const long long ldc = (long long)L * 2 * d;
+      const T* Kb = reinterpret_cast<const T*>(p.cross_kv) + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc +
+                    (long long)(ph >> 3) * 2 * d + h * HD;
+      const int n_keys = min(ATT_CHUNK, p.n_ctx - c * ATT_CHUNK);
+      prefetch_strided_l2(Kb, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
+      prefetch_strided_l2(Kb + d, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
+    }
+  }
 }
 
 template <typename T, int NB>
@@ -153,15 +155,11 @@ __device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos
   }
 }
 
-// One phase = (stage inputs into shared memory) + (one shared routine).  Thin: only argument setup is inlined.
-template <typename T, int NB>
-__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, float* xs, float* s_aux) {
-  float* s_red = s_aux + 2 * DEC_WARPS * NB;
-  float* wb = s_red + 2 * DEC_WARPS;  // LayerNorm weight | bias staged per phase
+// Arguments of the projection GEMV of phase `ph` (false: the phase has none).  Shared by the phase itself and by
+// the cross-barrier weight prefetch of the NEXT projection.
+template <typename T>
+__device__ __noinline__ bool wd_gemv_args(const WhisperDecParams& p, int step, int ph, GemvArgs& a) {
   const int L = p.layers, pos = step, d = p.d, B = p.B;
-  float best_v = -INFINITY;
-  int best_i = 0x7fffffff;
-  GemvArgs a;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
   a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f;
@@ -169,50 +167,68 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
     const int layer = ph >> 3;
     const WhisperDecLayer& w = p.lw[layer];
     switch (ph & 7) {
-      case 0: {  // LN1 + QKV (+ self-KV append)
-        stage_rows(p.x, B, d, xs, 1, w.ln1_w, w.ln1_b, 1e-5f, s_red, wb);
+      case 0: {
         const long long kvs = (long long)p.max_pos * d;
         a.W = w.w_qkv; a.N = 3 * d; a.bias = w.b_qkv; a.mode = EPI_QKV; a.out = p.q;
         a.kv0 = reinterpret_cast<T*>(p.self_kv) + ((long long)layer * 2) * kvs + (long long)pos * d;
         a.kv_which = kvs; a.kv_batch = (long long)L * 2 * kvs;
-      } break;
+      } return true;
+      case 2: a.W = w.w_o; a.N = d; a.bias = w.b_o; a.mode = EPI_RESID; a.out = p.x; return true;
+      case 3: a.W = w.w_cq; a.N = d; a.bias = w.b_cq; a.mode = EPI_STORE; a.out = p.q; return true;
+      case 5: a.W = w.w_co; a.N = d; a.bias = w.b_co; a.mode = EPI_RESID; a.out = p.x; return true;
+      case 6: a.W = w.w_fc1; a.N = p.ffn; a.bias = w.b_fc1; a.mode = EPI_GELU; a.out = p.h; a.ldo = p.ffn; return true;
+      case 7: a.W = w.w_fc2; a.N = d; a.K = p.ffn; a.bias = w.b_fc2; a.mode = EPI_RESID; a.out = p.x; return true;
+      default: return false;
+    }
+  }
+  const int g = step - (p.n_prefix - 1);
+  if (ph == 8 * L && g >= 0) {
+    a.W = p.embed; a.N = p.vocab; a.mode = EPI_LOGITS; a.suppress = p.suppress; a.first_step = (g == 0);
+    a.logits_out = p.logits_out ? p.logits_out + (long long)g * B * p.vocab : nullptr; a.logits_ld = p.vocab;
+    return true;
+  }
+  return false;
+}
+
+// One phase = (stage inputs into shared memory) + (one shared routine).  Thin: only argument setup is inlined.
+template <typename T, int NB>
+__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, float* xs, float* s_aux, GemvRing& ring) {
+  float* s_red = s_aux + 2 * DEC_WARPS * NB;
+  float* wb = s_red + 2 * DEC_WARPS;  // LayerNorm weight | bias staged per phase
+  const int L = p.layers, pos = step, d = p.d, B = p.B;
+  float best_v = -INFINITY;
+  int best_i = 0x7fffffff;
+  GemvArgs a;
+  const bool has_gemv = wd_gemv_args<T>(p, step, ph, a);
+  if (ph < 8 * L) {
+    const int layer = ph >> 3;
+    const WhisperDecLayer& w = p.lw[layer];
+    switch (ph & 7) {
+      case 0: stage_rows(p.x, B, d, xs, 1, w.ln1_w, w.ln1_b, 1e-5f, s_red, wb); break;
       case 1: wd_self_attn<T, NB>(p, layer, pos); return;
-      case 2:  // combine + out-proj + residual
+      case 2:
         combine_partials_to_smem<HD, 12>(p.part, B, p.heads, p.s_max, pos / ATT_CHUNK + 1, xs);
         __syncthreads();
-        a.W = w.w_o; a.N = d; a.bias = w.b_o; a.mode = EPI_RESID; a.out = p.x;
         break;
-      case 3:  // LN2 + cross q
-        stage_rows(p.x, B, d, xs, 1, w.ln2_w, w.ln2_b, 1e-5f, s_red, wb);
-        a.W = w.w_cq; a.N = d; a.bias = w.b_cq; a.mode = EPI_STORE; a.out = p.q;
-        break;
+      case 3: stage_rows(p.x, B, d, xs, 1, w.ln2_w, w.ln2_b, 1e-5f, s_red, wb); break;
       case 4: wd_cross_attn<T, NB>(p, layer); return;
       case 5:
         combine_partials_to_smem<HD, 12>(p.part, B, p.heads, p.s_max, (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, xs);
         __syncthreads();
-        a.W = w.w_co; a.N = d; a.bias = w.b_co; a.mode = EPI_RESID; a.out = p.x;
         break;
-      case 6:  // LN3 + fc1 + GELU
-        stage_rows(p.x, B, d, xs, 1, w.ln3_w, w.ln3_b, 1e-5f, s_red, wb);
-        a.W = w.w_fc1; a.N = p.ffn; a.bias = w.b_fc1; a.mode = EPI_GELU; a.out = p.h; a.ldo = p.ffn;
-        break;
-      default:  // fc2 + residual
-        stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb);
-        a.W = w.w_fc2; a.N = d; a.K = p.ffn; a.bias = w.b_fc2; a.mode = EPI_RESID; a.out = p.x;
-        break;
+      case 6: stage_rows(p.x, B, d, xs, 1, w.ln3_w, w.ln3_b, 1e-5f, s_red, wb); break;
+      default: stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb); break;
     }
-    gemv_generic<T, NB>(a, xs, B, best_v, best_i);
+    gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
     return;
   }
   const int g = step - (p.n_prefix - 1);  // index of the token generated at this step
   if (ph == 8 * L) {
-    if (g < 0) return;
+    if (!has_gemv) return;
     // final LayerNorm + tied output projection + suppress masks + per-CTA argmax candidates
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     stage_rows(p.x, B, d, xs, 1, p.lnf_w, p.lnf_b, 1e-5f, s_red, wb);
-    a.W = p.embed; a.N = p.vocab; a.mode = EPI_LOGITS; a.suppress = p.suppress; a.first_step = (g == 0);
-    a.logits_out = p.logits_out ? p.logits_out + (long long)g * B * p.vocab : nullptr; a.logits_ld = p.vocab;
-    gemv_generic<T, NB>(a, xs, B, best_v, best_i);
+    gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
     float* sv = s_aux;
     int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
     if (lane < NB) { sv[warp * NB + lane] = best_v; si[warp * NB + lane] = best_i; }
@@ -245,8 +261,27 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
   const int xs_floats = NB * max(p.d, p.ffn);
   float* xs = smem_f;
   float* s_aux = smem_f + xs_floats;
+  GemvRing ring;
+  {
+    const int fixed_floats = xs_floats + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * p.d;
+    unsigned char* rb = reinterpret_cast<unsigned char*>(smem_f) + (((size_t)fixed_floats * 4 + 127) & ~(size_t)127);
+    const int warp = threadIdx.x >> 5;
+    ring.slots = p.ring_slots;
+    ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rb + (size_t)DEC_WARPS * p.ring_slots * GV_SLOT_BYTES) + warp * p.ring_slots;
+    ring.bars_s = smem_u32(bars);
+    ring.slot = 0;
+    ring.parity = 0;
+    if ((threadIdx.x & 31) == 0) {
+      for (int i = 0; i < p.ring_slots; ++i) mbar_init(bars + i, 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+  }
   unsigned int epoch = 0;
   int trace_i = 0;
+  GemvArgs pre_args;
+  ring.pre_valid = 0; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = nullptr;
   const int n_ph = 8 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
@@ -257,14 +292,15 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
                            (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
       unsigned long long* tr = tracing ? sp.trace + ((blockIdx.x == 0 ? 0 : 1) * (long long)sp.trace_cap + trace_i) * 6 : nullptr;
       if (tracing) tr[0] = globaltimer_ns();
-      if (!skip) wd_phase<T, NB>(sp, step, ph, xs, s_aux);
+      if (!skip) wd_phase<T, NB>(sp, step, ph, xs, s_aux, ring);
       if (tracing) tr[4] = globaltimer_ns();
       if (coop && !skip) {
-        // warm L2 with the next phase's weight rows while we wait at the barrier
         int nph = ph + 1, nstep = step;
         if (nph == n_ph) { nph = 0; nstep = step + 1; }
-        if (nph == 8 * p.layers && nstep < p.n_prefix - 1) nph = n_ph;  // logits phase skipped
         if (nstep < step_end && nph < n_ph) wd_prefetch<T, NB>(sp, nstep, nph);
+        // (The cross-barrier shared-memory prefetch used by the Llama kernel does not pay here: measured 618 -> 750 us
+        //  per token -- any work placed before the barrier arrive is on the critical path of these 2-5 MB phases.
+        //  A lean L2 prefetch of the next projection's first row groups is all that stays.)
         grid_sync(p.sync_counter, epoch);
       }
       if (tracing) tr[5] = globaltimer_ns();
@@ -272,6 +308,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
     }
     if (coop && !p.forced && *reinterpret_cast<volatile int*>(p.n_done) >= p.B) break;
   }
+  gemv_drain<T>(pre_args, ring);  // early exit: never leave a bulk copy in flight
 }
 
 template <typename T>
@@ -291,17 +328,21 @@ __global__ void whisper_decode_init_kernel(const WhisperDecParams p) {
 
 template <typename T, int NB>
 int launch_nb(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStream_t stream) {
-  const size_t smem = ((size_t)NB * (size_t)max(p.d, p.ffn) + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * (size_t)p.d + 32) * sizeof(float);
+  const size_t fixed = (((size_t)NB * (size_t)max(p.d, p.ffn) + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * (size_t)p.d) * sizeof(float) + 127) & ~(size_t)127;
+  WhisperDecParams pr = p;
+  pr.ring_slots = (int)std::min<size_t>(4, (220 * 1024 - fixed - 1024) / ((size_t)DEC_WARPS * GV_SLOT_BYTES));
+  S2S_REQUIRE(pr.ring_slots >= 1, "whisper decode: no shared memory left for the weight ring");
+  const size_t smem = fixed + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
   auto kern = whisper_decode_kernel<T, NB>;
   S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  whisper_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(p);
+  whisper_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
   S2S_LAUNCH_CHECK();
   const int total_steps = p.n_prefix - 1 + p.max_new;
   const int n_ph = 8 * p.layers + 2;
   const int grid = ctx->num_sms;
   if (!debug_phases) {
     int sb = 0, se = total_steps, pb = 0, pe = n_ph, coop = 1;
-    WhisperDecParams pp = p;
+    WhisperDecParams pp = pr;
     void* args[] = {&pp, &sb, &se, &pb, &pe, &coop};
     S2S_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(DEC_THREADS), args, smem, stream));
     s2s_count_launch();
@@ -310,7 +351,7 @@ int launch_nb(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStr
     for (int s = 0; s < total_steps; ++s)
       for (int ph = 0; ph < n_ph; ++ph) {
         if (ph == 8 * p.layers && s < p.n_prefix - 1) continue;
-        kern<<<grid, DEC_THREADS, smem, stream>>>(p, s, s + 1, ph, ph + 1, 0);
+        kern<<<grid, DEC_THREADS, smem, stream>>>(pr, s, s + 1, ph, ph + 1, 0);
         S2S_LAUNCH_CHECK();
       }
   }

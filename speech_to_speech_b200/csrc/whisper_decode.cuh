@@ -41,6 +41,7 @@ struct WhisperDecParams {
   float* cand_val;             // [B][grid]
   int* cand_idx;               // [B][grid]
   unsigned int* sync_counter;  // [1], zeroed before launch
+  int ring_slots;               // weight-ring slots per warp (set by the launcher from the shared-memory budget)
   unsigned long long* trace;   // optional [2][trace_cap][3] globaltimer stamps (profiling aid)
   int trace_cap;
 };

@@ -285,6 +285,10 @@ class LlamaEngine:
                                         _ptr(forced), _ptr(logits), _stream_ptr(self.device)), "s2s_llama_decode")
         return (ids, lens, logits) if return_logits else (ids, lens)
 
+    def set_trace(self, trace: Optional[torch.Tensor]) -> None:
+        cap = 0 if trace is None else trace.shape[0]
+        check(self.lib.s2s_llama_set_trace(self.handle, _ptr(trace), cap), "s2s_llama_set_trace")
+
     def generate(self, prompt: Sequence[int], max_new_tokens: int, eos_id: int = -1, slot: int = 0) -> list[int]:
         """Host ids in, host ids out: (chunked) prefill + greedy decode.  generate() semantics of the reference."""
         arr, n = _lib.i32_array(prompt)
