@@ -68,7 +68,7 @@ __device__ __forceinline__ void prefetch_strided_l2(const void* base, long long 
 }
 
 // ---- stage B rows of x (fp32 [B, d], produced by other CTAs) into shared memory, optionally normalised ----
-// mode 0: plain copy; 1: LayerNorm (w, bias); 2: RMSNorm (w).  Two-pass statistics from shared memory.
+// mode 0: plain copy; 1: LayerNorm (w, bias); 2: RMSNorm (w).  One-pass statistics (sum, sum of squares) from shared memory.
 // The norm weights are fetched together with x (one round trip) into wb[2*d].  s_red: >= DEC_WARPS floats.
 // Ends with a __syncthreads().
 static __device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs, int mode, const float* w,
@@ -105,32 +105,25 @@ static __device__ __noinline__ void stage_rows(const float* x, int B, int d, flo
     const int row = r0 + warp / wpr, sub = warp % wpr, grp = (warp / wpr) * wpr;
     const bool valid = row < B;
     float* xr = xs + row * d;
-    float mean = 0.f;
-    if (mode == 1) {
-      float s = 0.f;
-      if (valid) {
-#pragma unroll 2
-        for (int i = sub * 32 + lane; i < d; i += wpr * 32) s += xr[i];
-      }
-      s = warp_sum(s);
-      if (lane == 0) s_red[warp] = s;
-      __syncthreads();
-      for (int k = 0; k < wpr; ++k) mean += s_red[grp + k];
-      mean /= (float)d;
-    }
-    float ss = 0.f;
+    // one pass: sum and sum of squares together (one block reduction); var = E[x^2] - mean^2 in fp32 is accurate
+    // to ~1e-6 * (1 + mean^2/var), far below the stated tolerances for residual-stream statistics
+    float s1 = 0.f, s2 = 0.f;
     if (valid) {
 #pragma unroll 2
       for (int i = sub * 32 + lane; i < d; i += wpr * 32) {
-        const float a = xr[i] - mean;
-        ss += a * a;
+        const float v = xr[i];
+        s1 += v;
+        s2 = fmaf(v, v, s2);
       }
     }
-    ss = warp_sum(ss);
-    if (lane == 0) s_red[DEC_WARPS + warp] = ss;  // second half of s_red: no barrier needed before reuse
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { s_red[warp] = s1; s_red[DEC_WARPS + warp] = s2; }
     __syncthreads();
-    float var = 0.f;
-    for (int k = 0; k < wpr; ++k) var += s_red[DEC_WARPS + grp + k];
+    float t1 = 0.f, t2 = 0.f;
+    for (int k = 0; k < wpr; ++k) { t1 += s_red[grp + k]; t2 += s_red[DEC_WARPS + grp + k]; }
+    const float mean = (mode == 1) ? t1 / (float)d : 0.f;
+    const float var = fmaxf(t2 - (float)d * mean * mean, 0.f);
     const float rstd = rsqrtf(var / (float)d + eps);
     if (valid) {
 #pragma unroll 2
@@ -227,7 +220,7 @@ __device__ __forceinline__ void gemv_pair_epilogue(const GemvArgs& a, int mode, 
 // flight are bounded by shared memory (128 KB per SM), not by registers, and the copies are not droppable hints.
 // The warp is its own producer and consumer, so no cross-warp synchronisation is needed: slot reuse is ordered
 // by program order + __syncwarp + fence.proxy.async.
-constexpr int GV_CH = 1024;                       // weights per row chunk (2 KB)
+constexpr int GV_CH = 1024;                       // weights per row chunk (2 KB); the code shifts by 10 for /GV_CH
 constexpr int GV_SLOT_BYTES = GV_R * GV_CH * 2;   // one slot: GV_R row chunks
 
 struct GemvRing {
@@ -288,8 +281,9 @@ __device__ __forceinline__ void gemv_prefetch(const GemvArgs& a, GemvRing& ring)
   const int first = dec_first_item(), istride = dec_item_stride();
   ring.pre_valid = 1; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = a.W;
   if (first * GV_R >= N) return;
-  const int n_groups = ((N + GV_R - 1) / GV_R - first + istride - 1) / istride;
-  const int cpr = (K + GV_CH - 1) / GV_CH;
+  int n_groups = 0;
+  for (int gi = first; gi * GV_R < N; gi += istride) ++n_groups;
+  const int cpr = (K + GV_CH - 1) >> 10;
   if (lane == 0) {
     int pg = 0, pc = 0, n_ahead = 0;
     unsigned int pslot = ring.slot;
@@ -332,8 +326,9 @@ __device__ __noinline__ void gemv_generic(const GemvArgs& a, uint32_t xs_s, int 
   const int N = a.N, K = a.K, mode = a.mode;
   const int first = dec_first_item(), istride = dec_item_stride();
   if (first * GV_R >= N) { ring.pre_valid = 0; return; }
-  const int n_groups = ((N + GV_R - 1) / GV_R - first + istride - 1) / istride;
-  const int cpr = (K + GV_CH - 1) / GV_CH;
+  int n_groups = 0;  // row groups of this warp (counted, not divided: 1-3 for the small projections)
+  for (int gi = first; gi * GV_R < N; gi += istride) ++n_groups;
+  const int cpr = (K + GV_CH - 1) >> 10;
   const int slots = ring.slots;
   // ---- producer prologue (normally already done by gemv_prefetch before the barrier) ----
   if (ring.pre_valid && ring.pre_W != a.W) __trap();  // prefetch bookkeeping bug: the ring holds another matrix

@@ -91,7 +91,7 @@ __device__ __noinline__ void ld_select(const LlamaDecParams& p, int step, float*
 }
 
 template <typename T>
-__device__ __noinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, int ph, GemvArgs& a) {
+__device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, int ph, GemvArgs& a) {
   const int L = p.layers, d = p.d, B = p.B, qd = p.heads * p.hd, kvd = p.kv_heads * p.hd;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = qd; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;

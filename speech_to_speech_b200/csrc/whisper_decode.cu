@@ -158,7 +158,7 @@ __device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos
 // Arguments of the projection GEMV of phase `ph` (false: the phase has none).  Shared by the phase itself and by
 // the cross-barrier weight prefetch of the NEXT projection.
 template <typename T>
-__device__ __noinline__ bool wd_gemv_args(const WhisperDecParams& p, int step, int ph, GemvArgs& a) {
+__device__ __forceinline__ bool wd_gemv_args(const WhisperDecParams& p, int step, int ph, GemvArgs& a) {
   const int L = p.layers, pos = step, d = p.d, B = p.B;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
