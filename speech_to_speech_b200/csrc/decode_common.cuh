@@ -18,14 +18,21 @@ constexpr int PART_PAD = 4;     // partial record = [o[hd], m, l, pad, pad] (16-
 
 // ---- grid barrier (all CTAs co-resident: cooperative launch) ------------------------------
 // Monotonic counter: barrier #e completes when counter == e * gridDim.x.  Bounded spin -> trap.
-__device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& epoch) {
+// Split-phase: grid_arrive() publishes this CTA's results; everything that does not depend on other CTAs (argument
+// setup, weight-ring issue, norm-weight loads for the NEXT phase) runs between arrive and wait, i.e. off the
+// critical path; grid_wait() then blocks until every CTA has arrived.
+__device__ __forceinline__ void grid_arrive(unsigned int* counter, unsigned int& epoch) {
   __syncthreads();  // CTA-scope: every thread's phase results happen-before thread 0's release below
   if (threadIdx.x == 0) {
     epoch += 1;
-    const unsigned int target = epoch * gridDim.x;
-    // release-add / acquire-poll at gpu scope (cumulative over the bar.sync above); no MEMBAR.SC, no L1 flush:
-    // all cross-CTA data is read with ld.global.cg / .nc, never through L1.
+    // release-add at gpu scope (cumulative over the bar.sync above); no MEMBAR.SC, no L1 flush: all cross-CTA
+    // data is read with ld.global.cg / .nc, never through L1.
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int epoch_thread0) {
+  if (threadIdx.x == 0) {
+    const unsigned int target = epoch_thread0 * gridDim.x;
     unsigned int v, spins = 0;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
@@ -33,6 +40,10 @@ __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& e
     } while (v < target);
   }
   __syncthreads();
+}
+__device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& epoch) {
+  grid_arrive(counter, epoch);
+  grid_wait(counter, epoch);
 }
 
 // Warp w of CTA c takes work items  w * gridDim.x + c, then + total_warps ...: consecutive items land on
@@ -71,8 +82,20 @@ __device__ __forceinline__ void prefetch_strided_l2(const void* base, long long 
 // mode 0: plain copy; 1: LayerNorm (w, bias); 2: RMSNorm (w).  One-pass statistics (sum, sum of squares) from shared memory.
 // The norm weights are fetched together with x (one round trip) into wb[2*d].  s_red: >= DEC_WARPS floats.
 // Ends with a __syncthreads().
+// Norm weights of a phase (w | bias -> wb[2*d]); callable ahead of time between grid_arrive and grid_wait.
+static __device__ __forceinline__ void stage_norm_weights(const float* w, const float* bias, int d, float* wb) {
+#pragma unroll 1
+  for (int i = threadIdx.x * 4; i < d; i += DEC_THREADS * 4) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w + i));
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bb = __ldg(reinterpret_cast<const float4*>(bias + i));
+    *reinterpret_cast<float4*>(wb + i) = g;
+    *reinterpret_cast<float4*>(wb + d + i) = bb;
+  }
+}
+
 static __device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs, int mode, const float* w,
-                                           const float* bias, float eps, float* s_red, float* wb) {
+                                           const float* bias, float eps, float* s_red, float* wb, int wb_ready = 0) {
   const int n = B * d;
   // x rows: two independent 16-byte loads per thread per trip (one trip for B*d <= 2048)
 #pragma unroll 1
@@ -84,16 +107,7 @@ static __device__ __noinline__ void stage_rows(const float* x, int B, int d, flo
     *reinterpret_cast<float4*>(xs + i) = v0;
     if (j < n) *reinterpret_cast<float4*>(xs + j) = v1;
   }
-  if (mode != 0) {
-#pragma unroll 1
-    for (int i = threadIdx.x * 4; i < d; i += DEC_THREADS * 4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(w + i));
-      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mode == 1) bb = __ldg(reinterpret_cast<const float4*>(bias + i));
-      *reinterpret_cast<float4*>(wb + i) = g;
-      *reinterpret_cast<float4*>(wb + d + i) = bb;
-    }
-  }
+  if (mode != 0 && !wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
   __syncthreads();
   if (mode == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

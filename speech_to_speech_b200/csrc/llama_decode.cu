@@ -120,19 +120,20 @@ __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, 
 }
 
 template <typename T, int NB>
-__device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, float* xs, float* s_aux, GemvRing& ring) {
+__device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, float* xs, float* s_aux, GemvRing& ring,
+                                         const GemvArgs* ready, int wb_ready) {
   float* s_red = s_aux + 2 * DEC_WARPS * NB;
   float* wb = s_red + 2 * DEC_WARPS;
   const int L = p.layers, d = p.d, B = p.B;
   float best_v = -INFINITY;
   int best_i = 0x7fffffff;
   GemvArgs a;
-  ld_gemv_args<T>(p, step, ph, a);
+  if (ready) a = *ready; else ld_gemv_args<T>(p, step, ph, a);
   if (ph < 5 * L) {
     const int layer = ph / 5;
     const LlamaDecLayer& w = p.lw[layer];
     switch (ph % 5) {
-      case 0: stage_rows(p.x, B, d, xs, 2, w.norm1, nullptr, p.eps, s_red, wb); break;
+      case 0: stage_rows(p.x, B, d, xs, 2, w.norm1, nullptr, p.eps, s_red, wb, wb_ready); break;
       case 1:
         if (p.hd == 128) ld_attn<T, 128>(p, layer, step); else ld_attn<T, 64>(p, layer, step);
         return;
@@ -142,7 +143,7 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
         else combine_partials_to_smem<64, 8>(p.part, B, p.heads, p.s_max, n_chunks, xs);
         __syncthreads();
       } break;
-      case 3: stage_rows(p.x, B, d, xs, 2, w.norm2, nullptr, p.eps, s_red, wb); break;
+      case 3: stage_rows(p.x, B, d, xs, 2, w.norm2, nullptr, p.eps, s_red, wb, wb_ready); break;
       default: stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb); break;
     }
     gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
@@ -150,7 +151,7 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
   }
   if (ph == 5 * L) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    stage_rows(p.x, B, d, xs, 2, p.norm_f, nullptr, p.eps, s_red, wb);
+    stage_rows(p.x, B, d, xs, 2, p.norm_f, nullptr, p.eps, s_red, wb, wb_ready);
     gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
     float* sv = s_aux;
     int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
@@ -204,6 +205,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   unsigned int epoch = 0;
   int trace_i = 0;
   GemvArgs pre_args;
+  int pre_tag = -1, wb_tag = -1;
   ring.pre_valid = 0; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = nullptr;
   const int n_ph = 5 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
@@ -212,19 +214,31 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
       const bool tracing = sp.trace && trace_i < sp.trace_cap && threadIdx.x == 0 && blockIdx.x == 0;
       unsigned long long* tr = tracing ? sp.trace + (long long)trace_i * 3 : nullptr;
       if (tracing) tr[0] = gtimer_ns();
-      ld_phase<T, NB>(sp, step, ph, xs, s_aux, ring);
+      ld_phase<T, NB>(sp, step, ph, xs, s_aux, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr, wb_tag == step * n_ph + ph);
       if (tracing) tr[1] = gtimer_ns();
       if (coop) {
+        grid_arrive(p.sync_counter, epoch);
+        // ---- between arrive and wait: prepare the next projection (arguments, first weight units, norm weights) ----
         if (!ring.pre_valid) {
           int nph = ph + 1, nstep = step;
           if (nph == n_ph) { nph = 0; nstep = step + 1; }
 #pragma unroll 1
           for (int look = 0; look < 3 && nstep < step_end; ++look) {
-            if (ld_gemv_args<T>(sp, nstep, nph, pre_args)) { gemv_prefetch<T>(pre_args, ring); break; }
+            if (ld_gemv_args<T>(sp, nstep, nph, pre_args)) {
+              gemv_prefetch<T>(pre_args, ring);
+              pre_tag = nstep * n_ph + nph;
+              const float* nw = nullptr;
+              if (nph < 5 * p.layers) {
+                const int sub = nph % 5;
+                if (sub == 0) nw = sp.lw[nph / 5].norm1; else if (sub == 3) nw = sp.lw[nph / 5].norm2;
+              } else { nw = sp.norm_f; }
+              if (nw) { stage_norm_weights(nw, nullptr, sp.d, s_aux + 2 * DEC_WARPS * NB + 2 * DEC_WARPS); wb_tag = pre_tag; }
+              break;
+            }
             if (++nph == n_ph) { nph = 0; ++nstep; }
           }
         }
-        grid_sync(p.sync_counter, epoch);
+        grid_wait(p.sync_counter, epoch);
       }
       if (tracing) tr[2] = gtimer_ns();
       ++trace_i;

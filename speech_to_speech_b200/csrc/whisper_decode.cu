@@ -37,23 +37,6 @@ static_assert(ATT_CHUNK == ATT_CHUNK_KEYS, "chunk size mismatch");
 template <typename T, int NB>
 __device__ __noinline__ void wd_prefetch(const WhisperDecParams& p, int step, int ph) {
   const int d = p.d, L = p.layers;
-  const T* W = nullptr;
-  int N = 0, K = d;
-  if (ph < 8 * L) {
-    const WhisperDecLayer& w = p.lw[ph >> 3];
-    switch (ph & 7) {
-      case 0: W = reinterpret_cast<const T*>(w.w_qkv); N = 3 * d; break;
-      case 2: W = reinterpret_cast<const T*>(w.w_o); N = d; break;
-      case 3: W = reinterpret_cast<const T*>(w.w_cq); N = d; break;
-      case 5: W = reinterpret_cast<const T*>(w.w_co); N = d; break;
-      case 6: W = reinterpret_cast<const T*>(w.w_fc1); N = p.ffn; break;
-      case 7: W = reinterpret_cast<const T*>(w.w_fc2); N = d; K = p.ffn; break;
-      default: break;
-    }
-  } else if (ph == 8 * L && step >= p.n_prefix - 1) {
-    W = reinterpret_cast<const T*>(p.embed); N = min(p.vocab, GV_PF * dec_item_stride() * GV_R);
-  }
-  if (W) prefetch_rows_l2<T, GV_R>(W, N, K);
   if (ph < 8 * L && (ph & 7) == 4) {  // this warp's first cross-attention item: 64 keys x (K | V) = 2 x 128 B per key
     const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, it = dec_first_item();
     if (it < p.B * p.heads * n_chunks) {
@@ -192,31 +175,33 @@ __device__ __forceinline__ bool wd_gemv_args(const WhisperDecParams& p, int step
 
 // One phase = (stage inputs into shared memory) + (one shared routine).  Thin: only argument setup is inlined.
 template <typename T, int NB>
-__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, float* xs, float* s_aux, GemvRing& ring) {
+__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, float* xs, float* s_aux, GemvRing& ring,
+                                         const GemvArgs* ready, int wb_ready) {
   float* s_red = s_aux + 2 * DEC_WARPS * NB;
   float* wb = s_red + 2 * DEC_WARPS;  // LayerNorm weight | bias staged per phase
   const int L = p.layers, pos = step, d = p.d, B = p.B;
   float best_v = -INFINITY;
   int best_i = 0x7fffffff;
   GemvArgs a;
-  const bool has_gemv = wd_gemv_args<T>(p, step, ph, a);
+  bool has_gemv = true;
+  if (ready) a = *ready; else has_gemv = wd_gemv_args<T>(p, step, ph, a);
   if (ph < 8 * L) {
     const int layer = ph >> 3;
     const WhisperDecLayer& w = p.lw[layer];
     switch (ph & 7) {
-      case 0: stage_rows(p.x, B, d, xs, 1, w.ln1_w, w.ln1_b, 1e-5f, s_red, wb); break;
+      case 0: stage_rows(p.x, B, d, xs, 1, w.ln1_w, w.ln1_b, 1e-5f, s_red, wb, wb_ready); break;
       case 1: wd_self_attn<T, NB>(p, layer, pos); return;
       case 2:
         combine_partials_to_smem<HD, 12>(p.part, B, p.heads, p.s_max, pos / ATT_CHUNK + 1, xs);
         __syncthreads();
         break;
-      case 3: stage_rows(p.x, B, d, xs, 1, w.ln2_w, w.ln2_b, 1e-5f, s_red, wb); break;
+      case 3: stage_rows(p.x, B, d, xs, 1, w.ln2_w, w.ln2_b, 1e-5f, s_red, wb, wb_ready); break;
       case 4: wd_cross_attn<T, NB>(p, layer); return;
       case 5:
         combine_partials_to_smem<HD, 12>(p.part, B, p.heads, p.s_max, (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, xs);
         __syncthreads();
         break;
-      case 6: stage_rows(p.x, B, d, xs, 1, w.ln3_w, w.ln3_b, 1e-5f, s_red, wb); break;
+      case 6: stage_rows(p.x, B, d, xs, 1, w.ln3_w, w.ln3_b, 1e-5f, s_red, wb, wb_ready); break;
       default: stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb); break;
     }
     gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
@@ -227,7 +212,7 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
     if (!has_gemv) return;
     // final LayerNorm + tied output projection + suppress masks + per-CTA argmax candidates
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    stage_rows(p.x, B, d, xs, 1, p.lnf_w, p.lnf_b, 1e-5f, s_red, wb);
+    stage_rows(p.x, B, d, xs, 1, p.lnf_w, p.lnf_b, 1e-5f, s_red, wb, wb_ready);
     gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
     float* sv = s_aux;
     int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
@@ -281,6 +266,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
   unsigned int epoch = 0;
   int trace_i = 0;
   GemvArgs pre_args;
+  int pre_tag = -1, wb_tag = -1;  // (step, phase) the prepared arguments / staged norm weights belong to
   ring.pre_valid = 0; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = nullptr;
   const int n_ph = 8 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
@@ -292,16 +278,37 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
                            (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
       unsigned long long* tr = tracing ? sp.trace + ((blockIdx.x == 0 ? 0 : 1) * (long long)sp.trace_cap + trace_i) * 6 : nullptr;
       if (tracing) tr[0] = globaltimer_ns();
-      if (!skip) wd_phase<T, NB>(sp, step, ph, xs, s_aux, ring);
+      if (!skip) wd_phase<T, NB>(sp, step, ph, xs, s_aux, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr,
+                                 wb_tag == step * n_ph + ph);
       if (tracing) tr[4] = globaltimer_ns();
       if (coop && !skip) {
+        grid_arrive(p.sync_counter, epoch);
+        // ---- between arrive and wait: everything for the NEXT phases that does not depend on other CTAs ----
         int nph = ph + 1, nstep = step;
         if (nph == n_ph) { nph = 0; nstep = step + 1; }
-        if (nstep < step_end && nph < n_ph) wd_prefetch<T, NB>(sp, nstep, nph);
-        // (The cross-barrier shared-memory prefetch used by the Llama kernel does not pay here: measured 618 -> 750 us
-        //  per token -- any work placed before the barrier arrive is on the critical path of these 2-5 MB phases.
-        //  A lean L2 prefetch of the next projection's first row groups is all that stays.)
-        grid_sync(p.sync_counter, epoch);
+        if (nstep < step_end) wd_prefetch<T, NB>(sp, nstep, nph);  // cross-attention K/V chunk -> L2
+        if (!ring.pre_valid) {
+#pragma unroll 1
+          for (int look = 0; look < 3 && nstep < step_end; ++look) {
+            const bool skip_n = (nph == 8 * p.layers) && (nstep < p.n_prefix - 1);
+            if (!skip_n && wd_gemv_args<T>(sp, nstep, nph, pre_args)) {
+              gemv_prefetch<T>(pre_args, ring);  // first weight units of the next projection -> shared memory
+              pre_tag = nstep * n_ph + nph;
+              // its LayerNorm weights -> shared memory (wb is idle until that phase stages its input)
+              const float *nw = nullptr, *nb = nullptr;
+              if (nph < 8 * p.layers) {
+                const WhisperDecLayer& w = sp.lw[nph >> 3];
+                const int sub = nph & 7;
+                if (sub == 0) { nw = w.ln1_w; nb = w.ln1_b; } else if (sub == 3) { nw = w.ln2_w; nb = w.ln2_b; }
+                else if (sub == 6) { nw = w.ln3_w; nb = w.ln3_b; }
+              } else { nw = sp.lnf_w; nb = sp.lnf_b; }
+              if (nw) { stage_norm_weights(nw, nb, sp.d, s_aux + 2 * DEC_WARPS * NB + 2 * DEC_WARPS); wb_tag = pre_tag; }
+              break;
+            }
+            if (++nph == n_ph) { nph = 0; ++nstep; }
+          }
+        }
+        grid_wait(p.sync_counter, epoch);
       }
       if (tracing) tr[5] = globaltimer_ns();
       if (!skip) ++trace_i;
