@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--model", default=MODEL)
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the device-timed region (use with ncu --profile-from-start off)")
+    ap.add_argument("--no-turn", action="store_true", help="skip the full-turn (STT -> LLM -> TTS post-proc) breakdown")
     ap.add_argument("--batch", type=int, default=8, help="sessions per launch for the secondary 'batched' figure (0 = skip)")
     args = ap.parse_args()
 
@@ -338,11 +339,57 @@ def main():
             "clocks": clocks,
             "batched": batched,
         }
+        if world == 1 and not args.no_turn:
+            try:
+                line["turn"] = full_turn(eng, opts, pinned[0].numpy(), local_rank)
+            except Exception as e:  # never lose the headline line because of the extra section
+                line["turn"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(g, args.cpu_baseline_utts)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def full_turn(whisper_eng, opts, audio, device):
+    """BASELINE configs[2] breakdown on one GPU, one session: Whisper-small STT -> Llama-3-8B (64-token prompt, 128-token
+    reply, bf16, random-init) -> TTS post-processing of a 640 ms codec chunk.  The Qwen3-TTS model itself is not built
+    (DESIGN.md section 7), so 'first_audio' below excludes the TTS model latency and says so."""
+    import torch
+    from oracle import weights as W
+    from speech_to_speech_b200 import engine as E
+    from speech_to_speech_b200.handlers.qwen3_tts_postproc import TTSPostProcessor
+    lg = W.LLAMA_GEOMETRIES["llama-3-8b"]
+    llm = E.LlamaEngine(lg.to_dict(), dtype="bfloat16", max_sessions=1, max_positions=1024, max_prefill=512, device=device)
+    llm.init_random(7)
+    post = TTSPostProcessor(device)
+    prompt = np.random.default_rng(0).integers(0, lg.vocab, 64).tolist()
+    chunk24k = (0.2 * np.sin(np.arange(15360) * 0.05)).astype(np.float32)  # 8 codec frames x 1920 samples
+    rows = []
+    for it in range(4):
+        t0 = time.perf_counter()
+        whisper_eng.transcribe([audio], opts)
+        t1 = time.perf_counter()
+        llm.reset(0)
+        nxt, _ = llm.prefill(0, prompt)
+        first = int(nxt[0])  # D2H: first reply token available on the host
+        t2 = time.perf_counter()
+        ids, lens = llm.decode([0], nxt, 19)  # first sentence ~20 tokens (what the TTS stage needs to start)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        ids, lens = llm.decode([0], ids[:, -1].contiguous(), 108)
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        post(chunk24k)
+        t5 = time.perf_counter()
+        rows.append([1e3 * (b - a) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4), (t4, t5))])
+    r = np.median(np.asarray(rows[1:]), axis=0)
+    llm.close()
+    return {"config": "whisper-small STT (128 tok) -> llama-3-8b bf16 (64-tok prompt, 128-tok reply) -> tts post-proc (640 ms chunk); 1 session",
+            "stt_ms": r[0], "llm_prefill_first_token_ms": r[1], "llm_first_sentence_20tok_ms": r[2], "llm_remaining_108tok_ms": r[3],
+            "tts_postproc_chunk_ms": r[4], "audio_in_to_first_sentence_ms": r[0] + r[1] + r[2],
+            "llm_decode_ms_per_token": (r[2] + r[3]) / 127.0,
+            "note": "Qwen3-TTS talker/codec not built (upstream absent, parity unpinned): first-audio latency would add its TTFA"}
 
 
 def cpu_baseline(g, n_utts):
