@@ -74,8 +74,15 @@ int s2s_attention(s2s_ctx* ctx, const void* q_d, const void* k_d, const void* v_
                   int32_t Tk, int32_t heads, int32_t kv_heads, int32_t hd, int64_t ldq, int64_t ldk, int64_t ldv,
                   int64_t ldo, float scale, int32_t causal, int32_t dtype, void* stream) {
   S2S_REQUIRE(ctx && q_d && k_d && v_d && o_d, "s2s_attention: null argument");
-  return attention_launch(q_d, k_d, v_d, o_d, B, Tq, Tk, heads, kv_heads, hd, ldq, ldk, ldv, ldo, scale, causal, dtype,
-                          (cudaStream_t)stream);
+  // test / bench entry point: the V^T scratch of the tcgen05 kernel is allocated per call here (the models own theirs)
+  const size_t elems = attention_tc_scratch_elems(B, Tk, kv_heads, hd);
+  void* vt = nullptr;
+  S2S_CHECK_CUDA(cudaMalloc(&vt, elems * 2));
+  const int rc = attention_tc_launch(ctx, q_d, k_d, v_d, o_d, B, Tq, Tk, heads, kv_heads, hd, ldq, ldk, ldv, ldo, scale, causal,
+                                      dtype, vt, elems, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(vt);
+  return rc;
 }
 
 }  // extern "C"

@@ -209,8 +209,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_map(s2s_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base,
-               const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+}  // namespace
+
+int tma_encode_map(s2s_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base,
+                   const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
   if (!fn) {
@@ -230,6 +232,8 @@ int encode_map(s2s_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int rank,
   return S2S_OK;
 }
 
+namespace {
+
 template <typename T, int BN>
 int launch_impl(s2s_ctx* ctx, const GemmProblem& p, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
@@ -239,13 +243,13 @@ int launch_impl(s2s_ctx* ctx, const GemmProblem& p, cudaStream_t stream) {
     cuuint64_t strides[2] = {(cuuint64_t)p.a_row_stride * 2, (cuuint64_t)p.a_batch_stride * 2};
     if (p.batch == 1) strides[1] = (cuuint64_t)p.a_row_stride * 2 * (cuuint64_t)p.M;  // unused but must be valid
     cuuint32_t box[3] = {BK, BM, 1};
-    S2S_CHECK(encode_map(ctx, &map_a, DT<T>::tma, 3, p.a, dims, strides, box));
+    S2S_CHECK(tma_encode_map(ctx, &map_a, DT<T>::tma, 3, p.a, dims, strides, box));
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
     cuuint64_t strides[1] = {(cuuint64_t)p.ldw * 2};
     cuuint32_t box[2] = {BK, BN};
-    S2S_CHECK(encode_map(ctx, &map_w, DT<T>::tma, 2, p.w, dims, strides, box));
+    S2S_CHECK(tma_encode_map(ctx, &map_w, DT<T>::tma, 2, p.w, dims, strides, box));
   }
   EpiParams ep;
   ep.bias = p.bias; ep.act = p.act; ep.out_h = p.out_h; ep.ldo_h = p.ldo_h; ep.out_f = p.out_f; ep.ldo_f = p.ldo_f;

@@ -30,3 +30,7 @@ struct GemmProblem {
 };
 
 int gemm_tc_launch(s2s_ctx* ctx, const GemmProblem& p, int dtype, cudaStream_t stream);
+
+// 128-byte-swizzled tiled TMA descriptor (cuTensorMapEncodeTiled through the runtime-resolved driver entry point)
+int tma_encode_map(s2s_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base,
+                   const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box);

@@ -14,11 +14,11 @@ int logmel_launch(const LogmelTables& tb, const float* pcm_d, long long pcm_stri
 int logmel_finalize_launch(const float* src, const float* mel_max, int normalize, int B, int n_mels, float* dst_f32,
                            void* mel_t, int dtype, cudaStream_t stream);
 
-// ---- attention.cu ----
-int attention_launch(const void* q, const void* k, const void* v, void* o, int B, int Tq, int Tk, int heads,
-                     int kv_heads, int hd, long long ldq, long long ldk, long long ldv, long long ldo, float scale,
-                     int causal, int dtype, cudaStream_t stream);
-
+// ---- attention_tc.cu (tcgen05 / TMEM / TMA) ----
+size_t attention_tc_scratch_elems(int B, int Tk, int kv_heads, int hd);  // 16-bit elements of V^T scratch
+int attention_tc_launch(s2s_ctx* ctx, const void* q, const void* k, const void* v, void* o, int B, int Tq, int Tk,
+                        int heads, int kv_heads, int hd, long long ldq, long long ldk, long long ldv, long long ldo,
+                        float scale, int causal, int dtype, void* vt_scratch, size_t vt_elems, cudaStream_t stream);
 // ---- elementwise.cu ----
 // y = LayerNorm(x) (bias != null) or RMSNorm(x) (bias == null); x fp32 [rows, d]; out_h 16-bit and/or out_f fp32
 int norm_rows_launch(const float* x, const float* w, const float* bias, float eps, long long rows, int d, void* out_h,

@@ -121,7 +121,8 @@ struct s2s_llama {
   // prefill workspace
   int* ids_d = nullptr;
   float *x = nullptr, *last_logits = nullptr;
-  void *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr;
+  void *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *vt = nullptr;
+  size_t vt_elems = 0;
   // decode state
   float *dx = nullptr, *dq = nullptr, *dh = nullptr, *part = nullptr, *cand_val = nullptr;
   int *slot_d = nullptr, *pos_d = nullptr, *done = nullptr, *n_done = nullptr, *cand_idx = nullptr, *out_ids = nullptr,
@@ -219,6 +220,8 @@ int build(s2s_llama* m) {
   S2S_CHECK(lalloc(m, &m->attn, (size_t)P * qd * esz));
   S2S_CHECK(lalloc(m, &m->hbuf, (size_t)P * f * esz));
   S2S_CHECK(lalloc(m, &m->last_logits, (size_t)c.vocab * 4));
+  m->vt_elems = attention_tc_scratch_elems(1, c.max_positions, c.kv_heads, hd);
+  S2S_CHECK(lalloc(m, &m->vt, m->vt_elems * esz));
   // decode state
   m->s_max = (c.max_positions + 63) / 64;
   const int grid = m->ctx->num_sms;
@@ -398,8 +401,8 @@ int s2s_llama_prefill(s2s_llama* m, int32_t slot, const int32_t* ids_h, int32_t 
                                                                  (__nv_bfloat16*)kc, (__nv_bfloat16*)vc);
     else rope_prefill_kernel<__half><<<n, 256, 0, st>>>((__half*)m->qkv, n, qd, kvd, hd, past, m->rope, (__half*)kc, (__half*)vc);
     S2S_LAUNCH_CHECK();
-    S2S_CHECK(attention_launch(m->qkv, kc, vc, m->attn, 1, n, past + n, c.heads, c.kv_heads, hd, ldq, kvd, kvd, qd,
-                               1.0f / sqrtf((float)hd), 1, dt, st));
+    S2S_CHECK(attention_tc_launch(m->ctx, m->qkv, kc, vc, m->attn, 1, n, past + n, c.heads, c.kv_heads, hd, ldq, kvd, kvd, qd,
+                                   1.0f / sqrtf((float)hd), 1, dt, m->vt, m->vt_elems, st));
     {
       GemmProblem p = lgemm(m->attn, qd, L.w_o, qd, n, d, qd);
       p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;

@@ -60,6 +60,8 @@ struct s2s_whisper {
   // workspace
   float *pcm = nullptr, *mel_f32 = nullptr, *mel_max = nullptr, *x = nullptr;
   int* n_samples_d = nullptr;
+  void* vt = nullptr;
+  size_t vt_elems = 0;
   void *mel_t = nullptr, *h1 = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr,
        *enc_out = nullptr, *cross_kv = nullptr;
   // decoder state
@@ -285,6 +287,8 @@ int alloc_workspace(s2s_whisper* m) {
   S2S_CHECK(dev_alloc(m, &m->hbuf, (size_t)rows * f * esz));
   S2S_CHECK(dev_alloc(m, &m->enc_out, (size_t)rows * d * esz));
   S2S_CHECK(dev_alloc(m, &m->cross_kv, (size_t)rows * c.dec_layers * 2 * d * esz));
+  m->vt_elems = attention_tc_scratch_elems(B, c.max_source_positions, c.heads, 64);
+  S2S_CHECK(dev_alloc(m, &m->vt, m->vt_elems * esz));
   // decoder
   m->s_max = (c.max_source_positions + ATT_CHUNK_KEYS - 1) / ATT_CHUNK_KEYS;
   const int grid = m->ctx->num_sms;
@@ -471,8 +475,8 @@ int s2s_whisper_encode(s2s_whisper* m, const float* mel_in_d, int32_t B, float* 
       p.bias = L.b_qkv; p.out_h = m->qkv; p.ldo_h = 3 * d;
       S2S_CHECK(gemm(m, p, st));
     }
-    S2S_CHECK(attention_launch(m->qkv, off(m->qkv, d, esz), off(m->qkv, 2 * d, esz), m->attn, B, T, T, c.heads, c.heads,
-                               64, 3 * d, 3 * d, 3 * d, d, 1.0f, 0, dt, st));
+    S2S_CHECK(attention_tc_launch(m->ctx, m->qkv, off(m->qkv, d, esz), off(m->qkv, 2 * d, esz), m->attn, B, T, T, c.heads,
+                                   c.heads, 64, 3 * d, 3 * d, 3 * d, d, 1.0f, 0, dt, m->vt, m->vt_elems, st));
     {
       GemmProblem p = plain_gemm(m->attn, d, L.w_o, d, rows, d, d);
       p.bias = L.b_o; p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
