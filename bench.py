@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the device-timed region (use with ncu --profile-from-start off)")
     ap.add_argument("--no-turn", action="store_true", help="skip the full-turn (STT -> LLM -> TTS post-proc) breakdown")
-    ap.add_argument("--batch", type=int, default=8, help="sessions per launch for the secondary 'batched' figure (0 = skip)")
+    ap.add_argument("--batch", type=int, default=16, help="sessions per launch for the secondary 'batched' figure (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

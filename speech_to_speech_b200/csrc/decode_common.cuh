@@ -13,7 +13,7 @@
 
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
-constexpr int ATT_CHUNK = 64;   // keys per attention work item
+constexpr int ATT_CHUNK = 64;   // record storage granularity: s_max = ceil(max keys / 64) records per (session, head)
 constexpr int PART_PAD = 4;     // partial record = [o[hd], m, l, pad, pad] (16-byte aligned records)
 
 // ---- grid barrier (all CTAs co-resident: cooperative launch) ------------------------------
@@ -78,26 +78,71 @@ __device__ __forceinline__ void prefetch_strided_l2(const void* base, long long 
   }
 }
 
-// ---- stage B rows of x (fp32 [B, d], produced by other CTAs) into shared memory, optionally normalised ----
-// mode 0: plain copy; 1: LayerNorm (w, bias); 2: RMSNorm (w).  One-pass statistics (sum, sum of squares) from shared memory.
-// The norm weights are fetched together with x (one round trip) into wb[2*d].  s_red: >= DEC_WARPS floats.
-// Ends with a __syncthreads().
-// Norm weights of a phase (w | bias -> wb[2*d]); callable ahead of time between grid_arrive and grid_wait.
+// ---- shared-memory operand layout of the skinny GEMM --------------------------------------------------------
+// The activation operand lives in shared memory as 16-bit rows xh[b][K + GV_XPAD]; the 64-byte pad puts
+// consecutive rows 64 bytes apart modulo 128, so the 16-byte fragment loads of a quarter-warp (2 rows x 4 k-groups)
+// touch 8 distinct 16-byte bank groups.
+// The weight operand is stored in GLOBAL memory already in fragment order ("tiled", weight_tiles.cu): tile = 8 rows,
+// window = 32 k; element (row 8*tile + g, k 32*w + 8*t + e) sits at ((tile * K/32 + w) * 32 + 4*g + t) * 8 + e.
+// Any run of windows of a tile is one contiguous block, so a ring unit is ONE bulk copy of up to 4 KB and a warp's
+// 16-byte fragment loads of a window read 512 consecutive bytes (conflict-free without padding).
+constexpr int DEC_MAX_B = 16;        // sessions per launch: the m dimension of mma.m16n8k16
+constexpr int GV_XPAD = 32;          // elements
+constexpr int GV_ROWS = 8;           // weight rows per tile: the n dimension of mma.m16n8k16
+constexpr int GV_UK = 256;           // k elements per ring unit (8 windows of 32)
+constexpr int GV_WIN_BYTES = GV_ROWS * 32 * 2;           // one 32-element k window of a tile: 512 B, fragment-major
+constexpr int GV_SLOT_BYTES = GV_ROWS * GV_UK * 2;       // 4096
+constexpr int GV_LAT_ELEMS = 352;    // cost model: one dependent round ~ streaming 352 k-elements of a tile
+
+// ---- dynamic shared-memory layout shared by the decode kernels (host computes the same numbers) ----------
+//   [ xh : B x (kmax + GV_XPAD) 16-bit | the fp32 copy used for norm statistics aliases its tail ]
+//   [ sv, si : argmax candidates | s_red | wb : norm weights | red : tail-round partial fragments ]
+//   [ weight rings : DEC_WARPS x slots x GV_SLOT_BYTES | mbarriers ]
+struct DecSmem {
+  unsigned int xs_off;     // fp32 statistics copy (B * d floats), inside the xh region
+  unsigned int aux_off;    // sv
+  unsigned int si_off, red_s_off, wb_off, redbuf_off, ring_off;
+};
+__host__ __device__ inline DecSmem dec_smem_layout(int B, int d, int kmax, int wb_floats) {
+  DecSmem L;
+  const unsigned int xh_small = (((unsigned)B * (unsigned)(d + GV_XPAD) * 2u) + 15u) & ~15u;
+  unsigned int xh_bytes = (unsigned)B * (unsigned)(kmax + GV_XPAD) * 2u;
+  const unsigned int with_stats = xh_small + (unsigned)B * (unsigned)d * 4u;
+  if (with_stats > xh_bytes) xh_bytes = with_stats;
+  xh_bytes = (xh_bytes + 127u) & ~127u;
+  L.xs_off = xh_small;
+  L.aux_off = xh_bytes;
+  L.si_off = L.aux_off + DEC_WARPS * DEC_MAX_B * 4;
+  L.red_s_off = L.si_off + DEC_WARPS * DEC_MAX_B * 4;
+  L.wb_off = L.red_s_off + 2 * DEC_WARPS * 4;
+  L.redbuf_off = (L.wb_off + (unsigned)wb_floats * 4u + 15u) & ~15u;
+  L.ring_off = (L.redbuf_off + 2u * DEC_THREADS * 16u + 127u) & ~127u;
+  return L;
+}
+// ring slots that fit next to the fixed part (at most 4 per warp)
+inline int dec_ring_slots(const DecSmem& L) {
+  const long long avail = 220LL * 1024 - (long long)L.ring_off - 256;  // static shared memory (parameter tables) takes ~5 KB
+  long long s = avail / ((long long)DEC_WARPS * (GV_SLOT_BYTES + 8));
+  return (int)(s > 4 ? 4 : s);
+}
+
+// Norm weights of a phase (w [| bias] -> wb[d (+ d)]); callable ahead of time between grid_arrive and grid_wait.
 static __device__ __forceinline__ void stage_norm_weights(const float* w, const float* bias, int d, float* wb) {
 #pragma unroll 1
   for (int i = threadIdx.x * 4; i < d; i += DEC_THREADS * 4) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(w + i));
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias) bb = __ldg(reinterpret_cast<const float4*>(bias + i));
-    *reinterpret_cast<float4*>(wb + i) = g;
-    *reinterpret_cast<float4*>(wb + d + i) = bb;
+    *reinterpret_cast<float4*>(wb + i) = __ldg(reinterpret_cast<const float4*>(w + i));
+    if (bias) *reinterpret_cast<float4*>(wb + d + i) = __ldg(reinterpret_cast<const float4*>(bias + i));
   }
 }
 
-static __device__ __noinline__ void stage_rows(const float* x, int B, int d, float* xs, int mode, const float* w,
-                                           const float* bias, float eps, float* s_red, float* wb, int wb_ready = 0) {
+// ---- stage B rows of the fp32 residual stream (produced by other CTAs) into xh, normalised ----------------
+// mode 1: LayerNorm (w, bias); 2: RMSNorm (w).  One-pass statistics (sum, sum of squares) over an fp32 copy in
+// shared memory (xs, B*d floats), then the normalised row is written as 16-bit into xh[b][d + GV_XPAD].
+// Ends with a __syncthreads().
+template <typename T>
+static __device__ __noinline__ void stage_rows_norm(const float* x, int B, int d, float* xs, T* xh, int mode, const float* w,
+                                                    const float* bias, float eps, float* s_red, float* wb, int wb_ready) {
   const int n = B * d;
-  // x rows: two independent 16-byte loads per thread per trip (one trip for B*d <= 2048)
 #pragma unroll 1
   for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 8) {
     const int j = i + DEC_THREADS * 4;
@@ -107,27 +152,28 @@ static __device__ __noinline__ void stage_rows(const float* x, int B, int d, flo
     *reinterpret_cast<float4*>(xs + i) = v0;
     if (j < n) *reinterpret_cast<float4*>(xs + j) = v1;
   }
-  if (mode != 0 && !wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
+  if (!wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
   __syncthreads();
-  if (mode == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int wpr = DEC_WARPS;  // warps per row: largest power of two with wpr * B <= DEC_WARPS (min 1)
   while (wpr > 1 && wpr * B > DEC_WARPS) wpr >>= 1;
   const int rows_per_iter = DEC_WARPS / wpr;
+  const int xstride = d + GV_XPAD;
 #pragma unroll 1
   for (int r0 = 0; r0 < B; r0 += rows_per_iter) {
     const int row = r0 + warp / wpr, sub = warp % wpr, grp = (warp / wpr) * wpr;
     const bool valid = row < B;
-    float* xr = xs + row * d;
+    const float* xr = xs + row * d;
     // one pass: sum and sum of squares together (one block reduction); var = E[x^2] - mean^2 in fp32 is accurate
     // to ~1e-6 * (1 + mean^2/var), far below the stated tolerances for residual-stream statistics
     float s1 = 0.f, s2 = 0.f;
     if (valid) {
 #pragma unroll 2
-      for (int i = sub * 32 + lane; i < d; i += wpr * 32) {
-        const float v = xr[i];
-        s1 += v;
-        s2 = fmaf(v, v, s2);
+      for (int i = (sub * 32 + lane) * 2; i < d; i += wpr * 64) {
+        const float2 v = *reinterpret_cast<const float2*>(xr + i);
+        s1 += v.x + v.y;
+        s2 = fmaf(v.x, v.x, s2);
+        s2 = fmaf(v.y, v.y, s2);
       }
     }
     s1 = warp_sum(s1);
@@ -140,32 +186,69 @@ static __device__ __noinline__ void stage_rows(const float* x, int B, int d, flo
     const float var = fmaxf(t2 - (float)d * mean * mean, 0.f);
     const float rstd = rsqrtf(var / (float)d + eps);
     if (valid) {
+      T* dst = xh + row * xstride;
 #pragma unroll 2
-      for (int i = sub * 32 + lane; i < d; i += wpr * 32) {
-        float y = (xr[i] - mean) * rstd * wb[i];
-        y += wb[d + i];
-        xr[i] = y;
+      for (int i = (sub * 32 + lane) * 2; i < d; i += wpr * 64) {
+        const float2 v = *reinterpret_cast<const float2*>(xr + i);
+        const float2 g = *reinterpret_cast<const float2*>(wb + i);
+        float y0 = (v.x - mean) * rstd * g.x, y1 = (v.y - mean) * rstd * g.y;
+        if (mode == 1) { const float2 bb = *reinterpret_cast<const float2*>(wb + d + i); y0 += bb.x; y1 += bb.y; }
+        *reinterpret_cast<uint32_t*>(dst + i) = DT<T>::pack2(y0, y1);
       }
     }
     __syncthreads();
   }
 }
 
-// ---- skinny GEMV: out[b][row] = sum_k W[row][k] * xs[b][k] ---------------------------------------
+// ---- stage B rows of a 16-bit activation (global [B, K], produced by other CTAs) into xh: 16-byte copies ----
+template <typename T>
+static __device__ __noinline__ void stage_rows_copy(const T* x, int B, int K, T* xh) {
+  const int vpr = K >> 3;  // 16-byte vectors per row
+  const int n = B * vpr;
+  const int xstride = K + GV_XPAD;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < n; i += DEC_THREADS * 4) {
+    uint4 v[4];
+    int row[4], col[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = i + u * DEC_THREADS;
+      if (idx < n) {
+        row[u] = idx / vpr; col[u] = idx - row[u] * vpr;
+        v[u] = __ldcg(reinterpret_cast<const uint4*>(x + (long long)row[u] * K) + col[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * DEC_THREADS < n) *(reinterpret_cast<uint4*>(xh + row[u] * xstride) + col[u]) = v[u];
+  }
+  __syncthreads();
+}
+
+// ---- skinny GEMM: out[b][row] = sum_k W[row][k] * x[b][k], b < B <= 16 -----------------------------------
 // ONE non-inlined routine serves every projection of every layer (runtime shapes and a runtime epilogue
 // mode): the decode step executes each phase once per layer, so per-phase inlined copies (245 KB of SASS)
 // turned the kernel into an instruction-cache streaming problem; sharing the routine keeps the hot loop resident.
-// A warp owns GV_R consecutive rows and keeps GV_R * GV_U independent 16-byte loads in flight per lane; the
-// bias / residual / mask reads are issued BEFORE the weight loads; the NEXT row group of the warp is L2-prefetched
-// while the current one is reduced.  Lane b (< B) applies the epilogue for batch row b.
-constexpr int GV_R = 2, GV_PF = 3;
+//
+// Tensor-core formulation (swap-AB): the batch is the m dimension of mma.sync.m16n8k16 (16 sessions, zero-padded),
+// a tile of 8 weight rows is the n dimension, so the weight stream is the B operand and the accumulator fragment
+// D[m = session][n = weight row] needs no cross-lane reduction; 1..16 sessions cost the same instruction stream.
+// The k index inside an instruction may be permuted freely as long as A and B agree, so lane (g, t) feeds both
+// from ONE 16-byte shared-memory load each: elements 8t..8t+7 of a 32-element k window serve two instructions.
+//
+// Work decomposition: tiles of 8 rows.  "Main rounds": while at least gridDim.x * 8 tiles remain, every warp of
+// the grid owns one tile and its full K (no synchronisation at all).  "Tail": the remaining < gridDim.x * 8 tiles
+// are split 2^ks_log ways along K so that all warps stream; the partial fragments of a tile meet in shared memory
+// (one __syncthreads per tail round, fixed summation order -> deterministic).  The small projections of the
+// Whisper decoder are all tail.
 enum GemvEpi { EPI_STORE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_QKV = 3, EPI_LOGITS = 4,
                EPI_QKV_ROPE = 5 /* row pairs */, EPI_SWIGLU = 6 /* row pairs */ };
 struct GemvArgs {
-  const void* W; int N, K;
+  const void* W; int N, K;     // W: TILED weights (see above), N rows (storage padded to a multiple of 8), K % 32 == 0
   const float* bias;           // [N] or null
   int mode;
-  float* out; int ldo;         // STORE / GELU / RESID (in-place residual stream) / QKV (q rows)
+  float* out; int ldo;         // STORE / RESID (in-place residual stream) / QKV (q rows): fp32
+  void* out_h; int ldh;        // GELU / SWIGLU: 16-bit activation [B, ldh]
   // QKV: rows [d, 2d) -> k cache, [2d, 3d) -> v cache (16-bit), element (b, c) at kv0 + which*kv_which + b*kv_batch + c
   void* kv0; long long kv_which, kv_batch; int d;
   // LOGITS
@@ -177,65 +260,70 @@ struct GemvArgs {
   float q_scale;               // softmax scale folded into the stored q (head_dim^-0.5)
 };
 
-// epilogue of one reduced row for batch row `lane`
+// epilogue of the row pair (row0, row0 + 1), row0 even, for session b.  v already carries the bias.
 template <typename T>
-__device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, int mode, int row, int lane, float v, float bias,
-                                              float resid, int sup, float& best_v, int& best_i) {
-  v += bias;
+__device__ __forceinline__ void gemv_pair_epilogue(const GemvArgs& a, int mode, int row0, int b, float v0, float v1,
+                                                   float r0, float r1, int sup0, int sup1, float& best_v, int& best_i) {
   if (mode == EPI_STORE) {
-    a.out[lane * a.ldo + row] = v;
+    *reinterpret_cast<float2*>(a.out + (long long)b * a.ldo + row0) = make_float2(v0, v1);
   } else if (mode == EPI_GELU) {
-    a.out[lane * a.ldo + row] = gelu_erf(v);
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(a.out_h) + (long long)b * a.ldh + row0) = DT<T>::pack2(gelu_erf(v0), gelu_erf(v1));
   } else if (mode == EPI_RESID) {
-    a.out[lane * a.ldo + row] = resid + v;
+    *reinterpret_cast<float2*>(a.out + (long long)b * a.ldo + row0) = make_float2(r0 + v0, r1 + v1);
   } else if (mode == EPI_QKV) {
-    if (row < a.d) {
-      a.out[lane * a.ldo + row] = v;
+    if (row0 < a.d) {
+      *reinterpret_cast<float2*>(a.out + (long long)b * a.ldo + row0) = make_float2(v0, v1);
     } else {
-      const int which = (row < 2 * a.d) ? 0 : 1;
-      reinterpret_cast<T*>(a.kv0)[which * a.kv_which + lane * a.kv_batch + (row - (which + 1) * a.d)] = DT<T>::from_f(v);
+      const int which = (row0 < 2 * a.d) ? 0 : 1;
+      T* dst = reinterpret_cast<T*>(a.kv0) + which * a.kv_which + b * a.kv_batch + (row0 - (which + 1) * a.d);
+      *reinterpret_cast<uint32_t*>(dst) = DT<T>::pack2(v0, v1);
     }
-  } else {  // EPI_LOGITS
-    if ((sup & 1) || (a.first_step && (sup & 2))) v = -INFINITY;
-    if (a.logits_out) a.logits_out[lane * a.logits_ld + row] = v;
-    if (v > best_v || (v == best_v && row < best_i)) { best_v = v; best_i = row; }
-  }
-}
-
-// epilogue of one reduced ROW PAIR (rows row0, row0 + 1) for batch row `lane`
-template <typename T>
-__device__ __forceinline__ void gemv_pair_epilogue(const GemvArgs& a, int mode, int row0, int lane, float v0, float v1) {
-  if (mode == EPI_SWIGLU) {
-    a.out[lane * a.ldo + (row0 >> 1)] = (v0 / (1.0f + __expf(-v0))) * v1;
-    return;
-  }
-  // EPI_QKV_ROPE
-  const int kv_end = a.q_rows + a.k_rows;
-  if (row0 < kv_end) {
-    const int p = __ldcg(a.pos + lane);
-    const float2 cs = a.rope[(long long)p * (a.hd >> 1) + ((row0 % a.hd) >> 1)];
-    const float r0 = v0 * cs.x - v1 * cs.y, r1 = v1 * cs.x + v0 * cs.y;
-    v0 = r0; v1 = r1;
-  }
-  if (row0 < a.q_rows) {
-    *reinterpret_cast<float2*>(a.out + lane * a.ldo + row0) = make_float2(v0 * a.q_scale, v1 * a.q_scale);
-  } else {
-    const int which = (row0 < kv_end) ? 0 : 1;
-    const int c = row0 - (which ? kv_end : a.q_rows);
-    T* dst = reinterpret_cast<T*>(a.kv0) + which * a.kv_which + (long long)a.slot[lane] * a.kv_slot +
-             (long long)__ldcg(a.pos + lane) * a.kv_ld + c;
-    *reinterpret_cast<uint32_t*>(dst) = DT<T>::pack2(v0, v1);
+  } else if (mode == EPI_LOGITS) {
+    if ((sup0 & 1) || (a.first_step && (sup0 & 2))) v0 = -INFINITY;
+    if ((sup1 & 1) || (a.first_step && (sup1 & 2))) v1 = -INFINITY;
+    const bool ok1 = row0 + 1 < a.N;
+    if (a.logits_out) {
+      a.logits_out[b * a.logits_ld + row0] = v0;
+      if (ok1) a.logits_out[b * a.logits_ld + row0 + 1] = v1;
+    }
+    if (v0 > best_v || (v0 == best_v && row0 < best_i)) { best_v = v0; best_i = row0; }
+    if (ok1 && (v1 > best_v || (v1 == best_v && row0 + 1 < best_i))) { best_v = v1; best_i = row0 + 1; }
+  } else if (mode == EPI_SWIGLU) {
+    reinterpret_cast<T*>(a.out_h)[(long long)b * a.ldh + (row0 >> 1)] = DT<T>::from_f((v0 / (1.0f + __expf(-v0))) * v1);
+  } else {  // EPI_QKV_ROPE
+    const int kv_end = a.q_rows + a.k_rows;
+    const int p = __ldcg(a.pos + b);
+    if (row0 < kv_end) {
+      const float2 cs = a.rope[(long long)p * (a.hd >> 1) + ((row0 % a.hd) >> 1)];
+      const float t0 = v0 * cs.x - v1 * cs.y, t1 = v1 * cs.x + v0 * cs.y;
+      v0 = t0; v1 = t1;
+    }
+    if (row0 < a.q_rows) {
+      *reinterpret_cast<float2*>(a.out + (long long)b * a.ldo + row0) = make_float2(v0 * a.q_scale, v1 * a.q_scale);
+    } else {
+      const int which = (row0 < kv_end) ? 0 : 1;
+      const int c = row0 - (which ? kv_end : a.q_rows);
+      T* dst = reinterpret_cast<T*>(a.kv0) + which * a.kv_which + (long long)a.slot[b] * a.kv_slot + (long long)p * a.kv_ld + c;
+      *reinterpret_cast<uint32_t*>(dst) = DT<T>::pack2(v0, v1);
+    }
   }
 }
 
 // ---- weight streaming through a per-warp shared-memory ring filled by the bulk-copy engine ---------------
-// Each warp owns `ring_slots` slots of GV_R rows x GV_CH 16-bit weights.  Lane 0 issues cp.async.bulk
-// (global -> shared, completion on the slot's mbarrier); the warp then multiplies from shared memory.  Bytes in
-// flight are bounded by shared memory (128 KB per SM), not by registers, and the copies are not droppable hints.
-// The warp is its own producer and consumer, so no cross-warp synchronisation is needed: slot reuse is ordered
-// by program order + __syncwarp + fence.proxy.async.
-constexpr int GV_CH = 1024;                       // weights per row chunk (2 KB); the code shifts by 10 for /GV_CH
-constexpr int GV_SLOT_BYTES = GV_R * GV_CH * 2;   // one slot: GV_R row chunks
+// Each warp owns `slots` slots of GV_ROWS x GV_UK 16-bit weights.  Lane 0 issues ONE cp.async.bulk per unit
+// (global -> shared, completion on the slot's mbarrier; one request per 4 KB keeps the per-SM copy engine far from
+// its request-rate limit -- 512-byte row copies measured 25 % slower); the warp then feeds the tensor core from
+// shared memory.  Bytes in flight are bounded by shared memory (16 KB per warp), not by registers, and the copies
+// are not droppable hints.  The warp is its own producer and consumer, so no cross-warp synchronisation is needed:
+// slot reuse is ordered by program order + __syncwarp + fence.proxy.async.
+struct GemvPlan {
+  int n_tiles;       // ceil(N / 8)
+  int main_rounds;   // rounds in which every warp of the grid owns one whole tile
+  int tail_base;     // first tile of the tail
+  int ks_log;        // tail: 2^ks_log warps share a tile, each streams K >> ks_log
+  int slice;         // K >> ks_log
+  int tail_rounds;   // tail rounds of this CTA (uniform over its warps)
+};
 
 struct GemvRing {
   uint32_t base_s;       // this warp's ring: 32-bit shared-space address (16-byte aligned)
@@ -243,9 +331,10 @@ struct GemvRing {
   int slots;
   unsigned int slot;     // next slot to consume and its phase parity; persist across phases (all lanes identical)
   unsigned int parity;
-  // units of the NEXT gemv already issued into the ring by gemv_prefetch() (weights do not depend on the barrier)
-  int pre_valid, pre_pg, pre_pc;
+  // the NEXT gemv, prepared by gemv_prefetch(): its plan and the producer cursor after the units already issued
+  int pre_valid, pre_pj, pre_pu, pre_nvalid;
   const void* pre_W;
+  GemvPlan plan;
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
@@ -257,11 +346,6 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
-__device__ __forceinline__ float4 lds16f(uint32_t addr) {
-  float4 r;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
-  return r;
-}
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
   uint32_t ok, spins = 0;
   do {
@@ -271,56 +355,118 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
-// producer side of one unit = chunk c of the GV_R rows starting at row0 (lane 0 only)
+// D[16x8] += A[16x16] * B[16x8], fp32 accumulate; a0/a2 = sessions 0-7 (k low / high half), a1/a3 = sessions 8-15
 template <typename T>
-__device__ __forceinline__ void gemv_issue_unit(const T* __restrict__ W, int N, int K, int row0, int c, uint32_t dst,
-                                                uint32_t bar) {
-  const int nrows = min(GV_R, N - row0);
-  const int len = min(GV_CH, K - c * GV_CH);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of the slot are done
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(nrows * len * 2)) : "memory");
-  const T* src = W + (long long)row0 * K + c * GV_CH;
-  bulk_g2s(dst, src, (uint32_t)(len * 2), bar);
-  if (nrows > 1) bulk_g2s(dst + GV_CH * 2, src + K, (uint32_t)(len * 2), bar);
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                        uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Issue the first `slots` units of a gemv into the (empty) ring.  Called right after the previous gemv finished,
-// i.e. BEFORE the grid barrier and the input staging of the phase that will consume them: the weight stream of the
-// next projection is already landing in shared memory while the chip synchronises.
-template <typename T>
-__device__ __forceinline__ void gemv_prefetch(const GemvArgs& a, GemvRing& ring) {
-  const int lane = threadIdx.x & 31;
-  const T* __restrict__ W = reinterpret_cast<const T*>(a.W);
-  const int N = a.N, K = a.K;
-  const int first = dec_first_item(), istride = dec_item_stride();
-  ring.pre_valid = 1; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = a.W;
-  if (first * GV_R >= N) return;
-  int n_groups = 0;
-  for (int gi = first; gi * GV_R < N; gi += istride) ++n_groups;
-  const int cpr = (K + GV_CH - 1) >> 10;
-  if (lane == 0) {
-    int pg = 0, pc = 0, n_ahead = 0;
-    unsigned int pslot = ring.slot;
-#pragma unroll 1
-    while (n_ahead < ring.slots && pg < n_groups) {
-      gemv_issue_unit<T>(W, N, K, (first + pg * istride) * GV_R, pc, ring.base_s + pslot * GV_SLOT_BYTES, ring.bars_s + pslot * 8);
-      if (++pc == cpr) { pc = 0; ++pg; }
-      if (++pslot == (unsigned)ring.slots) pslot = 0;
-      ++n_ahead;
+// How a projection [N, K] is cut into warp items on this grid (see the comment above).  K % 32 == 0.
+__device__ __forceinline__ void gemv_make_plan(int N, int K, GemvPlan& pl) {
+  const int grid = (int)gridDim.x;
+  const int slots = grid * DEC_WARPS;
+  pl.n_tiles = (N + GV_ROWS - 1) >> 3;
+  pl.main_rounds = pl.n_tiles / slots;
+  pl.tail_base = pl.main_rounds * slots;
+  const int tail = pl.n_tiles - pl.tail_base;
+  int best_log = 0, best_cost = 0x7fffffff;
+#pragma unroll
+  for (int lg = 0; lg <= 3; ++lg) {
+    const int sl = K >> lg;
+    if ((sl & 31) == 0 && sl >= 32) {
+      const int per_round = grid * (DEC_WARPS >> lg);
+      const int rounds = (tail + per_round - 1) / per_round;
+      const int cost = rounds * (GV_LAT_ELEMS + sl);
+      if (cost < best_cost) { best_cost = cost; best_log = lg; }
     }
-    ring.pre_pg = pg; ring.pre_pc = pc;
+  }
+  pl.ks_log = best_log;
+  pl.slice = K >> best_log;
+  const int stride = grid * (DEC_WARPS >> best_log);
+  pl.tail_rounds = (tail > (int)blockIdx.x) ? (tail - (int)blockIdx.x + stride - 1) / stride : 0;
+}
+
+// item j of warp `warp`: which tile, which K range.  Tiles are interleaved across CTAs so that consecutive tiles
+// stream on different SMs.  Returns false for an empty tail slot.
+__device__ __forceinline__ bool gemv_item(const GemvPlan& pl, int K, int j, int warp, int& tile, int& k0, int& klen) {
+  if (j < pl.main_rounds) {
+    tile = (j * DEC_WARPS + warp) * (int)gridDim.x + (int)blockIdx.x; k0 = 0; klen = K;
+    return true;
+  }
+  const int r = j - pl.main_rounds;
+  const int sub = warp >> pl.ks_log, sl = warp & ((1 << pl.ks_log) - 1);
+  tile = pl.tail_base + (r * (DEC_WARPS >> pl.ks_log) + sub) * (int)gridDim.x + (int)blockIdx.x;
+  k0 = sl * pl.slice; klen = pl.slice;
+  return tile < pl.n_tiles;
+}
+
+// producer side of unit u of item j (whole warp calls; lane 0 issues one contiguous bulk copy)
+template <typename T>
+__device__ __forceinline__ void gemv_issue_unit(const T* __restrict__ Wt, int K, const GemvPlan& pl, int j, int u,
+                                                uint32_t dst, uint32_t bar) {
+  int tile, k0, klen;
+  gemv_item(pl, K, j, threadIdx.x >> 5, tile, k0, klen);
+  const int kb = k0 + u * GV_UK;
+  const int len = min(GV_UK, k0 + klen - kb);
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t bytes = (uint32_t)(GV_ROWS * len * 2);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of the slot are done
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    bulk_g2s(dst, Wt + ((long long)tile * K + kb) * GV_ROWS, bytes, bar);
   }
 }
 
-// Wait for prefetched units that will never be consumed (early exit) so no bulk copy is in flight at CTA exit.
+__device__ __forceinline__ int gemv_units_of(const GemvPlan& pl, int K, int j) {
+  return ((j < pl.main_rounds ? K : pl.slice) + GV_UK - 1) >> 8;
+}
+
+// Plan the gemv and issue its first `slots` units into the (empty) ring.  Called between grid_arrive and
+// grid_wait of the phase BEFORE the one that consumes them: the weight stream of the next projection is already
+// landing in shared memory while the chip synchronises.
 template <typename T>
-__device__ __forceinline__ void gemv_drain(const GemvArgs& a, GemvRing& ring) {
+__device__ __forceinline__ void gemv_prefetch(const GemvArgs& a, GemvRing& ring) {
+  static_assert(GV_UK == 256, "gemv_units_of shifts by 8");
+  gemv_make_plan(a.N, a.K, ring.plan);
+  const GemvPlan& pl = ring.plan;
+  const int warp = threadIdx.x >> 5;
+  int nv = pl.main_rounds;
+#pragma unroll 1
+  for (int r = 0; r < pl.tail_rounds; ++r) {
+    int tile, k0, klen;
+    if (!gemv_item(pl, a.K, pl.main_rounds + r, warp, tile, k0, klen)) break;
+    ++nv;
+  }
+  ring.pre_nvalid = nv; ring.pre_valid = 1; ring.pre_W = a.W;
+  int pj = 0, pu = 0;
+  unsigned int pslot = ring.slot;
+#pragma unroll 1
+  for (int n = 0; n < ring.slots && pj < nv; ++n) {
+    gemv_issue_unit<T>(reinterpret_cast<const T*>(a.W), a.K, pl, pj, pu, ring.base_s + pslot * GV_SLOT_BYTES, ring.bars_s + pslot * 8);
+    if (++pu == gemv_units_of(pl, a.K, pj)) { pu = 0; ++pj; }
+    if (++pslot == (unsigned)ring.slots) pslot = 0;
+  }
+  ring.pre_pj = pj; ring.pre_pu = pu;
+}
+
+// Wait for prefetched units that will never be consumed (early exit) so no bulk copy is in flight at CTA exit.
+__device__ __forceinline__ void gemv_drain(int K, GemvRing& ring) {
   if (!ring.pre_valid) return;
-  const int first = dec_first_item(), istride = dec_item_stride();
   ring.pre_valid = 0;
-  if (first * GV_R >= a.N) return;
-  const int n_groups = ((a.N + GV_R - 1) / GV_R - first + istride - 1) / istride;
-  const int n_units = min(ring.slots, n_groups * ((a.K + GV_CH - 1) / GV_CH));
+  const GemvPlan& pl = ring.plan;
+  int total = 0;
+  for (int j = 0; j < ring.pre_nvalid && total < ring.slots; ++j) total += gemv_units_of(pl, K, j);
+  const int n_units = min(ring.slots, total);
   unsigned int cslot = ring.slot, cpar = ring.parity;
   for (int u = 0; u < n_units; ++u) {
     mbar_wait_s(ring.bars_s + cslot * 8, cpar);
@@ -329,107 +475,157 @@ __device__ __forceinline__ void gemv_drain(const GemvArgs& a, GemvRing& ring) {
   ring.slot = cslot; ring.parity = cpar;
 }
 
-// The unit stream of a warp: row groups first + j*istride (j = 0..n_groups-1), each split into cpr chunks.
-// Producer cursor (pg, pc) runs `slots` units ahead of the consumer cursor (g, c); no divisions in the loop.
-template <typename T, int NB>
-__device__ __noinline__ void gemv_generic(const GemvArgs& a, uint32_t xs_s, int B, float& best_v, int& best_i,
-                                          GemvRing& ring) {
-  static_assert(GV_R == 2, "two rows per group");
-  const int lane = threadIdx.x & 31;
+// best_v / best_i: running argmax of this lane for sessions g and g + 8 (EPI_LOGITS).
+// red_s: 2 * DEC_THREADS float4 (tail-round partial fragments, double-buffered by round parity).
+template <typename T>
+__device__ __noinline__ void gemv_mma(const GemvArgs& a, uint32_t xh_s, int B, float (&best_v)[2], int (&best_i)[2],
+                                      GemvRing& ring, float4* red_s) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const T* __restrict__ W = reinterpret_cast<const T*>(a.W);
   const int N = a.N, K = a.K, mode = a.mode;
-  const int first = dec_first_item(), istride = dec_item_stride();
-  if (first * GV_R >= N) { ring.pre_valid = 0; return; }
-  int n_groups = 0;  // row groups of this warp (counted, not divided: 1-3 for the small projections)
-  for (int gi = first; gi * GV_R < N; gi += istride) ++n_groups;
-  const int cpr = (K + GV_CH - 1) >> 10;
-  const int slots = ring.slots;
-  // ---- producer prologue (normally already done by gemv_prefetch before the barrier) ----
   if (ring.pre_valid && ring.pre_W != a.W) __trap();  // prefetch bookkeeping bug: the ring holds another matrix
   if (!ring.pre_valid) gemv_prefetch<T>(a, ring);
-  int pg = ring.pre_pg, pc = ring.pre_pc;  // lane 0's cursor
+  const GemvPlan pl = ring.plan;
   ring.pre_valid = 0;
+  int pj = ring.pre_pj, pu = ring.pre_pu;  // producer cursor (uniform over the warp)
+  const int n_valid = ring.pre_nvalid;
+  const int n_items = pl.main_rounds + pl.tail_rounds;
+  const int ks = 1 << pl.ks_log;
   unsigned int cslot = ring.slot, cpar = ring.parity;
-  const uint32_t lane_off = lane * 16;
+  const uint32_t xrow_lo = xh_s + (uint32_t)(g * (K + GV_XPAD) + t * 8) * 2;
+  const uint32_t xrow_hi = xrow_lo + (uint32_t)(8 * (K + GV_XPAD)) * 2;
+  const bool lo = g < B, hi = g + 8 < B;
+  const uint32_t wlane = (uint32_t)lane * 16;
 #pragma unroll 1
-  for (int g = 0; g < n_groups; ++g) {
-    const int row0 = (first + g * istride) * GV_R;
-    const int r1 = min(row0 + 1, N - 1);
-    const float bias0 = a.bias ? __ldg(a.bias + row0) : 0.f;
-    const float bias1 = a.bias ? __ldg(a.bias + r1) : 0.f;
-    float resid0 = 0.f, resid1 = 0.f;
+  for (int j = 0; j < n_items; ++j) {
+    int tile, k0, klen;
+    const bool valid = gemv_item(pl, K, j, warp, tile, k0, klen);
+    const bool split = (j >= pl.main_rounds) && ks > 1;
+    const bool owner = valid && (!split || (warp & (ks - 1)) == 0);  // this warp runs the tile's epilogue
+    const int row0 = tile * GV_ROWS + 2 * t;  // this lane's row pair
+    const bool rows_ok = owner && row0 < N;
+    // epilogue operands first: their round trip overlaps the weight stream
+    float bias0 = 0.f, bias1 = 0.f, rl0 = 0.f, rl1 = 0.f, rh0 = 0.f, rh1 = 0.f;
     int sup0 = 0, sup1 = 0;
-    if (mode == EPI_RESID) {
-      if (lane < B) { resid0 = __ldcg(a.out + lane * a.ldo + row0); resid1 = __ldcg(a.out + lane * a.ldo + r1); }
-    } else if (mode == EPI_LOGITS && a.suppress) {
-      sup0 = __ldg(a.suppress + row0); sup1 = __ldg(a.suppress + r1);
+    if (rows_ok) {
+      if (a.bias) { const float2 bb = __ldg(reinterpret_cast<const float2*>(a.bias + row0)); bias0 = bb.x; bias1 = bb.y; }
+      if (mode == EPI_RESID) {
+        if (lo) { const float2 r = __ldcg(reinterpret_cast<const float2*>(a.out + (long long)g * a.ldo + row0)); rl0 = r.x; rl1 = r.y; }
+        if (hi) { const float2 r = __ldcg(reinterpret_cast<const float2*>(a.out + (long long)(g + 8) * a.ldo + row0)); rh0 = r.x; rh1 = r.y; }
+      } else if (mode == EPI_LOGITS && a.suppress) {
+        sup0 = __ldg(a.suppress + row0);
+        sup1 = __ldg(a.suppress + min(row0 + 1, N - 1));
+      }
     }
-    float acc0[NB], acc1[NB], acc2[NB], acc3[NB];  // rows 0/1 x even/odd element pairs: four independent chains
-#pragma unroll
-    for (int b = 0; b < NB; ++b) acc0[b] = acc1[b] = acc2[b] = acc3[b] = 0.f;
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};  // two independent accumulator fragments
+    if (valid) {
+      const int upi = (klen + GV_UK - 1) >> 8;
 #pragma unroll 1
-    for (int c = 0; c < cpr; ++c) {
-      mbar_wait_s(ring.bars_s + cslot * 8, cpar);
-      const uint32_t src = ring.base_s + cslot * GV_SLOT_BYTES + lane_off;
-      const int len = min(GV_CH, K - c * GV_CH);
-      const uint32_t xk = xs_s + (uint32_t)(c * GV_CH + lane * 8) * 4;
-#pragma unroll 2
-      for (int e = lane * 8; e < len; e += 256) {
-        const uint32_t eo = (uint32_t)(e - lane * 8);
-        const uint4 w0 = lds16(src + eo * 2), w1 = lds16(src + GV_CH * 2 + eo * 2);
-        const float2 a0 = DT<T>::to_f2(w0.x), a1 = DT<T>::to_f2(w0.y), a2 = DT<T>::to_f2(w0.z), a3 = DT<T>::to_f2(w0.w);
-        const float2 c0 = DT<T>::to_f2(w1.x), c1 = DT<T>::to_f2(w1.y), c2 = DT<T>::to_f2(w1.z), c3 = DT<T>::to_f2(w1.w);
+      for (int u = 0; u < upi; ++u) {
+        mbar_wait_s(ring.bars_s + cslot * 8, cpar);
+        const uint32_t wsrc = ring.base_s + cslot * GV_SLOT_BYTES + wlane;
+        const int len = min(GV_UK, klen - u * GV_UK);
+        const uint32_t xk = (uint32_t)(k0 + u * GV_UK) * 2;
+#pragma unroll 4
+        for (int kk = 0; kk < len; kk += 32) {
+          const uint4 w = lds16(wsrc + kk * (GV_WIN_BYTES / 32));
+          uint4 xl = make_uint4(0u, 0u, 0u, 0u), xu = make_uint4(0u, 0u, 0u, 0u);
+          if (lo) xl = lds16(xrow_lo + xk + kk * 2);
+          if (hi) xu = lds16(xrow_hi + xk + kk * 2);
+          mma16816<T>(c, xl.x, xu.x, xl.y, xu.y, w.x, w.y);
+          mma16816<T>(e, xl.z, xu.z, xl.w, xu.w, w.z, w.w);
+        }
+        __syncwarp();
+        if (pj < n_valid) {  // refill the slot just drained
+          gemv_issue_unit<T>(W, K, pl, pj, pu, ring.base_s + cslot * GV_SLOT_BYTES, ring.bars_s + cslot * 8);
+          if (++pu == gemv_units_of(pl, K, pj)) { pu = 0; ++pj; }
+        }
+        if (++cslot == (unsigned)ring.slots) { cslot = 0; cpar ^= 1u; }
+      }
+    }
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          if (b < B) {
-            const float4 x0 = lds16f(xk + (uint32_t)(b * K) * 4 + eo * 4), x1 = lds16f(xk + (uint32_t)(b * K) * 4 + eo * 4 + 16);
-            acc0[b] = fmaf(a0.x, x0.x, acc0[b]); acc1[b] = fmaf(a0.y, x0.y, acc1[b]);
-            acc0[b] = fmaf(a1.x, x0.z, acc0[b]); acc1[b] = fmaf(a1.y, x0.w, acc1[b]);
-            acc0[b] = fmaf(a2.x, x1.x, acc0[b]); acc1[b] = fmaf(a2.y, x1.y, acc1[b]);
-            acc0[b] = fmaf(a3.x, x1.z, acc0[b]); acc1[b] = fmaf(a3.y, x1.w, acc1[b]);
-            acc2[b] = fmaf(c0.x, x0.x, acc2[b]); acc3[b] = fmaf(c0.y, x0.y, acc3[b]);
-            acc2[b] = fmaf(c1.x, x0.z, acc2[b]); acc3[b] = fmaf(c1.y, x0.w, acc3[b]);
-            acc2[b] = fmaf(c2.x, x1.x, acc2[b]); acc3[b] = fmaf(c2.y, x1.y, acc3[b]);
-            acc2[b] = fmaf(c3.x, x1.z, acc2[b]); acc3[b] = fmaf(c3.y, x1.w, acc3[b]);
-          }
+    for (int i = 0; i < 4; ++i) c[i] += e[i];
+    if (split) {
+      float4* buf = red_s + (j & 1) * DEC_THREADS;
+      buf[threadIdx.x] = make_float4(c[0], c[1], c[2], c[3]);
+      __syncthreads();
+      if (owner) {
+#pragma unroll 1
+        for (int s = 1; s < ks; ++s) {
+          const float4 o = buf[threadIdx.x + s * 32];
+          c[0] += o.x; c[1] += o.y; c[2] += o.z; c[3] += o.w;
         }
       }
-      __syncwarp();
-      if (lane == 0 && pg < n_groups) {  // refill the slot just drained
-        gemv_issue_unit<T>(W, N, K, (first + pg * istride) * GV_R, pc, ring.base_s + cslot * GV_SLOT_BYTES, ring.bars_s + cslot * 8);
-        if (++pc == cpr) { pc = 0; ++pg; }
-      }
-      if (++cslot == (unsigned)slots) { cslot = 0; cpar ^= 1u; }
     }
-    float v0 = 0.f, v1 = 0.f;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const float s0 = warp_sum(acc0[b] + acc1[b]), s1 = warp_sum(acc2[b] + acc3[b]);
-      if (b == 0 || lane == b) { v0 = s0; v1 = s1; }
-    }
-    if (lane < B) {
-      if (mode >= EPI_QKV_ROPE) {
-        gemv_pair_epilogue<T>(a, mode, row0, lane, v0 + bias0, v1 + bias1);
-      } else {
-        gemv_epilogue<T>(a, mode, row0, lane, v0, bias0, resid0, sup0, best_v, best_i);
-        if (row0 + 1 < N) gemv_epilogue<T>(a, mode, row0 + 1, lane, v1, bias1, resid1, sup1, best_v, best_i);
-      }
+    if (rows_ok) {
+      if (lo) gemv_pair_epilogue<T>(a, mode, row0, g, c[0] + bias0, c[1] + bias1, rl0, rl1, sup0, sup1, best_v[0], best_i[0]);
+      if (hi) gemv_pair_epilogue<T>(a, mode, row0, g + 8, c[2] + bias0, c[3] + bias1, rh0, rh1, sup0, sup1, best_v[1], best_i[1]);
     }
   }
   ring.slot = cslot;
   ring.parity = cpar;
 }
 
-// ---- attention over one chunk of <= 64 keys for one (batch, head): warp-level -----------------
-// 8 lanes cover one key row (HD/8 values per lane), 4 keys per warp step.  Keys are processed in two halves of
-// 32: the 8 K vectors and 8 V vectors of a half are loaded into registers before any arithmetic, so a half
-// costs one memory round trip.  q must already carry the softmax scale.  Writes [o[HD], m, l] (unnormalised).
+// Per-CTA argmax candidates after an EPI_LOGITS gemv: merge the lanes of a session (t = 0..3), then the warps.
+// sv / si: DEC_WARPS * DEC_MAX_B entries each.
+__device__ __forceinline__ void gemv_argmax_candidates(float (&best_v)[2], int (&best_i)[2], int B, float* sv, int* si,
+                                                       float* cand_val, int* cand_idx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    float bv = best_v[hh]; int bi = best_i[hh];
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (t == 0) { sv[warp * DEC_MAX_B + g + 8 * hh] = bv; si[warp * DEC_MAX_B + g + 8 * hh] = bi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < B) {
+    const int b = threadIdx.x;
+    float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll 1
+    for (int wv = 0; wv < DEC_WARPS; ++wv) {
+      const float v = sv[wv * DEC_MAX_B + b]; const int i = si[wv * DEC_MAX_B + b];
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+    cand_val[b * gridDim.x + blockIdx.x] = bv;
+    cand_idx[b * gridDim.x + blockIdx.x] = bi;
+  }
+}
+
+// ---- attention: CTA-level items ------------------------------------------------------------------------------
+// One item = (session, head, key split).  The 8 warps of the CTA stride over the item's 32-key blocks; each warp keeps
+// a running (m, l, o) over its blocks (one memory round trip per block: the 8 K and 8 V vectors of a block are
+// loaded before any arithmetic; 8 lanes cover one key row), the warp records meet in shared memory and warp 0
+// merges them into ONE global record [o[HD] unnormalised, m, l] per item.  The consumer phase (out-projection)
+// therefore merges only `splits` records per (session, head) -- 1 when sessions x heads already cover the grid --
+// instead of one record per 64 keys, which at 16 sessions made every CTA re-read 1.2 MB of records per layer.
+constexpr int ATT_BLK = 32;
+
+// Key splits per (session, head).  A warp walks its 32-key blocks serially (one memory round trip each), so the
+// phase time is ~ (items per CTA) x (blocks per warp per item + ~1 for the in-CTA merge); pick the split count that
+// minimises it, smallest on ties (fewer records to merge).  Bounded by the blocks, the record storage and 16.
+__host__ __device__ inline int attn_best_splits(int BH, int n_blocks, int s_max, int grid) {
+  int best = 1, best_cost = 0x7fffffff;
+  const int cap = n_blocks < s_max ? (n_blocks < 16 ? n_blocks : 16) : (s_max < 16 ? s_max : 16);
+  for (int S = 1; S <= cap; ++S) {
+    const int bps = (n_blocks + S - 1) / S;
+    const int cost = ((BH * S + grid - 1) / grid) * ((bps + DEC_WARPS - 1) / DEC_WARPS + 1);
+    if (cost < best_cost) { best_cost = cost; best = S; }
+  }
+  return best;
+}
+
+// q must already carry the softmax scale.  Blocks blk_first, blk_first + blk_stride, ... < blk_end (all start
+// below n_keys).  Writes this warp's record (shared memory): m = -inf, l = 0, o = 0 if it had no block.
 template <typename T, int HD>
-__device__ __noinline__ void attend_chunk(const float* q /*global fp32 [HD]*/, const T* K, const T* V,
-                                             long long ldk, long long ldv, int n_keys, float* part) {
+__device__ __noinline__ void attend_blocks(const float* q /*global fp32 [HD]*/, const T* K, const T* V, long long ldk,
+                                           long long ldv, int n_keys, int blk_first, int blk_end, int blk_stride, float* rec) {
   constexpr int PER = HD / 8;      // elements per lane
   constexpr int NV = PER / 8;      // 16-byte vectors per lane
-  constexpr int KH = 8;            // keys per lane slot per half
+  constexpr int KH = 8;            // keys per lane slot per block
   const int lane = threadIdx.x & 31;
   const int g = lane >> 3, j = lane & 7;
   float qr[PER];
@@ -444,9 +640,18 @@ __device__ __noinline__ void attend_chunk(const float* q /*global fp32 [HD]*/, c
   for (int i = 0; i < PER; ++i) o[i] = 0.f;
 
 #pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    const int kbase = half * 32;
-    if (kbase >= n_keys) break;
+  for (int blk = blk_first; blk < blk_end; blk += blk_stride) {
+    const int kbase = blk * ATT_BLK;
+    if (blk + blk_stride < blk_end) {  // warm L2 with this warp's next block while the current one is in flight
+      const int nk = kbase + blk_stride * ATT_BLK + lane;
+      if (nk < n_keys) {
+#pragma unroll
+        for (int o128 = 0; o128 < HD * (int)sizeof(T); o128 += 128) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(K + (long long)nk * ldk) + o128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(V + (long long)nk * ldv) + o128));
+        }
+      }
+    }
     uint4 kr[KH][NV], vr[KH][NV];
 #pragma unroll
     for (int i = 0; i < KH; ++i) {
@@ -484,8 +689,8 @@ __device__ __noinline__ void attend_chunk(const float* q /*global fp32 [HD]*/, c
     }
     mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 8));
     mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 16));
-    const float m_new = fmaxf(m, mh);          // finite: the half holds at least one key
-    const float corr = __expf(m - m_new);      // m = -inf on the first half -> 0
+    const float m_new = fmaxf(m, mh);          // finite: the block holds at least one key
+    const float corr = __expf(m - m_new);      // m = -inf on the first block -> 0
     l *= corr;
 #pragma unroll
     for (int i = 0; i < PER; ++i) o[i] *= corr;
@@ -519,60 +724,75 @@ __device__ __noinline__ void attend_chunk(const float* q /*global fp32 [HD]*/, c
   if (g == 0) {
 #pragma unroll
     for (int i = 0; i < PER; i += 4)
-      *reinterpret_cast<float4*>(part + j * PER + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+      *reinterpret_cast<float4*>(rec + j * PER + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
   }
-  if (lane == 0) { part[HD] = m; part[HD + 1] = l; }
+  if (lane == 0) { rec[HD] = m; rec[HD + 1] = l; }
 }
 
-// ---- merge attention partials into shared memory xs[b][h*HD + dd] (normalised) ---------------
-// part layout: [B][H][s_max][HD + 4]; n_chunks valid records per (b, h).  One warp per (b, h): lane c owns record
-// c's (m, l); the o vectors of up to CG records are fetched with independent loads issued together with the
-// (m, l) load, so a pass over <= CG records costs a single L2 round trip.
-template <int HD, int CG>
-__device__ __noinline__ void combine_partials_to_smem(const float* part, int B, int H, int s_max, int n_chunks,
-                                                         float* xs) {
-  static_assert(CG <= 32, "one lane per record");
-  constexpr int REC = HD + PART_PAD;
-  constexpr int DPL = HD / 32;  // dims per lane
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int bh = warp; bh < B * H; bh += DEC_WARPS) {
-    const float* pp = part + (long long)bh * s_max * REC;
-    float M = -INFINITY, den = 0.f;
-    float num[DPL];
+// ---- finishing an attention item (warp 0 of the CTA) ---------------------------------------------------------
+// Merge the DEC_WARPS warp records (shared memory).  splits == 1: the item is the whole (session, head): write the
+// normalised head output as 16-bit into out16[HD].  Otherwise write the global record, then count the item in
+// cnt (one counter per (session, head)); the CTA that completes the count merges the `splits` records and writes
+// out16 -- so the consumer phase just copies B x d 16-bit values instead of every CTA re-merging every record.
+// The grid barrier that ends the phase orders out16 before its readers; the counter is reset for the next use.
+template <typename T, int HD>
+__device__ __forceinline__ void attn_finish_item(const float* rec_s, float* part_bh /*[s_max][REC]*/, int s, int splits,
+                                                 unsigned int* cnt, T* out16) {
+  constexpr int REC = HD + PART_PAD, DPL = HD / 32;
+  const int lane = threadIdx.x & 31;
+  float mw = -INFINITY, lw = 0.f;
+  if (lane < DEC_WARPS) { mw = rec_s[lane * REC + HD]; lw = rec_s[lane * REC + HD + 1]; }
+  const float M = warp_max(mw);
+  const float wt = (mw > -INFINITY) ? __expf(mw - M) : 0.f;  // empty warp records (and an all-empty item) weigh 0
+  const float den = warp_sum(lw * wt);
+  float o[DPL];
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) num[i] = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < n_chunks; c0 += CG) {
-      const int cnt = min(CG, n_chunks - c0);
-      float mc = -INFINITY, lc = 0.f;
-      if (lane < cnt) {
-        const float2 ml = __ldcg(reinterpret_cast<const float2*>(pp + (long long)(c0 + lane) * REC + HD));
-        mc = ml.x; lc = ml.y;
-      }
-      float ov[CG][DPL];
+  for (int i = 0; i < DPL; ++i) o[i] = 0.f;
 #pragma unroll
-      for (int u = 0; u < CG; ++u)
+  for (int w = 0; w < DEC_WARPS; ++w) {
+    const float ww = __shfl_sync(0xffffffffu, wt, w);
 #pragma unroll
-        for (int i = 0; i < DPL; ++i)
-          ov[u][i] = (u < cnt) ? __ldcg(pp + (long long)(c0 + u) * REC + lane + 32 * i) : 0.f;
-      const float M_new = fmaxf(M, warp_max(mc));
-      const float corr = __expf(M - M_new);
-      const float wc = (lane < cnt) ? __expf(mc - M_new) : 0.f;
-      den = den * corr + warp_sum(lc * wc);
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) num[i] *= corr;
-      M = M_new;
-#pragma unroll
-      for (int u = 0; u < CG; ++u) {
-        const float wu = __shfl_sync(0xffffffffu, wc, u);
-#pragma unroll
-        for (int i = 0; i < DPL; ++i) num[i] = fmaf(ov[u][i], wu, num[i]);
-      }
-    }
-    const float inv = 1.f / den;
-    const int b = bh / H, h = bh % H;
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) xs[b * (H * HD) + h * HD + lane + 32 * i] = num[i] * inv;
+    for (int i = 0; i < DPL; ++i) o[i] = fmaf(rec_s[w * REC + lane + 32 * i], ww, o[i]);
   }
+  if (splits == 1) {
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) out16[lane + 32 * i] = DT<T>::from_f(o[i] * inv);
+    return;
+  }
+  float* out = part_bh + (long long)s * REC;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) out[lane + 32 * i] = o[i];
+  if (lane == 0) { out[HD] = M; out[HD + 1] = den; }
+  __syncwarp();
+  unsigned int prev = 0;
+  if (lane == 0) {
+    __threadfence();  // the record (all lanes, ordered by the __syncwarp) happens-before the count
+    prev = atomicAdd(cnt, 1u);
+    __threadfence();
+  }
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev != (unsigned)splits - 1) return;
+  // last split of this (session, head): merge the records (splits <= 16: one lane per record)
+  float mc = -INFINITY, lc = 0.f;
+  if (lane < splits) {
+    const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_bh + (long long)lane * REC + HD));
+    mc = ml.x; lc = ml.y;
+  }
+  float acc[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+  const float M2 = warp_max(mc);
+  const float wc = (mc > -INFINITY) ? __expf(mc - M2) : 0.f;
+  const float den2 = warp_sum(lc * wc);
+#pragma unroll 4
+  for (int u = 0; u < splits; ++u) {
+    const float wu = __shfl_sync(0xffffffffu, wc, u);
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = fmaf(__ldcg(part_bh + (long long)u * REC + lane + 32 * i), wu, acc[i]);
+  }
+  const float inv = 1.f / den2;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) out16[lane + 32 * i] = DT<T>::from_f(acc[i] * inv);
+  if (lane == 0) *cnt = 0u;
 }

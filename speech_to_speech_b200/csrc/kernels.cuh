@@ -26,3 +26,7 @@ int norm_rows_launch(const float* x, const float* w, const float* bias, float ep
 int convert_f32_launch(const float* src, void* dst, long long n, int dtype, cudaStream_t stream);
 int fill_random_launch(void* dst, long long n, int dtype, float scale, float offset, uint64_t seed,
                        cudaStream_t stream);
+// ---- weight_tiles.cu ----
+// row-major 16-bit [N, K] -> fragment-major tiled layout streamed by the decode kernels (see decode_common.cuh)
+size_t tiled_weight_elems(int N, int K);
+int tile_weights_launch(const void* W, int N, int K, void* Wt, cudaStream_t stream);

@@ -9,6 +9,7 @@
 //     and in the prefill RoPE kernel; q.k dot products are invariant under the common permutation.
 //   * gate_proj / up_proj rows are interleaved (gate_i, up_i): SwiGLU is fused into the producing GEMM / GEMV epilogue.
 #include <math.h>
+#include <algorithm>
 #include <string.h>
 
 #include <string>
@@ -111,8 +112,10 @@ struct s2s_llama {
   // weights
   void *embed = nullptr, *lm_head = nullptr;
   float* norm_f = nullptr;
-  std::vector<LlamaDecLayer> layers_h;
-  LlamaDecLayer* layers_d = nullptr;
+  std::vector<LlamaDecLayer> layers_h;   // row-major weights (prefill GEMMs)
+  std::vector<LlamaDecLayer> tiled_h;    // fragment-major copies streamed by the decode kernel
+  LlamaDecLayer* layers_d = nullptr;     // device copy of tiled_h
+  void* lm_head_t = nullptr;
   float2* rope = nullptr;
   // KV + sessions
   void* kv = nullptr;
@@ -125,6 +128,8 @@ struct s2s_llama {
   size_t vt_elems = 0;
   // decode state
   float *dx = nullptr, *dq = nullptr, *dh = nullptr, *part = nullptr, *cand_val = nullptr;
+  void* attn16 = nullptr;
+  unsigned int* attn_cnt = nullptr;
   int *slot_d = nullptr, *pos_d = nullptr, *done = nullptr, *n_done = nullptr, *cand_idx = nullptr, *out_ids = nullptr,
       *out_len = nullptr, *next_id = nullptr;
   unsigned int* sync_counter = nullptr;
@@ -135,7 +140,7 @@ struct s2s_llama {
 
 namespace {
 
-constexpr int MAX_DEC_B = 4;
+constexpr int MAX_DEC_B = 16;  // upper bound; the shared-memory budget of the geometry may allow fewer (llama_decode_max_batch)
 
 template <typename P> int lalloc(s2s_llama* m, P** out, size_t bytes, bool zero = true) {
   void* p = nullptr;
@@ -229,6 +234,8 @@ int build(s2s_llama* m) {
   S2S_CHECK(lalloc(m, &m->dq, (size_t)MAX_DEC_B * qd * 4));
   S2S_CHECK(lalloc(m, &m->dh, (size_t)MAX_DEC_B * f * 4));
   S2S_CHECK(lalloc(m, &m->part, (size_t)MAX_DEC_B * c.heads * m->s_max * (hd + 4) * 4));
+  S2S_CHECK(lalloc(m, &m->attn16, (size_t)MAX_DEC_B * qd * 2));
+  S2S_CHECK(lalloc(m, &m->attn_cnt, (size_t)MAX_DEC_B * c.heads * 4));
   S2S_CHECK(lalloc(m, &m->slot_d, MAX_DEC_B * 4));
   S2S_CHECK(lalloc(m, &m->pos_d, MAX_DEC_B * 4));
   S2S_CHECK(lalloc(m, &m->done, MAX_DEC_B * 4));
@@ -357,6 +364,36 @@ int s2s_llama_finalize(s2s_llama* m) {
       s2s_set_error("llama finalize: tensor '%s' was never bound", kv.first.c_str());
       return S2S_ERR_INVALID;
     }
+  // decode-side weight layout: fragment-major tiles (weight_tiles.cu), built once per (re)load
+  {
+    const auto& c = m->cfg;
+    const int d = c.d_model, qd = c.heads * c.head_dim, kvd = c.kv_heads * c.head_dim, f = c.ffn;
+    S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+    if (m->tiled_h.empty()) {
+      m->tiled_h = m->layers_h;
+      for (int i = 0; i < c.layers; ++i) {
+        LlamaDecLayer& T = m->tiled_h[i];
+        void *a, *b, *g, *dn;
+        S2S_CHECK(lalloc(m, &a, tiled_weight_elems(qd + 2 * kvd, d) * 2));
+        S2S_CHECK(lalloc(m, &b, tiled_weight_elems(d, qd) * 2));
+        S2S_CHECK(lalloc(m, &g, tiled_weight_elems(2 * f, d) * 2));
+        S2S_CHECK(lalloc(m, &dn, tiled_weight_elems(d, f) * 2));
+        T.w_qkv = a; T.w_o = b; T.w_gu = g; T.w_down = dn;
+      }
+      S2S_CHECK(lalloc(m, &m->lm_head_t, tiled_weight_elems(c.vocab, d) * 2));
+      S2S_CHECK_CUDA(cudaMemcpy(m->layers_d, m->tiled_h.data(), sizeof(LlamaDecLayer) * c.layers, cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < c.layers; ++i) {
+      const LlamaDecLayer& R = m->layers_h[i];
+      const LlamaDecLayer& T = m->tiled_h[i];
+      S2S_CHECK(tile_weights_launch(R.w_qkv, qd + 2 * kvd, d, const_cast<void*>(T.w_qkv), 0));
+      S2S_CHECK(tile_weights_launch(R.w_o, d, qd, const_cast<void*>(T.w_o), 0));
+      S2S_CHECK(tile_weights_launch(R.w_gu, 2 * f, d, const_cast<void*>(T.w_gu), 0));
+      S2S_CHECK(tile_weights_launch(R.w_down, d, f, const_cast<void*>(T.w_down), 0));
+    }
+    S2S_CHECK(tile_weights_launch(m->lm_head, c.vocab, d, m->lm_head_t, 0));
+    S2S_CHECK_CUDA(cudaDeviceSynchronize());
+  }
   m->finalized = true;
   return S2S_OK;
 }
@@ -448,7 +485,8 @@ int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int3
                      float* logits_out_d, void* stream) {
   S2S_REQUIRE(m && m->finalized && slots_h && first_ids_d && ids_out_d && len_out_d, "llama decode: null argument");
   const auto& c = m->cfg;
-  S2S_REQUIRE(B >= 1 && B <= MAX_DEC_B, "llama decode: B=%d outside [1,%d]", B, MAX_DEC_B);
+  const int max_b = std::min(MAX_DEC_B, llama_decode_max_batch(m->cfg.d_model, m->cfg.ffn, m->cfg.heads * m->cfg.head_dim));
+  S2S_REQUIRE(B >= 1 && B <= max_b, "llama decode: B=%d outside [1,%d] for this geometry", B, max_b);
   S2S_REQUIRE(n_steps >= 1, "llama decode: n_steps must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
   S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
@@ -467,10 +505,10 @@ int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int3
   LlamaDecParams p{};
   p.d = c.d_model; p.heads = c.heads; p.kv_heads = c.kv_heads; p.hd = c.head_dim; p.layers = c.layers; p.ffn = c.ffn;
   p.vocab = c.vocab; p.B = B; p.max_pos = c.max_positions; p.eps = c.rms_eps;
-  p.lw = m->layers_d; p.embed = m->embed; p.lm_head = m->lm_head; p.norm_f = m->norm_f; p.rope = m->rope;
+  p.lw = m->layers_d; p.embed = m->embed; p.lm_head = m->lm_head_t; p.norm_f = m->norm_f; p.rope = m->rope;
   p.x = m->dx; p.q = m->dq; p.h = m->dh; p.kv = m->kv;
   p.kv_slot_stride = m->kv_slot_stride; p.kv_layer_stride = m->kv_layer_stride; p.kv_which_stride = m->kv_which_stride;
-  p.part = m->part; p.s_max = m->s_max; p.slot = m->slot_d; p.pos = m->pos_d; p.max_len = max_len;
+  p.part = m->part; p.s_max = m->s_max; p.attn16 = m->attn16; p.attn_cnt = m->attn_cnt; p.slot = m->slot_d; p.pos = m->pos_d; p.max_len = max_len;
   p.first_ids = first_ids_d; p.n_steps = n_steps; p.eos = eos_id; p.out_ids = ids_out_d; p.out_len = len_out_d;
   p.forced = forced_d; p.logits_out = logits_out_d; p.done = m->done; p.n_done = m->n_done;
   p.cand_val = m->cand_val; p.cand_idx = m->cand_idx; p.sync_counter = m->sync_counter;

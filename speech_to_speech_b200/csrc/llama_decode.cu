@@ -23,28 +23,28 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
   return t;
 }
 
+// GQA attention over each session's cached keys: CTA-level items (session, q head, key split); see decode_common.cuh
 template <typename T, int HD>
-__device__ __noinline__ void ld_attn(const LlamaDecParams& p, int layer, int step) {
-  const int B = p.B, H = p.heads, grp = p.heads / p.kv_heads;
+__device__ __noinline__ void ld_attn(const LlamaDecParams& p, int layer, int step, float* rec_s) {
+  const int H = p.heads, grp = p.heads / p.kv_heads, warp = threadIdx.x >> 5;
   const int kvd = p.kv_heads * HD;
-  const int rec = HD + PART_PAD;
-  const int n_chunks = (p.max_len + step + ATT_CHUNK - 1) / ATT_CHUNK;
-  const int n_items = B * H * n_chunks;
+  constexpr int REC = HD + PART_PAD;
+  const int n_blocks = (p.max_len + step + ATT_BLK - 1) / ATT_BLK, BH = p.B * H;  // longest session
+  const int S = attn_best_splits(BH, n_blocks, p.s_max, (int)gridDim.x), bps = (n_blocks + S - 1) / S;
   const T* kv = reinterpret_cast<const T*>(p.kv);
 #pragma unroll 1
-  for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
-    const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
-    const int len = __ldcg(p.pos + b) + 1;
-    float* rec_out = p.part + ((long long)(b * H + h) * p.s_max + c) * rec;
-    const int n_keys = min(ATT_CHUNK, len - c * ATT_CHUNK);
-    if (n_keys <= 0) {  // this session is shorter: mark the record empty (weight exp(-inf) = 0 in the combine)
-      if ((threadIdx.x & 31) == 0) { rec_out[HD] = -INFINITY; rec_out[HD + 1] = 0.f; }
-      continue;
-    }
-    const T* Kb = kv + (long long)__ldg(p.slot + b) * p.kv_slot_stride + (long long)layer * p.kv_layer_stride +
-                  (long long)c * ATT_CHUNK * kvd + (h / grp) * HD;
-    const T* Vb = Kb + p.kv_which_stride;
-    attend_chunk<T, HD>(p.q + (long long)b * H * HD + h * HD, Kb, Vb, kvd, kvd, n_keys, rec_out);
+  for (int it = blockIdx.x; it < BH * S; it += gridDim.x) {
+    const int s = it % S, bh = it / S, h = bh % H, b = bh / H;
+    const int len = __ldcg(p.pos + b) + 1;  // this session's keys; splits past its end produce empty records
+    const int nb = (len + ATT_BLK - 1) / ATT_BLK;
+    const T* Kb = kv + (long long)__ldg(p.slot + b) * p.kv_slot_stride + (long long)layer * p.kv_layer_stride + (h / grp) * HD;
+    attend_blocks<T, HD>(p.q + (long long)b * H * HD + h * HD, Kb, Kb + p.kv_which_stride, kvd, kvd, len, s * bps + warp,
+                         min((s + 1) * bps, nb), DEC_WARPS, rec_s + warp * REC);
+    __syncthreads();
+    if (warp == 0)
+      attn_finish_item<T, HD>(rec_s, p.part + (long long)bh * p.s_max * REC, s, S, p.attn_cnt + bh,
+                              reinterpret_cast<T*>(p.attn16) + (long long)b * H * HD + h * HD);
+    __syncthreads();
   }
 }
 
@@ -93,7 +93,7 @@ __device__ __noinline__ void ld_select(const LlamaDecParams& p, int step, float*
 template <typename T>
 __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, int ph, GemvArgs& a) {
   const int L = p.layers, d = p.d, B = p.B, qd = p.heads * p.hd, kvd = p.kv_heads * p.hd;
-  a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = qd; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
+  a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = qd; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
   a.pos = p.pos; a.slot = p.slot; a.kv_slot = p.kv_slot_stride; a.kv_ld = kvd; a.rope = p.rope; a.hd = p.hd;
   a.q_rows = qd; a.k_rows = kvd; a.q_scale = rsqrtf((float)p.hd);
@@ -106,7 +106,7 @@ __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, 
         a.kv0 = reinterpret_cast<T*>(p.kv) + (long long)layer * p.kv_layer_stride; a.kv_which = p.kv_which_stride;
         return true;
       case 2: a.W = w.w_o; a.N = d; a.K = qd; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; return true;
-      case 3: a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out = p.h; a.ldo = p.ffn; return true;
+      case 3: a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out_h = p.h; a.ldh = p.ffn; return true;
       case 4: a.W = w.w_down; a.N = d; a.K = p.ffn; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; return true;
       default: return false;
     }
@@ -119,76 +119,67 @@ __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, 
   return false;
 }
 
-template <typename T, int NB>
-__device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, float* xs, float* s_aux, GemvRing& ring,
+template <typename T>
+struct LdSmem {
+  T* xh; float* xs; float* sv; int* si; float* s_red; float* wb; float4* red;
+};
+
+__host__ __device__ inline int ld_kmax(int d, int ffn, int qd) { return (d > ffn ? d : ffn) > qd ? (d > ffn ? d : ffn) : qd; }
+
+template <typename T>
+__device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, const LdSmem<T>& sm, GemvRing& ring,
                                          const GemvArgs* ready, int wb_ready) {
-  float* s_red = s_aux + 2 * DEC_WARPS * NB;
-  float* wb = s_red + 2 * DEC_WARPS;
   const int L = p.layers, d = p.d, B = p.B;
-  float best_v = -INFINITY;
-  int best_i = 0x7fffffff;
+  float best_v[2] = {-INFINITY, -INFINITY};
+  int best_i[2] = {0x7fffffff, 0x7fffffff};
   GemvArgs a;
   if (ready) a = *ready; else ld_gemv_args<T>(p, step, ph, a);
   if (ph < 5 * L) {
     const int layer = ph / 5;
     const LlamaDecLayer& w = p.lw[layer];
     switch (ph % 5) {
-      case 0: stage_rows(p.x, B, d, xs, 2, w.norm1, nullptr, p.eps, s_red, wb, wb_ready); break;
+      case 0: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm1, nullptr, p.eps, sm.s_red, sm.wb, wb_ready); break;
       case 1:
-        if (p.hd == 128) ld_attn<T, 128>(p, layer, step); else ld_attn<T, 64>(p, layer, step);
+        if (p.hd == 128) ld_attn<T, 128>(p, layer, step, reinterpret_cast<float*>(sm.red));
+        else ld_attn<T, 64>(p, layer, step, reinterpret_cast<float*>(sm.red));
         return;
-      case 2: {
-        const int n_chunks = (p.max_len + step + ATT_CHUNK - 1) / ATT_CHUNK;
-        if (p.hd == 128) combine_partials_to_smem<128, 8>(p.part, B, p.heads, p.s_max, n_chunks, xs);
-        else combine_partials_to_smem<64, 8>(p.part, B, p.heads, p.s_max, n_chunks, xs);
-        __syncthreads();
-      } break;
-      case 3: stage_rows(p.x, B, d, xs, 2, w.norm2, nullptr, p.eps, s_red, wb, wb_ready); break;
-      default: stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb); break;
+      case 2: stage_rows_copy<T>(reinterpret_cast<const T*>(p.attn16), B, p.heads * p.hd, sm.xh); break;
+      case 3: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm2, nullptr, p.eps, sm.s_red, sm.wb, wb_ready); break;
+      default: stage_rows_copy<T>(reinterpret_cast<const T*>(p.h), B, p.ffn, sm.xh); break;
     }
-    gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
+    gemv_mma<T>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     return;
   }
   if (ph == 5 * L) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    stage_rows(p.x, B, d, xs, 2, p.norm_f, nullptr, p.eps, s_red, wb, wb_ready);
-    gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
-    float* sv = s_aux;
-    int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
-    if (lane < NB) { sv[warp * NB + lane] = best_v; si[warp * NB + lane] = best_i; }
-    __syncthreads();
-    if (threadIdx.x < B) {
-      const int b = threadIdx.x;
-      float bv = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll 1
-      for (int wv = 0; wv < DEC_WARPS; ++wv) {
-        const float v = sv[wv * NB + b]; const int i = si[wv * NB + b];
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-      }
-      p.cand_val[b * gridDim.x + blockIdx.x] = bv;
-      p.cand_idx[b * gridDim.x + blockIdx.x] = bi;
-    }
+    stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, p.norm_f, nullptr, p.eps, sm.s_red, sm.wb, wb_ready);
+    gemv_mma<T>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
+    gemv_argmax_candidates(best_v, best_i, B, sm.sv, sm.si, p.cand_val, p.cand_idx);
   } else {
-    ld_select<T>(p, step, s_aux);
+    ld_select<T>(p, step, sm.sv);
   }
 }
 
-template <typename T, int NB>
+template <typename T>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph_begin, int ph_end, int coop) {
-  extern __shared__ __align__(16) float smem_f[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ LlamaDecParams sp;
   __shared__ LlamaDecLayer s_layers[64];
   if (threadIdx.x == 0) { sp = p; sp.lw = s_layers; }
   for (int i = threadIdx.x; i < p.layers; i += DEC_THREADS) s_layers[i] = p.lw[i];
   __syncthreads();
-  const int kmax = max(max(p.d, p.ffn), p.heads * p.hd);
-  float* xs = smem_f;
-  float* s_aux = smem_f + NB * kmax;
+  const DecSmem lay = dec_smem_layout(p.B, p.d, ld_kmax(p.d, p.ffn, p.heads * p.hd), p.d);
+  LdSmem<T> sm;
+  sm.xh = reinterpret_cast<T*>(smem_raw);
+  sm.xs = reinterpret_cast<float*>(smem_raw + lay.xs_off);
+  sm.sv = reinterpret_cast<float*>(smem_raw + lay.aux_off);
+  sm.si = reinterpret_cast<int*>(smem_raw + lay.si_off);
+  sm.s_red = reinterpret_cast<float*>(smem_raw + lay.red_s_off);
+  sm.wb = reinterpret_cast<float*>(smem_raw + lay.wb_off);
+  sm.red = reinterpret_cast<float4*>(smem_raw + lay.redbuf_off);
   GemvRing ring;
   {
-    const int fixed_floats = NB * kmax + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * p.d;
-    unsigned char* rb = reinterpret_cast<unsigned char*>(smem_f) + (((size_t)fixed_floats * 4 + 127) & ~(size_t)127);
+    unsigned char* rb = smem_raw + lay.ring_off;
     const int warp = threadIdx.x >> 5;
     ring.slots = p.ring_slots;
     ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
@@ -205,8 +196,9 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   unsigned int epoch = 0;
   int trace_i = 0;
   GemvArgs pre_args;
+  pre_args.K = p.d;
   int pre_tag = -1, wb_tag = -1;
-  ring.pre_valid = 0; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = nullptr;
+  ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
   const int n_ph = 5 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
@@ -214,7 +206,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
       const bool tracing = sp.trace && trace_i < sp.trace_cap && threadIdx.x == 0 && blockIdx.x == 0;
       unsigned long long* tr = tracing ? sp.trace + (long long)trace_i * 3 : nullptr;
       if (tracing) tr[0] = gtimer_ns();
-      ld_phase<T, NB>(sp, step, ph, xs, s_aux, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr, wb_tag == step * n_ph + ph);
+      ld_phase<T>(sp, step, ph, sm, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr, wb_tag == step * n_ph + ph);
       if (tracing) tr[1] = gtimer_ns();
       if (coop) {
         grid_arrive(p.sync_counter, epoch);
@@ -232,7 +224,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
                 const int sub = nph % 5;
                 if (sub == 0) nw = sp.lw[nph / 5].norm1; else if (sub == 3) nw = sp.lw[nph / 5].norm2;
               } else { nw = sp.norm_f; }
-              if (nw) { stage_norm_weights(nw, nullptr, sp.d, s_aux + 2 * DEC_WARPS * NB + 2 * DEC_WARPS); wb_tag = pre_tag; }
+              if (nw) { stage_norm_weights(nw, nullptr, sp.d, sm.wb); wb_tag = pre_tag; }
               break;
             }
             if (++nph == n_ph) { nph = 0; ++nstep; }
@@ -245,7 +237,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
     }
     if (coop && !p.forced && *reinterpret_cast<volatile int*>(p.n_done) >= p.B) break;
   }
-  gemv_drain<T>(pre_args, ring);
+  gemv_drain(pre_args.K, ring);
 }
 
 template <typename T>
@@ -258,19 +250,19 @@ __global__ void llama_decode_init_kernel(const LlamaDecParams p) {
     p.done[b] = 0;
     p.out_len[b] = 0;
     if (b == 0) { *p.n_done = 0; *p.sync_counter = 0; }
+    for (int h = 0; h < p.heads; ++h) p.attn_cnt[b * p.heads + h] = 0u;
   }
   for (int i = threadIdx.x; i < p.n_steps; i += blockDim.x) p.out_ids[b * p.n_steps + i] = p.eos;
 }
 
-template <typename T, int NB>
-int launch_nb(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
-  const int kmax = max(max(p.d, p.ffn), p.heads * p.hd);
-  const size_t fixed = (((size_t)NB * kmax + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * (size_t)p.d) * sizeof(float) + 127) & ~(size_t)127;
-  S2S_REQUIRE(fixed + (size_t)DEC_WARPS * GV_SLOT_BYTES + 2048 <= 220 * 1024, "llama decode: batch %d x K %d does not fit shared memory", NB, kmax);
+template <typename T>
+int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
+  const DecSmem lay = dec_smem_layout(p.B, p.d, ld_kmax(p.d, p.ffn, p.heads * p.hd), p.d);
   LlamaDecParams pr = p;
-  pr.ring_slots = (int)std::min<size_t>(4, (220 * 1024 - fixed - 1024) / ((size_t)DEC_WARPS * GV_SLOT_BYTES));
-  const size_t smem = fixed + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
-  auto kern = llama_decode_kernel<T, NB>;
+  pr.ring_slots = dec_ring_slots(lay);
+  S2S_REQUIRE(pr.ring_slots >= 2, "llama decode: batch %d x K %d does not fit shared memory", p.B, ld_kmax(p.d, p.ffn, p.heads * p.hd));
+  const size_t smem = (size_t)lay.ring_off + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
+  auto kern = llama_decode_kernel<T>;
   S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   llama_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
   S2S_LAUNCH_CHECK();
@@ -292,23 +284,22 @@ int launch_nb(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStrea
   return S2S_OK;
 }
 
-template <typename T>
-int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
-  if (p.B <= 1) return launch_nb<T, 1>(ctx, p, debug_phases, stream);
-  if (p.B <= 2) return launch_nb<T, 2>(ctx, p, debug_phases, stream);
-  if (p.B <= 4) return launch_nb<T, 4>(ctx, p, debug_phases, stream);
-  s2s_set_error("llama decode: batch %d > 4 must be split by the caller", p.B);
-  return S2S_ERR_INVALID;
-}
-
 }  // namespace
 
 int llama_decode_launch(s2s_ctx* ctx, const LlamaDecParams& p, int dtype, int debug_phases, cudaStream_t stream) {
   S2S_REQUIRE(p.hd == 64 || p.hd == 128, "llama decode: head_dim must be 64 or 128");
   S2S_REQUIRE(p.layers <= 64, "llama decode: at most 64 layers");
   S2S_REQUIRE(p.n_steps >= 1, "llama decode: n_steps must be >= 1");
+  S2S_REQUIRE(p.B >= 1 && p.B <= DEC_MAX_B, "llama decode: batch %d > %d must be split by the caller", p.B, DEC_MAX_B);
+  S2S_REQUIRE(p.d % 64 == 0 && p.ffn % 64 == 0 && (p.heads * p.hd) % 64 == 0, "llama decode: d, ffn, heads*hd must be multiples of 64");
   if (dtype == S2S_BF16) return launch_t<__nv_bfloat16>(ctx, p, debug_phases, stream);
   if (dtype == S2S_F16) return launch_t<__half>(ctx, p, debug_phases, stream);
   s2s_set_error("llama decode: unsupported dtype %d", dtype);
   return S2S_ERR_UNSUPPORTED;
+}
+
+int llama_decode_max_batch(int d, int ffn, int qd) {
+  for (int B = DEC_MAX_B; B >= 1; --B)
+    if (dec_ring_slots(dec_smem_layout(B, d, ld_kmax(d, ffn, qd), d)) >= 2) return B;
+  return 0;
 }

@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-struct LlamaDecLayer {          // device pointers; 16-bit weights [out, in] row-major
+struct LlamaDecLayer {          // device pointers; 16-bit weights [out, in]: TILED layout (weight_tiles.cu) in the kernel's table
   const void* w_qkv;            // [(H + 2 KV) * hd, d]; q and k rows stored pair-adjacent for RoPE (see llama.cu)
   const void* w_o;              // [d, H * hd]
   const void* w_gu;             // [2 * ffn, d], rows interleaved (gate_i, up_i)
@@ -15,17 +15,19 @@ struct LlamaDecParams {
   float eps;
   const LlamaDecLayer* lw;      // [layers] device
   const void* embed;            // [vocab, d] 16-bit
-  const void* lm_head;          // [vocab, d] 16-bit
+  const void* lm_head;          // [vocab, d] 16-bit, TILED layout
   const float* norm_f;          // [d]
   const float2* rope;           // [max_pos][hd/2] (cos, sin)
   // state
   float* x;                     // [B, d] residual stream
   float* q;                     // [B, H*hd]
-  float* h;                     // [B, ffn]
+  void* h;                      // [B, ffn] 16-bit (SwiGLU output)
   void* kv;                     // [slots][layers][2][max_pos][KV*hd] 16-bit
   long long kv_slot_stride, kv_layer_stride, kv_which_stride;
-  float* part;                  // [B][H][s_max][hd + 4]
+  float* part;                  // [B][H][s_max][hd + 4] split records of the attention phase
   int s_max;
+  void* attn16;                 // [B, H*hd] 16-bit attention output (input of o_proj)
+  unsigned int* attn_cnt;       // [B * H] finished splits per (session, head); zero between phases
   const int* slot;              // [B]
   int* pos;                     // [B] position of the token being processed (advanced by the kernel)
   int max_len;                  // max over b of (pos[b] + 1) at step 0
@@ -45,3 +47,5 @@ struct LlamaDecParams {
 };
 
 int llama_decode_launch(s2s_ctx* ctx, const LlamaDecParams& p, int dtype, int debug_phases, cudaStream_t stream);
+// largest batch per launch that keeps >= 2 weight-ring slots per warp in shared memory
+int llama_decode_max_batch(int d, int ffn, int qd);

@@ -52,8 +52,10 @@ struct s2s_whisper {
   float *conv1_b = nullptr, *conv2_b = nullptr, *enc_pos = nullptr, *dec_pos = nullptr, *ckv_b = nullptr;
   float *enc_lnf_w = nullptr, *enc_lnf_b = nullptr, *dec_lnf_w = nullptr, *dec_lnf_b = nullptr;
   std::vector<EncLayer> enc;
-  std::vector<WhisperDecLayer> dec_h;
-  WhisperDecLayer* dec_d = nullptr;
+  std::vector<WhisperDecLayer> dec_h;    // row-major decoder weights as bound
+  std::vector<WhisperDecLayer> dec_t;    // fragment-major copies streamed by the decode kernel
+  WhisperDecLayer* dec_d = nullptr;      // device copy of dec_t
+  void* embed_t = nullptr;
   // tables
   float *hann = nullptr, *twiddle = nullptr, *fb = nullptr;
   int2* fb_range = nullptr;
@@ -66,6 +68,8 @@ struct s2s_whisper {
        *enc_out = nullptr, *cross_kv = nullptr;
   // decoder state
   float *dx = nullptr, *dq = nullptr, *dh = nullptr, *part = nullptr, *cand_val = nullptr;
+  void* attn16 = nullptr;
+  unsigned int* attn_cnt = nullptr;
   void* self_kv = nullptr;
   int *tokens = nullptr, *out_ids = nullptr, *out_len = nullptr, *done = nullptr, *n_done = nullptr, *cand_idx = nullptr;
   unsigned char *suppress = nullptr, *suppress_lang = nullptr;
@@ -296,6 +300,8 @@ int alloc_workspace(s2s_whisper* m) {
   S2S_CHECK(dev_alloc(m, &m->dq, (size_t)B * d * 4));
   S2S_CHECK(dev_alloc(m, &m->dh, (size_t)B * f * 4));
   S2S_CHECK(dev_alloc(m, &m->part, (size_t)B * c.heads * m->s_max * 68 * 4));
+  S2S_CHECK(dev_alloc(m, &m->attn16, (size_t)B * d * esz));
+  S2S_CHECK(dev_alloc(m, &m->attn_cnt, (size_t)B * c.heads * 4));
   S2S_CHECK(dev_alloc(m, &m->self_kv, (size_t)B * c.dec_layers * 2 * c.max_target_positions * d * esz));
   S2S_CHECK(dev_alloc(m, &m->tokens, (size_t)B * c.max_target_positions * 4));
   S2S_CHECK(dev_alloc(m, &m->out_ids, (size_t)B * c.max_target_positions * 4));
@@ -415,6 +421,40 @@ int s2s_whisper_finalize(s2s_whisper* m) {
       return S2S_ERR_INVALID;
     }
   }
+  // decode-side weight layout: fragment-major tiles (weight_tiles.cu), built once per (re)load
+  {
+    const auto& c = m->cfg;
+    const int d = c.d_model, f = c.ffn;
+    S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+    if (m->dec_t.empty()) {
+      m->dec_t = m->dec_h;
+      for (int i = 0; i < c.dec_layers; ++i) {
+        WhisperDecLayer& T = m->dec_t[i];
+        void *a, *b, *cq, *co, *f1, *f2;
+        S2S_CHECK(dev_alloc(m, &a, tiled_weight_elems(3 * d, d) * 2));
+        S2S_CHECK(dev_alloc(m, &b, tiled_weight_elems(d, d) * 2));
+        S2S_CHECK(dev_alloc(m, &cq, tiled_weight_elems(d, d) * 2));
+        S2S_CHECK(dev_alloc(m, &co, tiled_weight_elems(d, d) * 2));
+        S2S_CHECK(dev_alloc(m, &f1, tiled_weight_elems(f, d) * 2));
+        S2S_CHECK(dev_alloc(m, &f2, tiled_weight_elems(d, f) * 2));
+        T.w_qkv = a; T.w_o = b; T.w_cq = cq; T.w_co = co; T.w_fc1 = f1; T.w_fc2 = f2;
+      }
+      S2S_CHECK(dev_alloc(m, &m->embed_t, tiled_weight_elems(c.vocab, d) * 2));
+      S2S_CHECK_CUDA(cudaMemcpy(m->dec_d, m->dec_t.data(), sizeof(WhisperDecLayer) * c.dec_layers, cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < c.dec_layers; ++i) {
+      const WhisperDecLayer& R = m->dec_h[i];
+      const WhisperDecLayer& T = m->dec_t[i];
+      S2S_CHECK(tile_weights_launch(R.w_qkv, 3 * d, d, const_cast<void*>(T.w_qkv), 0));
+      S2S_CHECK(tile_weights_launch(R.w_o, d, d, const_cast<void*>(T.w_o), 0));
+      S2S_CHECK(tile_weights_launch(R.w_cq, d, d, const_cast<void*>(T.w_cq), 0));
+      S2S_CHECK(tile_weights_launch(R.w_co, d, d, const_cast<void*>(T.w_co), 0));
+      S2S_CHECK(tile_weights_launch(R.w_fc1, f, d, const_cast<void*>(T.w_fc1), 0));
+      S2S_CHECK(tile_weights_launch(R.w_fc2, d, f, const_cast<void*>(T.w_fc2), 0));
+    }
+    S2S_CHECK(tile_weights_launch(m->embed, c.vocab, d, m->embed_t, 0));
+    S2S_CHECK_CUDA(cudaDeviceSynchronize());
+  }
   m->finalized = true;
   return S2S_OK;
 }
@@ -522,23 +562,25 @@ static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, in
     }
   S2S_CHECK_CUDA(cudaMemcpyAsync(m->tokens, tok.data(), tok.size() * 4, cudaMemcpyHostToDevice, st));
   S2S_CHECK_CUDA(cudaStreamSynchronize(st));  // tok is a stack-lifetime host buffer
-  for (int b0 = 0; b0 < B; b0 += 8) {
-    const int nb = (B - b0) < 8 ? (B - b0) : 8;
+  const int group = whisper_decode_max_batch(d, c.ffn);  // sessions per persistent launch (<= 16)
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int nb = (B - b0) < group ? (B - b0) : group;
     WhisperDecParams p{};
     p.d = d; p.heads = c.heads; p.layers = c.dec_layers; p.ffn = c.ffn; p.vocab = c.vocab; p.B = nb;
     p.max_pos = c.max_target_positions; p.n_ctx = c.max_source_positions;
-    p.lw = m->dec_d; p.embed = m->embed; p.pos = m->dec_pos; p.lnf_w = m->dec_lnf_w; p.lnf_b = m->dec_lnf_b;
-    p.x = m->dx + (size_t)b0 * d; p.q = m->dq + (size_t)b0 * d; p.h = m->dh + (size_t)b0 * c.ffn;
+    p.lw = m->dec_d; p.embed = m->embed; p.embed_t = m->embed_t; p.pos = m->dec_pos; p.lnf_w = m->dec_lnf_w; p.lnf_b = m->dec_lnf_b;
+    p.x = m->dx + (size_t)b0 * d; p.q = m->dq + (size_t)b0 * d; p.h = off(m->dh, (int64_t)b0 * c.ffn, esz);
     p.self_kv = off(m->self_kv, (int64_t)b0 * c.dec_layers * 2 * c.max_target_positions * d, esz);
     p.cross_kv = off(m->cross_kv, (int64_t)b0 * c.max_source_positions * c.dec_layers * 2 * d, esz);
     p.part = m->part + (size_t)b0 * c.heads * m->s_max * 68; p.s_max = m->s_max;
+    p.attn16 = off(m->attn16, (int64_t)b0 * d, esz); p.attn_cnt = m->attn_cnt + (size_t)b0 * c.heads;
     p.tokens = m->tokens + (size_t)b0 * c.max_target_positions;
     p.n_prefix = n_prefix; p.max_new = max_new; p.eos = eos; p.suppress = suppress_d;
     p.out_ids = ids_out_d + (size_t)b0 * max_new; p.out_len = len_out_d + b0;
     p.forced = forced_d ? forced_d + (size_t)b0 * max_new : nullptr;
     p.logits_out = nullptr;
     if (logits_out_d) {
-      S2S_REQUIRE(B <= 8, "decode: logits_out requires B <= 8");
+      S2S_REQUIRE(B <= group, "decode: logits_out requires B <= %d", group);
       p.logits_out = logits_out_d;
     }
     p.done = m->done + b0; p.n_done = m->n_done; p.cand_val = m->cand_val + (size_t)b0 * m->ctx->num_sms;

@@ -32,58 +32,72 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 constexpr int HD = 64;
 static_assert(ATT_CHUNK == ATT_CHUNK_KEYS, "chunk size mismatch");
 
-// L2 prefetch of what this warp will read first in the NEXT phase: weight rows of the projection, or its
-// cross-attention K/V chunk (called before the barrier).
-template <typename T, int NB>
+// L2 prefetch of what this warp will read first in the NEXT phase: its first cross-attention block (called
+// between grid_arrive and grid_wait).
+template <typename T>
 __device__ __noinline__ void wd_prefetch(const WhisperDecParams& p, int step, int ph) {
   const int d = p.d, L = p.layers;
-  if (ph < 8 * L && (ph & 7) == 4) {  // this warp's first cross-attention item: 64 keys x (K | V) = 2 x 128 B per key
-    const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, it = dec_first_item();
-    if (it < p.B * p.heads * n_chunks) {
-      const int c = it % n_chunks, bh = it / n_chunks, h = bh % p.heads, b = bh / p.heads;
-      const long long ldc = (long long)L * 2 * d;
-      const T* Kb = reinterpret_cast<const T*>(p.cross_kv) + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc +
-                    (long long)(ph >> 3) * 2 * d + h * HD;
-      const int n_keys = min(ATT_CHUNK, p.n_ctx - c * ATT_CHUNK);
-      prefetch_strided_l2(Kb, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
-      prefetch_strided_l2(Kb + d, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
+  if (ph < 8 * L && (ph & 7) == 4) {
+    const int BH = p.B * p.heads, n_blocks = (p.n_ctx + ATT_BLK - 1) / ATT_BLK;
+    const int S = p.cross_splits, bps = (n_blocks + S - 1) / S;
+    const int it = blockIdx.x;
+    if (it < BH * S) {
+      const int s = it % S, bh = it / S, h = bh % p.heads, b = bh / p.heads;
+      const int blk = s * bps + (threadIdx.x >> 5);
+      if (blk < min((s + 1) * bps, n_blocks)) {
+        const long long ldc = (long long)L * 2 * d;
+        const T* Kb = reinterpret_cast<const T*>(p.cross_kv) + ((long long)b * p.n_ctx + (long long)blk * ATT_BLK) * ldc +
+                      (long long)(ph >> 3) * 2 * d + h * HD;
+        const int n_keys = min(ATT_BLK, p.n_ctx - blk * ATT_BLK);
+        prefetch_strided_l2(Kb, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
+        prefetch_strided_l2(Kb + d, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
+      }
     }
   }
 }
 
-template <typename T, int NB>
-__device__ __noinline__ void wd_self_attn(const WhisperDecParams& p, int layer, int pos) {
-  const int d = p.d, B = p.B, H = p.heads, L = p.layers;
+// self-attention over the pos + 1 cached keys and cross-attention over the n_ctx encoder positions: CTA-level items
+template <typename T>
+__device__ __noinline__ void wd_self_attn(const WhisperDecParams& p, int layer, int pos, float* rec_s) {
+  const int d = p.d, H = p.heads, L = p.layers, warp = threadIdx.x >> 5;
+  constexpr int REC = HD + PART_PAD;
   const T* kcache = reinterpret_cast<const T*>(p.self_kv);
   const long long kv_layer_stride = (long long)p.max_pos * d;
-  const int rec = HD + PART_PAD;
-  const int n_chunks = pos / ATT_CHUNK + 1;
-  const int n_items = B * H * n_chunks;
+  const int n_keys = pos + 1, n_blocks = (n_keys + ATT_BLK - 1) / ATT_BLK, BH = p.B * H;
+  const int S = p.self_splits[n_blocks], bps = (n_blocks + S - 1) / S;
 #pragma unroll 1
-  for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
-    const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
-    const T* Kb = kcache + (((long long)b * L + layer) * 2 + 0) * kv_layer_stride + (long long)c * ATT_CHUNK * d + h * HD;
-    const T* Vb = Kb + kv_layer_stride;
-    const int n_keys = min(ATT_CHUNK, pos + 1 - c * ATT_CHUNK);
-    attend_chunk<T, HD>(p.q + b * d + h * HD, Kb, Vb, d, d, n_keys, p.part + ((long long)(b * H + h) * p.s_max + c) * rec);
+  for (int it = blockIdx.x; it < BH * S; it += gridDim.x) {
+    const int s = it % S, bh = it / S, h = bh % H, b = bh / H;
+    const T* Kb = kcache + (((long long)b * L + layer) * 2 + 0) * kv_layer_stride + h * HD;
+    attend_blocks<T, HD>(p.q + b * d + h * HD, Kb, Kb + kv_layer_stride, d, d, n_keys, s * bps + warp,
+                         min((s + 1) * bps, n_blocks), DEC_WARPS, rec_s + warp * REC);
+    __syncthreads();
+    if (warp == 0)
+      attn_finish_item<T, HD>(rec_s, p.part + (long long)bh * p.s_max * REC, s, S, p.attn_cnt + bh,
+                              reinterpret_cast<T*>(p.attn16) + (long long)b * d + h * HD);
+    __syncthreads();
   }
 }
 
-template <typename T, int NB>
-__device__ __noinline__ void wd_cross_attn(const WhisperDecParams& p, int layer) {
-  const int d = p.d, B = p.B, H = p.heads, L = p.layers;
-  const int rec = HD + PART_PAD;
-  const int n_chunks = (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK;
-  const int n_items = B * H * n_chunks;
+template <typename T>
+__device__ __noinline__ void wd_cross_attn(const WhisperDecParams& p, int layer, float* rec_s) {
+  const int d = p.d, H = p.heads, L = p.layers, warp = threadIdx.x >> 5;
+  constexpr int REC = HD + PART_PAD;
   const long long ldc = (long long)L * 2 * d;
   const T* ckv = reinterpret_cast<const T*>(p.cross_kv);
+  const int n_blocks = (p.n_ctx + ATT_BLK - 1) / ATT_BLK, BH = p.B * H;
+  const int S = p.cross_splits, bps = (n_blocks + S - 1) / S;
 #pragma unroll 1
-  for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
-    const int c = it % n_chunks, bh = it / n_chunks, h = bh % H, b = bh / H;
-    const T* Kb = ckv + ((long long)b * p.n_ctx + (long long)c * ATT_CHUNK) * ldc + (long long)layer * 2 * d + h * HD;
-    const T* Vb = Kb + d;
-    const int n_keys = min(ATT_CHUNK, p.n_ctx - c * ATT_CHUNK);
-    attend_chunk<T, HD>(p.q + b * d + h * HD, Kb, Vb, ldc, ldc, n_keys, p.part + ((long long)(b * H + h) * p.s_max + c) * rec);
+  for (int it = blockIdx.x; it < BH * S; it += gridDim.x) {
+    const int s = it % S, bh = it / S, h = bh % H, b = bh / H;
+    const T* Kb = ckv + (long long)b * p.n_ctx * ldc + (long long)layer * 2 * d + h * HD;
+    attend_blocks<T, HD>(p.q + b * d + h * HD, Kb, Kb + d, ldc, ldc, p.n_ctx, s * bps + warp,
+                         min((s + 1) * bps, n_blocks), DEC_WARPS, rec_s + warp * REC);
+    __syncthreads();
+    if (warp == 0)
+      attn_finish_item<T, HD>(rec_s, p.part + (long long)bh * p.s_max * REC, s, S, p.attn_cnt + bh,
+                              reinterpret_cast<T*>(p.attn16) + (long long)b * d + h * HD);
+    __syncthreads();
   }
 }
 
@@ -98,6 +112,9 @@ __device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos
     __syncthreads();
     if (warp == 0) {
       if (g >= 0) {
+        // bookkeeping operands first: their round trips overlap the candidate loads
+        const int was_done_i = p.done[b];
+        const int forced_tok = p.forced ? p.forced[b * p.max_new + g] : 0;
         float bv = -INFINITY; int bi = 0x7fffffff;
 #pragma unroll 1
         for (int c = lane; c < (int)gridDim.x; c += 32) {
@@ -111,7 +128,7 @@ __device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos
         }
         if (lane == 0) {
           int tok = bi;
-          const bool was_done = p.done[b] != 0;
+          const bool was_done = was_done_i != 0;
           if (was_done) tok = p.eos;
           p.out_ids[b * p.max_new + g] = tok;
           if (!was_done && !p.forced) {
@@ -119,7 +136,7 @@ __device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos
             else if (g == p.max_new - 1) { p.out_len[b] = p.max_new; }
           }
           if (p.forced && g == p.max_new - 1) p.out_len[b] = p.max_new;
-          const int feed = p.forced ? p.forced[b * p.max_new + g] : tok;
+          const int feed = p.forced ? forced_tok : tok;
           if (pos + 1 < p.max_pos) p.tokens[b * p.max_pos + pos + 1] = feed;
           *s_feed = feed;
         }
@@ -143,7 +160,7 @@ __device__ __noinline__ void wd_select(const WhisperDecParams& p, int g, int pos
 template <typename T>
 __device__ __forceinline__ bool wd_gemv_args(const WhisperDecParams& p, int step, int ph, GemvArgs& a) {
   const int L = p.layers, pos = step, d = p.d, B = p.B;
-  a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
+  a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
   a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f;
   if (ph < 8 * L) {
@@ -159,29 +176,33 @@ __device__ __forceinline__ bool wd_gemv_args(const WhisperDecParams& p, int step
       case 2: a.W = w.w_o; a.N = d; a.bias = w.b_o; a.mode = EPI_RESID; a.out = p.x; return true;
       case 3: a.W = w.w_cq; a.N = d; a.bias = w.b_cq; a.mode = EPI_STORE; a.out = p.q; return true;
       case 5: a.W = w.w_co; a.N = d; a.bias = w.b_co; a.mode = EPI_RESID; a.out = p.x; return true;
-      case 6: a.W = w.w_fc1; a.N = p.ffn; a.bias = w.b_fc1; a.mode = EPI_GELU; a.out = p.h; a.ldo = p.ffn; return true;
+      case 6: a.W = w.w_fc1; a.N = p.ffn; a.bias = w.b_fc1; a.mode = EPI_GELU; a.out_h = p.h; a.ldh = p.ffn; return true;
       case 7: a.W = w.w_fc2; a.N = d; a.K = p.ffn; a.bias = w.b_fc2; a.mode = EPI_RESID; a.out = p.x; return true;
       default: return false;
     }
   }
   const int g = step - (p.n_prefix - 1);
   if (ph == 8 * L && g >= 0) {
-    a.W = p.embed; a.N = p.vocab; a.mode = EPI_LOGITS; a.suppress = p.suppress; a.first_step = (g == 0);
+    a.W = p.embed_t; a.N = p.vocab; a.mode = EPI_LOGITS; a.suppress = p.suppress; a.first_step = (g == 0);
     a.logits_out = p.logits_out ? p.logits_out + (long long)g * B * p.vocab : nullptr; a.logits_ld = p.vocab;
     return true;
   }
   return false;
 }
 
+// Shared-memory views of one CTA (see dec_smem_layout)
+template <typename T>
+struct WdSmem {
+  T* xh; float* xs; float* sv; int* si; float* s_red; float* wb; float4* red;
+};
+
 // One phase = (stage inputs into shared memory) + (one shared routine).  Thin: only argument setup is inlined.
-template <typename T, int NB>
-__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, float* xs, float* s_aux, GemvRing& ring,
+template <typename T>
+__device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, const WdSmem<T>& sm, GemvRing& ring,
                                          const GemvArgs* ready, int wb_ready) {
-  float* s_red = s_aux + 2 * DEC_WARPS * NB;
-  float* wb = s_red + 2 * DEC_WARPS;  // LayerNorm weight | bias staged per phase
   const int L = p.layers, pos = step, d = p.d, B = p.B;
-  float best_v = -INFINITY;
-  int best_i = 0x7fffffff;
+  float best_v[2] = {-INFINITY, -INFINITY};
+  int best_i[2] = {0x7fffffff, 0x7fffffff};
   GemvArgs a;
   bool has_gemv = true;
   if (ready) a = *ready; else has_gemv = wd_gemv_args<T>(p, step, ph, a);
@@ -189,67 +210,51 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
     const int layer = ph >> 3;
     const WhisperDecLayer& w = p.lw[layer];
     switch (ph & 7) {
-      case 0: stage_rows(p.x, B, d, xs, 1, w.ln1_w, w.ln1_b, 1e-5f, s_red, wb, wb_ready); break;
-      case 1: wd_self_attn<T, NB>(p, layer, pos); return;
-      case 2:
-        combine_partials_to_smem<HD, 12>(p.part, B, p.heads, p.s_max, pos / ATT_CHUNK + 1, xs);
-        __syncthreads();
-        break;
-      case 3: stage_rows(p.x, B, d, xs, 1, w.ln2_w, w.ln2_b, 1e-5f, s_red, wb, wb_ready); break;
-      case 4: wd_cross_attn<T, NB>(p, layer); return;
-      case 5:
-        combine_partials_to_smem<HD, 12>(p.part, B, p.heads, p.s_max, (p.n_ctx + ATT_CHUNK - 1) / ATT_CHUNK, xs);
-        __syncthreads();
-        break;
-      case 6: stage_rows(p.x, B, d, xs, 1, w.ln3_w, w.ln3_b, 1e-5f, s_red, wb, wb_ready); break;
-      default: stage_rows(p.h, B, p.ffn, xs, 0, nullptr, nullptr, 0.f, s_red, wb); break;
+      case 0: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 1, w.ln1_w, w.ln1_b, 1e-5f, sm.s_red, sm.wb, wb_ready); break;
+      case 1: wd_self_attn<T>(p, layer, pos, reinterpret_cast<float*>(sm.red)); return;
+      case 2: stage_rows_copy<T>(reinterpret_cast<const T*>(p.attn16), B, d, sm.xh); break;
+      case 3: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 1, w.ln2_w, w.ln2_b, 1e-5f, sm.s_red, sm.wb, wb_ready); break;
+      case 4: wd_cross_attn<T>(p, layer, reinterpret_cast<float*>(sm.red)); return;
+      case 5: stage_rows_copy<T>(reinterpret_cast<const T*>(p.attn16), B, d, sm.xh); break;
+      case 6: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 1, w.ln3_w, w.ln3_b, 1e-5f, sm.s_red, sm.wb, wb_ready); break;
+      default: stage_rows_copy<T>(reinterpret_cast<const T*>(p.h), B, p.ffn, sm.xh); break;
     }
-    gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
+    gemv_mma<T>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     return;
   }
   const int g = step - (p.n_prefix - 1);  // index of the token generated at this step
   if (ph == 8 * L) {
     if (!has_gemv) return;
     // final LayerNorm + tied output projection + suppress masks + per-CTA argmax candidates
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    stage_rows(p.x, B, d, xs, 1, p.lnf_w, p.lnf_b, 1e-5f, s_red, wb, wb_ready);
-    gemv_generic<T, NB>(a, smem_u32(xs), B, best_v, best_i, ring);
-    float* sv = s_aux;
-    int* si = reinterpret_cast<int*>(s_aux + DEC_WARPS * NB);
-    if (lane < NB) { sv[warp * NB + lane] = best_v; si[warp * NB + lane] = best_i; }
-    __syncthreads();
-    if (threadIdx.x < B) {
-      const int b = threadIdx.x;
-      float bv = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll 1
-      for (int wv = 0; wv < DEC_WARPS; ++wv) {
-        const float v = sv[wv * NB + b]; const int i = si[wv * NB + b];
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-      }
-      p.cand_val[b * gridDim.x + blockIdx.x] = bv;
-      p.cand_idx[b * gridDim.x + blockIdx.x] = bi;
-    }
+    stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 1, p.lnf_w, p.lnf_b, 1e-5f, sm.s_red, sm.wb, wb_ready);
+    gemv_mma<T>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
+    gemv_argmax_candidates(best_v, best_i, B, sm.sv, sm.si, p.cand_val, p.cand_idx);
   } else {
-    wd_select<T>(p, g, pos, s_aux);
+    wd_select<T>(p, g, pos, sm.sv);
   }
 }
 
-template <typename T, int NB>
+template <typename T>
 __global__ void __launch_bounds__(DEC_THREADS, 1)
 whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, int ph_begin, int ph_end, int coop) {
-  extern __shared__ __align__(16) float smem_f[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ WhisperDecParams sp;
   __shared__ WhisperDecLayer s_layers[32];  // per-layer pointer tables: no global pointer chase inside a phase
   if (threadIdx.x == 0) { sp = p; sp.lw = s_layers; }
   for (int i = threadIdx.x; i < p.layers; i += DEC_THREADS) s_layers[i] = p.lw[i];
   __syncthreads();
-  const int xs_floats = NB * max(p.d, p.ffn);
-  float* xs = smem_f;
-  float* s_aux = smem_f + xs_floats;
+  const DecSmem lay = dec_smem_layout(p.B, p.d, max(p.d, p.ffn), 2 * p.d);
+  WdSmem<T> sm;
+  sm.xh = reinterpret_cast<T*>(smem_raw);
+  sm.xs = reinterpret_cast<float*>(smem_raw + lay.xs_off);
+  sm.sv = reinterpret_cast<float*>(smem_raw + lay.aux_off);
+  sm.si = reinterpret_cast<int*>(smem_raw + lay.si_off);
+  sm.s_red = reinterpret_cast<float*>(smem_raw + lay.red_s_off);
+  sm.wb = reinterpret_cast<float*>(smem_raw + lay.wb_off);
+  sm.red = reinterpret_cast<float4*>(smem_raw + lay.redbuf_off);
   GemvRing ring;
   {
-    const int fixed_floats = xs_floats + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * p.d;
-    unsigned char* rb = reinterpret_cast<unsigned char*>(smem_f) + (((size_t)fixed_floats * 4 + 127) & ~(size_t)127);
+    unsigned char* rb = smem_raw + lay.ring_off;
     const int warp = threadIdx.x >> 5;
     ring.slots = p.ring_slots;
     ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
@@ -266,8 +271,9 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
   unsigned int epoch = 0;
   int trace_i = 0;
   GemvArgs pre_args;
+  pre_args.K = p.d;
   int pre_tag = -1, wb_tag = -1;  // (step, phase) the prepared arguments / staged norm weights belong to
-  ring.pre_valid = 0; ring.pre_pg = 0; ring.pre_pc = 0; ring.pre_W = nullptr;
+  ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
   const int n_ph = 8 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
@@ -278,21 +284,21 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
                            (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
       unsigned long long* tr = tracing ? sp.trace + ((blockIdx.x == 0 ? 0 : 1) * (long long)sp.trace_cap + trace_i) * 6 : nullptr;
       if (tracing) tr[0] = globaltimer_ns();
-      if (!skip) wd_phase<T, NB>(sp, step, ph, xs, s_aux, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr,
-                                 wb_tag == step * n_ph + ph);
+      if (!skip) wd_phase<T>(sp, step, ph, sm, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr,
+                             wb_tag == step * n_ph + ph);
       if (tracing) tr[4] = globaltimer_ns();
       if (coop && !skip) {
         grid_arrive(p.sync_counter, epoch);
         // ---- between arrive and wait: everything for the NEXT phases that does not depend on other CTAs ----
         int nph = ph + 1, nstep = step;
         if (nph == n_ph) { nph = 0; nstep = step + 1; }
-        if (nstep < step_end) wd_prefetch<T, NB>(sp, nstep, nph);  // cross-attention K/V chunk -> L2
+        if (nstep < step_end) wd_prefetch<T>(sp, nstep, nph);  // cross-attention K/V chunk -> L2
         if (!ring.pre_valid) {
 #pragma unroll 1
           for (int look = 0; look < 3 && nstep < step_end; ++look) {
             const bool skip_n = (nph == 8 * p.layers) && (nstep < p.n_prefix - 1);
             if (!skip_n && wd_gemv_args<T>(sp, nstep, nph, pre_args)) {
-              gemv_prefetch<T>(pre_args, ring);  // first weight units of the next projection -> shared memory
+              gemv_prefetch<T>(pre_args, ring);  // plan + first weight units of the next projection -> shared memory
               pre_tag = nstep * n_ph + nph;
               // its LayerNorm weights -> shared memory (wb is idle until that phase stages its input)
               const float *nw = nullptr, *nb = nullptr;
@@ -302,7 +308,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
                 if (sub == 0) { nw = w.ln1_w; nb = w.ln1_b; } else if (sub == 3) { nw = w.ln2_w; nb = w.ln2_b; }
                 else if (sub == 6) { nw = w.ln3_w; nb = w.ln3_b; }
               } else { nw = sp.lnf_w; nb = sp.lnf_b; }
-              if (nw) { stage_norm_weights(nw, nb, sp.d, s_aux + 2 * DEC_WARPS * NB + 2 * DEC_WARPS); wb_tag = pre_tag; }
+              if (nw) { stage_norm_weights(nw, nb, sp.d, sm.wb); wb_tag = pre_tag; }
               break;
             }
             if (++nph == n_ph) { nph = 0; ++nstep; }
@@ -315,7 +321,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
     }
     if (coop && !p.forced && *reinterpret_cast<volatile int*>(p.n_done) >= p.B) break;
   }
-  gemv_drain<T>(pre_args, ring);  // early exit: never leave a bulk copy in flight
+  gemv_drain(pre_args.K, ring);  // early exit: never leave a bulk copy in flight
 }
 
 template <typename T>
@@ -329,18 +335,26 @@ __global__ void whisper_decode_init_kernel(const WhisperDecParams p) {
     p.done[b] = 0;
     p.out_len[b] = 0;
     if (b == 0) { *p.n_done = 0; *p.sync_counter = 0; }
+    for (int h = 0; h < p.heads; ++h) p.attn_cnt[b * p.heads + h] = 0u;
   }
   for (int i = threadIdx.x; i < p.max_new; i += blockDim.x) p.out_ids[b * p.max_new + i] = p.eos;
 }
 
-template <typename T, int NB>
-int launch_nb(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStream_t stream) {
-  const size_t fixed = (((size_t)NB * (size_t)max(p.d, p.ffn) + 2 * DEC_WARPS * NB + 2 * DEC_WARPS + 2 * (size_t)p.d) * sizeof(float) + 127) & ~(size_t)127;
+template <typename T>
+int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStream_t stream) {
+  const DecSmem lay = dec_smem_layout(p.B, p.d, std::max(p.d, p.ffn), 2 * p.d);
   WhisperDecParams pr = p;
-  pr.ring_slots = (int)std::min<size_t>(4, (220 * 1024 - fixed - 1024) / ((size_t)DEC_WARPS * GV_SLOT_BYTES));
-  S2S_REQUIRE(pr.ring_slots >= 1, "whisper decode: no shared memory left for the weight ring");
-  const size_t smem = fixed + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
-  auto kern = whisper_decode_kernel<T, NB>;
+  pr.ring_slots = dec_ring_slots(lay);
+  {
+    const int BH = p.B * p.heads, grid = ctx->num_sms;
+    pr.cross_splits = attn_best_splits(BH, (p.n_ctx + ATT_BLK - 1) / ATT_BLK, p.s_max, grid);
+    const int nb_max = (p.max_pos + ATT_BLK - 1) / ATT_BLK;
+    S2S_REQUIRE(nb_max < (int)sizeof(pr.self_splits), "whisper decode: max_target_positions %d too large", p.max_pos);
+    for (int nb = 1; nb <= nb_max; ++nb) pr.self_splits[nb] = (unsigned char)attn_best_splits(BH, nb, p.s_max, grid);
+  }
+  S2S_REQUIRE(pr.ring_slots >= 2, "whisper decode: batch %d leaves no shared memory for the weight ring", p.B);
+  const size_t smem = (size_t)lay.ring_off + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
+  auto kern = whisper_decode_kernel<T>;
   S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   whisper_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
   S2S_LAUNCH_CHECK();
@@ -365,25 +379,23 @@ int launch_nb(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStr
   return S2S_OK;
 }
 
-template <typename T>
-int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStream_t stream) {
-  if (p.B <= 1) return launch_nb<T, 1>(ctx, p, debug_phases, stream);
-  if (p.B <= 2) return launch_nb<T, 2>(ctx, p, debug_phases, stream);
-  if (p.B <= 4) return launch_nb<T, 4>(ctx, p, debug_phases, stream);
-  if (p.B <= 8) return launch_nb<T, 8>(ctx, p, debug_phases, stream);
-  s2s_set_error("whisper decode: batch %d > 8 must be split by the caller", p.B);
-  return S2S_ERR_INVALID;
-}
-
 }  // namespace
 
 int whisper_decode_launch(s2s_ctx* ctx, const WhisperDecParams& p, int dtype, int debug_phases, cudaStream_t stream) {
   S2S_REQUIRE(p.d / p.heads == HD, "whisper decode: head_dim must be 64");
   S2S_REQUIRE(p.layers <= 32, "whisper decode: at most 32 decoder layers");
+  S2S_REQUIRE(p.B >= 1 && p.B <= DEC_MAX_B, "whisper decode: batch %d > %d must be split by the caller", p.B, DEC_MAX_B);
+  S2S_REQUIRE(p.d % 64 == 0 && p.ffn % 64 == 0, "whisper decode: d and ffn must be multiples of 64");
   S2S_REQUIRE(p.n_prefix >= 1 && p.max_new >= 1 && p.n_prefix + p.max_new <= p.max_pos,
               "whisper decode: prompt %d + max_new %d exceeds max_target_positions %d", p.n_prefix, p.max_new, p.max_pos);
   if (dtype == S2S_F16) return launch_t<__half>(ctx, p, debug_phases, stream);
   if (dtype == S2S_BF16) return launch_t<__nv_bfloat16>(ctx, p, debug_phases, stream);
   s2s_set_error("whisper decode: unsupported dtype %d", dtype);
   return S2S_ERR_UNSUPPORTED;
+}
+
+int whisper_decode_max_batch(int d, int ffn) {
+  for (int B = DEC_MAX_B; B >= 1; --B)
+    if (dec_ring_slots(dec_smem_layout(B, d, std::max(d, ffn), 2 * d)) >= 2) return B;
+  return 1;
 }

@@ -4,7 +4,7 @@
 
 constexpr int ATT_CHUNK_KEYS = 64;  // keys per attention work item (== ATT_CHUNK in decode_common.cuh)
 
-struct WhisperDecLayer {      // all device pointers; 16-bit weights are [out, in] row-major
+struct WhisperDecLayer {      // all device pointers; 16-bit weights [out, in]: TILED layout (weight_tiles.cu) in the kernel's table
   const void* w_qkv; const float* b_qkv;   // [3d, d]; q rows pre-scaled by head_dim^-0.5, k bias = 0
   const void* w_o;   const float* b_o;     // [d, d]
   const void* w_cq;  const float* b_cq;    // cross-attention q [d, d] (pre-scaled)
@@ -17,17 +17,22 @@ struct WhisperDecLayer {      // all device pointers; 16-bit weights are [out, i
 struct WhisperDecParams {
   int d, heads, layers, ffn, vocab, B, max_pos, n_ctx;
   const WhisperDecLayer* lw;   // [layers] device
-  const void* embed;           // [vocab, d] 16-bit (tied output projection)
+  const void* embed;           // [vocab, d] 16-bit row-major (token embedding lookup)
+  const void* embed_t;         // the same matrix in the tiled layout (tied output projection)
   const float* pos;            // [max_pos, d]
   const float *lnf_w, *lnf_b;
   // state
   float* x;                    // [B, d] residual stream
   float* q;                    // [B, d]
-  float* h;                    // [B, ffn]
+  void* h;                     // [B, ffn] 16-bit (fc1 + GELU output)
   void* self_kv;               // [B][layers][2][max_pos][d] 16-bit
   const void* cross_kv;        // [B * n_ctx, layers * 2 * d] 16-bit
-  float* part;                 // [B][heads][s_max][64 + 4]
+  float* part;                 // [B][heads][s_max][64 + 4] split records of an attention phase
   int s_max;
+  void* attn16;                // [B, d] 16-bit attention output (input of the out-projections)
+  unsigned int* attn_cnt;      // [B * heads] finished splits per (session, head); zero between phases
+  int cross_splits;            // key splits per (session, head) in cross-attention (launcher: attn_best_splits)
+  unsigned char self_splits[32];  // ... in self-attention, indexed by the number of 32-key blocks
   // token bookkeeping
   int* tokens;                 // [B][max_pos]
   int n_prefix, max_new, eos;
@@ -47,3 +52,5 @@ struct WhisperDecParams {
 };
 
 int whisper_decode_launch(s2s_ctx* ctx, const WhisperDecParams& p, int dtype, int debug_phases, cudaStream_t stream);
+// largest batch per launch that keeps >= 2 weight-ring slots per warp in shared memory
+int whisper_decode_max_batch(int d, int ffn);

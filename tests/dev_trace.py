@@ -8,14 +8,15 @@ import bench
 
 name = sys.argv[1] if len(sys.argv) > 1 else "small"
 g = W.WHISPER_GEOMETRIES[name]
-eng = E.WhisperEngine(g.to_dict(), max_batch=1); eng.init_random(1)
+NB = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+eng = E.WhisperEngine(g.to_dict(), max_batch=NB); eng.init_random(1)
 opts = E.WhisperDecodeOptions(prefix=bench.PREFIX, eos_id=-1, max_new_tokens=16, suppress=bench.SUPPRESS, begin_suppress=bench.BEGIN_SUPPRESS)
-pcm = torch.from_numpy(W.synthetic_audio(0, 160000))[None].cuda()
-eng.logmel(pcm, [160000]); eng.encode(1)
-for _ in range(2): eng.decode(1, opts)
+pcm = torch.from_numpy(np.stack([W.synthetic_audio(i, 160000) for i in range(NB)])).cuda()
+eng.logmel(pcm, [160000] * NB); eng.encode(NB)
+for _ in range(2): eng.decode(NB, opts)
 cap = 4000
 tr = torch.zeros((2, cap, 6), dtype=torch.int64, device="cuda")
-eng.set_trace(tr); eng.decode(1, opts); torch.cuda.synchronize(); eng.set_trace(None)
+eng.set_trace(tr); eng.decode(NB, opts); torch.cuda.synchronize(); eng.set_trace(None)
 t = tr.cpu().numpy().astype(np.int64)
 L = g.dec_layers; nph = 8 * L + 2
 names = ["qkv", "self_attn", "self_out", "cross_q", "cross_attn", "cross_out", "fc1", "fc2"]

@@ -100,6 +100,23 @@ def test_two_sessions_of_different_length_decode_together(E):
         assert np.abs(lg[:, s] - refs[s][1][1:]).max() < LOGIT_TOL
 
 
+def test_ten_sessions_decode_together(E):
+    """10 sessions in one persistent launch (sessions 8, 9 sit in the upper half of the tensor-core tile)."""
+    nb = 10
+    g, w, eng = _engine(E, "micro", dtype="float16", max_sessions=nb)
+    rng = np.random.default_rng(11)
+    prompts = [rng.integers(0, g.vocab, 5 + 6 * s) for s in range(nb)]
+    refs = [R.greedy_generate(w, g, p, 5, return_logits=True) for p in prompts]
+    for s, p in enumerate(prompts):
+        eng.prefill(s, p.tolist())
+    first = torch.tensor([r[0][0] for r in refs], dtype=torch.int32, device="cuda")
+    forced = torch.tensor([r[0][1:] for r in refs], dtype=torch.int32, device="cuda")
+    ids, lens, logits = eng.decode(list(range(nb)), first, 4, forced=forced, return_logits=True)
+    lg = logits.cpu().numpy()
+    for s in range(nb):
+        assert np.abs(lg[:, s] - refs[s][1][1:]).max() < TOL["float16"], s
+
+
 def test_eos_stops_generation(E, golden_dir):
     g, w, eng = _engine(E, "micro")
     G = np.load(os.path.join(golden_dir, "llama_micro.npz"))

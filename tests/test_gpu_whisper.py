@@ -203,6 +203,33 @@ def test_batched_ragged_transcribe_matches_oracle(E, golden_dir):
         assert batch[i][:k] == ref[:k]
 
 
+def test_eleven_sessions_in_one_launch_match_oracle(E, golden_dir):
+    """11 sessions per persistent launch (sessions 8..10 use the upper half of the tensor-core tile): forced decode,
+    per-session logits against the oracle."""
+    nb = 11
+    g, w, eng = _engine(E, "micro", max_batch=nb)
+    G = np.load(os.path.join(golden_dir, "whisper_micro.npz"))
+    opts = _opts(E, G, 5)
+    auds = [W.synthetic_audio(100 + i, 160000 if i % 3 else 64000) for i in range(nb)]
+    pcm = np.zeros((nb, 480000), np.float32)
+    for i, a in enumerate(auds):
+        pcm[i, : len(a)] = a
+    eng.logmel(torch.from_numpy(pcm).cuda(), [len(a) for a in auds])
+    eng.encode(nb)
+    refs = []
+    for a in auds:
+        enc = R.encoder_forward(w, g, R.log_mel_spectrogram(a, g.n_mels))
+        refs.append(R.greedy_decode(w, g, enc, opts.prefix, 5, opts.eos_id, list(opts.suppress), list(opts.begin_suppress),
+                                    return_logits=True))
+    forced = torch.tensor(np.stack([np.asarray(r[0][:5]) for r in refs]), dtype=torch.int32, device="cuda")
+    ids, lens, logits = eng.decode(nb, opts, forced=forced, return_logits=True)
+    lg = logits.cpu().numpy()  # [steps, B, vocab]
+    for i, (ref_ids, ref_lg) in enumerate(refs):
+        fin = np.isfinite(ref_lg)
+        assert (np.isfinite(lg[:, i]) == fin).all()
+        assert np.abs(lg[:, i][fin] - ref_lg[fin]).max() < LOGIT_TOL, i
+
+
 def test_eos_stops_row_and_pads(E, golden_dir):
     """Make the golden's 3rd generated token the EOS id: decoding must stop there (len 3) and pad with EOS."""
     g, w, eng = _engine(E, "micro")
