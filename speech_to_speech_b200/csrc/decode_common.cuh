@@ -114,7 +114,7 @@ __host__ __device__ inline DecSmem dec_smem_layout(int B, int d, int kmax, int w
   L.aux_off = xh_bytes;
   L.si_off = L.aux_off + DEC_WARPS * DEC_MAX_B * 4;
   L.red_s_off = L.si_off + DEC_WARPS * DEC_MAX_B * 4;
-  L.wb_off = L.red_s_off + 2 * DEC_WARPS * 4;
+  L.wb_off = L.red_s_off + 2 * DEC_WARPS * DEC_MAX_B * 4;   // s_red: [row iterations <= 16][2][DEC_WARPS]
   L.redbuf_off = (L.wb_off + (unsigned)wb_floats * 4u + 15u) & ~15u;
   L.ring_off = (L.redbuf_off + 2u * DEC_THREADS * 16u + 127u) & ~127u;
   return L;
@@ -135,39 +135,41 @@ static __device__ __forceinline__ void stage_norm_weights(const float* w, const 
   }
 }
 
+// 16-byte asynchronous global -> shared copy through L2 (no registers held while in flight)
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- stage B rows of the fp32 residual stream (produced by other CTAs) into xh, normalised ----------------
-// mode 1: LayerNorm (w, bias); 2: RMSNorm (w).  One-pass statistics (sum, sum of squares) over an fp32 copy in
-// shared memory (xs, B*d floats), then the normalised row is written as 16-bit into xh[b][d + GV_XPAD].
+// mode 1: LayerNorm (w, bias); 2: RMSNorm (w).  All rows land in shared memory (xs, B*d floats) through cp.async:
+// every copy of the phase is in flight at once whatever B is (one L2 round trip, no registers), then one-pass
+// statistics (sum, sum of squares) and the normalised row is written as 16-bit into xh[b][d + GV_XPAD].
 // Ends with a __syncthreads().
 template <typename T>
 static __device__ __noinline__ void stage_rows_norm(const float* x, int B, int d, float* xs, T* xh, int mode, const float* w,
                                                     const float* bias, float eps, float* s_red, float* wb, int wb_ready) {
   const int n = B * d;
-#pragma unroll 1
-  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 8) {
-    const int j = i + DEC_THREADS * 4;
-    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(x + i));
-    float4 v1;
-    if (j < n) v1 = __ldcg(reinterpret_cast<const float4*>(x + j));
-    *reinterpret_cast<float4*>(xs + i) = v0;
-    if (j < n) *reinterpret_cast<float4*>(xs + j) = v1;
-  }
+  const uint32_t xs_s = smem_u32(xs);
+#pragma unroll 4
+  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 4) cp_async16(xs_s + (uint32_t)i * 4, x + i);
   if (!wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
+  cp_async_wait_all();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int wpr = DEC_WARPS;  // warps per row: largest power of two with wpr * B <= DEC_WARPS (min 1)
   while (wpr > 1 && wpr * B > DEC_WARPS) wpr >>= 1;
   const int rows_per_iter = DEC_WARPS / wpr;
   const int xstride = d + GV_XPAD;
+  const float inv_d = 1.f / (float)d;
+  // pass 1: every row's partial statistics (all iterations), ONE barrier; pass 2: normalise
+  const int sub = warp % wpr, rsel = warp / wpr;
 #pragma unroll 1
-  for (int r0 = 0; r0 < B; r0 += rows_per_iter) {
-    const int row = r0 + warp / wpr, sub = warp % wpr, grp = (warp / wpr) * wpr;
-    const bool valid = row < B;
-    const float* xr = xs + row * d;
-    // one pass: sum and sum of squares together (one block reduction); var = E[x^2] - mean^2 in fp32 is accurate
-    // to ~1e-6 * (1 + mean^2/var), far below the stated tolerances for residual-stream statistics
+  for (int r0 = 0, it = 0; r0 < B; r0 += rows_per_iter, ++it) {
+    const int row = r0 + rsel;
     float s1 = 0.f, s2 = 0.f;
-    if (valid) {
+    if (row < B) {
+      const float* xr = xs + row * d;
 #pragma unroll 2
       for (int i = (sub * 32 + lane) * 2; i < d; i += wpr * 64) {
         const float2 v = *reinterpret_cast<const float2*>(xr + i);
@@ -178,14 +180,20 @@ static __device__ __noinline__ void stage_rows_norm(const float* x, int B, int d
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
-    if (lane == 0) { s_red[warp] = s1; s_red[DEC_WARPS + warp] = s2; }
-    __syncthreads();
-    float t1 = 0.f, t2 = 0.f;
-    for (int k = 0; k < wpr; ++k) { t1 += s_red[grp + k]; t2 += s_red[DEC_WARPS + grp + k]; }
-    const float mean = (mode == 1) ? t1 / (float)d : 0.f;
-    const float var = fmaxf(t2 - (float)d * mean * mean, 0.f);
-    const float rstd = rsqrtf(var / (float)d + eps);
-    if (valid) {
+    if (lane == 0) { s_red[it * 2 * DEC_WARPS + warp] = s1; s_red[it * 2 * DEC_WARPS + DEC_WARPS + warp] = s2; }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int r0 = 0, it = 0; r0 < B; r0 += rows_per_iter, ++it) {
+    const int row = r0 + rsel, grp = rsel * wpr;
+    if (row < B) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int k = 0; k < wpr; ++k) { t1 += s_red[it * 2 * DEC_WARPS + grp + k]; t2 += s_red[it * 2 * DEC_WARPS + DEC_WARPS + grp + k]; }
+      const float mean = (mode == 1) ? t1 * inv_d : 0.f;
+      // var = E[x^2] - mean^2 in fp32: accurate to ~1e-6 * (1 + mean^2/var), far below the stated tolerances
+      const float var = fmaxf(t2 * inv_d - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      const float* xr = xs + row * d;
       T* dst = xh + row * xstride;
 #pragma unroll 2
       for (int i = (sub * 32 + lane) * 2; i < d; i += wpr * 64) {
@@ -196,32 +204,26 @@ static __device__ __noinline__ void stage_rows_norm(const float* x, int B, int d
         *reinterpret_cast<uint32_t*>(dst + i) = DT<T>::pack2(y0, y1);
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
 }
 
-// ---- stage B rows of a 16-bit activation (global [B, K], produced by other CTAs) into xh: 16-byte copies ----
+// ---- stage B rows of a 16-bit activation (global [B, K], produced by other CTAs) into xh: cp.async 16-byte
+// copies straight into the padded rows, all in flight together ----
 template <typename T>
 static __device__ __noinline__ void stage_rows_copy(const T* x, int B, int K, T* xh) {
   const int vpr = K >> 3;  // 16-byte vectors per row
   const int n = B * vpr;
-  const int xstride = K + GV_XPAD;
-#pragma unroll 1
-  for (int i = threadIdx.x; i < n; i += DEC_THREADS * 4) {
-    uint4 v[4];
-    int row[4], col[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = i + u * DEC_THREADS;
-      if (idx < n) {
-        row[u] = idx / vpr; col[u] = idx - row[u] * vpr;
-        v[u] = __ldcg(reinterpret_cast<const uint4*>(x + (long long)row[u] * K) + col[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (i + u * DEC_THREADS < n) *(reinterpret_cast<uint4*>(xh + row[u] * xstride) + col[u]) = v[u];
+  const uint32_t xh_s = smem_u32(xh);
+  const uint32_t row_bytes = (uint32_t)(K + GV_XPAD) * 2;
+  int row = threadIdx.x / vpr, col = threadIdx.x - row * vpr;  // (row, col) of vector index i
+#pragma unroll 2
+  for (int i = threadIdx.x; i < n; i += DEC_THREADS) {
+    cp_async16(xh_s + row * row_bytes + (uint32_t)col * 16, reinterpret_cast<const uint4*>(x + (long long)row * K) + col);
+    col += DEC_THREADS;
+    while (col >= vpr) { col -= vpr; ++row; }
   }
+  cp_async_wait_all();
   __syncthreads();
 }
 
@@ -604,16 +606,27 @@ __device__ __forceinline__ void gemv_argmax_candidates(float (&best_v)[2], int (
 // instead of one record per 64 keys, which at 16 sessions made every CTA re-read 1.2 MB of records per layer.
 constexpr int ATT_BLK = 32;
 
-// Key splits per (session, head).  A warp walks its 32-key blocks serially (one memory round trip each), so the
-// phase time is ~ (items per CTA) x (blocks per warp per item + ~1 for the in-CTA merge); pick the split count that
-// minimises it, smallest on ties (fewer records to merge).  Bounded by the blocks, the record storage and 16.
-__host__ __device__ inline int attn_best_splits(int BH, int n_blocks, int s_max, int grid) {
+// How an attention phase is cut into items.  A warp walks its 32-key blocks serially (one memory round trip each).
+//   CTA-level item  = (session, head, split): the 8 warps stride over the split's blocks, merge in shared memory;
+//                     best when sessions x heads is small (few, short items; 1 block per warp at batch 1).
+//   warp-level item = (session, head, split) owned by ONE warp, no CTA synchronisation at all; best when
+//                     sessions x heads x splits can occupy every warp of the grid (large batches).
+// Either way a split leaves one record and the last split to finish merges them (attn_finish_item).  The plan
+// minimises  rounds x (serial blocks per item + ~2 block-times of finishing), CTA-level on ties.
+// Returns splits | (warp_level << 7); splits <= 16 (CTA) / 32 (warp), bounded by the blocks and the record storage.
+constexpr int ATTN_WARP_LEVEL = 0x80;
+__host__ __device__ inline int attn_plan(int BH, int n_blocks, int s_max, int grid) {
   int best = 1, best_cost = 0x7fffffff;
-  const int cap = n_blocks < s_max ? (n_blocks < 16 ? n_blocks : 16) : (s_max < 16 ? s_max : 16);
-  for (int S = 1; S <= cap; ++S) {
+  const int lim = n_blocks < s_max ? n_blocks : s_max;
+  for (int S = 1; S <= (lim < 16 ? lim : 16); ++S) {
     const int bps = (n_blocks + S - 1) / S;
-    const int cost = ((BH * S + grid - 1) / grid) * ((bps + DEC_WARPS - 1) / DEC_WARPS + 1);
+    const int cost = ((BH * S + grid - 1) / grid) * ((bps + DEC_WARPS - 1) / DEC_WARPS + 2);
     if (cost < best_cost) { best_cost = cost; best = S; }
+  }
+  for (int S = 1; S <= (lim < 32 ? lim : 32); ++S) {
+    const int bpi = (n_blocks + S - 1) / S;
+    const int cost = ((BH * S + grid * DEC_WARPS - 1) / (grid * DEC_WARPS)) * (bpi + 2);
+    if (cost < best_cost) { best_cost = cost; best = S | ATTN_WARP_LEVEL; }
   }
   return best;
 }
@@ -730,18 +743,19 @@ __device__ __noinline__ void attend_blocks(const float* q /*global fp32 [HD]*/, 
 }
 
 // ---- finishing an attention item (warp 0 of the CTA) ---------------------------------------------------------
-// Merge the DEC_WARPS warp records (shared memory).  splits == 1: the item is the whole (session, head): write the
+// Merge the n_rec warp records in shared memory (DEC_WARPS for a CTA-level item, 1 for a warp-level item).  splits == 1: the item is the whole (session, head): write the
 // normalised head output as 16-bit into out16[HD].  Otherwise write the global record, then count the item in
 // cnt (one counter per (session, head)); the CTA that completes the count merges the `splits` records and writes
 // out16 -- so the consumer phase just copies B x d 16-bit values instead of every CTA re-merging every record.
 // The grid barrier that ends the phase orders out16 before its readers; the counter is reset for the next use.
 template <typename T, int HD>
-__device__ __forceinline__ void attn_finish_item(const float* rec_s, float* part_bh /*[s_max][REC]*/, int s, int splits,
-                                                 unsigned int* cnt, T* out16) {
+__device__ __forceinline__ void attn_finish_item(const float* rec_s, int n_rec /*DEC_WARPS or 1*/, float* part_bh /*[s_max][REC]*/,
+                                                 int s, int splits, unsigned int* cnt, T* out16) {
   constexpr int REC = HD + PART_PAD, DPL = HD / 32;
   const int lane = threadIdx.x & 31;
+  __syncwarp();
   float mw = -INFINITY, lw = 0.f;
-  if (lane < DEC_WARPS) { mw = rec_s[lane * REC + HD]; lw = rec_s[lane * REC + HD + 1]; }
+  if (lane < n_rec) { mw = rec_s[lane * REC + HD]; lw = rec_s[lane * REC + HD + 1]; }
   const float M = warp_max(mw);
   const float wt = (mw > -INFINITY) ? __expf(mw - M) : 0.f;  // empty warp records (and an all-empty item) weigh 0
   const float den = warp_sum(lw * wt);
@@ -750,9 +764,11 @@ __device__ __forceinline__ void attn_finish_item(const float* rec_s, float* part
   for (int i = 0; i < DPL; ++i) o[i] = 0.f;
 #pragma unroll
   for (int w = 0; w < DEC_WARPS; ++w) {
-    const float ww = __shfl_sync(0xffffffffu, wt, w);
+    if (w < n_rec) {
+      const float ww = __shfl_sync(0xffffffffu, wt, w);
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) o[i] = fmaf(rec_s[w * REC + lane + 32 * i], ww, o[i]);
+      for (int i = 0; i < DPL; ++i) o[i] = fmaf(rec_s[w * REC + lane + 32 * i], ww, o[i]);
+    }
   }
   if (splits == 1) {
     const float inv = 1.f / den;
@@ -773,7 +789,7 @@ __device__ __forceinline__ void attn_finish_item(const float* rec_s, float* part
   }
   prev = __shfl_sync(0xffffffffu, prev, 0);
   if (prev != (unsigned)splits - 1) return;
-  // last split of this (session, head): merge the records (splits <= 16: one lane per record)
+  // last split of this (session, head): merge the records (splits <= 32: one lane per record)
   float mc = -INFINITY, lc = 0.f;
   if (lane < splits) {
     const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_bh + (long long)lane * REC + HD));

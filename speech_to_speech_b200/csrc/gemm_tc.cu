@@ -45,6 +45,7 @@ struct EpiParams {
   int resid_mode;
   long long out_batch_rows;
   long long out_row_offset;
+  int head_major_rows;  // > 0: out_h is [row / hmr][N / 64][hmr][64] (64-column blocks contiguous per row range)
   int M, N, K;
 };
 
@@ -184,6 +185,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (ep.out_h) {
           T* dst = reinterpret_cast<T*>(ep.out_h) + orow * ep.ldo_h + n0;
+          if (ep.head_major_rows > 0) {
+            const long long ob = orow / ep.head_major_rows, ot = orow - ob * ep.head_major_rows;
+            dst = reinterpret_cast<T*>(ep.out_h) + ((ob * (ep.N >> 6) + (n0 >> 6)) * ep.head_major_rows + ot) * 64 + (n0 & 63);
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 q;
@@ -254,7 +259,7 @@ int launch_impl(s2s_ctx* ctx, const GemmProblem& p, cudaStream_t stream) {
   EpiParams ep;
   ep.bias = p.bias; ep.act = p.act; ep.out_h = p.out_h; ep.ldo_h = p.ldo_h; ep.out_f = p.out_f; ep.ldo_f = p.ldo_f;
   ep.resid = p.resid; ep.ld_resid = p.ld_resid; ep.resid_mode = p.resid_mode;
-  ep.out_batch_rows = p.out_batch_rows; ep.out_row_offset = p.out_row_offset;
+  ep.out_batch_rows = p.out_batch_rows; ep.out_row_offset = p.out_row_offset; ep.head_major_rows = p.head_major_rows;
   ep.M = p.M; ep.N = p.N; ep.K = p.K;
 
   static bool attr_set = false;  // per (T,BN) instantiation

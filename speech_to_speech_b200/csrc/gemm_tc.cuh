@@ -27,6 +27,9 @@ struct GemmProblem {
   int32_t resid_mode;   // 1: same row index as the output, 2: row index = m (broadcast over batch)
   int64_t out_batch_rows; // output row = b * out_batch_rows + out_row_offset + m
   int64_t out_row_offset;
+  // > 0: out_h is written as [row / R][N / 64][R][64] (R = head_major_rows): every 64-column block (one attention head)
+  // of a row range is contiguous -- the layout the decode kernels stream K/V in.  0: plain row-major with ldo_h.
+  int32_t head_major_rows;
 };
 
 int gemm_tc_launch(s2s_ctx* ctx, const GemmProblem& p, int dtype, cudaStream_t stream);

@@ -23,28 +23,37 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
   return t;
 }
 
-// GQA attention over each session's cached keys: CTA-level items (session, q head, key split); see decode_common.cuh
+// GQA attention over each session's cached keys; items (session, q head, key split) per attn_plan (decode_common.cuh)
 template <typename T, int HD>
 __device__ __noinline__ void ld_attn(const LlamaDecParams& p, int layer, int step, float* rec_s) {
   const int H = p.heads, grp = p.heads / p.kv_heads, warp = threadIdx.x >> 5;
   const int kvd = p.kv_heads * HD;
   constexpr int REC = HD + PART_PAD;
   const int n_blocks = (p.max_len + step + ATT_BLK - 1) / ATT_BLK, BH = p.B * H;  // longest session
-  const int S = attn_best_splits(BH, n_blocks, p.s_max, (int)gridDim.x), bps = (n_blocks + S - 1) / S;
+  const int plan = attn_plan(BH, n_blocks, p.s_max, (int)gridDim.x);
+  const int S = plan & 0x7f, bps = (n_blocks + S - 1) / S;
+  const bool wl = plan & ATTN_WARP_LEVEL;
   const T* kv = reinterpret_cast<const T*>(p.kv);
 #pragma unroll 1
-  for (int it = blockIdx.x; it < BH * S; it += gridDim.x) {
+  for (int it = wl ? dec_first_item() : (int)blockIdx.x; it < BH * S; it += wl ? dec_item_stride() : (int)gridDim.x) {
     const int s = it % S, bh = it / S, h = bh % H, b = bh / H;
     const int len = __ldcg(p.pos + b) + 1;  // this session's keys; splits past its end produce empty records
     const int nb = (len + ATT_BLK - 1) / ATT_BLK;
     const T* Kb = kv + (long long)__ldg(p.slot + b) * p.kv_slot_stride + (long long)layer * p.kv_layer_stride + (h / grp) * HD;
-    attend_blocks<T, HD>(p.q + (long long)b * H * HD + h * HD, Kb, Kb + p.kv_which_stride, kvd, kvd, len, s * bps + warp,
-                         min((s + 1) * bps, nb), DEC_WARPS, rec_s + warp * REC);
-    __syncthreads();
-    if (warp == 0)
-      attn_finish_item<T, HD>(rec_s, p.part + (long long)bh * p.s_max * REC, s, S, p.attn_cnt + bh,
-                              reinterpret_cast<T*>(p.attn16) + (long long)b * H * HD + h * HD);
-    __syncthreads();
+    float* part_bh = p.part + (long long)bh * p.s_max * REC;
+    T* out16 = reinterpret_cast<T*>(p.attn16) + (long long)b * H * HD + h * HD;
+    if (wl) {
+      attend_blocks<T, HD>(p.q + (long long)b * H * HD + h * HD, Kb, Kb + p.kv_which_stride, kvd, kvd, len, s * bps,
+                           min((s + 1) * bps, nb), 1, rec_s + warp * REC);
+      attn_finish_item<T, HD>(rec_s + warp * REC, 1, part_bh, s, S, p.attn_cnt + bh, out16);
+      __syncwarp();
+    } else {
+      attend_blocks<T, HD>(p.q + (long long)b * H * HD + h * HD, Kb, Kb + p.kv_which_stride, kvd, kvd, len, s * bps + warp,
+                           min((s + 1) * bps, nb), DEC_WARPS, rec_s + warp * REC);
+      __syncthreads();
+      if (warp == 0) attn_finish_item<T, HD>(rec_s, DEC_WARPS, part_bh, s, S, p.attn_cnt + bh, out16);
+      __syncthreads();
+    }
   }
 }
 

@@ -539,6 +539,7 @@ int s2s_whisper_encode(s2s_whisper* m, const float* mel_in_d, int32_t B, float* 
   {
     GemmProblem p = plain_gemm(m->enc_out, d, m->ckv_w, d, rows, c.dec_layers * 2 * d, d);
     p.bias = m->ckv_b; p.out_h = m->cross_kv; p.ldo_h = (int64_t)c.dec_layers * 2 * d;
+    p.head_major_rows = T;  // [b][layer][k|v][head][t][64]: a head's keys are contiguous for the decoder
     S2S_CHECK(gemm(m, p, st));
   }
   m->last_B = B;
@@ -571,7 +572,7 @@ static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, in
     p.lw = m->dec_d; p.embed = m->embed; p.embed_t = m->embed_t; p.pos = m->dec_pos; p.lnf_w = m->dec_lnf_w; p.lnf_b = m->dec_lnf_b;
     p.x = m->dx + (size_t)b0 * d; p.q = m->dq + (size_t)b0 * d; p.h = off(m->dh, (int64_t)b0 * c.ffn, esz);
     p.self_kv = off(m->self_kv, (int64_t)b0 * c.dec_layers * 2 * c.max_target_positions * d, esz);
-    p.cross_kv = off(m->cross_kv, (int64_t)b0 * c.max_source_positions * c.dec_layers * 2 * d, esz);
+    p.cross_kv = off(m->cross_kv, (int64_t)b0 * c.max_source_positions * c.dec_layers * 2 * d, esz);  // head-major
     p.part = m->part + (size_t)b0 * c.heads * m->s_max * 68; p.s_max = m->s_max;
     p.attn16 = off(m->attn16, (int64_t)b0 * d, esz); p.attn_cnt = m->attn_cnt + (size_t)b0 * c.heads;
     p.tokens = m->tokens + (size_t)b0 * c.max_target_positions;

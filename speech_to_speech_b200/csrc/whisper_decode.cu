@@ -36,69 +36,78 @@ static_assert(ATT_CHUNK == ATT_CHUNK_KEYS, "chunk size mismatch");
 // between grid_arrive and grid_wait).
 template <typename T>
 __device__ __noinline__ void wd_prefetch(const WhisperDecParams& p, int step, int ph) {
-  const int d = p.d, L = p.layers;
+  const int L = p.layers;
   if (ph < 8 * L && (ph & 7) == 4) {
     const int BH = p.B * p.heads, n_blocks = (p.n_ctx + ATT_BLK - 1) / ATT_BLK;
-    const int S = p.cross_splits, bps = (n_blocks + S - 1) / S;
-    const int it = blockIdx.x;
+    const int S = p.cross_plan & 0x7f, bps = (n_blocks + S - 1) / S;
+    const bool wl = p.cross_plan & ATTN_WARP_LEVEL;
+    const int it = wl ? dec_first_item() : (int)blockIdx.x;
     if (it < BH * S) {
       const int s = it % S, bh = it / S, h = bh % p.heads, b = bh / p.heads;
-      const int blk = s * bps + (threadIdx.x >> 5);
+      const int blk = s * bps + (wl ? 0 : (int)(threadIdx.x >> 5));
       if (blk < min((s + 1) * bps, n_blocks)) {
-        const long long ldc = (long long)L * 2 * d;
-        const T* Kb = reinterpret_cast<const T*>(p.cross_kv) + ((long long)b * p.n_ctx + (long long)blk * ATT_BLK) * ldc +
-                      (long long)(ph >> 3) * 2 * d + h * HD;
+        const long long head_elems = (long long)p.n_ctx * HD;
+        const T* Kb = reinterpret_cast<const T*>(p.cross_kv) +
+                      (((long long)b * L + (ph >> 3)) * 2 * p.heads + h) * head_elems + (long long)blk * ATT_BLK * HD;
         const int n_keys = min(ATT_BLK, p.n_ctx - blk * ATT_BLK);
-        prefetch_strided_l2(Kb, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
-        prefetch_strided_l2(Kb + d, ldc * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
+        prefetch_strided_l2(Kb, HD * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
+        prefetch_strided_l2(Kb + p.heads * head_elems, HD * (long long)sizeof(T), n_keys, HD * (int)sizeof(T));
       }
     }
   }
 }
 
-// self-attention over the pos + 1 cached keys and cross-attention over the n_ctx encoder positions: CTA-level items
+// One attention phase over `n_keys` keys of every (session, head), cut into items by `plan` (attn_plan).
+// Kbase(b, h) / the K->V offset / the row stride describe the cache; rec_s: DEC_WARPS records of shared memory.
 template <typename T>
-__device__ __noinline__ void wd_self_attn(const WhisperDecParams& p, int layer, int pos, float* rec_s) {
-  const int d = p.d, H = p.heads, L = p.layers, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void wd_attn_items(const WhisperDecParams& p, int plan, int n_keys, const T* kv0, long long b_stride,
+                                              long long h_stride, long long v_off, long long ld, float* rec_s) {
+  const int d = p.d, H = p.heads, warp = threadIdx.x >> 5;
   constexpr int REC = HD + PART_PAD;
-  const T* kcache = reinterpret_cast<const T*>(p.self_kv);
-  const long long kv_layer_stride = (long long)p.max_pos * d;
-  const int n_keys = pos + 1, n_blocks = (n_keys + ATT_BLK - 1) / ATT_BLK, BH = p.B * H;
-  const int S = p.self_splits[n_blocks], bps = (n_blocks + S - 1) / S;
+  const int n_blocks = (n_keys + ATT_BLK - 1) / ATT_BLK, BH = p.B * H;
+  const int S = plan & 0x7f, bps = (n_blocks + S - 1) / S;
+  if (plan & ATTN_WARP_LEVEL) {
+#pragma unroll 1
+    for (int it = dec_first_item(); it < BH * S; it += dec_item_stride()) {
+      const int s = it % S, bh = it / S, h = bh % H, b = bh / H;
+      const T* Kb = kv0 + b * b_stride + h * h_stride;
+      attend_blocks<T, HD>(p.q + b * d + h * HD, Kb, Kb + v_off, ld, ld, n_keys, s * bps, min((s + 1) * bps, n_blocks), 1,
+                           rec_s + warp * REC);
+      attn_finish_item<T, HD>(rec_s + warp * REC, 1, p.part + (long long)bh * p.s_max * REC, s, S, p.attn_cnt + bh,
+                              reinterpret_cast<T*>(p.attn16) + (long long)b * d + h * HD);
+      __syncwarp();
+    }
+    return;
+  }
 #pragma unroll 1
   for (int it = blockIdx.x; it < BH * S; it += gridDim.x) {
     const int s = it % S, bh = it / S, h = bh % H, b = bh / H;
-    const T* Kb = kcache + (((long long)b * L + layer) * 2 + 0) * kv_layer_stride + h * HD;
-    attend_blocks<T, HD>(p.q + b * d + h * HD, Kb, Kb + kv_layer_stride, d, d, n_keys, s * bps + warp,
-                         min((s + 1) * bps, n_blocks), DEC_WARPS, rec_s + warp * REC);
+    const T* Kb = kv0 + b * b_stride + h * h_stride;
+    attend_blocks<T, HD>(p.q + b * d + h * HD, Kb, Kb + v_off, ld, ld, n_keys, s * bps + warp, min((s + 1) * bps, n_blocks),
+                         DEC_WARPS, rec_s + warp * REC);
     __syncthreads();
     if (warp == 0)
-      attn_finish_item<T, HD>(rec_s, p.part + (long long)bh * p.s_max * REC, s, S, p.attn_cnt + bh,
+      attn_finish_item<T, HD>(rec_s, DEC_WARPS, p.part + (long long)bh * p.s_max * REC, s, S, p.attn_cnt + bh,
                               reinterpret_cast<T*>(p.attn16) + (long long)b * d + h * HD);
     __syncthreads();
   }
 }
 
+// self-attention over the pos + 1 cached keys: cache [b][layer][k|v][pos][d]
+template <typename T>
+__device__ __noinline__ void wd_self_attn(const WhisperDecParams& p, int layer, int pos, float* rec_s) {
+  const long long kvs = (long long)p.max_pos * p.d;
+  const T* kv0 = reinterpret_cast<const T*>(p.self_kv) + (long long)layer * 2 * kvs;
+  wd_attn_items<T>(p, p.self_plan[(pos + ATT_BLK) / ATT_BLK], pos + 1, kv0, (long long)p.layers * 2 * kvs, HD, kvs, p.d, rec_s);
+}
+
+// cross-attention over the n_ctx encoder positions: cache [b][layer][k|v][head][t][64]
 template <typename T>
 __device__ __noinline__ void wd_cross_attn(const WhisperDecParams& p, int layer, float* rec_s) {
-  const int d = p.d, H = p.heads, L = p.layers, warp = threadIdx.x >> 5;
-  constexpr int REC = HD + PART_PAD;
-  const long long ldc = (long long)L * 2 * d;
-  const T* ckv = reinterpret_cast<const T*>(p.cross_kv);
-  const int n_blocks = (p.n_ctx + ATT_BLK - 1) / ATT_BLK, BH = p.B * H;
-  const int S = p.cross_splits, bps = (n_blocks + S - 1) / S;
-#pragma unroll 1
-  for (int it = blockIdx.x; it < BH * S; it += gridDim.x) {
-    const int s = it % S, bh = it / S, h = bh % H, b = bh / H;
-    const T* Kb = ckv + (long long)b * p.n_ctx * ldc + (long long)layer * 2 * d + h * HD;
-    attend_blocks<T, HD>(p.q + b * d + h * HD, Kb, Kb + d, ldc, ldc, p.n_ctx, s * bps + warp,
-                         min((s + 1) * bps, n_blocks), DEC_WARPS, rec_s + warp * REC);
-    __syncthreads();
-    if (warp == 0)
-      attn_finish_item<T, HD>(rec_s, p.part + (long long)bh * p.s_max * REC, s, S, p.attn_cnt + bh,
-                              reinterpret_cast<T*>(p.attn16) + (long long)b * d + h * HD);
-    __syncthreads();
-  }
+  const long long head_elems = (long long)p.n_ctx * HD;
+  const T* kv0 = reinterpret_cast<const T*>(p.cross_kv) + (long long)layer * 2 * p.heads * head_elems;
+  wd_attn_items<T>(p, p.cross_plan, p.n_ctx, kv0, (long long)p.layers * 2 * p.heads * head_elems, head_elems,
+                   p.heads * head_elems, HD, rec_s);
 }
 
 // global argmax, EOS / length bookkeeping, next-token embedding
@@ -199,7 +208,7 @@ struct WdSmem {
 // One phase = (stage inputs into shared memory) + (one shared routine).  Thin: only argument setup is inlined.
 template <typename T>
 __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, int ph, const WdSmem<T>& sm, GemvRing& ring,
-                                         const GemvArgs* ready, int wb_ready) {
+                                         const GemvArgs* ready, int wb_ready, unsigned long long* tr) {
   const int L = p.layers, pos = step, d = p.d, B = p.B;
   float best_v[2] = {-INFINITY, -INFINITY};
   int best_i[2] = {0x7fffffff, 0x7fffffff};
@@ -219,6 +228,7 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
       case 6: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 1, w.ln3_w, w.ln3_b, 1e-5f, sm.s_red, sm.wb, wb_ready); break;
       default: stage_rows_copy<T>(reinterpret_cast<const T*>(p.h), B, p.ffn, sm.xh); break;
     }
+    if (tr) tr[1] = globaltimer_ns();  // inputs staged
     gemv_mma<T>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     return;
   }
@@ -285,7 +295,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
       unsigned long long* tr = tracing ? sp.trace + ((blockIdx.x == 0 ? 0 : 1) * (long long)sp.trace_cap + trace_i) * 6 : nullptr;
       if (tracing) tr[0] = globaltimer_ns();
       if (!skip) wd_phase<T>(sp, step, ph, sm, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr,
-                             wb_tag == step * n_ph + ph);
+                             wb_tag == step * n_ph + ph, tr);
       if (tracing) tr[4] = globaltimer_ns();
       if (coop && !skip) {
         grid_arrive(p.sync_counter, epoch);
@@ -347,10 +357,10 @@ int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStre
   pr.ring_slots = dec_ring_slots(lay);
   {
     const int BH = p.B * p.heads, grid = ctx->num_sms;
-    pr.cross_splits = attn_best_splits(BH, (p.n_ctx + ATT_BLK - 1) / ATT_BLK, p.s_max, grid);
+    pr.cross_plan = attn_plan(BH, (p.n_ctx + ATT_BLK - 1) / ATT_BLK, p.s_max, grid);
     const int nb_max = (p.max_pos + ATT_BLK - 1) / ATT_BLK;
-    S2S_REQUIRE(nb_max < (int)sizeof(pr.self_splits), "whisper decode: max_target_positions %d too large", p.max_pos);
-    for (int nb = 1; nb <= nb_max; ++nb) pr.self_splits[nb] = (unsigned char)attn_best_splits(BH, nb, p.s_max, grid);
+    S2S_REQUIRE(nb_max < (int)sizeof(pr.self_plan), "whisper decode: max_target_positions %d too large", p.max_pos);
+    for (int nb = 1; nb <= nb_max; ++nb) pr.self_plan[nb] = (unsigned char)attn_plan(BH, nb, p.s_max, grid);
   }
   S2S_REQUIRE(pr.ring_slots >= 2, "whisper decode: batch %d leaves no shared memory for the weight ring", p.B);
   const size_t smem = (size_t)lay.ring_off + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;

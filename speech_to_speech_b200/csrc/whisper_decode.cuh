@@ -26,13 +26,13 @@ struct WhisperDecParams {
   float* q;                    // [B, d]
   void* h;                     // [B, ffn] 16-bit (fc1 + GELU output)
   void* self_kv;               // [B][layers][2][max_pos][d] 16-bit
-  const void* cross_kv;        // [B * n_ctx, layers * 2 * d] 16-bit
+  const void* cross_kv;        // [B][layers][k|v][heads][n_ctx][64] 16-bit (head-major: GEMM epilogue head_major_rows)
   float* part;                 // [B][heads][s_max][64 + 4] split records of an attention phase
   int s_max;
   void* attn16;                // [B, d] 16-bit attention output (input of the out-projections)
   unsigned int* attn_cnt;      // [B * heads] finished splits per (session, head); zero between phases
-  int cross_splits;            // key splits per (session, head) in cross-attention (launcher: attn_best_splits)
-  unsigned char self_splits[32];  // ... in self-attention, indexed by the number of 32-key blocks
+  int cross_plan;              // item plan of the cross-attention phases (launcher: attn_plan)
+  unsigned char self_plan[32]; // ... of self-attention, indexed by the number of 32-key blocks
   // token bookkeeping
   int* tokens;                 // [B][max_pos]
   int n_prefix, max_new, eos;

@@ -28,8 +28,8 @@ for cta in (0, 1):
     seg = slice(idx, idx + 4 * nph)
     for k in range(8):
         sel = [idx + s * nph + l * 8 + k for s in range(4) for l in range(L)]
-        seg = [np.where(t[cta, sel, j] > 0, t[cta, sel, j] - t[cta, sel, 0], 0).mean() for j in (1, 2, 3)]
-        print(f"  {names[k]:10s} body {body[sel].mean():8.0f}  barrier {bar[sel].mean():8.0f}   [args {seg[0]:5.0f} | staged {seg[1]:5.0f} | gemv done {seg[2]:5.0f}]")
+        stg = np.where(t[cta, sel, 1] > 0, t[cta, sel, 1] - t[cta, sel, 0], 0).mean()
+        print(f"  {names[k]:10s} body {body[sel].mean():8.0f}  barrier {bar[sel].mean():8.0f}   [inputs staged after {stg:5.0f}]")
     sel = [idx + s * nph + 8 * L for s in range(4)]
     print(f"  {'logits':10s} body {body[sel].mean():8.0f}  barrier {bar[sel].mean():8.0f}")
     sel = [idx + s * nph + 8 * L + 1 for s in range(4)]
