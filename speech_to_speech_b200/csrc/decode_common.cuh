@@ -30,14 +30,45 @@ __device__ __forceinline__ void grid_arrive(unsigned int* counter, unsigned int&
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
   }
 }
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Polling the counter costs one L2 round trip (~0.7 us) per sample; with a single load in flight the release is
+// noticed on average half a round trip late.  Thread 0 therefore keeps FOUR relaxed loads in flight, issued a
+// quarter round trip apart; the pipeline is self-clocking (each consumed load is re-issued at once), so the counter
+// is sampled every ~0.18 us.  An acquire fence after the successful sample orders the other CTAs' data.
 __device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int epoch_thread0) {
   if (threadIdx.x == 0) {
     const unsigned int target = epoch_thread0 * gridDim.x;
-    unsigned int v, spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      if (++spins > (1u << 28)) __trap();
-    } while (v < target);
+    unsigned int v0 = ld_relaxed_gpu(counter), v1 = 0, v2 = 0, v3 = 0;
+    if (v0 < target) {
+      long long t = clock64();
+      while (clock64() - t < 330) {}
+      v1 = ld_relaxed_gpu(counter);
+      t = clock64();
+      while (clock64() - t < 330) {}
+      v2 = ld_relaxed_gpu(counter);
+      t = clock64();
+      while (clock64() - t < 330) {}
+      v3 = ld_relaxed_gpu(counter);
+      unsigned int spins = 0;
+      while (true) {
+        if (v0 >= target) break;
+        v0 = ld_relaxed_gpu(counter);
+        if (v1 >= target) break;
+        v1 = ld_relaxed_gpu(counter);
+        if (v2 >= target) break;
+        v2 = ld_relaxed_gpu(counter);
+        if (v3 >= target) break;
+        v3 = ld_relaxed_gpu(counter);
+        if (++spins > (1u << 26)) __trap();
+      }
+    }
+    // No fence here (fence.acq_rel.gpu = MEMBAR.SC.GPU + L1 invalidate, ~1 us, and it would wait for the polls still
+    // in flight): every read of another CTA's data is an L2 access (ld.global.cg / cp.async.cg / bulk copy) issued
+    // after the bar.sync below, and the producers' red.release made their data visible at L2 before the count.
   }
   __syncthreads();
 }
@@ -126,20 +157,23 @@ inline int dec_ring_slots(const DecSmem& L) {
   return (int)(s > 4 ? 4 : s);
 }
 
-// Norm weights of a phase (w [| bias] -> wb[d (+ d)]); callable ahead of time between grid_arrive and grid_wait.
-static __device__ __forceinline__ void stage_norm_weights(const float* w, const float* bias, int d, float* wb) {
-#pragma unroll 1
-  for (int i = threadIdx.x * 4; i < d; i += DEC_THREADS * 4) {
-    *reinterpret_cast<float4*>(wb + i) = __ldg(reinterpret_cast<const float4*>(w + i));
-    if (bias) *reinterpret_cast<float4*>(wb + d + i) = __ldg(reinterpret_cast<const float4*>(bias + i));
-  }
-}
-
 // 16-byte asynchronous global -> shared copy through L2 (no registers held while in flight)
 __device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Norm weights of a phase (w [| bias] -> wb[d (+ d)]), asynchronous: callable between grid_arrive and grid_wait
+// without putting their L2 round trip on the barrier's critical path; they are complete after the consumer's
+// cp_async_wait_all() + __syncthreads() (stage_rows_norm).
+static __device__ __forceinline__ void stage_norm_weights(const float* w, const float* bias, int d, float* wb) {
+  const uint32_t wb_s = smem_u32(wb);
+#pragma unroll 1
+  for (int i = threadIdx.x * 4; i < d; i += DEC_THREADS * 4) {
+    cp_async16(wb_s + (uint32_t)i * 4, w + i);
+    if (bias) cp_async16(wb_s + (uint32_t)(d + i) * 4, bias + i);
+  }
+}
 
 // ---- stage B rows of the fp32 residual stream (produced by other CTAs) into xh, normalised ----------------
 // mode 1: LayerNorm (w, bias); 2: RMSNorm (w).  All rows land in shared memory (xs, B*d floats) through cp.async:
@@ -260,6 +294,7 @@ struct GemvArgs {
   // cache element (b, c): kv0 + which*kv_which + slot[b]*kv_slot + pos[b]*kv_ld + c ; rope[pos][j] = (cos, sin)
   const int* pos; const int* slot; long long kv_slot; int kv_ld; const float2* rope; int hd, q_rows, k_rows;
   float q_scale;               // softmax scale folded into the stored q (head_dim^-0.5)
+  int plan_id;                 // index into GemvRing::plans_s (>= 0) or -1: plan on the fly
 };
 
 // epilogue of the row pair (row0, row0 + 1), row0 even, for session b.  v already carries the bias.
@@ -337,6 +372,7 @@ struct GemvRing {
   int pre_valid, pre_pj, pre_pu, pre_nvalid;
   const void* pre_W;
   GemvPlan plan;
+  const GemvPlan* plans_s;  // shared memory: plans of the kernel's projection shapes, computed once at kernel start
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
@@ -439,7 +475,7 @@ __device__ __forceinline__ int gemv_units_of(const GemvPlan& pl, int K, int j) {
 template <typename T>
 __device__ __forceinline__ void gemv_prefetch(const GemvArgs& a, GemvRing& ring) {
   static_assert(GV_UK == 256, "gemv_units_of shifts by 8");
-  gemv_make_plan(a.N, a.K, ring.plan);
+  if (a.plan_id >= 0) ring.plan = ring.plans_s[a.plan_id]; else gemv_make_plan(a.N, a.K, ring.plan);
   const GemvPlan& pl = ring.plan;
   const int warp = threadIdx.x >> 5;
   int nv = pl.main_rounds;
@@ -782,11 +818,9 @@ __device__ __forceinline__ void attn_finish_item(const float* rec_s, int n_rec /
   if (lane == 0) { out[HD] = M; out[HD + 1] = den; }
   __syncwarp();
   unsigned int prev = 0;
-  if (lane == 0) {
-    __threadfence();  // the record (all lanes, ordered by the __syncwarp) happens-before the count
-    prev = atomicAdd(cnt, 1u);
-    __threadfence();
-  }
+  if (lane == 0)  // release: the record (all lanes, ordered by the __syncwarp) happens-before the count; acquire: the
+                  // other splits' records happen-before the merge below (read with ld.global.cg)
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(cnt) : "memory");
   prev = __shfl_sync(0xffffffffu, prev, 0);
   if (prev != (unsigned)splits - 1) return;
   // last split of this (session, head): merge the records (splits <= 32: one lane per record)

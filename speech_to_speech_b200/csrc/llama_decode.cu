@@ -105,23 +105,23 @@ __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, 
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = qd; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
   a.pos = p.pos; a.slot = p.slot; a.kv_slot = p.kv_slot_stride; a.kv_ld = kvd; a.rope = p.rope; a.hd = p.hd;
-  a.q_rows = qd; a.k_rows = kvd; a.q_scale = rsqrtf((float)p.hd);
+  a.q_rows = qd; a.k_rows = kvd; a.q_scale = rsqrtf((float)p.hd); a.plan_id = -1;
   if (ph < 5 * L) {
     const int layer = ph / 5;
     const LlamaDecLayer& w = p.lw[layer];
     switch (ph % 5) {
       case 0:
-        a.W = w.w_qkv; a.N = qd + 2 * kvd; a.mode = EPI_QKV_ROPE; a.out = p.q; a.ldo = qd;
+        a.W = w.w_qkv; a.N = qd + 2 * kvd; a.mode = EPI_QKV_ROPE; a.out = p.q; a.ldo = qd; a.plan_id = 0;
         a.kv0 = reinterpret_cast<T*>(p.kv) + (long long)layer * p.kv_layer_stride; a.kv_which = p.kv_which_stride;
         return true;
-      case 2: a.W = w.w_o; a.N = d; a.K = qd; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; return true;
-      case 3: a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out_h = p.h; a.ldh = p.ffn; return true;
-      case 4: a.W = w.w_down; a.N = d; a.K = p.ffn; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; return true;
+      case 2: a.W = w.w_o; a.N = d; a.K = qd; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; a.plan_id = 1; return true;
+      case 3: a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out_h = p.h; a.ldh = p.ffn; a.plan_id = 2; return true;
+      case 4: a.W = w.w_down; a.N = d; a.K = p.ffn; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; a.plan_id = 3; return true;
       default: return false;
     }
   }
   if (ph == 5 * L) {
-    a.W = p.lm_head; a.N = p.vocab; a.mode = EPI_LOGITS;
+    a.W = p.lm_head; a.N = p.vocab; a.mode = EPI_LOGITS; a.plan_id = 4;
     a.logits_out = p.logits_out ? p.logits_out + (long long)step * B * p.vocab : nullptr; a.logits_ld = p.vocab;
     return true;
   }
@@ -174,6 +174,11 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ LlamaDecParams sp;
   __shared__ LlamaDecLayer s_layers[64];
+  __shared__ GemvPlan s_plans[5];  // qkv | o_proj | gate/up | down | lm_head
+  if (threadIdx.x < 5) {
+    const int i = threadIdx.x, qd = p.heads * p.hd, kvd = p.kv_heads * p.hd;
+    gemv_make_plan(i == 0 ? qd + 2 * kvd : i == 2 ? 2 * p.ffn : i == 4 ? p.vocab : p.d, i == 1 ? qd : i == 3 ? p.ffn : p.d, s_plans[i]);
+  }
   if (threadIdx.x == 0) { sp = p; sp.lw = s_layers; }
   for (int i = threadIdx.x; i < p.layers; i += DEC_THREADS) s_layers[i] = p.lw[i];
   __syncthreads();
@@ -196,6 +201,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
     ring.bars_s = smem_u32(bars);
     ring.slot = 0;
     ring.parity = 0;
+    ring.plans_s = s_plans;
     if ((threadIdx.x & 31) == 0) {
       for (int i = 0; i < p.ring_slots; ++i) mbar_init(bars + i, 1);
       fence_barrier_init();

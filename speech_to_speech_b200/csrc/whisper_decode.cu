@@ -171,28 +171,28 @@ __device__ __forceinline__ bool wd_gemv_args(const WhisperDecParams& p, int step
   const int L = p.layers, pos = step, d = p.d, B = p.B;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
-  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f;
+  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.plan_id = 1;
   if (ph < 8 * L) {
     const int layer = ph >> 3;
     const WhisperDecLayer& w = p.lw[layer];
     switch (ph & 7) {
       case 0: {
         const long long kvs = (long long)p.max_pos * d;
-        a.W = w.w_qkv; a.N = 3 * d; a.bias = w.b_qkv; a.mode = EPI_QKV; a.out = p.q;
+        a.W = w.w_qkv; a.N = 3 * d; a.bias = w.b_qkv; a.mode = EPI_QKV; a.out = p.q; a.plan_id = 0;
         a.kv0 = reinterpret_cast<T*>(p.self_kv) + ((long long)layer * 2) * kvs + (long long)pos * d;
         a.kv_which = kvs; a.kv_batch = (long long)L * 2 * kvs;
       } return true;
       case 2: a.W = w.w_o; a.N = d; a.bias = w.b_o; a.mode = EPI_RESID; a.out = p.x; return true;
       case 3: a.W = w.w_cq; a.N = d; a.bias = w.b_cq; a.mode = EPI_STORE; a.out = p.q; return true;
       case 5: a.W = w.w_co; a.N = d; a.bias = w.b_co; a.mode = EPI_RESID; a.out = p.x; return true;
-      case 6: a.W = w.w_fc1; a.N = p.ffn; a.bias = w.b_fc1; a.mode = EPI_GELU; a.out_h = p.h; a.ldh = p.ffn; return true;
-      case 7: a.W = w.w_fc2; a.N = d; a.K = p.ffn; a.bias = w.b_fc2; a.mode = EPI_RESID; a.out = p.x; return true;
+      case 6: a.W = w.w_fc1; a.N = p.ffn; a.bias = w.b_fc1; a.mode = EPI_GELU; a.out_h = p.h; a.ldh = p.ffn; a.plan_id = 2; return true;
+      case 7: a.W = w.w_fc2; a.N = d; a.K = p.ffn; a.bias = w.b_fc2; a.mode = EPI_RESID; a.out = p.x; a.plan_id = 3; return true;
       default: return false;
     }
   }
   const int g = step - (p.n_prefix - 1);
   if (ph == 8 * L && g >= 0) {
-    a.W = p.embed_t; a.N = p.vocab; a.mode = EPI_LOGITS; a.suppress = p.suppress; a.first_step = (g == 0);
+    a.W = p.embed_t; a.N = p.vocab; a.mode = EPI_LOGITS; a.plan_id = 4; a.suppress = p.suppress; a.first_step = (g == 0);
     a.logits_out = p.logits_out ? p.logits_out + (long long)g * B * p.vocab : nullptr; a.logits_ld = p.vocab;
     return true;
   }
@@ -250,6 +250,11 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ WhisperDecParams sp;
   __shared__ WhisperDecLayer s_layers[32];  // per-layer pointer tables: no global pointer chase inside a phase
+  __shared__ GemvPlan s_plans[5];           // qkv [3d,d] | [d,d] | fc1 [ffn,d] | fc2 [d,ffn] | logits [vocab,d]
+  if (threadIdx.x < 5) {
+    const int i = threadIdx.x;
+    gemv_make_plan(i == 0 ? 3 * p.d : i == 2 ? p.ffn : i == 4 ? p.vocab : p.d, i == 3 ? p.ffn : p.d, s_plans[i]);
+  }
   if (threadIdx.x == 0) { sp = p; sp.lw = s_layers; }
   for (int i = threadIdx.x; i < p.layers; i += DEC_THREADS) s_layers[i] = p.lw[i];
   __syncthreads();
@@ -272,6 +277,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
     ring.bars_s = smem_u32(bars);
     ring.slot = 0;
     ring.parity = 0;
+    ring.plans_s = s_plans;
     if ((threadIdx.x & 31) == 0) {
       for (int i = 0; i < p.ring_slots; ++i) mbar_init(bars + i, 1);
       fence_barrier_init();
@@ -299,6 +305,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
       if (tracing) tr[4] = globaltimer_ns();
       if (coop && !skip) {
         grid_arrive(p.sync_counter, epoch);
+        if (tracing) tr[2] = globaltimer_ns();  // arrived (results published)
         // ---- between arrive and wait: everything for the NEXT phases that does not depend on other CTAs ----
         int nph = ph + 1, nstep = step;
         if (nph == n_ph) { nph = 0; nstep = step + 1; }
@@ -324,6 +331,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
             if (++nph == n_ph) { nph = 0; ++nstep; }
           }
         }
+        if (tracing) tr[3] = globaltimer_ns();  // next phase prepared
         grid_wait(p.sync_counter, epoch);
       }
       if (tracing) tr[5] = globaltimer_ns();

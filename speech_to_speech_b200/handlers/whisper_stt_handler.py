@@ -5,16 +5,22 @@ Mirrors /root/reference/src/speech_to_speech/STT/whisper_stt_handler.py: same `s
 language bookkeeping ("-auto" suffix, sticky last_language restricted to SUPPORTED_LANGUAGES, progressive mode).
 What changes is what the handler calls: `processor(...)` + `model.generate(...)` become ONE call into the C ABI
 (`s2s_whisper_transcribe`: H2D PCM, log-mel, encoder, greedy decode, D2H ids); only the BPE detokenisation
-(`processor.batch_decode`, CPU, :259) stays in Python.  No CPU fallback: a non-CUDA `device` raises."""
+(`processor.batch_decode`, CPU, :259) stays in Python.  No CPU fallback: a non-CUDA `device` raises.
+
+`max_batch > 1` (set it to the number of pipeline units, `--num_pipelines`) makes every handler instance of the
+process with the same (model, dtype, device) share ONE engine -- one copy of the weights -- behind a SessionBatcher
+(`batcher.py`): utterances of concurrent sessions that arrive within `batch_wait_ms` are transcribed by one launch."""
 from __future__ import annotations
 
 import logging
 import re
+import threading
 from typing import Any, Iterator, Optional
 
 import numpy as np
 
 from ..host import resolve
+from ..batcher import SessionBatcher, acquire_shared, release_shared
 
 logger = logging.getLogger(__name__)
 _api = resolve()
@@ -58,6 +64,40 @@ class TokenTable:
         return cls(base, vocab - 1, base + 10, base + 11, base + 12, langs, [1, 2, 7, base, base + 10, base + 11], [220, vocab - 1])
 
 
+class _EngineBundle:
+    """An engine with what is needed to drive it; private to one handler or shared through the batcher."""
+
+    def __init__(self, E: Any, engine: Any, tokens: "TokenTable", decode_text: Any, max_batch: int, batch_wait_s: float):
+        self.E, self.engine, self.tokens, self.decode_text = E, engine, tokens, decode_text
+        self.lock = threading.Lock()  # the engine handle is used by one thread at a time (INTEGRATION.md)
+        self.batcher = SessionBatcher(self._run_batch, max_batch, batch_wait_s, "s2s-stt-batcher") if max_batch > 1 else None
+
+    @staticmethod
+    def _key(o: Any) -> tuple:
+        return (tuple(o.prefix), int(o.eos_id), int(o.max_new_tokens), tuple(o.suppress), tuple(o.begin_suppress))
+
+    def _run_batch(self, key: tuple, audios: list) -> list:
+        opts = self.E.WhisperDecodeOptions(prefix=list(key[0]), eos_id=key[1], max_new_tokens=key[2], suppress=list(key[3]),
+                                           begin_suppress=list(key[4]))
+        with self.lock:
+            return self.engine.transcribe(audios, opts)
+
+    def transcribe(self, audio: np.ndarray, opts: Any) -> list[int]:
+        if self.batcher is not None:
+            return self.batcher.call(self._key(opts), audio)
+        with self.lock:
+            return self.engine.transcribe([audio], opts)[0]
+
+    def detect_language(self, audio: np.ndarray, sot: int, lang_ids: list[int]) -> int:
+        with self.lock:
+            return int(self.engine.detect_language_host(audio, sot, lang_ids))
+
+    def close(self) -> None:
+        if self.batcher is not None:
+            self.batcher.close()
+        self.engine.close()
+
+
 class B200WhisperSTTHandler(_api.BaseSTTHandler):
     """Speech-to-text on the B200 engine.  `model_name`: a local transformers Whisper checkpoint directory / hub id
     (weights are read once on the CPU and copied into the engine), or "random:<geometry>[:seed]" for seeded
@@ -68,7 +108,7 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
 
     def setup(self, model_name: str = "distil-whisper/distil-large-v3", device: str = "cuda", torch_dtype: str = "float16",
               compile_mode: Optional[str] = None, language: Optional[str] = None, gen_kwargs: dict[str, Any] = {},
-              max_batch: int = 1) -> None:
+              max_batch: int = 1, batch_wait_ms: float = 4.0) -> None:
         if not str(device).startswith("cuda"):
             raise ValueError(f"B200WhisperSTTHandler runs on CUDA (sm_100a) only, got device={device!r}; there is no CPU fallback")
         from .. import engine as E  # raises ImportError if libs2s_b200.so is not built
@@ -84,33 +124,43 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
             self.gen_kwargs["language"] = self.last_language
         self._E = E
         self.processor = None
-        self._load(model_name)
+        self.max_batch = max(1, int(max_batch))
+        self.batch_wait_s = float(batch_wait_ms) / 1000.0
+        self._shared_key = None
+        if self.max_batch > 1:
+            self._shared_key = ("whisper", model_name, torch_dtype, self.device_index, self.max_batch)
+            self.bundle = acquire_shared(self._shared_key, lambda: self._load(model_name), lambda b: b.close())
+        else:
+            self.bundle = self._load(model_name)
+        self.engine, self.tokens, self._decode_text = self.bundle.engine, self.bundle.tokens, self.bundle.decode_text
         self.warmup()
 
     # -- loading ---------------------------------------------------------------------------------
-    def _load(self, model_name: str) -> None:
+    def _load(self, model_name: str) -> _EngineBundle:
         E = self._E
         if model_name.startswith("random:"):
             parts = model_name.split(":")
             geom = GEOMETRIES[parts[1]]
             seed = int(parts[2]) if len(parts) > 2 else 0
-            self.engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=1, device=self.device_index)
-            self.engine.init_random(seed)
-            self.tokens = TokenTable.synthetic(geom["vocab"])
-            self._decode_text = lambda ids: " ".join(f"<{i}>" for i in ids)
-            return
+            engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=self.max_batch, device=self.device_index)
+            engine.init_random(seed)
+            return _EngineBundle(E, engine, TokenTable.synthetic(geom["vocab"]), lambda ids: " ".join(f"<{i}>" for i in ids),
+                                 self.max_batch, self.batch_wait_s)
         from transformers import AutoModelForSpeechSeq2Seq, AutoProcessor
-        self.processor = AutoProcessor.from_pretrained(model_name)
+        processor = AutoProcessor.from_pretrained(model_name)
         hf = AutoModelForSpeechSeq2Seq.from_pretrained(model_name)
         c = hf.config
         geom = dict(d_model=c.d_model, heads=c.encoder_attention_heads, enc_layers=c.encoder_layers, dec_layers=c.decoder_layers,
                     ffn=c.encoder_ffn_dim, n_mels=c.num_mel_bins, vocab=c.vocab_size,
                     max_source_positions=c.max_source_positions, max_target_positions=c.max_target_positions)
-        self.engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=1, device=self.device_index)
-        self.engine.load_state_dict({k: v for k, v in hf.state_dict().items() if not k.startswith("proj_out")})
-        self.tokens = TokenTable.from_generation_config(hf.generation_config)
+        engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=self.max_batch, device=self.device_index)
+        engine.load_state_dict({k: v for k, v in hf.state_dict().items() if not k.startswith("proj_out")})
+        tokens = TokenTable.from_generation_config(hf.generation_config)
         del hf
-        self._decode_text = lambda ids: self.processor.batch_decode([ids], skip_special_tokens=True, decode_with_timestamps=False)[0]
+        self.processor = processor
+        return _EngineBundle(E, engine, tokens,
+                             lambda ids: processor.batch_decode([ids], skip_special_tokens=True, decode_with_timestamps=False)[0],
+                             self.max_batch, self.batch_wait_s)
 
     def warmup(self) -> None:
         logger.info("Warming up %s", type(self).__name__)
@@ -136,12 +186,12 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         t = self.tokens
         if not t.lang_to_id:
             return None
-        tok = self.engine.detect_language_host(np.ascontiguousarray(audio[:480000], dtype=np.float32), t.sot,
-                                               list(t.lang_to_id.values()))
+        tok = self.bundle.detect_language(np.ascontiguousarray(audio[:480000], dtype=np.float32), t.sot,
+                                          list(t.lang_to_id.values()))
         return t.id_to_lang.get(int(tok))
 
     def _transcribe(self, audio: np.ndarray, language: str) -> list[int]:
-        ids = self.engine.transcribe([np.ascontiguousarray(audio, dtype=np.float32)], self._options(language))[0]
+        ids = self.bundle.transcribe(np.ascontiguousarray(audio, dtype=np.float32), self._options(language))
         return [i for i in ids if i != self.tokens.eos]
 
     # -- the slot -----------------------------------------------------------------------------------
@@ -168,9 +218,14 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
                                  turn_revision=vad_audio.turn_revision, speech_stopped_at_s=vad_audio.created_at_s)
 
     def cleanup(self) -> None:
-        eng = getattr(self, "engine", None)
-        if eng is not None:
-            eng.close()
+        bundle = getattr(self, "bundle", None)
+        if bundle is None:
+            return
+        self.bundle = None
+        if self._shared_key is not None:
+            release_shared(self._shared_key)  # the last handler of the process closes the shared engine
+        else:
+            bundle.close()
 
 
 # Whisper geometries (transformers WhisperConfig values of the public checkpoints)

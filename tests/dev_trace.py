@@ -29,7 +29,8 @@ for cta in (0, 1):
     for k in range(8):
         sel = [idx + s * nph + l * 8 + k for s in range(4) for l in range(L)]
         stg = np.where(t[cta, sel, 1] > 0, t[cta, sel, 1] - t[cta, sel, 0], 0).mean()
-        print(f"  {names[k]:10s} body {body[sel].mean():8.0f}  barrier {bar[sel].mean():8.0f}   [inputs staged after {stg:5.0f}]")
+        arr = (t[cta, sel, 2] - t[cta, sel, 4]).mean(); prep = (t[cta, sel, 3] - t[cta, sel, 2]).mean(); poll = (t[cta, sel, 5] - t[cta, sel, 3]).mean()
+        print(f"  {names[k]:10s} body {body[sel].mean():8.0f}  barrier {bar[sel].mean():8.0f}   [inputs staged after {stg:5.0f} | arrive {arr:5.0f} | prepare next {prep:5.0f} | poll {poll:5.0f}]")
     sel = [idx + s * nph + 8 * L for s in range(4)]
     print(f"  {'logits':10s} body {body[sel].mean():8.0f}  barrier {bar[sel].mean():8.0f}")
     sel = [idx + s * nph + 8 * L + 1 for s in range(4)]

@@ -1,0 +1,158 @@
+"""CPU tests of the session batcher (speech_to_speech_b200/batcher.py) and of handlers sharing one engine through it:
+requests of concurrent sessions are merged into one launch, never across different decoder prompts, results and
+exceptions are routed back to the session that asked."""
+import threading
+import time
+from threading import Thread
+
+import numpy as np
+import pytest
+
+from speech_to_speech_b200.batcher import SessionBatcher, acquire_shared, release_shared
+from test_handlers import make_handler, vad
+
+
+def test_concurrent_requests_share_a_launch_and_results_are_routed():
+    seen = []
+
+    def run(key, items):
+        seen.append((key, list(items)))
+        time.sleep(0.01)
+        return [x * 10 for x in items]
+
+    b = SessionBatcher(run, max_batch=8, max_wait_s=0.05)
+    try:
+        out = {}
+
+        def worker(i):
+            out[i] = b.call("k", i)
+
+        ths = [Thread(target=worker, args=(i,)) for i in range(8)]
+        [t.start() for t in ths]
+        [t.join(5) for t in ths]
+        assert out == {i: i * 10 for i in range(8)}
+        assert b.items_run == 8 and b.batches_run <= 2 and b.largest_batch >= 4  # 8 arrivals inside the 50 ms window
+        assert all(k == "k" for k, _ in seen)
+    finally:
+        b.close()
+
+
+def test_full_batch_is_dispatched_without_waiting_and_overflow_is_requeued():
+    sizes = []
+    b = SessionBatcher(lambda k, it: (sizes.append(len(it)), list(it))[1], max_batch=4, max_wait_s=5.0)
+    try:
+        futs = [b.submit("k", i) for i in range(8)]  # two full batches: must not wait for the 5 s window
+        t0 = time.monotonic()
+        assert [f.result(2) for f in futs] == list(range(8))
+        assert time.monotonic() - t0 < 2 and sizes == [4, 4]
+    finally:
+        b.close()
+
+
+def test_single_request_is_flushed_after_the_window():
+    b = SessionBatcher(lambda k, it: list(it), max_batch=16, max_wait_s=0.02)
+    try:
+        t0 = time.monotonic()
+        assert b.call("k", 7, timeout=2) == 7
+        assert 0.015 <= time.monotonic() - t0 < 1.0
+    finally:
+        b.close()
+
+
+def test_different_keys_are_never_mixed():
+    seen = []
+    b = SessionBatcher(lambda k, it: (seen.append((k, tuple(it))), [(k, x) for x in it])[1], max_batch=8, max_wait_s=0.03)
+    try:
+        futs = [b.submit("en" if i % 2 else "de", i) for i in range(10)]
+        res = [f.result(2) for f in futs]
+        assert res == [("en" if i % 2 else "de", i) for i in range(10)]
+        for k, items in seen:
+            assert all((("en" if i % 2 else "de") == k) for i in items)
+    finally:
+        b.close()
+
+
+def test_exception_reaches_every_waiter_and_the_batcher_survives():
+    calls = {"n": 0}
+
+    def run(key, items):
+        calls["n"] += 1
+        if calls["n"] == 1:
+            raise RuntimeError("device error")
+        return list(items)
+
+    b = SessionBatcher(run, max_batch=4, max_wait_s=0.02)
+    try:
+        futs = [b.submit("k", i) for i in range(3)]
+        for f in futs:
+            with pytest.raises(RuntimeError, match="device error"):
+                f.result(2)
+        assert b.call("k", 5, timeout=2) == 5
+    finally:
+        b.close()
+
+
+def test_close_serves_the_queue_and_rejects_new_work():
+    b = SessionBatcher(lambda k, it: list(it), max_batch=4, max_wait_s=10.0)
+    f = b.submit("k", 1)
+    b.close()
+    assert f.result(1) == 1
+    with pytest.raises(RuntimeError):
+        b.submit("k", 2)
+
+
+def test_shared_registry_builds_once_and_closes_on_last_release():
+    built, closed = [], []
+    a = acquire_shared(("x", 1), lambda: built.append(1) or object(), lambda v: closed.append(v))
+    c = acquire_shared(("x", 1), lambda: built.append(1) or object(), lambda v: closed.append(v))
+    assert a is c and built == [1]
+    release_shared(("x", 1))
+    assert closed == []
+    release_shared(("x", 1))
+    assert closed == [a]
+
+
+class BatchEngine:
+    """Fake engine that records how many utterances each launch carried."""
+
+    def __init__(self):
+        self.batches = []
+        self.lock = threading.Lock()
+
+    def transcribe(self, audio, opts):
+        with self.lock:
+            self.batches.append((len(audio), tuple(opts.prefix)))
+        time.sleep(0.005)
+        return [[len(a), 7, opts.eos_id] for a in audio]
+
+    def detect_language_host(self, audio, sot, lang_ids):
+        return lang_ids[0]
+
+    def close(self):
+        pass
+
+
+def test_handlers_of_concurrent_sessions_share_one_engine_launch():
+    """6 handler instances (= 6 pipeline units of the reference) on one bundle: their utterances are merged, each
+    session gets its own transcription back (the fake encodes the utterance length in the first id)."""
+    eng = BatchEngine()
+    api, h0 = make_handler("en", max_batch=8, engine=eng)
+    handlers = [h0]
+    for _ in range(5):
+        _, h = make_handler("en", max_batch=8, engine=eng)
+        h.bundle.close()              # drop the private bundle the fixture built ...
+        h.bundle = h0.bundle          # ... and share the first one, as acquire_shared() does in setup()
+        handlers.append(h)
+    outs = {}
+
+    def session(i):
+        outs[i] = list(handlers[i].process(vad(api, n=16000 + 160 * i)))[0]
+
+    ths = [Thread(target=session, args=(i,)) for i in range(6)]
+    [t.start() for t in ths]
+    [t.join(5) for t in ths]
+    for i in range(6):
+        assert outs[i].text.split()[0] == str(16000 + 160 * i)
+    assert sum(n for n, _ in eng.batches) == 6 and max(n for n, _ in eng.batches) >= 3
+    assert len({p for _, p in eng.batches}) == 1
+    h0.bundle.close()

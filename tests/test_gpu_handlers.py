@@ -39,6 +39,37 @@ def test_whisper_handler_random_model_through_stage_loop():
     th.join(timeout=10)
 
 
+def test_concurrent_sessions_share_one_engine_and_match_the_single_session_path():
+    """6 pipeline units (handler instances) with max_batch=8: one shared engine, their utterances ride one launch;
+    every session's ids equal what the one-session handler produces for the same audio."""
+    from speech_to_speech_b200.host import resolve
+    from speech_to_speech_b200.handlers.whisper_stt_handler import B200WhisperSTTHandler
+    api = resolve()
+    kw = {"model_name": "random:tiny:3", "device": "cuda", "torch_dtype": "float16", "language": "en",
+          "gen_kwargs": {"max_new_tokens": 10, "task": "transcribe"}}
+    single = B200WhisperSTTHandler(Event(), queue_in=Queue(), queue_out=Queue(), setup_kwargs=dict(kw))
+    auds = [W.synthetic_audio(40 + i, 32000 + 16000 * (i % 3)) for i in range(6)]
+    want = [list(single.process(api.VADAudio(audio=a, mode="final")))[0].text for a in auds]
+    single.cleanup()
+    units = [B200WhisperSTTHandler(Event(), queue_in=Queue(), queue_out=Queue(),
+                                   setup_kwargs=dict(kw, max_batch=8, batch_wait_ms=50.0)) for _ in range(6)]
+    assert all(u.bundle is units[0].bundle for u in units)  # ONE engine, one copy of the weights
+    got = {}
+
+    def session(i):
+        got[i] = list(units[i].process(api.VADAudio(audio=auds[i], mode="final")))[0].text
+
+    before = units[0].bundle.batcher.batches_run
+    ths = [Thread(target=session, args=(i,)) for i in range(6)]
+    [t.start() for t in ths]
+    [t.join(120) for t in ths]
+    assert [got[i] for i in range(6)] == want
+    b = units[0].bundle.batcher
+    assert b.largest_batch >= 2 and b.batches_run - before < 6
+    for u in units:
+        u.cleanup()
+
+
 def test_whisper_handler_auto_language_reports_detected_code():
     from speech_to_speech_b200.host import resolve
     from speech_to_speech_b200.handlers.whisper_stt_handler import B200WhisperSTTHandler

@@ -26,7 +26,7 @@ class FakeEngine:
 
     def transcribe(self, audio, opts):
         self.calls.append(("transcribe", len(audio[0]), list(opts.prefix), opts.max_new_tokens))
-        return [[11, 22, 33, opts.eos_id]]
+        return [[11, 22, 33, opts.eos_id] for _ in audio]
 
     def detect_language_host(self, audio, sot, lang_ids):
         self.calls.append(("detect", sot, len(audio)))
@@ -36,7 +36,7 @@ class FakeEngine:
         self.calls.append(("close",))
 
 
-def make_handler(language="en", gen_kwargs=None):
+def make_handler(language="en", gen_kwargs=None, max_batch=1, engine=None):
     """Bypass setup() (model load) like the reference's tests do; wire the attributes process() reads."""
     api = resolve()
     h = object.__new__(WH.B200WhisperSTTHandler)
@@ -65,9 +65,10 @@ def make_handler(language="en", gen_kwargs=None):
         begin_suppress: tuple = ()
 
     h._E = SimpleNamespace(WhisperDecodeOptions=Opts)
-    h.engine = FakeEngine()
-    h.tokens = WH.TokenTable.synthetic(51865)
-    h._decode_text = lambda ids: " ".join(map(str, ids))
+    h.max_batch, h.batch_wait_s, h._shared_key = max_batch, 0.02, None
+    h.bundle = WH._EngineBundle(h._E, engine or FakeEngine(), WH.TokenTable.synthetic(51865), lambda ids: " ".join(map(str, ids)),
+                                max_batch, 0.02)
+    h.engine, h.tokens, h._decode_text = h.bundle.engine, h.bundle.tokens, h.bundle.decode_text
     h.processor = None
     return api, h
 
