@@ -180,16 +180,10 @@ static __device__ __forceinline__ void stage_norm_weights(const float* w, const 
 // every copy of the phase is in flight at once whatever B is (one L2 round trip, no registers), then one-pass
 // statistics (sum, sum of squares) and the normalised row is written as 16-bit into xh[b][d + GV_XPAD].
 // Ends with a __syncthreads().
+// statistics + normalisation of B rows already in shared memory (xs) -> xh; ends with a __syncthreads()
 template <typename T>
-static __device__ __noinline__ void stage_rows_norm(const float* x, int B, int d, float* xs, T* xh, int mode, const float* w,
-                                                    const float* bias, float eps, float* s_red, float* wb, int wb_ready) {
-  const int n = B * d;
-  const uint32_t xs_s = smem_u32(xs);
-#pragma unroll 4
-  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 4) cp_async16(xs_s + (uint32_t)i * 4, x + i);
-  if (!wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
-  cp_async_wait_all();
-  __syncthreads();
+static __device__ __forceinline__ void norm_from_smem(const float* xs, int B, int d, T* xh, int mode, float eps, float* s_red,
+                                                      const float* wb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int wpr = DEC_WARPS;  // warps per row: largest power of two with wpr * B <= DEC_WARPS (min 1)
   while (wpr > 1 && wpr * B > DEC_WARPS) wpr >>= 1;
@@ -240,6 +234,57 @@ static __device__ __noinline__ void stage_rows_norm(const float* x, int B, int d
     }
   }
   __syncthreads();
+}
+
+template <typename T>
+static __device__ __noinline__ void stage_rows_norm(const float* x, int B, int d, float* xs, T* xh, int mode, const float* w,
+                                                    const float* bias, float eps, float* s_red, float* wb, int wb_ready) {
+  const int n = B * d;
+  const uint32_t xs_s = smem_u32(xs);
+#pragma unroll 4
+  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 4) cp_async16(xs_s + (uint32_t)i * 4, x + i);
+  if (!wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
+  cp_async_wait_all();
+  __syncthreads();
+  norm_from_smem<T>(xs, B, d, xh, mode, eps, s_red, wb);
+}
+
+// Same, for a residual stream that is still in pieces: x_eff = x + add_bias + sum_p parts[p] (fixed order ->
+// deterministic), with the n_parts partial out-projections of the previous phase (one per head) at stride
+// part_stride.  All pieces land in `scratch` ((n_parts + 1) * B * d floats) through cp.async in one round trip;
+// x_eff replaces piece 0, is normalised into xh and, when x_out != null (ONE designated CTA), written back as the new
+// residual stream for the later phases.
+template <typename T>
+static __device__ __noinline__ void stage_rows_norm_sum(const float* x, const float* parts, int n_parts, long long part_stride,
+                                                        const float* add_bias, float* x_out, int B, int d, float* scratch,
+                                                        T* xh, int mode, const float* w, const float* bias, float eps,
+                                                        float* s_red, float* wb, int wb_ready) {
+  const int n = B * d;
+  const uint32_t sc_s = smem_u32(scratch);
+#pragma unroll 2
+  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 4) {
+    cp_async16(sc_s + (uint32_t)i * 4, x + i);
+#pragma unroll 1
+    for (int p = 0; p < n_parts; ++p) cp_async16(sc_s + (uint32_t)((p + 1) * n + i) * 4, parts + p * part_stride + i);
+  }
+  if (!wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
+  cp_async_wait_all();
+  // each thread sums the columns it copied itself: no barrier needed before the sum
+#pragma unroll 1
+  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 4) {
+    float4 acc = *reinterpret_cast<const float4*>(scratch + i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(add_bias + (i % d)));
+    acc.x += bb.x; acc.y += bb.y; acc.z += bb.z; acc.w += bb.w;
+#pragma unroll 4
+    for (int p = 0; p < n_parts; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(scratch + (p + 1) * n + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(scratch + i) = acc;
+    if (x_out) *reinterpret_cast<float4*>(x_out + i) = acc;
+  }
+  __syncthreads();
+  norm_from_smem<T>(scratch, B, d, xh, mode, eps, s_red, wb);
 }
 
 // ---- stage B rows of a 16-bit activation (global [B, K], produced by other CTAs) into xh: cp.async 16-byte
@@ -298,16 +343,19 @@ struct GemvArgs {
 };
 
 // epilogue of the row pair (row0, row0 + 1), row0 even, for session b.  v already carries the bias.
-template <typename T>
+// LLAMA selects which modes exist in the instantiation (smaller code per model family).  Kept inline: with ~220 KB of
+// the SM's 256 KB configured as shared memory the L1 data cache is tiny, so the stack traffic of a call (argument
+// struct, saved registers) goes to L2 -- measured +1 us per phase for a non-inlined epilogue / argument builder.
+template <typename T, bool LLAMA>
 __device__ __forceinline__ void gemv_pair_epilogue(const GemvArgs& a, int mode, int row0, int b, float v0, float v1,
                                                    float r0, float r1, int sup0, int sup1, float& best_v, int& best_i) {
   if (mode == EPI_STORE) {
     *reinterpret_cast<float2*>(a.out + (long long)b * a.ldo + row0) = make_float2(v0, v1);
-  } else if (mode == EPI_GELU) {
+  } else if (!LLAMA && mode == EPI_GELU) {
     *reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(a.out_h) + (long long)b * a.ldh + row0) = DT<T>::pack2(gelu_erf(v0), gelu_erf(v1));
   } else if (mode == EPI_RESID) {
     *reinterpret_cast<float2*>(a.out + (long long)b * a.ldo + row0) = make_float2(r0 + v0, r1 + v1);
-  } else if (mode == EPI_QKV) {
+  } else if (!LLAMA && mode == EPI_QKV) {
     if (row0 < a.d) {
       *reinterpret_cast<float2*>(a.out + (long long)b * a.ldo + row0) = make_float2(v0, v1);
     } else {
@@ -325,9 +373,9 @@ __device__ __forceinline__ void gemv_pair_epilogue(const GemvArgs& a, int mode, 
     }
     if (v0 > best_v || (v0 == best_v && row0 < best_i)) { best_v = v0; best_i = row0; }
     if (ok1 && (v1 > best_v || (v1 == best_v && row0 + 1 < best_i))) { best_v = v1; best_i = row0 + 1; }
-  } else if (mode == EPI_SWIGLU) {
+  } else if (LLAMA && mode == EPI_SWIGLU) {
     reinterpret_cast<T*>(a.out_h)[(long long)b * a.ldh + (row0 >> 1)] = DT<T>::from_f((v0 / (1.0f + __expf(-v0))) * v1);
-  } else {  // EPI_QKV_ROPE
+  } else if (LLAMA) {  // EPI_QKV_ROPE
     const int kv_end = a.q_rows + a.k_rows;
     const int p = __ldcg(a.pos + b);
     if (row0 < kv_end) {
@@ -360,7 +408,16 @@ struct GemvPlan {
   int ks_log;        // tail: 2^ks_log warps share a tile, each streams K >> ks_log
   int slice;         // K >> ks_log
   int tail_rounds;   // tail rounds of this CTA (uniform over its warps)
+  // The CTAs that share the projection and what they share.  Whole-grid projection: vgrid = gridDim.x, vbid =
+  // blockIdx.x, identity tile map, whole rows.  Cluster-local projection (whisper_decode cluster kernel): the vgrid
+  // CTAs of a cluster cut `n_tiles` LOCAL tiles; local tile lt is global tile map_base + (lt >> map_gshift) *
+  // map_gstride + (lt & mask) (e.g. the q, k and v rows of one head), and only columns [k_off, k_off + K) of the
+  // k_full-long weight rows are multiplied (e.g. one head's slice of an out-projection).
+  int vgrid, vbid, map_base, map_gshift, map_gstride, k_off, k_full;
 };
+__device__ __forceinline__ int gemv_global_tile(const GemvPlan& pl, int lt) {
+  return pl.map_base + (lt >> pl.map_gshift) * pl.map_gstride + (lt & ((1 << pl.map_gshift) - 1));
+}
 
 struct GemvRing {
   uint32_t base_s;       // this warp's ring: 32-bit shared-space address (16-byte aligned)
@@ -410,11 +467,11 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], uint32_t 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// How a projection [N, K] is cut into warp items on this grid (see the comment above).  K % 32 == 0.
-__device__ __forceinline__ void gemv_make_plan(int N, int K, GemvPlan& pl) {
-  const int grid = (int)gridDim.x;
+// How n_tiles (local) tiles x K columns are cut into warp items on a (virtual) grid of vgrid CTAs.  K % 32 == 0.
+__device__ __forceinline__ void gemv_make_plan_ex(int n_tiles, int K, int vgrid, int vbid, GemvPlan& pl) {
+  const int grid = vgrid;
   const int slots = grid * DEC_WARPS;
-  pl.n_tiles = (N + GV_ROWS - 1) >> 3;
+  pl.n_tiles = n_tiles;
   pl.main_rounds = pl.n_tiles / slots;
   pl.tail_base = pl.main_rounds * slots;
   const int tail = pl.n_tiles - pl.tail_base;
@@ -432,19 +489,24 @@ __device__ __forceinline__ void gemv_make_plan(int N, int K, GemvPlan& pl) {
   pl.ks_log = best_log;
   pl.slice = K >> best_log;
   const int stride = grid * (DEC_WARPS >> best_log);
-  pl.tail_rounds = (tail > (int)blockIdx.x) ? (tail - (int)blockIdx.x + stride - 1) / stride : 0;
+  pl.tail_rounds = (tail > vbid) ? (tail - vbid + stride - 1) / stride : 0;
+  pl.vgrid = vgrid; pl.vbid = vbid; pl.map_base = 0; pl.map_gshift = 30; pl.map_gstride = 0; pl.k_off = 0; pl.k_full = K;
+}
+// whole-grid projection [N, K]
+__device__ __forceinline__ void gemv_make_plan(int N, int K, GemvPlan& pl) {
+  gemv_make_plan_ex((N + GV_ROWS - 1) >> 3, K, (int)gridDim.x, (int)blockIdx.x, pl);
 }
 
-// item j of warp `warp`: which tile, which K range.  Tiles are interleaved across CTAs so that consecutive tiles
+// item j of warp `warp`: which (local) tile, which K range.  Tiles are interleaved across CTAs so that consecutive tiles
 // stream on different SMs.  Returns false for an empty tail slot.
 __device__ __forceinline__ bool gemv_item(const GemvPlan& pl, int K, int j, int warp, int& tile, int& k0, int& klen) {
   if (j < pl.main_rounds) {
-    tile = (j * DEC_WARPS + warp) * (int)gridDim.x + (int)blockIdx.x; k0 = 0; klen = K;
+    tile = (j * DEC_WARPS + warp) * pl.vgrid + pl.vbid; k0 = 0; klen = K;
     return true;
   }
   const int r = j - pl.main_rounds;
   const int sub = warp >> pl.ks_log, sl = warp & ((1 << pl.ks_log) - 1);
-  tile = pl.tail_base + (r * (DEC_WARPS >> pl.ks_log) + sub) * (int)gridDim.x + (int)blockIdx.x;
+  tile = pl.tail_base + (r * (DEC_WARPS >> pl.ks_log) + sub) * pl.vgrid + pl.vbid;
   k0 = sl * pl.slice; klen = pl.slice;
   return tile < pl.n_tiles;
 }
@@ -461,7 +523,7 @@ __device__ __forceinline__ void gemv_issue_unit(const T* __restrict__ Wt, int K,
     const uint32_t bytes = (uint32_t)(GV_ROWS * len * 2);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of the slot are done
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    bulk_g2s(dst, Wt + ((long long)tile * K + kb) * GV_ROWS, bytes, bar);
+    bulk_g2s(dst, Wt + ((long long)gemv_global_tile(pl, tile) * pl.k_full + pl.k_off + kb) * GV_ROWS, bytes, bar);
   }
 }
 
@@ -515,7 +577,7 @@ __device__ __forceinline__ void gemv_drain(int K, GemvRing& ring) {
 
 // best_v / best_i: running argmax of this lane for sessions g and g + 8 (EPI_LOGITS).
 // red_s: 2 * DEC_THREADS float4 (tail-round partial fragments, double-buffered by round parity).
-template <typename T>
+template <typename T, bool LLAMA>
 __device__ __noinline__ void gemv_mma(const GemvArgs& a, uint32_t xh_s, int B, float (&best_v)[2], int (&best_i)[2],
                                       GemvRing& ring, float4* red_s) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -540,7 +602,7 @@ __device__ __noinline__ void gemv_mma(const GemvArgs& a, uint32_t xh_s, int B, f
     const bool valid = gemv_item(pl, K, j, warp, tile, k0, klen);
     const bool split = (j >= pl.main_rounds) && ks > 1;
     const bool owner = valid && (!split || (warp & (ks - 1)) == 0);  // this warp runs the tile's epilogue
-    const int row0 = tile * GV_ROWS + 2 * t;  // this lane's row pair
+    const int row0 = gemv_global_tile(pl, tile) * GV_ROWS + 2 * t;  // this lane's row pair
     const bool rows_ok = owner && row0 < N;
     // epilogue operands first: their round trip overlaps the weight stream
     float bias0 = 0.f, bias1 = 0.f, rl0 = 0.f, rl1 = 0.f, rh0 = 0.f, rh1 = 0.f;
@@ -596,8 +658,8 @@ __device__ __noinline__ void gemv_mma(const GemvArgs& a, uint32_t xh_s, int B, f
       }
     }
     if (rows_ok) {
-      if (lo) gemv_pair_epilogue<T>(a, mode, row0, g, c[0] + bias0, c[1] + bias1, rl0, rl1, sup0, sup1, best_v[0], best_i[0]);
-      if (hi) gemv_pair_epilogue<T>(a, mode, row0, g + 8, c[2] + bias0, c[3] + bias1, rh0, rh1, sup0, sup1, best_v[1], best_i[1]);
+      if (lo) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g, c[0] + bias0, c[1] + bias1, rl0, rl1, sup0, sup1, best_v[0], best_i[0]);
+      if (hi) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g + 8, c[2] + bias0, c[3] + bias1, rh0, rh1, sup0, sup1, best_v[1], best_i[1]);
     }
   }
   ring.slot = cslot;
@@ -778,6 +840,34 @@ __device__ __noinline__ void attend_blocks(const float* q /*global fp32 [HD]*/, 
   if (lane == 0) { rec[HD] = m; rec[HD + 1] = l; }
 }
 
+// one warp: merge n <= 32 global records [o[HD] unnormalised, m, l] of a (session, head) (one lane per record) and
+// write the normalised head output as 16-bit into out16[HD] (global or shared)
+template <typename T, int HD>
+__device__ __forceinline__ void attn_merge_records(const float* part_bh, int n, T* out16) {
+  constexpr int REC = HD + PART_PAD, DPL = HD / 32;
+  const int lane = threadIdx.x & 31;
+  float mc = -INFINITY, lc = 0.f;
+  if (lane < n) {
+    const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_bh + (long long)lane * REC + HD));
+    mc = ml.x; lc = ml.y;
+  }
+  float acc[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+  const float M2 = warp_max(mc);
+  const float wc = (mc > -INFINITY) ? __expf(mc - M2) : 0.f;
+  const float den2 = warp_sum(lc * wc);
+#pragma unroll 4
+  for (int u = 0; u < n; ++u) {
+    const float wu = __shfl_sync(0xffffffffu, wc, u);
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = fmaf(__ldcg(part_bh + (long long)u * REC + lane + 32 * i), wu, acc[i]);
+  }
+  const float inv = 1.f / den2;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) out16[lane + 32 * i] = DT<T>::from_f(acc[i] * inv);
+}
+
 // ---- finishing an attention item (warp 0 of the CTA) ---------------------------------------------------------
 // Merge the n_rec warp records in shared memory (DEC_WARPS for a CTA-level item, 1 for a warp-level item).  splits == 1: the item is the whole (session, head): write the
 // normalised head output as 16-bit into out16[HD].  Otherwise write the global record, then count the item in
@@ -816,6 +906,7 @@ __device__ __forceinline__ void attn_finish_item(const float* rec_s, int n_rec /
 #pragma unroll
   for (int i = 0; i < DPL; ++i) out[lane + 32 * i] = o[i];
   if (lane == 0) { out[HD] = M; out[HD + 1] = den; }
+  if (!cnt) return;  // the caller orders and merges the records itself (cluster kernel: barrier.cluster)
   __syncwarp();
   unsigned int prev = 0;
   if (lane == 0)  // release: the record (all lanes, ordered by the __syncwarp) happens-before the count; acquire: the
@@ -823,26 +914,7 @@ __device__ __forceinline__ void attn_finish_item(const float* rec_s, int n_rec /
     asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(cnt) : "memory");
   prev = __shfl_sync(0xffffffffu, prev, 0);
   if (prev != (unsigned)splits - 1) return;
-  // last split of this (session, head): merge the records (splits <= 32: one lane per record)
-  float mc = -INFINITY, lc = 0.f;
-  if (lane < splits) {
-    const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_bh + (long long)lane * REC + HD));
-    mc = ml.x; lc = ml.y;
-  }
-  float acc[DPL];
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
-  const float M2 = warp_max(mc);
-  const float wc = (mc > -INFINITY) ? __expf(mc - M2) : 0.f;
-  const float den2 = warp_sum(lc * wc);
-#pragma unroll 4
-  for (int u = 0; u < splits; ++u) {
-    const float wu = __shfl_sync(0xffffffffu, wc, u);
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) acc[i] = fmaf(__ldcg(part_bh + (long long)u * REC + lane + 32 * i), wu, acc[i]);
-  }
-  const float inv = 1.f / den2;
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) out16[lane + 32 * i] = DT<T>::from_f(acc[i] * inv);
+  // last split of this (session, head): merge the records
+  attn_merge_records<T, HD>(part_bh, splits, out16);
   if (lane == 0) *cnt = 0u;
 }

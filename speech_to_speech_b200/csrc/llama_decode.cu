@@ -137,12 +137,16 @@ __host__ __device__ inline int ld_kmax(int d, int ffn, int qd) { return (d > ffn
 
 template <typename T>
 __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, const LdSmem<T>& sm, GemvRing& ring,
-                                         const GemvArgs* ready, int wb_ready) {
+                                         GemvArgs* ready, GemvArgs& a_scratch, int wb_ready) {
   const int L = p.layers, d = p.d, B = p.B;
   float best_v[2] = {-INFINITY, -INFINITY};
   int best_i[2] = {0x7fffffff, 0x7fffffff};
-  GemvArgs a;
-  if (ready) a = *ready; else ld_gemv_args<T>(p, step, ph, a);
+  // argument struct and ring state live in shared memory (all threads write identical values), not on the stack
+  if (!ready && (ph >= 5 * L ? ph == 5 * L : ph % 5 != 1)) {
+    if (threadIdx.x < 32) ld_gemv_args<T>(p, step, ph, a_scratch);  // one warp writes the shared struct
+    __syncthreads();
+  }
+  GemvArgs& a = ready ? *ready : a_scratch;
   if (ph < 5 * L) {
     const int layer = ph / 5;
     const LlamaDecLayer& w = p.lw[layer];
@@ -156,12 +160,12 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
       case 3: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm2, nullptr, p.eps, sm.s_red, sm.wb, wb_ready); break;
       default: stage_rows_copy<T>(reinterpret_cast<const T*>(p.h), B, p.ffn, sm.xh); break;
     }
-    gemv_mma<T>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
+    gemv_mma<T, true>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     return;
   }
   if (ph == 5 * L) {
     stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, p.norm_f, nullptr, p.eps, sm.s_red, sm.wb, wb_ready);
-    gemv_mma<T>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
+    gemv_mma<T, true>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     gemv_argmax_candidates(best_v, best_i, B, sm.sv, sm.si, p.cand_val, p.cand_idx);
   } else {
     ld_select<T>(p, step, sm.sv);
@@ -175,6 +179,8 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   __shared__ LlamaDecParams sp;
   __shared__ LlamaDecLayer s_layers[64];
   __shared__ GemvPlan s_plans[5];  // qkv | o_proj | gate/up | down | lm_head
+  __shared__ GemvArgs s_args[2];   // [0] prepared for the next projection, [1] built in-phase
+  __shared__ GemvRing s_rings[DEC_WARPS];
   if (threadIdx.x < 5) {
     const int i = threadIdx.x, qd = p.heads * p.hd, kvd = p.kv_heads * p.hd;
     gemv_make_plan(i == 0 ? qd + 2 * kvd : i == 2 ? 2 * p.ffn : i == 4 ? p.vocab : p.d, i == 1 ? qd : i == 3 ? p.ffn : p.d, s_plans[i]);
@@ -191,7 +197,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   sm.s_red = reinterpret_cast<float*>(smem_raw + lay.red_s_off);
   sm.wb = reinterpret_cast<float*>(smem_raw + lay.wb_off);
   sm.red = reinterpret_cast<float4*>(smem_raw + lay.redbuf_off);
-  GemvRing ring;
+  GemvRing& ring = s_rings[threadIdx.x >> 5];
   {
     unsigned char* rb = smem_raw + lay.ring_off;
     const int warp = threadIdx.x >> 5;
@@ -210,7 +216,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   }
   unsigned int epoch = 0;
   int trace_i = 0;
-  GemvArgs pre_args;
+  GemvArgs& pre_args = s_args[0];
   pre_args.K = p.d;
   int pre_tag = -1, wb_tag = -1;
   ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
@@ -221,7 +227,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
       const bool tracing = sp.trace && trace_i < sp.trace_cap && threadIdx.x == 0 && blockIdx.x == 0;
       unsigned long long* tr = tracing ? sp.trace + (long long)trace_i * 3 : nullptr;
       if (tracing) tr[0] = gtimer_ns();
-      ld_phase<T>(sp, step, ph, sm, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr, wb_tag == step * n_ph + ph);
+      ld_phase<T>(sp, step, ph, sm, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr, s_args[1], wb_tag == step * n_ph + ph);
       if (tracing) tr[1] = gtimer_ns();
       if (coop) {
         grid_arrive(p.sync_counter, epoch);
@@ -231,7 +237,9 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
           if (nph == n_ph) { nph = 0; nstep = step + 1; }
 #pragma unroll 1
           for (int look = 0; look < 3 && nstep < step_end; ++look) {
-            if (ld_gemv_args<T>(sp, nstep, nph, pre_args)) {
+            if (nph >= 5 * p.layers ? nph == 5 * p.layers : nph % 5 != 1) {
+              if (threadIdx.x < 32) ld_gemv_args<T>(sp, nstep, nph, pre_args);  // one warp writes the shared struct
+              __syncthreads();
               gemv_prefetch<T>(pre_args, ring);
               pre_tag = nstep * n_ph + nph;
               const float* nw = nullptr;

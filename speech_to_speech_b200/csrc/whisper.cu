@@ -68,6 +68,8 @@ struct s2s_whisper {
        *enc_out = nullptr, *cross_kv = nullptr;
   // decoder state
   float *dx = nullptr, *dq = nullptr, *dh = nullptr, *part = nullptr, *cand_val = nullptr;
+  float *dx_alt = nullptr, *part_x0 = nullptr, *part_x1 = nullptr;  // cluster decode kernel (1-2 sessions)
+  int cluster_decode = 1;
   void* attn16 = nullptr;
   unsigned int* attn_cnt = nullptr;
   void* self_kv = nullptr;
@@ -301,6 +303,9 @@ int alloc_workspace(s2s_whisper* m) {
   S2S_CHECK(dev_alloc(m, &m->dh, (size_t)B * f * 4));
   S2S_CHECK(dev_alloc(m, &m->part, (size_t)B * c.heads * m->s_max * 68 * 4));
   S2S_CHECK(dev_alloc(m, &m->attn16, (size_t)B * d * esz));
+  S2S_CHECK(dev_alloc(m, &m->dx_alt, (size_t)2 * d * 4));
+  S2S_CHECK(dev_alloc(m, &m->part_x0, (size_t)c.heads * 2 * d * 4));
+  S2S_CHECK(dev_alloc(m, &m->part_x1, (size_t)c.heads * 2 * d * 4));
   S2S_CHECK(dev_alloc(m, &m->attn_cnt, (size_t)B * c.heads * 4));
   S2S_CHECK(dev_alloc(m, &m->self_kv, (size_t)B * c.dec_layers * 2 * c.max_target_positions * d * esz));
   S2S_CHECK(dev_alloc(m, &m->tokens, (size_t)B * c.max_target_positions * 4));
@@ -348,6 +353,8 @@ int s2s_whisper_create(s2s_ctx* ctx, const s2s_whisper_config* cfg, s2s_whisper*
   if (r != S2S_OK) { s2s_whisper_destroy(m); return r; }
   const char* dbg = getenv("S2S_DEBUG_PHASES");
   m->debug_phases = (dbg && dbg[0] == '1') ? 1 : 0;
+  const char* cl = getenv("S2S_WHISPER_CLUSTER");  // "0": always use the 8-phase kernel (A/B comparisons)
+  m->cluster_decode = (cl && cl[0] == '0') ? 0 : 1;
   *out = m;
   return S2S_OK;
 }
@@ -575,6 +582,8 @@ static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, in
     p.cross_kv = off(m->cross_kv, (int64_t)b0 * c.max_source_positions * c.dec_layers * 2 * d, esz);  // head-major
     p.part = m->part + (size_t)b0 * c.heads * m->s_max * 68; p.s_max = m->s_max;
     p.attn16 = off(m->attn16, (int64_t)b0 * d, esz); p.attn_cnt = m->attn_cnt + (size_t)b0 * c.heads;
+    // 1-2 sessions: the cluster kernel (4 grid-wide phases per layer); its buffers hold one group at a time
+    p.x_alt = m->dx_alt; p.part_x0 = m->part_x0; p.part_x1 = m->part_x1; p.cluster_size = m->cluster_decode ? 8 : 0;
     p.tokens = m->tokens + (size_t)b0 * c.max_target_positions;
     p.n_prefix = n_prefix; p.max_new = max_new; p.eos = eos; p.suppress = suppress_d;
     p.out_ids = ids_out_d + (size_t)b0 * max_new; p.out_len = len_out_d + b0;
@@ -587,6 +596,7 @@ static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, in
     p.done = m->done + b0; p.n_done = m->n_done; p.cand_val = m->cand_val + (size_t)b0 * m->ctx->num_sms;
     p.cand_idx = m->cand_idx + (size_t)b0 * m->ctx->num_sms; p.sync_counter = m->sync_counter;
     p.trace = m->trace; p.trace_cap = m->trace_cap;
+    { const char* tm = getenv("S2S_TRACE_MODE"); p.trace_mode = (tm && tm[0] == '1') ? 1 : 0; }
     S2S_CHECK(whisper_decode_launch(m->ctx, p, c.compute_dtype, m->debug_phases, st));
   }
   return S2S_OK;

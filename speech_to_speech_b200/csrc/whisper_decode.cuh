@@ -22,7 +22,11 @@ struct WhisperDecParams {
   const float* pos;            // [max_pos, d]
   const float *lnf_w, *lnf_b;
   // state
-  float* x;                    // [B, d] residual stream
+  float* x;                    // [B, d] residual stream (X0)
+  float* x_alt;                // [B, d] second residual buffer (X1) -- cluster kernel
+  float* part_x0;              // [heads][B][d] per-head partial out-projections (self block) -- cluster kernel
+  float* part_x1;              // [heads][B][d] ... (cross block)
+  int cluster_size;            // CTAs per cluster in the cluster kernel (0: 8-phase kernel)
   float* q;                    // [B, d]
   void* h;                     // [B, ffn] 16-bit (fc1 + GELU output)
   void* self_kv;               // [B][layers][2][max_pos][d] 16-bit
@@ -49,6 +53,7 @@ struct WhisperDecParams {
   int ring_slots;               // weight-ring slots per warp (set by the launcher from the shared-memory budget)
   unsigned long long* trace;   // optional [2][trace_cap][3] globaltimer stamps (profiling aid)
   int trace_cap;
+  int trace_mode;              // which intra-phase stamps the cluster kernel records (profiling aid)
 };
 
 int whisper_decode_launch(s2s_ctx* ctx, const WhisperDecParams& p, int dtype, int debug_phases, cudaStream_t stream);
