@@ -54,7 +54,9 @@ def decode_bytes_per_launch(g, n_prefix, max_new) -> dict:
     steps = n_prefix - 1 + max_new
     self_kv = sum(L * 2 * (p + 1) * d * 2 for p in range(steps))
     total = steps * (L * w_layer + cross_kv) + max_new * logits + self_kv
-    return {"per_token_step": L * w_layer + cross_kv + logits, "per_launch": total, "steps": steps}
+    return {"per_token_step": L * w_layer + cross_kv + logits, "per_launch": total, "steps": steps,
+            # B sessions per launch share the weight and logits streams; cross-KV and self-KV are per session
+            "per_launch_batched": lambda B: steps * (L * w_layer + B * cross_kv) + max_new * logits + B * self_kv}
 
 
 class ClockSampler:
@@ -284,15 +286,19 @@ def main():
             eng.logmel(pcm_b, [N_SAMPLES] * Bn); eng.encode(Bn); eng.decode(Bn, opts)
         torch.cuda.synchronize()
         nb_steps = max(3, args.steps // 4)
-        evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nb_steps)]
+        evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(nb_steps)]
         barrier()
         for i in range(nb_steps):
             flush.fill_(i & 0xFF)
             evb[i][0].record()
-            eng.logmel(pcm_b, [N_SAMPLES] * Bn); eng.encode(Bn); eng.decode(Bn, opts)
+            eng.logmel(pcm_b, [N_SAMPLES] * Bn); eng.encode(Bn)
+            evb[i][2].record()
+            eng.decode(Bn, opts)
             evb[i][1].record()
         barrier()
-        b_ms = [a.elapsed_time(b) for a, b in evb]
+        b_ms = [a.elapsed_time(b) for a, b, _ in evb]
+        b_dec_ms = sum(m.elapsed_time(b) for _, b, m in evb) / nb_steps
         tb = []
         for i in range(nb_steps):
             t = time.perf_counter(); eng.transcribe(host_b, opts); tb.append(time.perf_counter() - t)
@@ -301,6 +307,7 @@ def main():
         batched = {"batch_per_gpu": Bn, "steps": nb_steps, "ms_per_step": b_tot / nb_steps,
                    "value": world * Bn * AUDIO_S / (b_tot / nb_steps / 1e3),
                    "e2e_value": world * Bn * AUDIO_S / (b_e2e / nb_steps), "latency_ms_p50": statistics.median(b_ms),
+                   "decode_ms": b_dec_ms,
                    "note": "same kernels, Bn utterances per launch; every session still gets its full 128-token decode"}
     clocks = sampler.stop() if rank == 0 else None
 
@@ -318,6 +325,20 @@ def main():
         nb = decode_bytes_per_launch(g, len(PREFIX), MAX_NEW)
         dec_avg_ms = sum(dec_ms) / len(dec_ms)
         achieved = nb["per_launch"] / 1e9 / (dec_avg_ms / 1e3)
+        cluster_on = os.environ.get("S2S_WHISPER_CLUSTER", "1") != "0"
+        kernel_name = ("whisper_decode_cluster_kernel (persistent, 8-CTA cluster per head, 1 launch per utterance)" if cluster_on
+                       else "whisper_decode_kernel (persistent, 1 launch per utterance)")
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "ncu_decode_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj.get("cluster" if cluster_on else "grid", {}).get("dram_bytes_per_launch")
+        if batched is not None:
+            bb = nb["per_launch_batched"](batched["batch_per_gpu"])
+            ach_b = bb / 1e9 / (batched["decode_ms"] / 1e3)
+            batched["roofline"] = {"kernel": "whisper_decode_kernel (persistent, %d sessions per launch)" % batched["batch_per_gpu"],
+                                   "bound": "hbm", "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak,
+                                   "algorithmic_bytes_per_launch": bb}
         line = {
             "metric": METRIC, "value": value, "unit": "sessions", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -332,9 +353,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "sessions", "h2d_bytes_per_step": N_SAMPLES * 4,
                     "d2h_bytes_per_step": MAX_NEW * 4 + 4},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "whisper_decode_kernel (persistent, 1 launch per utterance)", "bound": "hbm",
+            "roofline": {"kernel": kernel_name, "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes_per_launch": nb["per_launch"], "peak_source": peak_src,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": nb["per_launch"], "peak_source": peak_src,
                          "share_of_step": dec_avg_ms / ms_per_step},
             "clocks": clocks,
             "batched": batched,
