@@ -332,13 +332,15 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "ncu_decode_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            traffic = tj.get("cluster" if cluster_on else "grid", {}).get("dram_bytes_per_launch")
+            traffic = tj.get("cluster_b1" if cluster_on else "grid_b1", {}).get("dram_bytes_per_launch")
         if batched is not None:
             bb = nb["per_launch_batched"](batched["batch_per_gpu"])
             ach_b = bb / 1e9 / (batched["decode_ms"] / 1e3)
             batched["roofline"] = {"kernel": "whisper_decode_kernel (persistent, %d sessions per launch)" % batched["batch_per_gpu"],
                                    "bound": "hbm", "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak,
-                                   "algorithmic_bytes_per_launch": bb}
+                                   "algorithmic_bytes_per_launch": bb,
+                                   "traffic": (json.load(open(tpath)).get("grid_b%d" % batched["batch_per_gpu"], {}).get("dram_bytes_per_launch")
+                                               if os.path.exists(tpath) else None)}
         line = {
             "metric": METRIC, "value": value, "unit": "sessions", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -63,7 +63,7 @@ def reps(dst, files):
                 v = float(v.replace(",", ""))
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
             if "whisper_decode" in name:
-                key = "cluster" if "cluster" in name else "grid"
+                key = "cluster_b1" if "cluster" in name else "grid_b16"   # the captures of tests/dev_ncu_decode.py 1 / 16
                 traffic[key] = {"kernel": name.split("(")[0], "dram_bytes_per_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
                                 "source": os.path.basename(fpath)}
         out.append("")
