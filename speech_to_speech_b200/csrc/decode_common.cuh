@@ -82,23 +82,7 @@ __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& e
 __device__ __forceinline__ int dec_first_item() { return (threadIdx.x >> 5) * gridDim.x + blockIdx.x; }
 __device__ __forceinline__ int dec_item_stride() { return gridDim.x * DEC_WARPS; }
 
-// Warm L2 with the weight rows this warp will stream in the NEXT phase (issued before the grid barrier, so the
-// HBM fetch overlaps the barrier latency).  One 128-byte line per lane per instruction.
-template <typename T, int R>
-__device__ __forceinline__ void prefetch_rows_l2(const T* W, int N, int K) {
-  const int lane = threadIdx.x & 31;
-  const int row_bytes = K * (int)sizeof(T);
-#pragma unroll 1
-  for (int row0 = dec_first_item() * R; row0 < N; row0 += dec_item_stride() * R) {
-    const int nrows = min(R, N - row0);
-    const char* base = reinterpret_cast<const char*>(W + (long long)row0 * K);
-    const int total = nrows * row_bytes;
-#pragma unroll 1
-    for (int o = lane * 128; o < total; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
-  }
-}
-
-// Same idea for one attention work item: n_keys rows of `row_bytes` bytes at stride ld_bytes (K and V adjacent).
+// L2 warm-up of one attention work item: n_rows rows of `row_bytes` bytes at stride ld_bytes.
 __device__ __forceinline__ void prefetch_strided_l2(const void* base, long long ld_bytes, int n_rows, int row_bytes) {
   const int lane = threadIdx.x & 31;
   const int lines_per_row = (row_bytes + 127) >> 7;
@@ -415,7 +399,7 @@ struct GemvPlan {
   // k_full-long weight rows are multiplied (e.g. one head's slice of an out-projection).
   int vgrid, vbid, map_base, map_gshift, map_gstride, k_off, k_full;
 };
-__device__ __forceinline__ int gemv_global_tile(const GemvPlan& pl, int lt) {
+__host__ __device__ __forceinline__ int gemv_global_tile(const GemvPlan& pl, int lt) {
   return pl.map_base + (lt >> pl.map_gshift) * pl.map_gstride + (lt & ((1 << pl.map_gshift) - 1));
 }
 
@@ -468,7 +452,7 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], uint32_t 
 }
 
 // How n_tiles (local) tiles x K columns are cut into warp items on a (virtual) grid of vgrid CTAs.  K % 32 == 0.
-__device__ __forceinline__ void gemv_make_plan_ex(int n_tiles, int K, int vgrid, int vbid, GemvPlan& pl) {
+__host__ __device__ __forceinline__ void gemv_make_plan_ex(int n_tiles, int K, int vgrid, int vbid, GemvPlan& pl) {
   const int grid = vgrid;
   const int slots = grid * DEC_WARPS;
   pl.n_tiles = n_tiles;
@@ -499,7 +483,7 @@ __device__ __forceinline__ void gemv_make_plan(int N, int K, GemvPlan& pl) {
 
 // item j of warp `warp`: which (local) tile, which K range.  Tiles are interleaved across CTAs so that consecutive tiles
 // stream on different SMs.  Returns false for an empty tail slot.
-__device__ __forceinline__ bool gemv_item(const GemvPlan& pl, int K, int j, int warp, int& tile, int& k0, int& klen) {
+__host__ __device__ __forceinline__ bool gemv_item(const GemvPlan& pl, int K, int j, int warp, int& tile, int& k0, int& klen) {
   if (j < pl.main_rounds) {
     tile = (j * DEC_WARPS + warp) * pl.vgrid + pl.vbid; k0 = 0; klen = K;
     return true;
@@ -527,7 +511,7 @@ __device__ __forceinline__ void gemv_issue_unit(const T* __restrict__ Wt, int K,
   }
 }
 
-__device__ __forceinline__ int gemv_units_of(const GemvPlan& pl, int K, int j) {
+__host__ __device__ __forceinline__ int gemv_units_of(const GemvPlan& pl, int K, int j) {
   return ((j < pl.main_rounds ? K : pl.slice) + GV_UK - 1) >> 8;
 }
 

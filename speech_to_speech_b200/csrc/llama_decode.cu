@@ -5,11 +5,11 @@
 // :225-289 attention, :171-184 MLP, :53-71 RMSNorm, :140-168 RoPE).  The reference streams the 16 GB of bf16
 // weights once per token through ~10 library kernels per layer and synchronises with the host every token
 // (TextIteratorStreamer); here a token step is 5 phases per layer inside one launch:
-//   0: RMSNorm + QKV GEMV + RoPE + KV append     1: attention partials (GQA, 64-key chunks)
-//   2: combine + o_proj + residual               3: RMSNorm + gate/up GEMV + SwiGLU      4: down + residual
+//   0: RMSNorm + QKV projection + RoPE + KV append   1: GQA attention items (32-key blocks, last split merges)
+//   2: o_proj + residual                             3: RMSNorm + gate/up projection + SwiGLU     4: down + residual
 //   then 5L: final RMSNorm + lm_head + per-CTA argmax      5L+1: global argmax, EOS bookkeeping, next embedding
-// Every phase streams its weights with 16-byte coalesced read-only loads (decode_common.cuh); HBM-bound:
-// 16.06 GB / token for Llama-3-8B.
+// Projections are swap-AB tensor-core GEMVs (sessions on m) fed from per-warp bulk-copy rings of fragment-major weights
+// (decode_common.cuh, weight_tiles.cu); HBM-bound: 15.0 GB / token for Llama-3-8B.
 #include <algorithm>
 
 #include "llama_decode.cuh"

@@ -6,15 +6,18 @@
 // reference launches ~10 tiny kernels per layer per token and syncs with the host every token for the EOS
 // check; here the host launches once per utterance batch and reads the ids at the end.
 //
-// One CTA per SM (148), 512 threads.  A token step is a fixed sequence of phases separated by a grid barrier:
-//   per layer  0: LN1 + QKV GEMV (+ self-KV append)      1: self-attention partials (64-key chunks)
-//              2: combine + out-proj + residual           3: LN2 + cross-q GEMV
-//              4: cross-attention partials over 1500 keys 5: combine + out-proj + residual
-//              6: LN3 + fc1 + GELU                        7: fc2 + residual
-//   then       8L: final LN + tied logits GEMV + suppress masks + per-CTA argmax
+// One CTA per SM (148), 256 threads, 1-16 sessions per launch.  A token step is a fixed sequence of phases separated by
+// a grid barrier:
+//   per layer  0: LN1 + QKV projection (+ self-KV append)   1: self-attention items (32-key blocks, last split merges)
+//              2: out-projection + residual                 3: LN2 + cross-q projection
+//              4: cross-attention items over 1500 keys      5: out-projection + residual
+//              6: LN3 + fc1 + GELU                          7: fc2 + residual
+//   then       8L: final LN + tied logits projection + suppress masks + per-CTA argmax
 //              8L+1: global argmax, EOS / length bookkeeping, next-token embedding
-// Every phase is a coalesced 16-byte weight/KV stream with fp32 accumulation: the kernel is HBM-bound
-// (decoder weights + per-utterance cross-KV per token).
+// Projections are swap-AB tensor-core GEMVs fed from per-warp bulk-copy weight rings (decode_common.cuh); the kernel is
+// HBM/latency-bound (decoder weights once per step for the whole batch + per-session cross-KV).
+// A second kernel in this file (whisper_decode_cluster_kernel) serves single sessions with one thread-block cluster per
+// attention head and four grid-wide phases per layer.
 #include <algorithm>
 
 #include "whisper_decode.cuh"
