@@ -104,6 +104,9 @@ int s2s_whisper_detect_language(s2s_whisper* m, int32_t sot_id, const int32_t* l
  * %globaltimer (ns) at [phase begin, after staging, -, -, phase body end, barrier exit] of the first
  * `capacity` phases into trace_d[2][capacity][6] (u64).  NULL disables tracing.                                          */
 int s2s_whisper_set_trace(s2s_whisper* m, uint64_t* trace_d, int32_t capacity);
+/* Sessions one persistent decode launch can carry for this geometry (<= 16; larger batches are split by the library).
+ * The session batcher (speech_to_speech_b200/batcher.py) sizes its batches with it. */
+int32_t s2s_whisper_max_decode_batch(s2s_whisper* m);
 /* End-to-end with HOST buffers: H2D of pcm, log-mel, encode, greedy decode, D2H of ids; synchronous.
  * pcm_h: [B, pcm_stride] f32 (pinned or pageable), ids_out_h: [B, max_new_tokens], len_out_h: [B].  */
 int s2s_whisper_transcribe(s2s_whisper* m, const s2s_whisper_decode_opts* opts, const float* pcm_h,
@@ -154,6 +157,8 @@ int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int3
                      const int32_t* forced_d, float* logits_out_d, void* stream);
 /* Profiling aid (see s2s_whisper_set_trace): CTA 0's [phase begin, body end, barrier exit] stamps, trace_d[capacity][3]. */
 int s2s_llama_set_trace(s2s_llama* m, uint64_t* trace_d, int32_t capacity);
+/* Largest B accepted by s2s_llama_decode for this geometry (shared-memory budget of the decode kernel, <= 16). */
+int32_t s2s_llama_max_decode_batch(s2s_llama* m);
 /* End-to-end with HOST buffers: (chunked) prefill + greedy decode, synchronous.  ids_out_h[0] is the argmax of the
  * prompt's last position, n_steps tokens in total (generate() semantics of the reference's pipeline call). */
 int s2s_llama_generate(s2s_llama* m, int32_t slot, const int32_t* prompt_h, int32_t n_prompt, int32_t n_steps,

@@ -15,10 +15,10 @@ EXPORTED = [
     "s2s_init", "s2s_destroy", "s2s_last_error", "s2s_launch_count",
     "s2s_whisper_create", "s2s_whisper_destroy", "s2s_whisper_bind_tensor", "s2s_whisper_init_random",
     "s2s_whisper_finalize", "s2s_whisper_logmel", "s2s_whisper_encode", "s2s_whisper_decode",
-    "s2s_whisper_detect_language", "s2s_whisper_transcribe", "s2s_whisper_set_trace",
+    "s2s_whisper_detect_language", "s2s_whisper_transcribe", "s2s_whisper_set_trace", "s2s_whisper_max_decode_batch",
     "s2s_gemm", "s2s_attention",
     "s2s_llama_create", "s2s_llama_destroy", "s2s_llama_bind_tensor", "s2s_llama_init_random",
-    "s2s_llama_finalize", "s2s_llama_session_reset", "s2s_llama_prefill", "s2s_llama_decode", "s2s_llama_generate", "s2s_llama_set_trace",
+    "s2s_llama_finalize", "s2s_llama_session_reset", "s2s_llama_prefill", "s2s_llama_decode", "s2s_llama_generate", "s2s_llama_set_trace", "s2s_llama_max_decode_batch",
     "s2s_tts_postproc",
 ]
 
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     lib.s2s_whisper_detect_language.argtypes = [vp, i32, C.POINTER(i32), i32, i32, vp, vp]
     lib.s2s_whisper_transcribe.argtypes = [vp, C.POINTER(WhisperDecodeOpts), vp, i64, C.POINTER(i32), i32, vp, vp, vp]
     lib.s2s_whisper_set_trace.argtypes = [vp, vp, i32]
+    lib.s2s_whisper_max_decode_batch.argtypes = [vp]
+    lib.s2s_whisper_max_decode_batch.restype = i32
     lib.s2s_gemm.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.s2s_attention.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, i64, f32, i32, i32, vp]
     lib.s2s_llama_create.argtypes = [vp, C.POINTER(LlamaConfig), C.POINTER(vp)]
@@ -95,6 +97,8 @@ def load() -> C.CDLL:
     lib.s2s_llama_decode.argtypes = [vp, C.POINTER(i32), i32, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.s2s_llama_generate.argtypes = [vp, i32, C.POINTER(i32), i32, i32, i32, vp, vp, vp]
     lib.s2s_llama_set_trace.argtypes = [vp, vp, i32]
+    lib.s2s_llama_max_decode_batch.argtypes = [vp]
+    lib.s2s_llama_max_decode_batch.restype = i32
     lib.s2s_tts_postproc.argtypes = [vp, vp, i32, vp, i32, vp, C.POINTER(i32), vp]
     _lib = lib
     return lib

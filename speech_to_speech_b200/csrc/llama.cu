@@ -518,6 +518,11 @@ int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int3
   return S2S_OK;
 }
 
+int32_t s2s_llama_max_decode_batch(s2s_llama* m) {
+  if (!m) return 0;
+  return std::min(MAX_DEC_B, llama_decode_max_batch(m->cfg.d_model, m->cfg.ffn, m->cfg.heads * m->cfg.head_dim));
+}
+
 int s2s_llama_set_trace(s2s_llama* m, uint64_t* trace_d, int32_t capacity) {
   S2S_REQUIRE(m, "llama set_trace: null model");
   m->trace = reinterpret_cast<unsigned long long*>(trace_d);

@@ -628,6 +628,11 @@ int s2s_whisper_decode(s2s_whisper* m, const s2s_whisper_decode_opts* o, int32_t
                      forced_d, logits_out_d, st);
 }
 
+int32_t s2s_whisper_max_decode_batch(s2s_whisper* m) {
+  if (!m) return 0;
+  return whisper_decode_max_batch(m->cfg.d_model, m->cfg.ffn);
+}
+
 int s2s_whisper_set_trace(s2s_whisper* m, uint64_t* trace_d, int32_t capacity) {
   S2S_REQUIRE(m, "set_trace: null model");
   m->trace = reinterpret_cast<unsigned long long*>(trace_d);

@@ -285,6 +285,10 @@ class LlamaEngine:
                                         _ptr(forced), _ptr(logits), _stream_ptr(self.device)), "s2s_llama_decode")
         return (ids, lens, logits) if return_logits else (ids, lens)
 
+    def max_decode_batch(self) -> int:
+        """Sessions one decode launch can carry for this geometry (shared-memory budget of the kernel)."""
+        return int(self.lib.s2s_llama_max_decode_batch(self.handle))
+
     def set_trace(self, trace: Optional[torch.Tensor]) -> None:
         cap = 0 if trace is None else trace.shape[0]
         check(self.lib.s2s_llama_set_trace(self.handle, _ptr(trace), cap), "s2s_llama_set_trace")

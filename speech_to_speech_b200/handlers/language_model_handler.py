@@ -6,12 +6,19 @@ gen_kwargs)` (:217-224) and `_generate(chat, language_code, gen, ctx, runtime_co
 reuses the reference's own `_stream_tokens` / sentence batching / cancel logic unchanged (:309-560).  Where the
 reference spawns a thread running `pipeline("text-generation")` with a TextIteratorStreamer (:883-888), we run
 `s2s_llama_prefill` once and then `s2s_llama_decode` in short persistent launches, detokenising on the host between
-launches, so cancellation is polled every `stream_chunk_tokens` tokens.  No CPU fallback."""
+launches, so cancellation is polled every `stream_chunk_tokens` tokens.  No CPU fallback.
+
+`gen_kwargs["max_sessions"] = N` (N = number of pipeline units) makes all handler instances of the process with the same
+(model, dtype, device) share ONE engine -- one copy of the weights, N KV-cache slots -- and merges the decode chunks of
+concurrent sessions into one persistent launch through the SessionBatcher (`batcher.py`): the kernel serves up to
+`engine.max_decode_batch()` sessions of different lengths per launch at the cost of one weight stream."""
 from __future__ import annotations
 
 import logging
+import threading
 from typing import Any, Callable, Iterator, Optional, Sequence
 
+from ..batcher import SessionBatcher, acquire_shared, release_shared
 from ..host import _stub_optional
 
 logger = logging.getLogger(__name__)
@@ -27,21 +34,34 @@ LLAMA_GEOMETRIES = {
 class TokenStreamer:
     """Greedy generation as an iterator of text fragments (the role TextIteratorStreamer plays in the reference)."""
 
-    def __init__(self, engine: Any, decode_text: Callable[[Sequence[int]], str], eos_ids: Sequence[int], chunk: int = 8, slot: int = 0):
+    def __init__(self, engine: Any, decode_text: Callable[[Sequence[int]], str], eos_ids: Sequence[int], chunk: int = 8, slot: int = 0,
+                 decode_chunk: Optional[Callable[[int, int, int, int], list]] = None, lock: Optional[Any] = None):
         self.engine, self.decode_text, self.eos_ids, self.chunk, self.slot = engine, decode_text, set(int(e) for e in eos_ids), max(1, chunk), slot
         self.generated: list[int] = []
+        # decode_chunk(slot, first_token, n, eos) -> ids: the shared-engine path routes it through the session batcher;
+        # lock serialises prefill on a shared engine (one thread per engine handle at a time)
+        self._decode_chunk = decode_chunk or self._decode_direct
+        self._lock = lock or threading.Lock()
 
-    def stream(self, prompt_ids: Sequence[int], max_new_tokens: int, should_stop: Callable[[], bool] = lambda: False) -> Iterator[str]:
+    def _decode_direct(self, slot: int, tok: int, n: int, eos: int) -> list:
         import torch
         eng = self.engine
-        eng.reset(self.slot)
+        first = torch.tensor([tok], dtype=torch.int32, device=f"cuda:{eng.device}")
+        with self._lock:
+            ids, lens = eng.decode([slot], first, n, eos_id=eos)
+            return ids[0, : int(lens[0]) if int(lens[0]) > 0 else n].tolist()
+
+    def stream(self, prompt_ids: Sequence[int], max_new_tokens: int, should_stop: Callable[[], bool] = lambda: False) -> Iterator[str]:
+        eng = self.engine
         max_prefill = eng.cfg.max_prefill
         nxt = None
-        for o in range(0, len(prompt_ids), max_prefill):
-            nxt, _ = eng.prefill(self.slot, list(prompt_ids[o:o + max_prefill]))
+        with self._lock:
+            eng.reset(self.slot)
+            for o in range(0, len(prompt_ids), max_prefill):
+                nxt, _ = eng.prefill(self.slot, list(prompt_ids[o:o + max_prefill]))
+            tok = int(nxt[0])
         self.generated = []
         emitted = ""
-        tok = int(nxt[0])
         eos_for_kernel = next(iter(self.eos_ids)) if len(self.eos_ids) == 1 else -1
         while len(self.generated) < max_new_tokens:
             if tok in self.eos_ids:
@@ -54,9 +74,7 @@ class TokenStreamer:
             if should_stop() or len(self.generated) >= max_new_tokens:
                 break
             n = min(self.chunk, max_new_tokens - len(self.generated))
-            first = torch.tensor([tok], dtype=torch.int32, device=f"cuda:{eng.device}")
-            ids, lens = eng.decode([self.slot], first, n, eos_id=eos_for_kernel)
-            out = ids[0, : int(lens[0]) if int(lens[0]) > 0 else n].tolist()
+            out = self._decode_chunk(self.slot, tok, n, eos_for_kernel)
             stop = False
             for t in out[:-1]:
                 if t in self.eos_ids:
@@ -69,6 +87,48 @@ class TokenStreamer:
         text = self.decode_text(self.generated) if self.generated else ""
         if len(text) > len(emitted):  # flush the tail (tokens appended by the last launch before EOS / budget end)
             yield text[len(emitted):]
+
+
+class _LlamaBundle:
+    """One engine shared by the handler instances of a process: KV-cache slots handed out per handler, prefill serialised
+    by a lock, decode chunks of concurrent sessions merged into one launch by the SessionBatcher."""
+
+    def __init__(self, engine: Any, tokenizer: Any, eos_ids: list, max_sessions: int, batch_wait_s: float):
+        self.engine, self.tokenizer, self.eos_ids = engine, tokenizer, eos_ids
+        self.lock = threading.Lock()
+        self._free = list(range(max_sessions))
+        mb = max(1, min(int(engine.max_decode_batch()), max_sessions))
+        self.batcher = SessionBatcher(self._run_batch, mb, batch_wait_s, "s2s-llm-batcher") if max_sessions > 1 else None
+
+    def acquire_slot(self) -> int:
+        with self.lock:
+            if not self._free:
+                raise RuntimeError("all KV-cache slots of the shared LLM engine are in use (raise max_sessions)")
+            return self._free.pop(0)
+
+    def release_slot(self, slot: int) -> None:
+        with self.lock:
+            self._free.append(slot)
+
+    def _run_batch(self, key: tuple, items: list) -> list:
+        import torch
+        n, eos = key
+        slots = [it[0] for it in items]
+        first = torch.tensor([it[1] for it in items], dtype=torch.int32, device=f"cuda:{self.engine.device}")
+        with self.lock:
+            ids, lens = self.engine.decode(slots, first, n, eos_id=eos)
+            ids, lens = ids.tolist(), lens.tolist()
+        return [row[: (ln if ln > 0 else n)] for row, ln in zip(ids, lens)]
+
+    def decode_chunk(self, slot: int, tok: int, n: int, eos: int) -> list:
+        if self.batcher is None:
+            return self._run_batch((n, eos), [(slot, tok)])[0]
+        return self.batcher.call((n, eos), (slot, tok))
+
+    def close(self) -> None:
+        if self.batcher is not None:
+            self.batcher.close()
+        self.engine.close()
 
 
 def _reference_base():
@@ -105,16 +165,18 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
         self.gen_kwargs = dict(gen_kwargs)
         self.stream_chunk_tokens = int(self.gen_kwargs.pop("stream_chunk_tokens", 8))
         max_pos = int(self.gen_kwargs.pop("max_positions", 4096))
-        if model_name.startswith("random:"):
-            parts = model_name.split(":")
-            geom = LLAMA_GEOMETRIES[parts[1]]
-            self.engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=1, max_positions=max_pos, max_prefill=512, device=dev)
-            self.engine.init_random(int(parts[2]) if len(parts) > 2 else 0)
-            self.tokenizer = _IdTokenizer(geom["vocab"])
-            self.eos_ids = [geom["vocab"] - 1]
-        else:
+        max_sessions = max(1, int(self.gen_kwargs.pop("max_sessions", 1)))
+        batch_wait_s = float(self.gen_kwargs.pop("batch_wait_ms", 2.0)) / 1000.0
+
+        def build() -> _LlamaBundle:
+            if model_name.startswith("random:"):
+                parts = model_name.split(":")
+                geom = LLAMA_GEOMETRIES[parts[1]]
+                engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=max_sessions, max_positions=max_pos, max_prefill=512, device=dev)
+                engine.init_random(int(parts[2]) if len(parts) > 2 else 0)
+                return _LlamaBundle(engine, _IdTokenizer(geom["vocab"]), [geom["vocab"] - 1], max_sessions, batch_wait_s)
             from transformers import AutoModelForCausalLM, AutoTokenizer
-            self.tokenizer = AutoTokenizer.from_pretrained(model_name)
+            tokenizer = AutoTokenizer.from_pretrained(model_name)
             hf = AutoModelForCausalLM.from_pretrained(model_name)
             c = hf.config
             if c.model_type not in ("llama", "mistral"):
@@ -122,13 +184,20 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
             geom = dict(d_model=c.hidden_size, layers=c.num_hidden_layers, heads=c.num_attention_heads, kv_heads=c.num_key_value_heads,
                         head_dim=getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads, ffn=c.intermediate_size,
                         vocab=c.vocab_size, rope_theta=float(getattr(c, "rope_theta", 10000.0)), rms_eps=float(c.rms_norm_eps))
-            self.engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=1, max_positions=max_pos, max_prefill=512, device=dev)
-            self.engine.load_state_dict(hf.state_dict())
+            engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=max_sessions, max_positions=max_pos, max_prefill=512, device=dev)
+            engine.load_state_dict(hf.state_dict())
             eos = hf.generation_config.eos_token_id
-            self.eos_ids = list(eos) if isinstance(eos, (list, tuple)) else [int(eos)]
+            eos_ids = list(eos) if isinstance(eos, (list, tuple)) else [int(eos)]
             del hf
+            return _LlamaBundle(engine, tokenizer, eos_ids, max_sessions, batch_wait_s)
+
+        self._shared_key = ("llama", model_name, torch_dtype, dev, max_sessions, max_pos) if max_sessions > 1 else None
+        self.bundle = acquire_shared(self._shared_key, build, lambda b: b.close()) if self._shared_key else build()
+        self.engine, self.tokenizer, self.eos_ids = self.bundle.engine, self.bundle.tokenizer, self.bundle.eos_ids
+        self.slot = self.bundle.acquire_slot()
         self.streamer = TokenStreamer(self.engine, lambda ids: self.tokenizer.decode(list(ids), skip_special_tokens=True),
-                                      self.eos_ids, self.stream_chunk_tokens)
+                                      self.eos_ids, self.stream_chunk_tokens, slot=self.slot, decode_chunk=self.bundle.decode_chunk,
+                                      lock=self.bundle.lock)
 
     def generate_text_stream(self, prompt_ids: Sequence[int], max_new_tokens: Optional[int] = None,
                              should_stop: Callable[[], bool] = lambda: False) -> Iterator[str]:
@@ -152,9 +221,15 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
             pass
 
     def cleanup(self) -> None:
-        eng = getattr(self, "engine", None)
-        if eng is not None:
-            eng.close()
+        bundle = getattr(self, "bundle", None)
+        if bundle is None:
+            return
+        self.bundle = None
+        bundle.release_slot(self.slot)
+        if self._shared_key is not None:
+            release_shared(self._shared_key)  # the last handler of the process closes the shared engine
+        else:
+            bundle.close()
 
 
 class _IdTokenizer:

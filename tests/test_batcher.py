@@ -156,3 +156,66 @@ def test_handlers_of_concurrent_sessions_share_one_engine_launch():
     assert sum(n for n, _ in eng.batches) == 6 and max(n for n, _ in eng.batches) >= 3
     assert len({p for _, p in eng.batches}) == 1
     h0.bundle.close()
+
+
+def test_llm_decode_chunks_of_concurrent_sessions_share_a_launch():
+    """3 sessions streaming from ONE shared Llama bundle: their decode chunks are merged into multi-session launches
+    (the fake engine records the slots per launch) and every session still gets its own token sequence."""
+    import torch
+    from types import SimpleNamespace
+    from speech_to_speech_b200.handlers.language_model_handler import TokenStreamer, _IdTokenizer, _LlamaBundle
+
+    class FakeLlama:
+        device = "cpu"
+        cfg = SimpleNamespace(max_prefill=64)
+
+        def __init__(self):
+            self.launches, self.state = [], {}
+
+        def max_decode_batch(self):
+            return 4
+
+        def reset(self, slot):
+            self.state[slot] = 0
+
+        def prefill(self, slot, ids):
+            self.state[slot] = 1000 * (slot + 1)          # session s generates 1000(s+1), 1000(s+1)+1, ...
+            return torch.tensor([self.state[slot]]), None
+
+        def decode(self, slots, first, n, eos_id=-1):
+            self.launches.append(list(slots))
+            time.sleep(0.003)
+            rows = []
+            for s, f in zip(slots, first.tolist()):
+                rows.append([f + 1 + i for i in range(n)])
+            return torch.tensor(rows), torch.tensor([n] * len(slots))
+
+        def close(self):
+            pass
+
+    eng = FakeLlama()
+    tok = _IdTokenizer(100000)
+    real_tensor = torch.tensor
+    torch.tensor = lambda data, dtype=None, device=None: real_tensor(data, dtype=dtype)  # no CUDA on the CPU box
+    try:
+        bundle = _LlamaBundle(eng, tok, [7], max_sessions=3, batch_wait_s=0.05)
+        outs = {}
+
+        def session(i):
+            slot = bundle.acquire_slot()
+            st = TokenStreamer(eng, lambda ids: tok.decode(ids), [7], chunk=4, slot=slot, decode_chunk=bundle.decode_chunk, lock=bundle.lock)
+            "".join(st.stream([1, 2, 3], max_new_tokens=13))
+            outs[slot] = st.generated
+            bundle.release_slot(slot)
+
+        ths = [Thread(target=session, args=(i,)) for i in range(3)]
+        [t.start() for t in ths]
+        [t.join(10) for t in ths]
+    finally:
+        torch.tensor = real_tensor
+        bundle.close()
+    assert sorted(outs) == [0, 1, 2]
+    for slot, gen in outs.items():
+        assert gen == [1000 * (slot + 1) + i for i in range(13)]
+    assert max(len(l) for l in eng.launches) >= 2                 # chunks of different sessions rode one launch
+    assert all(len(set(l)) == len(l) for l in eng.launches)       # a session appears at most once per launch

@@ -99,6 +99,46 @@ def test_llm_token_streamer_matches_oracle_ids():
     assert text == "".join(f"<{i}> " for i in st.generated)
 
 
+def test_llm_handlers_share_one_engine_and_merge_decode_chunks():
+    """3 pipeline units with gen_kwargs max_sessions=3: ONE engine (one weight copy, 3 KV slots); the decode chunks of the
+    concurrent sessions ride multi-session launches; results are reproducible and start like the single-session path."""
+    from speech_to_speech_b200.handlers.language_model_handler import B200LanguageModelHandler
+
+    def make(**kw):
+        h = object.__new__(B200LanguageModelHandler)
+        h._load_model("random:micro:5", "cuda", "float16", dict({"max_new_tokens": 24, "stream_chunk_tokens": 6, "max_positions": 256}, **kw))
+        return h
+
+    rng = np.random.default_rng(3)
+    prompts = [rng.integers(0, 2048, 9 + 5 * i).tolist() for i in range(3)]
+    single = make()
+    want = []
+    for p in prompts:
+        "".join(single.generate_text_stream(p, 24))
+        want.append(list(single.streamer.generated))
+    single.cleanup()
+    units = [make(max_sessions=3, batch_wait_ms=40.0) for _ in range(3)]
+    assert all(u.bundle is units[0].bundle for u in units) and sorted(u.slot for u in units) == [0, 1, 2]
+    runs = []
+    for _ in range(2):
+        got = {}
+
+        def session(i):
+            "".join(units[i].generate_text_stream(prompts[i], 24))
+            got[i] = list(units[i].streamer.generated)
+
+        ths = [Thread(target=session, args=(i,)) for i in range(3)]
+        [t.start() for t in ths]
+        [t.join(120) for t in ths]
+        runs.append([got[i] for i in range(3)])
+    assert runs[0] == runs[1]                                     # same launches -> same ids
+    for i in range(3):
+        assert len(runs[0][i]) >= 4 and runs[0][i][:4] == want[i][:4]
+    assert units[0].bundle.batcher.largest_batch >= 2
+    for u in units:
+        u.cleanup()
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 100, 1919, 1920, 15360, 48001])
 def test_tts_postproc_is_bit_exact_vs_scipy(n):
     from speech_to_speech_b200.handlers.qwen3_tts_postproc import TTSPostProcessor
