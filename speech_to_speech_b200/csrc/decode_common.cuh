@@ -4,10 +4,13 @@
 // A decode step at small batch is a chain of tiny matrix-vector phases; per phase every SM touches only a few
 // KB, so the phase time is (HBM/L2 round trips on its critical path) + (grid barrier), not bytes / bandwidth.
 // Everything here is therefore written for memory-level parallelism: all loads of a phase are independent and
-// issued back to back (explicit register staging, compile-time unrolling) so that each phase costs ONE round
-// trip; work items are interleaved across CTAs so all 148 SMs pull from HBM; buffers produced by other CTAs
-// inside the launch are read with ld.global.cg (L2) so a stale L1 line can never be observed; weights use the
-// read-only no-L1-allocate path.  Reductions are warp shuffles; accumulation is fp32.
+// issued back to back (cp.async / cp.async.bulk into shared memory, or explicit register staging) so that each
+// phase costs ONE round trip; work items are interleaved across CTAs so all SMs pull from HBM; buffers produced by
+// other CTAs inside the launch are read through L2 (ld.global.cg, cp.async.cg, bulk copies) so a stale L1 line can
+// never be observed.  Projections run on the tensor cores (mma.sync, sessions on the m dimension), attention and
+// normalisation on the CUDA cores; accumulation is fp32.  State shared by the threads of a CTA (argument structs,
+// ring bookkeeping) lives in shared memory, not on the stack: the L1 left next to ~150-220 KB of shared memory is
+// too small for 256 private copies.
 #pragma once
 #include "common.cuh"
 
