@@ -124,7 +124,8 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
             self.gen_kwargs["language"] = self.last_language
         self._E = E
         self.processor = None
-        self.max_batch = max(1, int(max_batch))
+        # one persistent decode launch carries up to 16 sessions; more concurrent sessions queue in the batcher
+        self.max_batch = max(1, min(int(max_batch), 16))
         self.batch_wait_s = float(batch_wait_ms) / 1000.0
         self._shared_key = None
         if self.max_batch > 1:
