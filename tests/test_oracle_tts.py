@@ -1,0 +1,57 @@
+"""CPU: the TTS post-processing oracle (oracle/tts_post_ref.py) against scipy and -- when the reference tree is present --
+against the reference handler's own helper methods (`Qwen3TTSHandler._resample_to_pipeline_sr`, `_to_int16`,
+TTS/qwen3_tts_handler.py:612-613, 674-680).  Bit-exact: the CUDA kernel is then held to the same vectors on the GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import tts_post_ref as T
+
+REF_SRC = "/root/reference/src"
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 61, 100, 333, 1919, 1920])
+def test_direct_restatement_is_bit_identical_to_scipy(n):
+    x = (0.3 * np.random.default_rng(n).standard_normal(n)).astype(np.float32)
+    ref = T.resample_to_16k(x, 24000)
+    got = T.resample_direct(x)
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    assert np.array_equal(got, ref.astype(np.float32))
+
+
+def test_int16_conversion_clips_and_truncates_like_numpy():
+    x = np.array([0.0, 0.5, -0.5, 0.99999, 1.0, 1.5, -1.0, -1.5, 1e-6, -1e-6], np.float32)
+    assert T.to_int16(x).tolist() == [0, 16384, -16384, 32767, 32767, 32767, -32768, -32768, 0, 0]
+
+
+def test_stream_blocks_trims_leading_silence_and_pads_the_tail():
+    sil = np.zeros(2400, np.float32)
+    tone = (0.2 * np.sin(2 * np.pi * 440 * np.arange(4800) / 24000)).astype(np.float32)
+    blocks = T.stream_blocks([sil, sil, tone, tone], blocksize=512)
+    assert all(b.dtype == np.int16 and b.shape == (512,) for b in blocks)
+    flat = np.concatenate(blocks)
+    # 2 x 4800 samples @24k -> 6400 @16k; the two silent chunks are dropped entirely; zero-padded to a block multiple
+    assert len(flat) == 13 * 512 and np.abs(flat[:6400]).max() > 3000 and not flat[6400:].any()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference tree not present (GPU box)")
+def test_oracle_equals_the_reference_handler_helpers():
+    sys.path.insert(0, REF_SRC)
+    try:
+        from speech_to_speech.TTS.qwen3_tts_handler import Qwen3TTSHandler
+    except Exception as e:  # optional heavy deps of the handler module missing
+        pytest.skip(f"reference TTS handler not importable here: {e}")
+    finally:
+        sys.path.remove(REF_SRC)
+    h = object.__new__(Qwen3TTSHandler)
+    rng = np.random.default_rng(7)
+    for n in (1, 480, 1920, 15360, 48001):
+        x = (0.4 * rng.standard_normal(n)).astype(np.float32)
+        ref16k = Qwen3TTSHandler._resample_to_pipeline_sr(h, x, 24000)
+        assert np.array_equal(T.resample_to_16k(x, 24000), ref16k)
+        assert np.array_equal(T.to_int16(ref16k), Qwen3TTSHandler._to_int16(h, ref16k))
+        assert np.array_equal(T.postproc(x), Qwen3TTSHandler._to_int16(h, ref16k))
+    same = rng.standard_normal(100).astype(np.float32)
+    assert Qwen3TTSHandler._resample_to_pipeline_sr(h, same, 16000) is same  # pipeline rate passes through untouched
