@@ -219,3 +219,41 @@ def test_llm_decode_chunks_of_concurrent_sessions_share_a_launch():
         assert gen == [1000 * (slot + 1) + i for i in range(13)]
     assert max(len(l) for l in eng.launches) >= 2                 # chunks of different sessions rode one launch
     assert all(len(set(l)) == len(l) for l in eng.launches)       # a session appears at most once per launch
+
+
+def test_random_arrivals_keep_every_result_with_its_request():
+    """Randomised load: 6 producer threads, 3 keys, random gaps; every future gets exactly its own (key, item) back,
+    batches never exceed max_batch and never mix keys."""
+    import random
+    seen = []
+
+    def run(key, items):
+        seen.append((key, len(items)))
+        time.sleep(random.random() * 0.002)
+        return [(key, it) for it in items]
+
+    b = SessionBatcher(run, max_batch=5, max_wait_s=0.003)
+    results, lock = {}, threading.Lock()
+
+    def producer(pid):
+        rnd = random.Random(pid)
+        for n in range(40):
+            key = rnd.choice(["en", "de", "fr"])
+            item = (pid, n)
+            fut = b.submit(key, item)
+            if rnd.random() < 0.5:
+                time.sleep(rnd.random() * 0.002)
+            with lock:
+                results[item] = (key, fut)
+
+    try:
+        ths = [Thread(target=producer, args=(p,)) for p in range(6)]
+        [t.start() for t in ths]
+        [t.join(30) for t in ths]
+        assert len(results) == 240
+        for item, (key, fut) in results.items():
+            assert fut.result(5) == (key, item)
+        assert sum(n for _, n in seen) == 240 and max(n for _, n in seen) <= 5
+        assert b.items_run == 240
+    finally:
+        b.close()
