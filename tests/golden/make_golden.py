@@ -1,7 +1,7 @@
 """Generate golden vectors from `transformers` (the package the reference delegates to).
 
 Run in the builder container (transformers 5.5.0, CPU):
-    python tests/golden/make_golden.py [whisper|llama|tts|all]
+    python tests/golden/make_golden.py [whisper|llama|code2wav|all]
 
 The reference holds no golden mel/logits/ids for this path, so the
 pin is the upstream model code itself: WhisperFeatureExtractor + WhisperForConditionalGeneration
@@ -178,6 +178,36 @@ def llama_golden(name: str):
     print(f"llama_{name}: gen={gen[:10]}...")
 
 
+def code2wav_golden(name: str = "micro"):
+    """Qwen3OmniMoeCode2Wav (the published cousin of the Qwen3-TTS 12 Hz codec decoder; oracle/code2wav_ref.py) at seeded
+    weights: codes [Q, T] -> waveform, plus the pre-transformer output."""
+    import torch
+    from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeCode2WavConfig
+    from transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe import Qwen3OmniMoeCode2Wav
+    from oracle import code2wav_ref as C
+
+    g = C.GEOMETRIES[name]
+    w = C.make_weights(g, 0)
+    cfg = Qwen3OmniMoeCode2WavConfig(codebook_size=g.codebook_size, hidden_size=g.hidden, num_attention_heads=g.heads,
+                                     num_key_value_heads=g.kv_heads, intermediate_size=g.inter, num_hidden_layers=g.layers,
+                                     num_quantizers=g.quantizers, upsample_rates=g.upsample_rates,
+                                     upsampling_ratios=g.upsampling_ratios, decoder_dim=g.decoder_dim,
+                                     sliding_window=g.sliding_window, max_position_embeddings=g.max_positions, rms_norm_eps=g.rms_eps)
+    m = Qwen3OmniMoeCode2Wav(cfg).eval()
+    assert set(m.state_dict().keys()) == set(w.keys())
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    codes = np.random.default_rng(1).integers(0, g.codebook_size, (g.quantizers, 20)).astype(np.int64)
+    with torch.no_grad():
+        t = torch.from_numpy(codes)[None]
+        hidden = m.pre_transformer(inputs_embeds=m.code_embedding(t + m.code_offset).mean(1)).last_hidden_state[0].numpy()
+        wav = m(t)[0, 0].numpy()
+        chunked = m.chunked_decode(t, chunk_size=8, left_context_size=6)[0, 0].numpy()
+    path = os.path.join(OUT, f"code2wav_{name}.npz")
+    np.savez_compressed(path, codes=codes, hidden=hidden.astype(np.float32), wav=wav.astype(np.float32),
+                        chunked=chunked.astype(np.float32), chunk_size=8, left_context=6, transformers_version=__import__("transformers").__version__)
+    print("wrote", path, wav.shape, float(np.abs(wav).max()))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("whisper", "all"):
@@ -186,3 +216,5 @@ if __name__ == "__main__":
     if what in ("llama", "all"):
         for n in LLAMA_CASES:
             llama_golden(n)
+    if what in ("code2wav", "all"):
+        code2wav_golden("micro")
