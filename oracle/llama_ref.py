@@ -10,6 +10,7 @@ The reference (`/root/reference/src/speech_to_speech/LLM/language_model.py:800-8
   attention         TF:187-289 (GQA repeat_kv, softmax in fp32, scaling hd^-0.5, causal)
   mlp               TF:171-184 (down(silu(gate(x)) * up(x)))
   forward / greedy  TF:355-500 + GenerationMixin greedy (argmax of the last position)
+  qk_norm (Qwen3)   transformers models/qwen3/modeling_qwen3.py Qwen3Attention: RMSNorm(head_dim) on q and k before RoPE
 
 Pinned against transformers by tests/golden/make_golden.py -> tests/golden/llama_*.npz.  float32 throughout.
 """
@@ -77,6 +78,9 @@ def forward(w, g: LlamaGeometry, ids: np.ndarray, cache: KVCache, return_hidden:
         q = (h @ w[p + "self_attn.q_proj.weight"].T).reshape(T, g.heads, g.head_dim)
         k = (h @ w[p + "self_attn.k_proj.weight"].T).reshape(T, g.kv_heads, g.head_dim)
         v = (h @ w[p + "self_attn.v_proj.weight"].T).reshape(T, g.kv_heads, g.head_dim)
+        if getattr(g, "qk_norm", False):
+            q = rms_norm(q, w[p + "self_attn.q_norm.weight"], g.rms_eps)
+            k = rms_norm(k, w[p + "self_attn.k_norm.weight"], g.rms_eps)
         q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
         cache.k[i] = np.concatenate([cache.k[i], k], 0)
         cache.v[i] = np.concatenate([cache.v[i], v.astype(np.float32)], 0)

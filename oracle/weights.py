@@ -62,6 +62,7 @@ class LlamaGeometry:
     rope_theta: float = 500000.0
     rms_eps: float = 1e-5
     max_positions: int = 8192
+    qk_norm: bool = False   # Qwen3: RMSNorm over head_dim on q and k before RoPE (transformers modeling_qwen3.py)
 
     def to_dict(self):
         return asdict(self)
@@ -72,6 +73,9 @@ LLAMA_GEOMETRIES = {
     "mini": LlamaGeometry(1024, 4, 8, 2, 128, 3584, 32064),
     "llama-3-8b-2l": LlamaGeometry(4096, 2, 32, 8, 128, 14336, 128256),
     "llama-3-8b": LlamaGeometry(4096, 32, 32, 8, 128, 14336, 128256),
+    # Qwen3 family (the reference's DEFAULT LLM is Qwen/Qwen3-4B-Instruct-2507, language_model_base_arguments.py:6-9):
+    # oracle only so far -- the CUDA engine rejects qk_norm until its kernels apply it
+    "qwen3-micro": LlamaGeometry(256, 2, 4, 2, 64, 512, 2048, rope_theta=1000000.0, rms_eps=1e-6, qk_norm=True),
 }
 
 
@@ -196,6 +200,9 @@ def make_llama_weights(geom: LlamaGeometry, seed: int = 0, rnd=round_bf16) -> di
         lin(p + "self_attn.k_proj", geom.kv_heads * hd, d, std=2.0 / np.sqrt(d))
         lin(p + "self_attn.v_proj", geom.kv_heads * hd, d, std=0.8 / np.sqrt(d))
         lin(p + "self_attn.o_proj", d, geom.heads * hd, std=1.0 / np.sqrt(d))
+        if geom.qk_norm:
+            w[p + "self_attn.q_norm.weight"] = rnd(1.0 + _normal(seed, p + "self_attn.q_norm.weight", (hd,), 0.1, lambda a: a))
+            w[p + "self_attn.k_norm.weight"] = rnd(1.0 + _normal(seed, p + "self_attn.k_norm.weight", (hd,), 0.1, lambda a: a))
         lin(p + "mlp.gate_proj", f, d, std=1.0 / np.sqrt(d))
         lin(p + "mlp.up_proj", f, d, std=1.0 / np.sqrt(d))
         lin(p + "mlp.down_proj", d, f, std=0.7 / np.sqrt(f))

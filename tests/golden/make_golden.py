@@ -123,6 +123,18 @@ def build_hf_llama(geom: W.LlamaGeometry, weights):
     import torch
     from transformers import LlamaConfig, LlamaForCausalLM
 
+    if geom.qk_norm:  # Qwen3 family: same decoder with RMSNorm on q / k heads
+        from transformers import Qwen3Config, Qwen3ForCausalLM
+        cfg = Qwen3Config(
+            vocab_size=geom.vocab, hidden_size=geom.d_model, intermediate_size=geom.ffn, num_hidden_layers=geom.layers,
+            num_attention_heads=geom.heads, num_key_value_heads=geom.kv_heads, head_dim=geom.head_dim,
+            max_position_embeddings=geom.max_positions, rms_norm_eps=geom.rms_eps, rope_theta=geom.rope_theta,
+            tie_word_embeddings=False, attention_bias=False, use_sliding_window=False,
+        )
+        cfg._attn_implementation = "eager"
+        model = Qwen3ForCausalLM(cfg).eval()
+        model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in weights.items()}, strict=True)
+        return model
     cfg = LlamaConfig(
         vocab_size=geom.vocab, hidden_size=geom.d_model, intermediate_size=geom.ffn,
         num_hidden_layers=geom.layers, num_attention_heads=geom.heads, num_key_value_heads=geom.kv_heads,
@@ -139,6 +151,7 @@ def build_hf_llama(geom: W.LlamaGeometry, weights):
 LLAMA_CASES = {
     "micro": dict(prompt_len=24, max_new=16, seed=3),
     "mini": dict(prompt_len=64, max_new=24, seed=4),
+    "qwen3-micro": dict(prompt_len=24, max_new=16, seed=5),
 }
 
 

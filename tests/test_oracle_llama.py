@@ -7,7 +7,7 @@ import pytest
 from oracle import weights as W, llama_ref as R
 
 
-@pytest.mark.parametrize("name", ["micro", "mini"])
+@pytest.mark.parametrize("name", ["micro", "mini", "qwen3-micro"])  # qwen3-micro: Qwen3ForCausalLM (qk_norm), oracle only
 def test_greedy_ids_logits_and_hidden_match_transformers(golden_dir, name):
     g = W.LLAMA_GEOMETRIES[name]
     w = W.make_llama_weights(g, 0)
