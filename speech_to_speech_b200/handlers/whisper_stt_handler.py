@@ -187,8 +187,12 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         t = self.tokens
         if not t.lang_to_id:
             return None
-        tok = self.bundle.detect_language(np.ascontiguousarray(audio[:480000], dtype=np.float32), t.sot,
-                                          list(t.lang_to_id.values()))
+        try:
+            tok = self.bundle.detect_language(np.ascontiguousarray(audio[:480000], dtype=np.float32), t.sot,
+                                              list(t.lang_to_id.values()))
+        except Exception as e:  # the reference survives a failing detection and falls back (:188-197)
+            logger.warning("Whisper language detection failed (%s); falling back to the previous language", e)
+            return None
         return t.id_to_lang.get(int(tok))
 
     def _transcribe(self, audio: np.ndarray, language: str) -> list[int]:

@@ -28,9 +28,15 @@ class FakeEngine:
         self.calls.append(("transcribe", len(audio[0]), list(opts.prefix), opts.max_new_tokens))
         return [[11, 22, 33, opts.eos_id] for _ in audio]
 
+    detect_result = "third"   # "third": lang_ids[2]; an int: that id; None: an id outside the table; an Exception: raised
+
     def detect_language_host(self, audio, sot, lang_ids):
         self.calls.append(("detect", sot, len(audio)))
-        return lang_ids[2]
+        if isinstance(self.detect_result, Exception):
+            raise self.detect_result
+        if self.detect_result is None:
+            return -1
+        return lang_ids[2] if self.detect_result == "third" else self.detect_result
 
     def close(self):
         self.calls.append(("close",))
@@ -103,6 +109,14 @@ def test_progressive_mode_yields_partial():
     assert len(out) == 1 and isinstance(out[0], api.PartialTranscription) and out[0].text == "11 22 33"
 
 
+def test_absent_mode_still_yields_transcription():
+    """Items without a `mode` attribute are final segments (reference tests/test_whisper_progressive_transcription.py:215)."""
+    api, h = make_handler("en")
+    item = SimpleNamespace(audio=np.zeros(8000, np.float32), turn_id="t9", turn_revision=1, created_at_s=12.5)
+    out = list(h.process(item))
+    assert len(out) == 1 and isinstance(out[0], api.Transcription) and out[0].speech_stopped_at_s == 12.5
+
+
 def test_auto_language_detects_then_forces_and_marks_auto():
     api, h = make_handler("auto")
     out = list(h.process(vad(api)))
@@ -112,6 +126,50 @@ def test_auto_language_detects_then_forces_and_marks_auto():
     assert kinds == ["detect", "transcribe"]
     assert h.engine.calls[-1][2][1] == h.tokens.lang_to_id[detected]
     assert h.last_language == (detected if detected in WH.SUPPORTED_LANGUAGES else None)
+
+
+# ---- the language bookkeeping scenarios of the reference's tests/test_whisper_language_detection.py, on this handler ----
+def test_detection_does_not_mutate_gen_kwargs():
+    api, h = make_handler("auto", gen_kwargs={"task": "transcribe"})
+    list(h.process(vad(api)))
+    assert h.gen_kwargs == {"task": "transcribe"}
+
+
+def test_unsupported_detected_language_is_reported_not_retranscribed():
+    """A detected language outside SUPPORTED_LANGUAGES is forced for this utterance and reported, one transcription
+    only, and does not become the sticky fallback (reference :287-306)."""
+    api, h = make_handler("auto")
+    h.last_language = "de"
+    h.engine.detect_result = h.tokens.lang_to_id["ru"]
+    out = list(h.process(vad(api)))[0]
+    assert out.language_code == "ru-auto" and h.last_language == "de"
+    calls = [c for c in h.engine.calls if c[0] == "transcribe"]
+    assert len(calls) == 1 and calls[0][2][1] == h.tokens.lang_to_id["ru"]
+
+
+def test_no_detection_falls_back_to_last_language_then_english():
+    api, h = make_handler("auto")
+    h.engine.detect_result = None                      # the detector returns nothing usable
+    h.last_language = "de"
+    assert list(h.process(vad(api)))[0].language_code == "de-auto"
+    h.last_language = None
+    out = list(h.process(vad(api)))[0]
+    assert out.language_code == "en-auto"
+    assert [c[0] for c in h.engine.calls].count("transcribe") == 2   # one generate per utterance, no retry
+
+
+def test_detect_language_failure_is_survivable():
+    api, h = make_handler("auto")
+    h.last_language = "de"
+    h.engine.detect_result = RuntimeError("no kernel")
+    out = list(h.process(vad(api)))[0]
+    assert out.text == "11 22 33" and out.language_code == "de-auto"
+    assert [c[0] for c in h.engine.calls].count("transcribe") == 1
+
+
+def test_language_code_has_no_auto_suffix_when_start_language_is_not_auto():
+    api, h = make_handler("en")
+    assert list(h.process(vad(api)))[0].language_code == "en"
 
 
 def test_runs_inside_the_stage_thread_loop_and_survives_errors():
