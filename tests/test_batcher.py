@@ -20,7 +20,7 @@ def test_concurrent_requests_share_a_launch_and_results_are_routed():
         time.sleep(0.01)
         return [x * 10 for x in items]
 
-    b = SessionBatcher(run, max_batch=8, max_wait_s=0.05)
+    b = SessionBatcher(run, max_batch=8, max_wait_s=0.25)  # generous window: thread start-up jitter on a loaded box
     try:
         out = {}
 
@@ -31,7 +31,7 @@ def test_concurrent_requests_share_a_launch_and_results_are_routed():
         [t.start() for t in ths]
         [t.join(5) for t in ths]
         assert out == {i: i * 10 for i in range(8)}
-        assert b.items_run == 8 and b.batches_run <= 2 and b.largest_batch >= 4  # 8 arrivals inside the 50 ms window
+        assert b.items_run == 8 and b.batches_run <= 2 and b.largest_batch >= 4  # 8 arrivals inside the window
         assert all(k == "k" for k, _ in seen)
     finally:
         b.close()
@@ -198,7 +198,7 @@ def test_llm_decode_chunks_of_concurrent_sessions_share_a_launch():
     real_tensor = torch.tensor
     torch.tensor = lambda data, dtype=None, device=None: real_tensor(data, dtype=dtype)  # no CUDA on the CPU box
     try:
-        bundle = _LlamaBundle(eng, tok, [7], max_sessions=3, batch_wait_s=0.05)
+        bundle = _LlamaBundle(eng, tok, [7], max_sessions=3, batch_wait_s=0.2)
         outs = {}
 
         def session(i):

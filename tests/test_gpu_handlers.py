@@ -52,7 +52,7 @@ def test_concurrent_sessions_share_one_engine_and_match_the_single_session_path(
     want = [list(single.process(api.VADAudio(audio=a, mode="final")))[0].text for a in auds]
     single.cleanup()
     units = [B200WhisperSTTHandler(Event(), queue_in=Queue(), queue_out=Queue(),
-                                   setup_kwargs=dict(kw, max_batch=8, batch_wait_ms=50.0)) for _ in range(6)]
+                                   setup_kwargs=dict(kw, max_batch=8, batch_wait_ms=200.0)) for _ in range(6)]
     assert all(u.bundle is units[0].bundle for u in units)  # ONE engine, one copy of the weights
     got = {}
 
@@ -117,7 +117,7 @@ def test_llm_handlers_share_one_engine_and_merge_decode_chunks():
         "".join(single.generate_text_stream(p, 24))
         want.append(list(single.streamer.generated))
     single.cleanup()
-    units = [make(max_sessions=3, batch_wait_ms=40.0) for _ in range(3)]
+    units = [make(max_sessions=3, batch_wait_ms=200.0) for _ in range(3)]
     assert all(u.bundle is units[0].bundle for u in units) and sorted(u.slot for u in units) == [0, 1, 2]
     runs = []
     for _ in range(2):

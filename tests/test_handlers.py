@@ -71,9 +71,9 @@ def make_handler(language="en", gen_kwargs=None, max_batch=1, engine=None):
         begin_suppress: tuple = ()
 
     h._E = SimpleNamespace(WhisperDecodeOptions=Opts)
-    h.max_batch, h.batch_wait_s, h._shared_key = max_batch, 0.02, None
+    h.max_batch, h.batch_wait_s, h._shared_key = max_batch, 0.2, None
     h.bundle = WH._EngineBundle(h._E, engine or FakeEngine(), WH.TokenTable.synthetic(51865), lambda ids: " ".join(map(str, ids)),
-                                max_batch, 0.02)
+                                max_batch, 0.2)
     h.engine, h.tokens, h._decode_text = h.bundle.engine, h.bundle.tokens, h.bundle.decode_text
     h.processor = None
     return api, h
