@@ -55,3 +55,40 @@ def test_oracle_equals_the_reference_handler_helpers():
         assert np.array_equal(T.postproc(x), Qwen3TTSHandler._to_int16(h, ref16k))
     same = rng.standard_normal(100).astype(np.float32)
     assert Qwen3TTSHandler._resample_to_pipeline_sr(h, same, 16000) is same  # pipeline rate passes through untouched
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference tree not present (GPU box)")
+def test_patched_tts_handler_keeps_the_reference_pinned_token_budgets():
+    """The only golden values the reference's tests hold on this path are `_estimate_max_new_tokens` = 360 / 576 / cap
+    (tests/test_qwen3_tts_handler_backend.py:915-964).  The handler class with the GPU post-processing patched in must
+    still produce them (the estimator stays the reference's own Python) and must leave non-24 kHz audio on the scipy path."""
+    sys.path.insert(0, REF_SRC)
+    try:
+        from speech_to_speech.TTS.qwen3_tts_handler import Qwen3TTSHandler
+    except Exception as e:
+        pytest.skip(f"reference TTS handler not importable here: {e}")
+    finally:
+        sys.path.remove(REF_SRC)
+    from speech_to_speech_b200.handlers.qwen3_tts_postproc import patch_handler_class
+
+    cls = patch_handler_class(Qwen3TTSHandler)
+    assert issubclass(cls, Qwen3TTSHandler)
+    h = object.__new__(cls)
+    h.streaming_chunk_size, h.max_new_tokens = 8, 1536
+    long_text = " ".join(["This is a deliberately long sentence for the Qwen3 TTS budget estimator."] * 12)
+    assert h._estimate_max_new_tokens("Hello there.") == 360
+    assert h._estimate_max_new_tokens("我懂，心情不好时会让人特别疲惫。") == 360
+    cjk_long = ("上海是一座充满活力的现代化大都市，既有繁华的金融中心和摩天大楼，也有老城厢的弄堂风情"
+                "和江南水乡的韵味。这里交通便利，餐饮选择丰富，从精致西餐到地道小馆应有尽有。同时，上海"
+                "还是文化与创新的交汇点，艺术展览、科技展会和国际活动频繁。如果你喜欢快节奏的生活和多元"
+                "的氛围，上海会是个很吸引人的地方。你想了解哪方面的具体信息呢？")
+    assert h._estimate_max_new_tokens(cjk_long) == 576
+    budget = h._estimate_max_new_tokens(long_text)
+    assert budget > 360 and budget % 8 == 0 and budget <= 1536
+    h.max_new_tokens = 400
+    assert h._estimate_max_new_tokens(long_text) == 400
+    # audio that is not 24 kHz never touches the GPU path: identical to the reference's scipy result
+    x = (0.2 * np.random.default_rng(0).standard_normal(4410)).astype(np.float32)
+    ref = Qwen3TTSHandler._resample_to_pipeline_sr(object.__new__(Qwen3TTSHandler), x, 44100)
+    assert np.array_equal(h._resample_to_pipeline_sr(x, 44100), ref)
+    assert np.array_equal(h._to_int16(ref), Qwen3TTSHandler._to_int16(object.__new__(Qwen3TTSHandler), ref))
