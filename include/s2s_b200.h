@@ -94,14 +94,16 @@ int s2s_whisper_encode(s2s_whisper* m, const float* mel_in_d, int32_t B, float* 
 /* Greedy decode of the B utterances encoded last.  ids_out_d: [B, max_new_tokens] i32 (generated
  * tokens incl. EOS, then EOS padding), len_out_d: [B] i32.  forced_d (optional, [B, max_new_tokens]):
  * teacher-forced feedback tokens for parity tests.  logits_out_d (optional): [max_new_tokens, B, vocab]
- * f32 processed logits of every generation step.                                              */
+ * f32 processed logits of every generation step (B <= s2s_whisper_max_decode_batch).  Up to 16 sessions share one
+ * persistent launch (larger B is split); a single session uses the thread-block-cluster kernel.     */
 int s2s_whisper_decode(s2s_whisper* m, const s2s_whisper_decode_opts* opts, int32_t B, int32_t* ids_out_d,
                        int32_t* len_out_d, const int32_t* forced_d, float* logits_out_d, void* stream);
 /* One decoder step from <|sot|>, logits restricted to lang_ids -> lang_out_d[B] (detect_language). */
 int s2s_whisper_detect_language(s2s_whisper* m, int32_t sot_id, const int32_t* lang_ids_h, int32_t n_lang,
                                 int32_t B, int32_t* lang_out_d, void* stream);
 /* Profiling aid: when trace_d != NULL the next decode launches record, for CTA 0 and the last CTA, the
- * %globaltimer (ns) at [phase begin, after staging, -, -, phase body end, barrier exit] of the first
+ * %globaltimer (ns) at [phase begin, inputs staged, arrived at the grid barrier, next phase prepared, phase body end,
+ * barrier exit] (the cluster kernel uses slots 2 and 3 for its intra-phase milestones) of the first
  * `capacity` phases into trace_d[2][capacity][6] (u64).  NULL disables tracing.                                          */
 int s2s_whisper_set_trace(s2s_whisper* m, uint64_t* trace_d, int32_t capacity);
 /* Sessions one persistent decode launch can carry for this geometry (<= 16; larger batches are split by the library).
@@ -148,7 +150,7 @@ int s2s_llama_session_reset(s2s_llama* m, int32_t slot);
  * next_id_d optional [1] i32 = argmax of the last position.                                 */
 int s2s_llama_prefill(s2s_llama* m, int32_t slot, const int32_t* ids_h, int32_t n, float* logits_out_d,
                       int32_t* next_id_d, void* stream);
-/* Greedy decode for B (<= 4) sessions in one persistent launch.  slots_h[B]; first_ids_d[B] are the tokens to
+/* Greedy decode for B (<= s2s_llama_max_decode_batch: 16, 4 for Llama-3-8B) sessions in one persistent launch.  slots_h[B]; first_ids_d[B] are the tokens to
  * feed first (the prefill argmax); ids_out_d [B, n_steps] receives the n_steps tokens generated AFTER them; eos stops
  * a row (eos_id < 0 disables); forced_d optional [B, n_steps] teacher-forced feedback; logits_out_d optional
  * [n_steps, B, vocab].                                                                              */
