@@ -722,10 +722,11 @@ int launch_cluster_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, 
   static thread_local size_t cached_smem = 0;
   static thread_local int cached_heads = -1, cached_cs = 0, cached_n = 0;
   int cs = 0, n_clusters = 0;
-  if (cached_smem == smem && cached_heads == p.heads) { cs = cached_cs; n_clusters = cached_n; }
+  const bool cache_hit = cached_smem == smem && cached_heads == p.heads;
+  if (cache_hit) { cs = cached_cs; n_clusters = cached_n; }
   // only the 8-CTA configuration is validated on hardware (12 heads of Whisper-small on 14-15 co-resident clusters);
   // geometries whose heads do not fit (large-v3: 20 heads) use the 8-phase kernel
-  for (int cand = 8; cand >= 8 && !cs && cached_smem != smem; cand >>= 1) {
+  for (int cand = 8; cand >= 8 && !cs && !cache_hit; cand >>= 1) {
     cudaLaunchConfig_t qc{};
     qc.gridDim = dim3((ctx->num_sms / cand) * cand); qc.blockDim = dim3(DEC_THREADS); qc.dynamicSmemBytes = smem;
     cudaLaunchAttribute qa[1];
