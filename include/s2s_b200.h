@@ -135,7 +135,10 @@ typedef struct {
   int32_t max_sessions;   /* KV-cache slots */
   int32_t max_positions;  /* per session */
   int32_t max_prefill;    /* longest prompt chunk per call */
-  int32_t qk_norm;        /* 1 = Qwen3-style per-head RMSNorm on q,k (TTS talker); 0 = Llama */
+  int32_t qk_norm;        /* 1 = Qwen3-style per-head RMSNorm(head_dim) on q,k before RoPE (transformers
+                             modeling_qwen3.py Qwen3Attention: the reference's default LLM family and the TTS talker); 0 = Llama */
+  int32_t n_tables;       /* 0/1 = one embedding table + one output head; >1 = one pair per codebook
+                             ("model.embed_tokens.<i>.weight", "lm_head.<i>.weight"), used by the TTS code predictor */
 } s2s_llama_config;
 
 int s2s_llama_create(s2s_ctx* ctx, const s2s_llama_config* cfg, s2s_llama** out);

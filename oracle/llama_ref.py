@@ -64,11 +64,16 @@ class KVCache:
         return self.k[0].shape[0]
 
 
-def forward(w, g: LlamaGeometry, ids: np.ndarray, cache: KVCache, return_hidden: bool = False):
-    """ids [T] appended to the cache -> logits [T, vocab] (fp32)."""
-    T = len(ids)
+def forward(w, g: LlamaGeometry, ids: np.ndarray, cache: KVCache, return_hidden: bool = False, inputs_embeds=None):
+    """ids [T] (or inputs_embeds [T, d], the `inputs_embeds=` path of the HF models) appended to the cache ->
+    logits [T, vocab] (fp32)."""
+    if inputs_embeds is not None:
+        x = np.asarray(inputs_embeds, np.float32)
+        T = x.shape[0]
+    else:
+        T = len(ids)
+        x = w["model.embed_tokens.weight"][ids].astype(np.float32)
     past = cache.length
-    x = w["model.embed_tokens.weight"][ids].astype(np.float32)
     cos, sin = rope_cos_sin(g, np.arange(past, past + T))
     hs = [x]
     grp = g.heads // g.kv_heads

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs2s_b200.so")
+# S2S_LIB_PATH: developer aid (A/B of two builds); the product always loads the in-tree library
+LIB_PATH = os.environ.get("S2S_LIB_PATH") or os.path.join(_HERE, "libs2s_b200.so")
 
 S2S_F32, S2S_F16, S2S_BF16 = 0, 1, 2
 DTYPE_CODES = {"float32": S2S_F32, "float16": S2S_F16, "bfloat16": S2S_BF16}
@@ -43,7 +44,7 @@ class LlamaConfig(C.Structure):
         ("head_dim", C.c_int32), ("ffn", C.c_int32), ("vocab", C.c_int32),
         ("rope_theta", C.c_float), ("rms_eps", C.c_float),
         ("compute_dtype", C.c_int32), ("max_sessions", C.c_int32), ("max_positions", C.c_int32),
-        ("max_prefill", C.c_int32), ("qk_norm", C.c_int32),
+        ("max_prefill", C.c_int32), ("qk_norm", C.c_int32), ("n_tables", C.c_int32),
     ]
 
 

@@ -41,8 +41,12 @@ __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
 // Polling the counter costs one L2 round trip (~0.7 us) per sample; with a single load in flight the release is
 // noticed on average half a round trip late.  Thread 0 therefore keeps FOUR relaxed loads in flight, issued a
 // quarter round trip apart; the pipeline is self-clocking (each consumed load is re-issued at once), so the counter
-// is sampled every ~0.18 us.  An acquire fence after the successful sample orders the other CTAs' data.
-__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int epoch_thread0) {
+// is sampled every ~0.18 us.  After the successful sample thread 0 executes fence.acq_rel.gpu: relaxed load + fence is
+// the PTX acquire pattern, it synchronises with every producer's red.release, and the bar.sync that follows extends
+// the ordering to the CTA's other threads (causality order is transitive over barriers).  `relaxed` != 0 skips the
+// fence (A/B measurements only, S2S_SYNC_RELAXED=1): without it the cross-CTA reads race under the PTX memory model
+// even when every one of them is an L2 access.
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int epoch_thread0, int relaxed = 0) {
   if (threadIdx.x == 0) {
     const unsigned int target = epoch_thread0 * gridDim.x;
     unsigned int v0 = ld_relaxed_gpu(counter), v1 = 0, v2 = 0, v3 = 0;
@@ -69,15 +73,18 @@ __device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int ep
         if (++spins > (1u << 26)) __trap();
       }
     }
-    // No fence here (fence.acq_rel.gpu = MEMBAR.SC.GPU + L1 invalidate, ~1 us, and it would wait for the polls still
-    // in flight): every read of another CTA's data is an L2 access (ld.global.cg / cp.async.cg / bulk copy) issued
-    // after the bar.sync below, and the producers' red.release made their data visible at L2 before the count.
+    if (!relaxed) asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();
 }
 __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& epoch) {
   grid_arrive(counter, epoch);
   grid_wait(counter, epoch);
+}
+// host: S2S_SYNC_RELAXED=1 selects the unfenced barrier waits (measurement aid, never the default)
+inline int dec_sync_relaxed_env() {
+  const char* e = getenv("S2S_SYNC_RELAXED");  // read per launch so one process can A/B
+  return (e && e[0] == '1') ? 1 : 0;
 }
 
 // Warp w of CTA c takes work items  w * gridDim.x + c, then + total_warps ...: consecutive items land on
@@ -326,6 +333,8 @@ struct GemvArgs {
   // cache element (b, c): kv0 + which*kv_which + slot[b]*kv_slot + pos[b]*kv_ld + c ; rope[pos][j] = (cos, sin)
   const int* pos; const int* slot; long long kv_slot; int kv_ld; const float2* rope; int hd, q_rows, k_rows;
   float q_scale;               // softmax scale folded into the stored q (head_dim^-0.5)
+  float* kraw;                 // Qwen3 (qk_norm): non-null -> q and k are stored RAW (fp32: q -> out, k -> kraw[b][k_rows]); the
+                               // per-head RMSNorm + RoPE + cache append run in the following phase (llama_decode.cu ld_qknorm)
   int plan_id;                 // index into GemvRing::plans_s (>= 0) or -1: plan on the fly
 };
 
@@ -365,6 +374,11 @@ __device__ __forceinline__ void gemv_pair_epilogue(const GemvArgs& a, int mode, 
   } else if (LLAMA) {  // EPI_QKV_ROPE
     const int kv_end = a.q_rows + a.k_rows;
     const int p = __ldcg(a.pos + b);
+    if (a.kraw && row0 < kv_end) {
+      float* dst = row0 < a.q_rows ? a.out + (long long)b * a.ldo + row0 : a.kraw + (long long)b * a.k_rows + (row0 - a.q_rows);
+      *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+      return;
+    }
     if (row0 < kv_end) {
       const float2 cs = a.rope[(long long)p * (a.hd >> 1) + ((row0 % a.hd) >> 1)];
       const float t0 = v0 * cs.x - v1 * cs.y, t1 = v1 * cs.x + v0 * cs.y;

@@ -20,20 +20,9 @@
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "llama_decode.cuh"
+#include "llama_model.cuh"
 
 namespace {
-
-enum LSlotKind { L_PLAIN = 0, L_ROPE_PERM = 1, L_INTERLEAVE = 2 };
-struct LSlot {
-  void* dst = nullptr;
-  bool half = false;
-  int64_t rows = 0, cols = 0;
-  int kind = L_PLAIN;
-  int hd = 0;          // ROPE_PERM
-  int parity = 0;      // INTERLEAVE: 0 gate, 1 up
-  bool bound = false;
-  float rnd_scale = 0.02f, rnd_offset = 0.f;
-};
 
 template <typename T>
 __global__ void embed_gather_kernel(const int* __restrict__ ids, const T* __restrict__ embed, float* __restrict__ x, int d) {
@@ -61,6 +50,40 @@ __global__ void rope_prefill_kernel(T* __restrict__ qkv, int n, int qd, int kvd,
     else if (i < qd + kvd) *reinterpret_cast<uint32_t*>(kcache + (long long)(past + t) * kvd + (i - qd)) = u;
     else *reinterpret_cast<uint32_t*>(vcache + (long long)(past + t) * kvd + (i - qd - kvd)) = u;
   }
+}
+
+// Qwen3 (qk_norm): per (token, head) RMSNorm over head_dim (fp32 statistics, Qwen3RMSNorm) then RoPE; q in place,
+// k -> cache, v -> cache.  One CTA per token, a warp per head; rows and norm weights are stored pair-adjacent.
+template <typename T, int HD>
+__global__ void qknorm_rope_prefill_kernel(T* __restrict__ qkv, int H, int KV, int past, const float2* __restrict__ rope,
+                                           const float* __restrict__ qn, const float* __restrict__ kn, float eps,
+                                           T* __restrict__ kcache, T* __restrict__ vcache) {
+  constexpr int PER = HD / 32;
+  const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int qd = H * HD, kvd = KV * HD, ld = qd + 2 * kvd;
+  T* row = qkv + (long long)t * ld;
+  const float2* cs = rope + (long long)(past + t) * (HD >> 1);
+  for (int h = warp; h < H + KV; h += nw) {
+    T* src = row + h * HD + lane * PER;
+    const float* g = (h < H ? qn : kn) + lane * PER;
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i += 2) { const float2 f = DT<T>::to_f2(*reinterpret_cast<const uint32_t*>(src + i)); v[i] = f.x; v[i + 1] = f.y; }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) ss = fmaf(v[i], v[i], ss);
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss * (1.0f / (float)HD) + eps);
+    T* dst = h < H ? src : kcache + (long long)(past + t) * kvd + (h - H) * HD + lane * PER;
+#pragma unroll
+    for (int i = 0; i < PER; i += 2) {
+      const float2 c = cs[(lane * PER + i) >> 1];
+      const float a0 = v[i] * rstd * g[i], a1 = v[i + 1] * rstd * g[i + 1];
+      *reinterpret_cast<uint32_t*>(dst + i) = DT<T>::pack2(a0 * c.x - a1 * c.y, a1 * c.x + a0 * c.y);
+    }
+  }
+  for (int i = threadIdx.x * 2; i < kvd; i += blockDim.x * 2)
+    *reinterpret_cast<uint32_t*>(vcache + (long long)(past + t) * kvd + i) = *reinterpret_cast<const uint32_t*>(row + qd + kvd + i);
 }
 
 __global__ void argmax_row_kernel(const float* __restrict__ logits, int n, int* __restrict__ out) {
@@ -101,46 +124,9 @@ inline float src_f32(const void* data, int64_t i, int dtype) {
 
 }  // namespace
 
-struct s2s_llama {
-  s2s_ctx* ctx = nullptr;
-  s2s_llama_config cfg{};
-  bool finalized = false;
-  int debug_phases = 0;
-  std::vector<void*> allocs;
-  std::unordered_map<std::string, LSlot> slots;
-  bool lm_head_bound = false;
-  // weights
-  void *embed = nullptr, *lm_head = nullptr;
-  float* norm_f = nullptr;
-  std::vector<LlamaDecLayer> layers_h;   // row-major weights (prefill GEMMs)
-  std::vector<LlamaDecLayer> tiled_h;    // fragment-major copies streamed by the decode kernel
-  LlamaDecLayer* layers_d = nullptr;     // device copy of tiled_h
-  void* lm_head_t = nullptr;
-  float2* rope = nullptr;
-  // KV + sessions
-  void* kv = nullptr;
-  long long kv_slot_stride = 0, kv_layer_stride = 0, kv_which_stride = 0;
-  std::vector<int> len;  // tokens in each slot
-  // prefill workspace
-  int* ids_d = nullptr;
-  float *x = nullptr, *last_logits = nullptr;
-  void *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *vt = nullptr;
-  size_t vt_elems = 0;
-  // decode state
-  float *dx = nullptr, *dq = nullptr, *dh = nullptr, *part = nullptr, *cand_val = nullptr;
-  void* attn16 = nullptr;
-  unsigned int* attn_cnt = nullptr;
-  int *slot_d = nullptr, *pos_d = nullptr, *done = nullptr, *n_done = nullptr, *cand_idx = nullptr, *out_ids = nullptr,
-      *out_len = nullptr, *next_id = nullptr;
-  unsigned int* sync_counter = nullptr;
-  int s_max = 0;
-  unsigned long long* trace = nullptr;
-  int trace_cap = 0;
-};
-
 namespace {
 
-constexpr int MAX_DEC_B = 16;  // upper bound; the shared-memory budget of the geometry may allow fewer (llama_decode_max_batch)
+constexpr int MAX_DEC_B = LLAMA_MAX_DEC_B;
 
 template <typename P> int lalloc(s2s_llama* m, P** out, size_t bytes, bool zero = true) {
   void* p = nullptr;
@@ -164,18 +150,28 @@ int build(s2s_llama* m) {
   const int d = c.d_model, f = c.ffn, hd = c.head_dim, qd = c.heads * hd, kvd = c.kv_heads * hd;
   const int esz = 2;
   auto off = [&](void* base, int64_t elems) { return reinterpret_cast<char*>(base) + elems * esz; };
-  S2S_CHECK(lalloc(m, &m->embed, (size_t)c.vocab * d * esz));
-  S2S_CHECK(lalloc(m, &m->lm_head, (size_t)c.vocab * d * esz));
+  m->n_tables = c.n_tables > 1 ? c.n_tables : 1;
+  m->embed_table_elems = (size_t)c.vocab * d;
+  m->head_table_elems = (size_t)c.vocab * d;
+  S2S_CHECK(lalloc(m, &m->embed, m->n_tables * m->embed_table_elems * esz));
+  S2S_CHECK(lalloc(m, &m->lm_head, m->n_tables * m->head_table_elems * esz));
   S2S_CHECK(lalloc(m, &m->norm_f, d * 4));
-  lslot(m, "model.embed_tokens.weight", m->embed, true, c.vocab, d, 0.02f);
-  lslot(m, "lm_head.weight", m->lm_head, true, c.vocab, d, 0.02f);
+  if (m->n_tables == 1) {
+    lslot(m, "model.embed_tokens.weight", m->embed, true, c.vocab, d, 0.02f);
+    lslot(m, "lm_head.weight", m->lm_head, true, c.vocab, d, 0.02f);
+  } else {  // code predictor: one table / head per codebook (Qwen3OmniMoeTalkerCodePredictorModel.codec_embedding, .lm_head)
+    for (int t = 0; t < m->n_tables; ++t) {
+      lslot(m, "model.embed_tokens." + std::to_string(t) + ".weight", off(m->embed, (int64_t)t * m->embed_table_elems), true, c.vocab, d, 0.02f);
+      lslot(m, "lm_head." + std::to_string(t) + ".weight", off(m->lm_head, (int64_t)t * m->head_table_elems), true, c.vocab, d, 0.02f);
+    }
+  }
   lslot(m, "model.norm.weight", m->norm_f, false, d, 1, 0.1f, 1.0f);
   m->layers_h.resize(c.layers);
   const float sd = 1.0f / sqrtf((float)d);
   for (int i = 0; i < c.layers; ++i) {
     const std::string p = "model.layers." + std::to_string(i) + ".";
     void *w_qkv, *w_o, *w_gu, *w_down;
-    float *n1, *n2;
+    float *n1, *n2, *qn = nullptr, *kn = nullptr;
     S2S_CHECK(lalloc(m, &w_qkv, (size_t)(qd + 2 * kvd) * d * esz));
     S2S_CHECK(lalloc(m, &w_o, (size_t)d * qd * esz));
     S2S_CHECK(lalloc(m, &w_gu, (size_t)2 * f * d * esz));
@@ -191,8 +187,14 @@ int build(s2s_llama* m) {
     lslot(m, p + "mlp.down_proj.weight", w_down, true, d, f, 0.7f / sqrtf((float)f));
     lslot(m, p + "input_layernorm.weight", n1, false, d, 1, 0.1f, 1.0f);
     lslot(m, p + "post_attention_layernorm.weight", n2, false, d, 1, 0.1f, 1.0f);
+    if (c.qk_norm) {  // Qwen3Attention.q_norm / k_norm: RMSNorm(head_dim), permuted like the q/k rows
+      S2S_CHECK(lalloc(m, &qn, hd * 4));
+      S2S_CHECK(lalloc(m, &kn, hd * 4));
+      lslot(m, p + "self_attn.q_norm.weight", qn, false, hd, 1, 0.1f, 1.0f, L_ROPE_PERM, hd);
+      lslot(m, p + "self_attn.k_norm.weight", kn, false, hd, 1, 0.1f, 1.0f, L_ROPE_PERM, hd);
+    }
     LlamaDecLayer& L = m->layers_h[i];
-    L.w_qkv = w_qkv; L.w_o = w_o; L.w_gu = w_gu; L.w_down = w_down; L.norm1 = n1; L.norm2 = n2;
+    L.w_qkv = w_qkv; L.w_o = w_o; L.w_gu = w_gu; L.w_down = w_down; L.norm1 = n1; L.norm2 = n2; L.q_norm = qn; L.k_norm = kn;
   }
   S2S_CHECK(lalloc(m, &m->layers_d, sizeof(LlamaDecLayer) * c.layers));
   S2S_CHECK_CUDA(cudaMemcpy(m->layers_d, m->layers_h.data(), sizeof(LlamaDecLayer) * c.layers, cudaMemcpyHostToDevice));
@@ -246,6 +248,7 @@ int build(s2s_llama* m) {
   S2S_CHECK(lalloc(m, &m->out_len, MAX_DEC_B * 4));
   S2S_CHECK(lalloc(m, &m->next_id, 16));
   S2S_CHECK(lalloc(m, &m->sync_counter, 16));
+  S2S_CHECK(lalloc(m, &m->kraw, (size_t)MAX_DEC_B * kvd * 4));
   return S2S_OK;
 }
 
@@ -258,6 +261,100 @@ GemmProblem lgemm(const void* a, int64_t lda, const void* w, int64_t ldw, int64_
 
 }  // namespace
 
+int llama_max_decode_batch_of(const s2s_llama* m) {
+  return std::min(MAX_DEC_B, llama_decode_max_batch(m->cfg.d_model, m->cfg.ffn, m->cfg.heads * m->cfg.head_dim));
+}
+
+void llama_fill_dec_params(s2s_llama* m, LlamaDecParams& p) {
+  const auto& c = m->cfg;
+  p.d = c.d_model; p.heads = c.heads; p.kv_heads = c.kv_heads; p.hd = c.head_dim; p.layers = c.layers; p.ffn = c.ffn;
+  p.vocab = c.vocab; p.max_pos = c.max_positions; p.eps = c.rms_eps;
+  p.lw = m->layers_d; p.embed = m->embed; p.lm_head = m->lm_head_t; p.norm_f = m->norm_f; p.rope = m->rope;
+  p.x = m->dx; p.q = m->dq; p.h = m->dh; p.kv = m->kv;
+  p.kv_slot_stride = m->kv_slot_stride; p.kv_layer_stride = m->kv_layer_stride; p.kv_which_stride = m->kv_which_stride;
+  p.part = m->part; p.s_max = m->s_max; p.attn16 = m->attn16; p.attn_cnt = m->attn_cnt;
+  p.done = m->done; p.n_done = m->n_done; p.cand_val = m->cand_val; p.cand_idx = m->cand_idx; p.sync_counter = m->sync_counter;
+  p.trace = m->trace; p.trace_cap = m->trace_cap;
+  p.qk_norm = c.qk_norm ? 1 : 0; p.kraw = m->kraw;
+}
+
+int llama_prefill_rows(s2s_llama* m, int slot, int n, float* logits_out_d, int32_t* next_id_d, float* hidden_out_d,
+                       cudaStream_t st) {
+  const auto& c = m->cfg;
+  S2S_REQUIRE(n >= 1 && n <= c.max_prefill, "llama prefill: n=%d outside [1,%d]", n, c.max_prefill);
+  const int past = m->len[slot];
+  S2S_REQUIRE(past + n <= c.max_positions, "llama prefill: %d + %d tokens exceed max_positions %d", past, n, c.max_positions);
+  const int d = c.d_model, f = c.ffn, hd = c.head_dim, qd = c.heads * hd, kvd = c.kv_heads * hd, dt = c.compute_dtype;
+  const int ldq = qd + 2 * kvd;
+  const bool bf = dt == S2S_BF16;
+  char* kvb = reinterpret_cast<char*>(m->kv) + (size_t)slot * m->kv_slot_stride * 2;
+  for (int i = 0; i < c.layers; ++i) {
+    const LlamaDecLayer& L = m->layers_h[i];
+    char* kc = kvb + (size_t)i * m->kv_layer_stride * 2;
+    char* vc = kc + (size_t)m->kv_which_stride * 2;
+    S2S_CHECK(norm_rows_launch(m->x, L.norm1, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
+    {
+      GemmProblem p = lgemm(m->xn, d, L.w_qkv, d, n, ldq, d);
+      p.out_h = m->qkv; p.ldo_h = ldq;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    if (c.qk_norm) {
+#define S2S_QKN(T, HD) qknorm_rope_prefill_kernel<T, HD><<<n, 256, 0, st>>>((T*)m->qkv, c.heads, c.kv_heads, past, m->rope, \
+                                                                             L.q_norm, L.k_norm, c.rms_eps, (T*)kc, (T*)vc)
+      if (bf) { if (hd == 128) S2S_QKN(__nv_bfloat16, 128); else S2S_QKN(__nv_bfloat16, 64); }
+      else { if (hd == 128) S2S_QKN(__half, 128); else S2S_QKN(__half, 64); }
+#undef S2S_QKN
+    } else if (bf) {
+      rope_prefill_kernel<__nv_bfloat16><<<n, 256, 0, st>>>((__nv_bfloat16*)m->qkv, n, qd, kvd, hd, past, m->rope,
+                                                            (__nv_bfloat16*)kc, (__nv_bfloat16*)vc);
+    } else {
+      rope_prefill_kernel<__half><<<n, 256, 0, st>>>((__half*)m->qkv, n, qd, kvd, hd, past, m->rope, (__half*)kc, (__half*)vc);
+    }
+    S2S_LAUNCH_CHECK();
+    S2S_CHECK(attention_tc_launch(m->ctx, m->qkv, kc, vc, m->attn, 1, n, past + n, c.heads, c.kv_heads, hd, ldq, kvd, kvd, qd,
+                                   1.0f / sqrtf((float)hd), 1, dt, m->vt, m->vt_elems, st));
+    {
+      GemmProblem p = lgemm(m->attn, qd, L.w_o, qd, n, d, qd);
+      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    S2S_CHECK(norm_rows_launch(m->x, L.norm2, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
+    {
+      GemmProblem p = lgemm(m->xn, d, L.w_gu, d, n, 2 * f, d);
+      p.act = 2; p.out_h = m->hbuf; p.ldo_h = f;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    {
+      GemmProblem p = lgemm(m->hbuf, f, L.w_down, f, n, d, f);
+      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+  }
+  if (hidden_out_d)
+    S2S_CHECK_CUDA(cudaMemcpyAsync(hidden_out_d, m->x + (size_t)(n - 1) * d, (size_t)d * 4, cudaMemcpyDeviceToDevice, st));
+  S2S_CHECK(norm_rows_launch(m->x, m->norm_f, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
+  if (logits_out_d) {
+    GemmProblem p = lgemm(m->xn, d, m->lm_head, d, n, c.vocab, d);
+    p.out_f = logits_out_d; p.ldo_f = c.vocab;
+    S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+  }
+  if (next_id_d) {
+    const float* last = nullptr;
+    if (logits_out_d) {
+      last = logits_out_d + (size_t)(n - 1) * c.vocab;
+    } else {
+      GemmProblem p = lgemm(reinterpret_cast<char*>(m->xn) + (size_t)(n - 1) * d * 2, d, m->lm_head, d, 1, c.vocab, d);
+      p.out_f = m->last_logits; p.ldo_f = c.vocab;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+      last = m->last_logits;
+    }
+    argmax_row_kernel<<<1, 1024, 0, st>>>(last, c.vocab, next_id_d);
+    S2S_LAUNCH_CHECK();
+  }
+  m->len[slot] = past + n;
+  return S2S_OK;
+}
+
 extern "C" {
 
 int s2s_llama_create(s2s_ctx* ctx, const s2s_llama_config* cfg, s2s_llama** out) {
@@ -266,7 +363,6 @@ int s2s_llama_create(s2s_ctx* ctx, const s2s_llama_config* cfg, s2s_llama** out)
   S2S_REQUIRE(cfg->heads % cfg->kv_heads == 0, "llama: heads %% kv_heads != 0");
   S2S_REQUIRE(cfg->d_model % 64 == 0 && cfg->ffn % 64 == 0 && cfg->vocab % 64 == 0, "llama: d_model, ffn, vocab must be multiples of 64");
   S2S_REQUIRE(cfg->compute_dtype == S2S_BF16 || cfg->compute_dtype == S2S_F16, "llama: compute_dtype must be bf16/f16");
-  S2S_REQUIRE(cfg->qk_norm == 0, "llama: qk_norm (Qwen3-style) is not implemented yet");
   S2S_REQUIRE(cfg->max_sessions >= 1 && cfg->max_positions >= 64 && cfg->max_prefill >= 1, "llama: bad capacity");
   S2S_REQUIRE(cfg->layers >= 1 && cfg->layers <= 64, "llama: layers in [1,64]");
   S2S_CHECK_CUDA(cudaSetDevice(ctx->device));
@@ -305,7 +401,11 @@ int s2s_llama_bind_tensor(s2s_llama* m, const char* name, const void* data_h, co
   const bool bf = m->cfg.compute_dtype == S2S_BF16;
   if (!s.half) {
     std::vector<float> tmp((size_t)n);
-    for (int64_t i = 0; i < n; ++i) tmp[(size_t)i] = src_f32(data_h, i, dtype);
+    for (int64_t i = 0; i < n; ++i) {
+      int64_t di = i;
+      if (s.kind == L_ROPE_PERM) { const int64_t half = s.hd / 2, j = i % s.hd; di = (i / s.hd) * s.hd + (j < half ? 2 * j : 2 * (j - half) + 1); }
+      tmp[(size_t)di] = src_f32(data_h, i, dtype);
+    }
     S2S_CHECK_CUDA(cudaMemcpy(s.dst, tmp.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
   } else {
     // row-wise conversion + placement
@@ -327,7 +427,7 @@ int s2s_llama_bind_tensor(s2s_llama* m, const char* name, const void* data_h, co
     }
   }
   s.bound = true;
-  if (strcmp(name, "lm_head.weight") == 0) m->lm_head_bound = true;
+  if (strncmp(name, "lm_head.", 8) == 0) m->lm_head_bound = true;
   return S2S_OK;
 }
 
@@ -354,7 +454,7 @@ int s2s_llama_init_random(s2s_llama* m, uint64_t seed) {
 
 int s2s_llama_finalize(s2s_llama* m) {
   S2S_REQUIRE(m, "llama finalize: null model");
-  if (!m->lm_head_bound && m->slots["model.embed_tokens.weight"].bound) {
+  if (m->n_tables == 1 && !m->lm_head_bound && m->slots["model.embed_tokens.weight"].bound) {
     // tied embeddings (tie_word_embeddings=True): lm_head shares embed_tokens
     S2S_CHECK_CUDA(cudaMemcpy(m->lm_head, m->embed, (size_t)m->cfg.vocab * m->cfg.d_model * 2, cudaMemcpyDeviceToDevice));
     m->slots["lm_head.weight"].bound = true;
@@ -380,7 +480,8 @@ int s2s_llama_finalize(s2s_llama* m) {
         S2S_CHECK(lalloc(m, &dn, tiled_weight_elems(d, f) * 2));
         T.w_qkv = a; T.w_o = b; T.w_gu = g; T.w_down = dn;
       }
-      S2S_CHECK(lalloc(m, &m->lm_head_t, tiled_weight_elems(c.vocab, d) * 2));
+      m->head_t_table_elems = tiled_weight_elems(c.vocab, d);
+      S2S_CHECK(lalloc(m, &m->lm_head_t, m->n_tables * m->head_t_table_elems * 2));
       S2S_CHECK_CUDA(cudaMemcpy(m->layers_d, m->tiled_h.data(), sizeof(LlamaDecLayer) * c.layers, cudaMemcpyHostToDevice));
     }
     for (int i = 0; i < c.layers; ++i) {
@@ -391,7 +492,9 @@ int s2s_llama_finalize(s2s_llama* m) {
       S2S_CHECK(tile_weights_launch(R.w_gu, 2 * f, d, const_cast<void*>(T.w_gu), 0));
       S2S_CHECK(tile_weights_launch(R.w_down, d, f, const_cast<void*>(T.w_down), 0));
     }
-    S2S_CHECK(tile_weights_launch(m->lm_head, c.vocab, d, m->lm_head_t, 0));
+    for (int t = 0; t < m->n_tables; ++t)
+      S2S_CHECK(tile_weights_launch(reinterpret_cast<char*>(m->lm_head) + (size_t)t * m->head_table_elems * 2, c.vocab, d,
+                                    reinterpret_cast<char*>(m->lm_head_t) + (size_t)t * m->head_t_table_elems * 2, 0));
     S2S_CHECK_CUDA(cudaDeviceSynchronize());
   }
   m->finalized = true;
@@ -410,74 +513,15 @@ int s2s_llama_prefill(s2s_llama* m, int32_t slot, const int32_t* ids_h, int32_t 
   const auto& c = m->cfg;
   S2S_REQUIRE(slot >= 0 && slot < c.max_sessions, "llama prefill: bad slot %d", slot);
   S2S_REQUIRE(n >= 1 && n <= c.max_prefill, "llama prefill: n=%d outside [1,%d]", n, c.max_prefill);
-  const int past = m->len[slot];
-  S2S_REQUIRE(past + n <= c.max_positions, "llama prefill: %d + %d tokens exceed max_positions %d", past, n, c.max_positions);
   for (int i = 0; i < n; ++i) S2S_REQUIRE(ids_h[i] >= 0 && ids_h[i] < c.vocab, "llama prefill: token %d out of range", ids_h[i]);
   cudaStream_t st = (cudaStream_t)stream;
   S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
-  const int d = c.d_model, f = c.ffn, hd = c.head_dim, qd = c.heads * hd, kvd = c.kv_heads * hd, dt = c.compute_dtype;
-  const int ldq = qd + 2 * kvd;
   S2S_CHECK_CUDA(cudaMemcpyAsync(m->ids_d, ids_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   S2S_CHECK_CUDA(cudaStreamSynchronize(st));  // ids_h may be a temporary of the caller
-  const bool bf = dt == S2S_BF16;
-  if (bf) embed_gather_kernel<__nv_bfloat16><<<n, 256, 0, st>>>(m->ids_d, (const __nv_bfloat16*)m->embed, m->x, d);
-  else embed_gather_kernel<__half><<<n, 256, 0, st>>>(m->ids_d, (const __half*)m->embed, m->x, d);
+  if (c.compute_dtype == S2S_BF16) embed_gather_kernel<__nv_bfloat16><<<n, 256, 0, st>>>(m->ids_d, (const __nv_bfloat16*)m->embed, m->x, c.d_model);
+  else embed_gather_kernel<__half><<<n, 256, 0, st>>>(m->ids_d, (const __half*)m->embed, m->x, c.d_model);
   S2S_LAUNCH_CHECK();
-  char* kvb = reinterpret_cast<char*>(m->kv) + (size_t)slot * m->kv_slot_stride * 2;
-  for (int i = 0; i < c.layers; ++i) {
-    const LlamaDecLayer& L = m->layers_h[i];
-    char* kc = kvb + (size_t)i * m->kv_layer_stride * 2;
-    char* vc = kc + (size_t)m->kv_which_stride * 2;
-    S2S_CHECK(norm_rows_launch(m->x, L.norm1, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
-    {
-      GemmProblem p = lgemm(m->xn, d, L.w_qkv, d, n, ldq, d);
-      p.out_h = m->qkv; p.ldo_h = ldq;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-    }
-    if (bf) rope_prefill_kernel<__nv_bfloat16><<<n, 256, 0, st>>>((__nv_bfloat16*)m->qkv, n, qd, kvd, hd, past, m->rope,
-                                                                 (__nv_bfloat16*)kc, (__nv_bfloat16*)vc);
-    else rope_prefill_kernel<__half><<<n, 256, 0, st>>>((__half*)m->qkv, n, qd, kvd, hd, past, m->rope, (__half*)kc, (__half*)vc);
-    S2S_LAUNCH_CHECK();
-    S2S_CHECK(attention_tc_launch(m->ctx, m->qkv, kc, vc, m->attn, 1, n, past + n, c.heads, c.kv_heads, hd, ldq, kvd, kvd, qd,
-                                   1.0f / sqrtf((float)hd), 1, dt, m->vt, m->vt_elems, st));
-    {
-      GemmProblem p = lgemm(m->attn, qd, L.w_o, qd, n, d, qd);
-      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-    }
-    S2S_CHECK(norm_rows_launch(m->x, L.norm2, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
-    {
-      GemmProblem p = lgemm(m->xn, d, L.w_gu, d, n, 2 * f, d);
-      p.act = 2; p.out_h = m->hbuf; p.ldo_h = f;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-    }
-    {
-      GemmProblem p = lgemm(m->hbuf, f, L.w_down, f, n, d, f);
-      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-    }
-  }
-  S2S_CHECK(norm_rows_launch(m->x, m->norm_f, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
-  if (logits_out_d) {
-    GemmProblem p = lgemm(m->xn, d, m->lm_head, d, n, c.vocab, d);
-    p.out_f = logits_out_d; p.ldo_f = c.vocab;
-    S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-  }
-  if (next_id_d) {
-    const float* last = nullptr;
-    if (logits_out_d) {
-      last = logits_out_d + (size_t)(n - 1) * c.vocab;
-    } else {
-      GemmProblem p = lgemm(reinterpret_cast<char*>(m->xn) + (size_t)(n - 1) * d * 2, d, m->lm_head, d, 1, c.vocab, d);
-      p.out_f = m->last_logits; p.ldo_f = c.vocab;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-      last = m->last_logits;
-    }
-    argmax_row_kernel<<<1, 1024, 0, st>>>(last, c.vocab, next_id_d);
-    S2S_LAUNCH_CHECK();
-  }
-  m->len[slot] = past + n;
-  return S2S_OK;
+  return llama_prefill_rows(m, slot, n, logits_out_d, next_id_d, nullptr, st);
 }
 
 int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int32_t* first_ids_d, int32_t n_steps,
@@ -485,9 +529,10 @@ int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int3
                      float* logits_out_d, void* stream) {
   S2S_REQUIRE(m && m->finalized && slots_h && first_ids_d && ids_out_d && len_out_d, "llama decode: null argument");
   const auto& c = m->cfg;
-  const int max_b = std::min(MAX_DEC_B, llama_decode_max_batch(m->cfg.d_model, m->cfg.ffn, m->cfg.heads * m->cfg.head_dim));
+  const int max_b = llama_max_decode_batch_of(m);
   S2S_REQUIRE(B >= 1 && B <= max_b, "llama decode: B=%d outside [1,%d] for this geometry", B, max_b);
   S2S_REQUIRE(n_steps >= 1, "llama decode: n_steps must be >= 1");
+  S2S_REQUIRE(m->n_tables == 1, "llama decode: multi-table models are driven by the TTS entry points");
   cudaStream_t st = (cudaStream_t)stream;
   S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
   int pos_h[MAX_DEC_B], max_len = 0;
@@ -503,16 +548,10 @@ int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int3
   S2S_CHECK_CUDA(cudaMemcpyAsync(m->pos_d, pos_h, B * 4, cudaMemcpyHostToDevice, st));
   S2S_CHECK_CUDA(cudaStreamSynchronize(st));
   LlamaDecParams p{};
-  p.d = c.d_model; p.heads = c.heads; p.kv_heads = c.kv_heads; p.hd = c.head_dim; p.layers = c.layers; p.ffn = c.ffn;
-  p.vocab = c.vocab; p.B = B; p.max_pos = c.max_positions; p.eps = c.rms_eps;
-  p.lw = m->layers_d; p.embed = m->embed; p.lm_head = m->lm_head_t; p.norm_f = m->norm_f; p.rope = m->rope;
-  p.x = m->dx; p.q = m->dq; p.h = m->dh; p.kv = m->kv;
-  p.kv_slot_stride = m->kv_slot_stride; p.kv_layer_stride = m->kv_layer_stride; p.kv_which_stride = m->kv_which_stride;
-  p.part = m->part; p.s_max = m->s_max; p.attn16 = m->attn16; p.attn_cnt = m->attn_cnt; p.slot = m->slot_d; p.pos = m->pos_d; p.max_len = max_len;
+  llama_fill_dec_params(m, p);
+  p.B = B; p.slot = m->slot_d; p.pos = m->pos_d; p.max_len = max_len;
   p.first_ids = first_ids_d; p.n_steps = n_steps; p.eos = eos_id; p.out_ids = ids_out_d; p.out_len = len_out_d;
-  p.forced = forced_d; p.logits_out = logits_out_d; p.done = m->done; p.n_done = m->n_done;
-  p.cand_val = m->cand_val; p.cand_idx = m->cand_idx; p.sync_counter = m->sync_counter;
-  p.trace = m->trace; p.trace_cap = m->trace_cap;
+  p.forced = forced_d; p.logits_out = logits_out_d;
   S2S_CHECK(llama_decode_launch(m->ctx, p, c.compute_dtype, m->debug_phases, st));
   for (int b = 0; b < B; ++b) m->len[slots_h[b]] += n_steps;
   return S2S_OK;
@@ -520,7 +559,7 @@ int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int3
 
 int32_t s2s_llama_max_decode_batch(s2s_llama* m) {
   if (!m) return 0;
-  return std::min(MAX_DEC_B, llama_decode_max_batch(m->cfg.d_model, m->cfg.ffn, m->cfg.heads * m->cfg.head_dim));
+  return llama_max_decode_batch_of(m);
 }
 
 int s2s_llama_set_trace(s2s_llama* m, uint64_t* trace_d, int32_t capacity) {

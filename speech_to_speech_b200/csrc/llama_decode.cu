@@ -8,6 +8,8 @@
 //   0: RMSNorm + QKV projection + RoPE + KV append   1: GQA attention items (32-key blocks, last split merges)
 //   2: o_proj + residual                             3: RMSNorm + gate/up projection + SwiGLU     4: down + residual
 //   then 5L: final RMSNorm + lm_head + per-CTA argmax      5L+1: global argmax, EOS bookkeeping, next embedding
+// Qwen3 family (qk_norm, transformers modeling_qwen3.py Qwen3Attention): phase 0 stores RAW q / k, an extra phase applies
+// RMSNorm(head_dim) + RoPE per (session, head) and appends k to the cache: 6 phases per layer.
 // Projections are swap-AB tensor-core GEMVs (sessions on m) fed from per-warp bulk-copy rings of fragment-major weights
 // (decode_common.cuh, weight_tiles.cu); HBM-bound: 15.0 GB / token for Llama-3-8B.
 #include <algorithm>
@@ -57,6 +59,78 @@ __device__ __noinline__ void ld_attn(const LlamaDecParams& p, int layer, int ste
   }
 }
 
+
+// phase kinds: 0 qkv, 1 attention, 2 o_proj, 3 gate/up, 4 down, 5 q/k norm + RoPE (Qwen3), 6 logits, 7 select
+__host__ __device__ __forceinline__ int ld_nsub(const LlamaDecParams& p) { return p.qk_norm ? 6 : 5; }
+__device__ __forceinline__ int ld_kind(const LlamaDecParams& p, int ph) {
+  const int ns = ld_nsub(p);
+  if (ph >= ns * p.layers) return ph == ns * p.layers ? 6 : 7;
+  const int sub = ph % ns;
+  if (!p.qk_norm || sub == 0) return sub;
+  return sub == 1 ? 5 : sub - 1;
+}
+__device__ __forceinline__ bool ld_multi(const LlamaDecParams& p) { return p.head_stride != 0; }
+// output head of `step` (multi-table mode: step 0 predicts nothing)
+__device__ __forceinline__ bool ld_has_head(const LlamaDecParams& p, int step) { return !(ld_multi(p) && step == 0); }
+__device__ __forceinline__ bool ld_has_gemv(const LlamaDecParams& p, int step, int ph) {
+  const int k = ld_kind(p, ph);
+  return k == 0 || k == 2 || k == 3 || k == 4 || (k == 6 && ld_has_head(p, step));
+}
+
+// Qwen3: per (session, head) RMSNorm over head_dim of the raw q / k rows (fp32 statistics, Qwen3RMSNorm), then RoPE;
+// q is scaled by head_dim^-0.5 and written back in place, k goes to the cache at the token's position.  One warp per
+// item; rows are stored pair-adjacent (2j, 2j+1) = rotate_half partners (j, j + hd/2), and so are the norm weights.
+template <typename T, int HD>
+__device__ __noinline__ void ld_qknorm(const LlamaDecParams& p, int layer) {
+  constexpr int PER = HD / 32;  // 2 or 4 consecutive elements per lane = 1 or 2 rotation pairs
+  const int H = p.heads, KV = p.kv_heads, lane = threadIdx.x & 31;
+  const int n_items = p.B * (H + KV);
+  const LlamaDecLayer& w = p.lw[layer];
+  const float q_scale = rsqrtf((float)HD);
+#pragma unroll 1
+  for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
+    const int b = it / (H + KV), h = it % (H + KV);
+    const bool is_q = h < H;
+    float* src = is_q ? p.q + (long long)b * H * HD + h * HD : p.kraw + (long long)b * KV * HD + (h - H) * HD;
+    const float* nw = is_q ? w.q_norm : w.k_norm;
+    float v[PER], g[PER];
+    if (PER == 4) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(src + lane * 4));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      const float4 u = __ldg(reinterpret_cast<const float4*>(nw + lane * 4));
+      g[0] = u.x; g[1] = u.y; g[2] = u.z; g[3] = u.w;
+    } else {
+      const float2 t = __ldcg(reinterpret_cast<const float2*>(src + lane * 2));
+      v[0] = t.x; v[1] = t.y;
+      const float2 u = __ldg(reinterpret_cast<const float2*>(nw + lane * 2));
+      g[0] = u.x; g[1] = u.y;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) ss = fmaf(v[i], v[i], ss);
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss * (1.0f / (float)HD) + p.eps);
+    const int pos = __ldcg(p.pos + b);
+    float y[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i += 2) {
+      const float2 cs = p.rope[(long long)pos * (HD >> 1) + ((lane * PER + i) >> 1)];
+      const float a0 = v[i] * rstd * g[i], a1 = v[i + 1] * rstd * g[i + 1];
+      y[i] = a0 * cs.x - a1 * cs.y;
+      y[i + 1] = a1 * cs.x + a0 * cs.y;
+    }
+    if (is_q) {
+#pragma unroll
+      for (int i = 0; i < PER; i += 2) *reinterpret_cast<float2*>(src + lane * PER + i) = make_float2(y[i] * q_scale, y[i + 1] * q_scale);
+    } else {
+      T* dst = reinterpret_cast<T*>(p.kv) + (long long)__ldg(p.slot + b) * p.kv_slot_stride + (long long)layer * p.kv_layer_stride +
+               (long long)pos * (KV * HD) + (h - H) * HD + lane * PER;
+#pragma unroll
+      for (int i = 0; i < PER; i += 2) *reinterpret_cast<uint32_t*>(dst + i) = DT<T>::pack2(y[i], y[i + 1]);
+    }
+  }
+}
+
 template <typename T>
 __device__ __noinline__ void ld_select(const LlamaDecParams& p, int step, float* s_aux) {
   const int d = p.d, B = p.B;
@@ -67,15 +141,19 @@ __device__ __noinline__ void ld_select(const LlamaDecParams& p, int step, float*
     __syncthreads();
     if (warp == 0) {
       float bv = -INFINITY; int bi = 0x7fffffff;
+      if (ld_has_head(p, step)) {
 #pragma unroll 1
-      for (int c = lane; c < (int)gridDim.x; c += 32) {
-        const float v = __ldcg(p.cand_val + b * gridDim.x + c); const int i = __ldcg(p.cand_idx + b * gridDim.x + c);
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-      }
+        for (int c = lane; c < (int)gridDim.x; c += 32) {
+          const float v = __ldcg(p.cand_val + b * gridDim.x + c); const int i = __ldcg(p.cand_idx + b * gridDim.x + c);
+          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+      } else {
+        bi = p.first_ids[b];  // multi-table mode, step 0: nothing predicted, the known first id is fed
       }
       if (lane == 0) {
         int tok = bi;
@@ -93,7 +171,9 @@ __device__ __noinline__ void ld_select(const LlamaDecParams& p, int step, float*
     }
     __syncthreads();
     const int feed = *s_feed;
-    const T* e = reinterpret_cast<const T*>(p.embed) + (long long)feed * d;
+    const T* tab = reinterpret_cast<const T*>(p.embed);
+    if (ld_multi(p)) tab = step == 0 ? reinterpret_cast<const T*>(p.embed0) : tab + (long long)(step - 1) * p.embed_stride;
+    const T* e = tab + (long long)feed * d;
 #pragma unroll 2
     for (int i = threadIdx.x; i < d; i += DEC_THREADS) p.x[(long long)b * d + i] = DT<T>::to_f(e[i]);
   }
@@ -101,18 +181,20 @@ __device__ __noinline__ void ld_select(const LlamaDecParams& p, int step, float*
 
 template <typename T>
 __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, int ph, GemvArgs& a) {
-  const int L = p.layers, d = p.d, B = p.B, qd = p.heads * p.hd, kvd = p.kv_heads * p.hd;
+  const int d = p.d, B = p.B, qd = p.heads * p.hd, kvd = p.kv_heads * p.hd;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = qd; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
   a.pos = p.pos; a.slot = p.slot; a.kv_slot = p.kv_slot_stride; a.kv_ld = kvd; a.rope = p.rope; a.hd = p.hd;
-  a.q_rows = qd; a.k_rows = kvd; a.q_scale = rsqrtf((float)p.hd); a.plan_id = -1;
-  if (ph < 5 * L) {
-    const int layer = ph / 5;
+  a.q_rows = qd; a.k_rows = kvd; a.q_scale = rsqrtf((float)p.hd); a.kraw = nullptr; a.plan_id = -1;
+  const int kind = ld_kind(p, ph);
+  if (kind < 6) {
+    const int layer = ph / ld_nsub(p);
     const LlamaDecLayer& w = p.lw[layer];
-    switch (ph % 5) {
+    switch (kind) {
       case 0:
         a.W = w.w_qkv; a.N = qd + 2 * kvd; a.mode = EPI_QKV_ROPE; a.out = p.q; a.ldo = qd; a.plan_id = 0;
         a.kv0 = reinterpret_cast<T*>(p.kv) + (long long)layer * p.kv_layer_stride; a.kv_which = p.kv_which_stride;
+        a.kraw = p.qk_norm ? p.kraw : nullptr;
         return true;
       case 2: a.W = w.w_o; a.N = d; a.K = qd; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; a.plan_id = 1; return true;
       case 3: a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out_h = p.h; a.ldh = p.ffn; a.plan_id = 2; return true;
@@ -120,8 +202,9 @@ __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, 
       default: return false;
     }
   }
-  if (ph == 5 * L) {
-    a.W = p.lm_head; a.N = p.vocab; a.mode = EPI_LOGITS; a.plan_id = 4;
+  if (kind == 6 && ld_has_head(p, step)) {
+    a.W = ld_multi(p) ? reinterpret_cast<const T*>(p.lm_head) + (long long)(step - 1) * p.head_stride : p.lm_head;
+    a.N = p.vocab; a.mode = EPI_LOGITS; a.plan_id = 4; a.suppress = p.suppress;
     a.logits_out = p.logits_out ? p.logits_out + (long long)step * B * p.vocab : nullptr; a.logits_ld = p.vocab;
     return true;
   }
@@ -138,23 +221,27 @@ __host__ __device__ inline int ld_kmax(int d, int ffn, int qd) { return (d > ffn
 template <typename T>
 __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int ph, const LdSmem<T>& sm, GemvRing& ring,
                                          GemvArgs* ready, GemvArgs& a_scratch, int wb_ready) {
-  const int L = p.layers, d = p.d, B = p.B;
+  const int d = p.d, B = p.B;
   float best_v[2] = {-INFINITY, -INFINITY};
   int best_i[2] = {0x7fffffff, 0x7fffffff};
   // argument struct and ring state live in shared memory (all threads write identical values), not on the stack
-  if (!ready && (ph >= 5 * L ? ph == 5 * L : ph % 5 != 1)) {
+  const int kind = ld_kind(p, ph);
+  if (!ready && ld_has_gemv(p, step, ph)) {
     if (threadIdx.x < 32) ld_gemv_args<T>(p, step, ph, a_scratch);  // one warp writes the shared struct
     __syncthreads();
   }
   GemvArgs& a = ready ? *ready : a_scratch;
-  if (ph < 5 * L) {
-    const int layer = ph / 5;
+  if (kind < 6) {
+    const int layer = ph / ld_nsub(p);
     const LlamaDecLayer& w = p.lw[layer];
-    switch (ph % 5) {
+    switch (kind) {
       case 0: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm1, nullptr, p.eps, sm.s_red, sm.wb, wb_ready); break;
       case 1:
         if (p.hd == 128) ld_attn<T, 128>(p, layer, step, reinterpret_cast<float*>(sm.red));
         else ld_attn<T, 64>(p, layer, step, reinterpret_cast<float*>(sm.red));
+        return;
+      case 5:
+        if (p.hd == 128) ld_qknorm<T, 128>(p, layer); else ld_qknorm<T, 64>(p, layer);
         return;
       case 2: stage_rows_copy<T>(reinterpret_cast<const T*>(p.attn16), B, p.heads * p.hd, sm.xh); break;
       case 3: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm2, nullptr, p.eps, sm.s_red, sm.wb, wb_ready); break;
@@ -163,7 +250,9 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
     gemv_mma<T, true>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     return;
   }
-  if (ph == 5 * L) {
+  if (kind == 6) {
+    if (p.hidden_out && blockIdx.x == 0)  // the residual stream before the final norm (Qwen3-TTS: input of the code predictor)
+      for (int i = threadIdx.x; i < B * d; i += DEC_THREADS) p.hidden_out[(long long)step * B * d + i] = __ldcg(p.x + i);
     stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, p.norm_f, nullptr, p.eps, sm.s_red, sm.wb, wb_ready);
     gemv_mma<T, true>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     gemv_argmax_candidates(best_v, best_i, B, sm.sv, sm.si, p.cand_val, p.cand_idx);
@@ -220,16 +309,17 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   pre_args.K = p.d;
   int pre_tag = -1, wb_tag = -1;
   ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
-  const int n_ph = 5 * p.layers + 2;
+  const int n_ph = ld_nsub(p) * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
     for (int ph = pb; ph < pe; ++ph) {
       const bool tracing = sp.trace && trace_i < sp.trace_cap && threadIdx.x == 0 && blockIdx.x == 0;
       unsigned long long* tr = tracing ? sp.trace + (long long)trace_i * 3 : nullptr;
       if (tracing) tr[0] = gtimer_ns();
-      ld_phase<T>(sp, step, ph, sm, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr, s_args[1], wb_tag == step * n_ph + ph);
+      const bool skip = ld_kind(sp, ph) == 6 && !ld_has_head(sp, step);  // nothing to predict: no work, no barrier
+      if (!skip) ld_phase<T>(sp, step, ph, sm, ring, (pre_tag == step * n_ph + ph) ? &pre_args : nullptr, s_args[1], wb_tag == step * n_ph + ph);
       if (tracing) tr[1] = gtimer_ns();
-      if (coop) {
+      if (coop && !skip) {
         grid_arrive(p.sync_counter, epoch);
         // ---- between arrive and wait: prepare the next projection (arguments, first weight units, norm weights) ----
         if (!ring.pre_valid) {
@@ -237,23 +327,22 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
           if (nph == n_ph) { nph = 0; nstep = step + 1; }
 #pragma unroll 1
           for (int look = 0; look < 3 && nstep < step_end; ++look) {
-            if (nph >= 5 * p.layers ? nph == 5 * p.layers : nph % 5 != 1) {
+            if (ld_has_gemv(sp, nstep, nph)) {
               if (threadIdx.x < 32) ld_gemv_args<T>(sp, nstep, nph, pre_args);  // one warp writes the shared struct
               __syncthreads();
               gemv_prefetch<T>(pre_args, ring);
               pre_tag = nstep * n_ph + nph;
               const float* nw = nullptr;
-              if (nph < 5 * p.layers) {
-                const int sub = nph % 5;
-                if (sub == 0) nw = sp.lw[nph / 5].norm1; else if (sub == 3) nw = sp.lw[nph / 5].norm2;
-              } else { nw = sp.norm_f; }
+              const int nk = ld_kind(sp, nph);
+              if (nk == 0) nw = sp.lw[nph / ld_nsub(sp)].norm1; else if (nk == 3) nw = sp.lw[nph / ld_nsub(sp)].norm2;
+              else if (nk == 6) nw = sp.norm_f;
               if (nw) { stage_norm_weights(nw, nullptr, sp.d, sm.wb); wb_tag = pre_tag; }
               break;
             }
             if (++nph == n_ph) { nph = 0; ++nstep; }
           }
         }
-        grid_wait(p.sync_counter, epoch);
+        grid_wait(p.sync_counter, epoch, p.sync_relaxed);
       }
       if (tracing) tr[2] = gtimer_ns();
       ++trace_i;
@@ -266,9 +355,13 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
 template <typename T>
 __global__ void llama_decode_init_kernel(const LlamaDecParams p) {
   const int b = blockIdx.x;
-  const int tok = p.first_ids[b];
-  const T* e = reinterpret_cast<const T*>(p.embed) + (long long)tok * p.d;
-  for (int i = threadIdx.x; i < p.d; i += blockDim.x) p.x[(long long)b * p.d + i] = DT<T>::to_f(e[i]);
+  if (p.x_in) {
+    for (int i = threadIdx.x; i < p.d; i += blockDim.x) p.x[(long long)b * p.d + i] = p.x_in[(long long)b * p.d + i];
+  } else {
+    const int tok = p.first_ids[b];
+    const T* e = reinterpret_cast<const T*>(p.embed) + (long long)tok * p.d;
+    for (int i = threadIdx.x; i < p.d; i += blockDim.x) p.x[(long long)b * p.d + i] = DT<T>::to_f(e[i]);
+  }
   if (threadIdx.x == 0) {
     p.done[b] = 0;
     p.out_len[b] = 0;
@@ -282,6 +375,7 @@ template <typename T>
 int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
   const DecSmem lay = dec_smem_layout(p.B, p.d, ld_kmax(p.d, p.ffn, p.heads * p.hd), p.d);
   LlamaDecParams pr = p;
+  pr.sync_relaxed = dec_sync_relaxed_env();
   pr.ring_slots = dec_ring_slots(lay);
   S2S_REQUIRE(pr.ring_slots >= 2, "llama decode: batch %d x K %d does not fit shared memory", p.B, ld_kmax(p.d, p.ffn, p.heads * p.hd));
   const size_t smem = (size_t)lay.ring_off + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
@@ -289,7 +383,7 @@ int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream
   S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   llama_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
   S2S_LAUNCH_CHECK();
-  const int n_ph = 5 * p.layers + 2;
+  const int n_ph = ld_nsub(p) * p.layers + 2;
   const int grid = ctx->num_sms;
   if (!debug_phases) {
     int sb = 0, se = p.n_steps, pb = 0, pe = n_ph, coop = 1;
@@ -300,6 +394,7 @@ int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream
   } else {
     for (int s = 0; s < p.n_steps; ++s)
       for (int ph = 0; ph < n_ph; ++ph) {
+        if (ph == n_ph - 2 && pr.head_stride != 0 && s == 0) continue;  // multi-table mode: step 0 predicts nothing
         kern<<<grid, DEC_THREADS, smem, stream>>>(pr, s, s + 1, ph, ph + 1, 0);
         S2S_LAUNCH_CHECK();
       }

@@ -8,6 +8,7 @@ struct LlamaDecLayer {          // device pointers; 16-bit weights [out, in]: TI
   const void* w_gu;             // [2 * ffn, d], rows interleaved (gate_i, up_i)
   const void* w_down;           // [d, ffn]
   const float *norm1, *norm2;   // RMSNorm weights [d]
+  const float *q_norm, *k_norm; // Qwen3 (qk_norm): per-head RMSNorm weights [hd], stored pair-adjacent like the q/k rows; else null
 };
 
 struct LlamaDecParams {
@@ -41,9 +42,22 @@ struct LlamaDecParams {
   int* done; int* n_done;
   float* cand_val; int* cand_idx;   // [B][grid]
   unsigned int* sync_counter;
+  // ---- Qwen3 family (qk_norm): 6 phases per layer, the extra one applies RMSNorm(head_dim) + RoPE to the raw q / k rows
+  int qk_norm;
+  float* kraw;                  // [B][KV*hd] fp32 raw k rows of the current token
+  // ---- embedding-driven use (Qwen3-TTS talker and code predictor, qwen3tts.cu) ----
+  const float* x_in;            // [B][d] fp32 or null: the input of step 0 is this vector instead of embed[first_ids]
+  float* hidden_out;            // [n_steps][B][d] fp32 or null: the residual stream BEFORE the final norm of every step
+  const unsigned char* suppress;// [vocab] or null: bit0 = never predict this id (EPI_LOGITS mask)
+  // multi-table mode (code predictor: one embedding table and one output head per codebook): step 0 consumes x_in and
+  // predicts nothing, then feeds first_ids through `embed0`; step s >= 1 predicts with lm_head + (s-1)*head_stride and
+  // feeds its argmax through embed + (s-1)*embed_stride (strides in elements; 0 = single-table mode)
+  long long embed_stride, head_stride;
+  const void* embed0;           // [vocab0, d] 16-bit
   int ring_slots;               // weight-ring slots per warp (set by the launcher)
   unsigned long long* trace;    // optional [cap][3] globaltimer stamps of CTA 0 (phase begin, body end, barrier exit)
   int trace_cap;
+  int sync_relaxed;             // 1: barrier waits without the acquire fence (A/B measurement aid)
 };
 
 int llama_decode_launch(s2s_ctx* ctx, const LlamaDecParams& p, int dtype, int debug_phases, cudaStream_t stream);

@@ -181,7 +181,7 @@ __device__ __forceinline__ bool wd_gemv_args(const WhisperDecParams& p, int step
   const int L = p.layers, pos = step, d = p.d, B = p.B;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
-  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.plan_id = 1;
+  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.kraw = nullptr; a.plan_id = 1;
   if (ph < 8 * L) {
     const int layer = ph >> 3;
     const WhisperDecLayer& w = p.lw[layer];
@@ -353,7 +353,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
           }
         }
         if (tracing) tr[3] = globaltimer_ns();  // next phase prepared
-        grid_wait(p.sync_counter, epoch);
+        grid_wait(p.sync_counter, epoch, p.sync_relaxed);
       }
       if (tracing) tr[5] = globaltimer_ns();
       if (!skip) ++trace_i;
@@ -393,10 +393,14 @@ __device__ __forceinline__ unsigned int cluster_id_x() {
 // ONE thread publishes the CTA's writes (bar.sync + fence by thread 0: cumulative, like grid_arrive); the hardware barrier
 // itself is relaxed -- barrier.cluster.arrive.release makes EVERY thread execute MEMBAR.ALL.GPU, which serialises
 // (measured 6 us per barrier with 256 threads).  Readers use L2 accesses (ld.global.cg) after the wait.
-__device__ __forceinline__ void cluster_barrier() {
+__device__ __forceinline__ void cluster_barrier(int relaxed) {
   __syncthreads();
   if (threadIdx.x == 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
   asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+  if (!relaxed) {  // acquire side, mirrored: one fencing thread, then the CTA barrier extends the order to the others
+    if (threadIdx.x == 0) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    __syncthreads();
+  }
 }
 
 struct WdcCtx { int cid, rank, cs; };
@@ -412,7 +416,7 @@ __device__ __forceinline__ bool wdc_gemv_args(const WhisperDecParams& p, const W
   const int L = p.layers, pos = step, d = p.d, B = p.B;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
-  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.plan_id = -1;
+  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.kraw = nullptr; a.plan_id = -1;
   if (ph < 4 * L) {
     const int layer = ph >> 2;
     const WhisperDecLayer& w = p.lw[layer];
@@ -481,7 +485,7 @@ __device__ __forceinline__ void wdc_block(const WhisperDecParams& p, const WdcCt
   // C. start streaming the head's out-projection slice
   gemv_prefetch<T>(ao, ring);
   // D. q (and the new k, v cache rows) of the head are visible to the whole cluster
-  cluster_barrier();
+  cluster_barrier(p.sync_relaxed);
   if (tr && p.trace_mode == 0) tr[3] = globaltimer_ns();
   // E. attention: 32-key blocks over (CTA rank, warp); one record per CTA
   float* rec_s = reinterpret_cast<float*>(sm.red);
@@ -509,7 +513,7 @@ __device__ __forceinline__ void wdc_block(const WhisperDecParams& p, const WdcCt
     }
   }
   // F. every CTA's record of the head is visible to the cluster
-  cluster_barrier();
+  cluster_barrier(p.sync_relaxed);
   if (tr && p.trace_mode == 1) tr[2] = globaltimer_ns();
   // G. merge the CS records (redundantly in every CTA: one L2 round trip, no further hand-off) -> o_h as x operand
   if (warp < B) attn_merge_records<T, HD>(p.part + (long long)(warp * H + h) * p.s_max * REC, cx.cs, sm.xh + warp * (HD + GV_XPAD));
@@ -680,7 +684,7 @@ whisper_decode_cluster_kernel(const WhisperDecParams p, int step_begin, int step
             if (++nph == n_ph) { nph = 0; ++nstep; }
           }
         }
-        grid_wait(p.sync_counter, epoch);
+        grid_wait(p.sync_counter, epoch, p.sync_relaxed);
       }
       if (tracing) tr[5] = globaltimer_ns();
       if (!skip) ++trace_i;
@@ -740,6 +744,7 @@ int launch_cluster_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, 
   cached_smem = smem; cached_heads = p.heads; cached_cs = cs; cached_n = n_clusters;
   if (!cs) return S2S_OK;
   WhisperDecParams pr = p;
+  pr.sync_relaxed = dec_sync_relaxed_env();
   pr.ring_slots = slots;
   pr.cluster_size = cs;
   whisper_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
@@ -779,6 +784,7 @@ int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStre
   }
   const DecSmem lay = dec_smem_layout(p.B, p.d, std::max(p.d, p.ffn), 2 * p.d);
   WhisperDecParams pr = p;
+  pr.sync_relaxed = dec_sync_relaxed_env();
   pr.ring_slots = dec_ring_slots(lay);
   {
     const int BH = p.B * p.heads, grid = ctx->num_sms;

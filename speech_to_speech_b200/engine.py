@@ -240,7 +240,8 @@ class LlamaEngine:
             int(g["d_model"]), int(g["layers"]), int(g["heads"]), int(g["kv_heads"]), int(g["head_dim"]), int(g["ffn"]),
             int(g["vocab"]), float(g.get("rope_theta", 500000.0)), float(g.get("rms_eps", 1e-5)), DTYPE_CODES[dtype],
             max_sessions, min(max_positions, int(g.get("max_positions", max_positions))), max_prefill,
-            int(bool(g.get("qk_norm", False))))  # Qwen3-style q/k RMSNorm: rejected loudly by s2s_llama_create until built
+            int(bool(g.get("qk_norm", False))),  # Qwen3-style per-head q/k RMSNorm before RoPE
+            int(g.get("n_tables", 1)))
         self.max_positions = self.cfg.max_positions
         self.handle = C.c_void_p()
         check(self.lib.s2s_llama_create(self.ctx, C.byref(self.cfg), C.byref(self.handle)), "s2s_llama_create")

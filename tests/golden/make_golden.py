@@ -1,7 +1,7 @@
 """Generate golden vectors from `transformers` (the package the reference delegates to).
 
 Run in the builder container (transformers 5.5.0, CPU):
-    python tests/golden/make_golden.py [whisper|llama|code2wav|all]
+    python tests/golden/make_golden.py [whisper|llama|code2wav|qwen3tts|all]
 
 The reference holds no golden mel/logits/ids for this path, so the
 pin is the upstream model code itself: WhisperFeatureExtractor + WhisperForConditionalGeneration
@@ -221,6 +221,92 @@ def code2wav_golden(name: str = "micro"):
     print("wrote", path, wav.shape, float(np.abs(wav).max()))
 
 
+def qwen3tts_golden(name: str = "micro", text_len: int = 6, max_frames: int = 10):
+    """Talker + code predictor of the published cousin (`Qwen3OmniMoeTalkerForConditionalGeneration`, transformers) at
+    seeded weights, driven exactly like `Qwen3OmniMoeForConditionalGeneration.generate` step 2 drives it, with the two
+    substitutions oracle/qwen3tts_ref.py states: the talker's MoE block is replaced by the dense
+    `Qwen3OmniMoeTalkerTextMLP` (the real Qwen3-TTS talker is dense), and both `generate` calls run greedily
+    (do_sample=False, no repetition penalty).  Records the codes of every frame and the talker / predictor logits."""
+    import torch
+    from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeTalkerConfig
+    from transformers.models.qwen3_omni_moe import modeling_qwen3_omni_moe as M
+    from oracle import qwen3tts_ref as R
+
+    g = R.GEOMETRIES[name]
+    w = R.make_weights(g, 0)
+    t, c = g.talker, g.predictor
+    rope = {"rope_type": "default", "rope_theta": t.rope_theta}
+    tc = dict(vocab_size=t.vocab, hidden_size=t.d_model, intermediate_size=t.ffn, num_hidden_layers=t.layers,
+              num_attention_heads=t.heads, num_key_value_heads=t.kv_heads, head_dim=t.head_dim, rms_norm_eps=t.rms_eps,
+              num_experts=2, num_experts_per_tok=1, moe_intermediate_size=64, shared_expert_intermediate_size=64,
+              rope_parameters=dict(rope, mrope_section=[t.head_dim // 8, t.head_dim // 8 + t.head_dim // 16, t.head_dim // 4 - t.head_dim // 8 - t.head_dim // 16 + t.head_dim // 8],
+                                   mrope_interleaved=True))
+    # three sections that add up to head_dim / 2 (the split is irrelevant here: all three carry the same text position)
+    sec = tc["rope_parameters"]["mrope_section"]
+    sec[2] = t.head_dim // 2 - sec[0] - sec[1]
+    cp = dict(vocab_size=c.vocab, hidden_size=c.d_model, intermediate_size=c.ffn, num_hidden_layers=c.layers,
+              num_attention_heads=c.heads, num_key_value_heads=c.kv_heads, head_dim=c.head_dim, rms_norm_eps=c.rms_eps,
+              num_code_groups=g.n_groups, rope_parameters={"rope_type": "default", "rope_theta": c.rope_theta})
+    speaker = 2301
+    cfg = Qwen3OmniMoeTalkerConfig(text_config=tc, code_predictor_config=cp, num_code_groups=g.n_groups,
+                                   thinker_hidden_size=g.text_hidden, codec_eos_token_id=g.codec_eos,
+                                   codec_nothink_id=g.codec_nothink, codec_think_bos_id=g.codec_think_bos,
+                                   codec_think_eos_id=g.codec_think_eos, codec_pad_id=g.codec_pad, codec_bos_id=g.codec_bos,
+                                   speaker_id={"aiden": speaker}, spatial_merge_size=2)
+    m = M.Qwen3OmniMoeTalkerForConditionalGeneration(cfg).eval()
+    for layer in m.model.layers:   # substitution 1: dense MLP
+        layer.mlp = M.Qwen3OmniMoeTalkerTextMLP(cfg.text_config, intermediate_size=t.ffn)
+    sd = m.state_dict()
+    own = {}
+    for k in sd:
+        if k.startswith("hidden_projection."):
+            own[k] = sd[k]          # multimodal path of the cousin: unused by a text-only TTS turn
+        else:
+            assert k in w, k
+            own[k] = torch.from_numpy(w[k])
+    assert set(w) - set(sd) == {"text_embedding.weight"}, set(w) - set(sd)
+    m.load_state_dict(own)
+    emb = torch.from_numpy(w["text_embedding.weight"])
+    text_ids = np.random.default_rng(11).integers(0, g.tts_bos - 8, text_len).tolist()
+    ids = torch.tensor([[g.im_start, g.assistant, g.newline] + text_ids])
+
+    # ---- Qwen3OmniMoeForConditionalGeneration.generate, "2. Prepare talker input" (TF:4019-4075), text-only turn
+    class Host:   # the attributes _get_talker_assistant_parts reads from the top-level model
+        pass
+    host = Host()
+    host.talker = m
+    host.config = type("C", (), {"talker_config": cfg, "tts_pad_token_id": g.tts_pad})()
+    with torch.no_grad():
+        special = torch.tensor([[g.tts_bos, g.tts_eos, g.tts_pad]])
+        bos_e, eos_e, pad_e = m.text_projection(emb[special]).chunk(3, dim=1)
+        embeds, in_ids, trailing = M.Qwen3OmniMoeForConditionalGeneration._get_talker_assistant_parts(
+            host, 0, ids.shape[1], speaker, emb[ids], pad_e, bos_e, eos_e)
+        orig = m.code_predictor.generate
+
+        pred_scores = []
+
+        def greedy_predictor(**kw):   # substitution 2: greedy code predictor
+            kw.update(do_sample=False, top_k=None, top_p=None, output_scores=True)
+            out = orig(**kw)
+            pred_scores.append(torch.stack([s[0] for s in out.scores]).numpy())
+            return out
+        m.code_predictor.generate = greedy_predictor
+        suppress = [i for i in range(t.vocab - 1024, t.vocab) if i != g.codec_eos]
+        res = m.generate(inputs_embeds=embeds, trailing_text_hidden=trailing, tts_pad_embed=pad_e, talker_input_ids=in_ids,
+                         max_new_tokens=max_frames, do_sample=False, eos_token_id=g.codec_eos, suppress_tokens=suppress,
+                         output_hidden_states=True, return_dict_in_generate=True, output_scores=True, pad_token_id=g.codec_pad,
+                         attention_mask=torch.ones_like(in_ids))
+        codes = torch.stack([h[-1] for h in res.hidden_states if h[-1] is not None], dim=1)[0].numpy()   # [F, 16]
+        t_scores = torch.stack([s[0] for s in res.scores]).numpy()
+    path = os.path.join(OUT, f"qwen3tts_{name}.npz")
+    np.savez_compressed(path, text_ids=np.asarray(text_ids, np.int32), speaker=speaker, codes=codes.astype(np.int32),
+                        code0_all=res.sequences[0].numpy().astype(np.int32), talker_logits=t_scores.astype(np.float32),
+                        predictor_logits=np.stack(pred_scores).astype(np.float32), prompt_embeds=embeds[0].numpy().astype(np.float32),
+                        trailing=trailing[0].numpy().astype(np.float32), max_frames=max_frames,
+                        transformers_version=__import__("transformers").__version__)
+    print("wrote", path, codes.shape, codes[:2].tolist(), "code0", res.sequences[0].tolist())
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("whisper", "all"):
@@ -231,3 +317,5 @@ if __name__ == "__main__":
             llama_golden(n)
     if what in ("code2wav", "all"):
         code2wav_golden("micro")
+    if what in ("qwen3tts", "all"):
+        qwen3tts_golden("micro")
