@@ -169,6 +169,87 @@ int32_t s2s_llama_max_decode_batch(s2s_llama* m);
 int s2s_llama_generate(s2s_llama* m, int32_t slot, const int32_t* prompt_h, int32_t n_prompt, int32_t n_steps,
                        int32_t eos_id, int32_t* ids_out_h, int32_t* len_out_h, void* stream);
 
+/* ---- TTS codec decoder: codebook ids -> 24 kHz waveform ---------------------------------------------
+ * Replaces the codec-decode half of faster-qwen3-tts' `generate_*_streaming` (called from
+ * S/TTS/qwen3_tts_handler.py:930-942, 968-976, 994-1001; the package is absent everywhere, so the arithmetic is pinned to
+ * the published cousin transformers Qwen3OmniMoeCode2Wav, modeling_qwen3_omni_moe.py:3283-3790 -- unpinned vs upstream). */
+typedef struct {
+  int32_t codebook_size, hidden, heads, kv_heads, inter, layers, quantizers;
+  int32_t n_upsample_rates, upsample_rates[8];       /* decoder blocks: (8, 5, 4, 3) */
+  int32_t n_upsampling_ratios, upsampling_ratios[4]; /* ConvNeXt upsamplers: (2, 2)  */
+  int32_t decoder_dim, sliding_window;
+  float rope_theta, rms_eps;
+  int32_t max_frames;   /* longest decode call: left context + chunk (33 for chunk_size 8 behind 25 frames of history) */
+} s2s_codec_config;
+typedef struct s2s_codec s2s_codec;
+int s2s_codec_create(s2s_ctx* ctx, const s2s_codec_config* cfg, s2s_codec** out);
+int s2s_codec_destroy(s2s_codec* m);
+/* names = the cousin's state dict ("code_embedding.weight", "pre_transformer.layers.0.self_attn.q_proj.weight", ...) */
+int s2s_codec_bind_tensor(s2s_codec* m, const char* name, const void* data_h, const int64_t* shape, int32_t ndim,
+                          int32_t dtype);
+int s2s_codec_init_random(s2s_codec* m, uint64_t seed);
+int s2s_codec_finalize(s2s_codec* m);
+/* codes_d [T][quantizers] i32 (frame-major) -> wav_out_d f32: the samples of frames [ctx_frames, T), i.e. one step of
+ * Qwen3OmniMoeCode2Wav.chunked_decode (:3779-3790).  wav_out_d must hold s2s_codec_samples(m, T) floats;
+ * *n_out_h = samples written; hidden_out_d optional [T, hidden] (pre-transformer output, for tests). */
+int s2s_codec_decode(s2s_codec* m, const int32_t* codes_d, int32_t T, int32_t ctx_frames, float* wav_out_d,
+                     int32_t* n_out_h, float* hidden_out_d, void* stream);
+int32_t s2s_codec_samples(s2s_codec* m, int32_t T);   /* waveform length of a T-frame decode before the context drop */
+int32_t s2s_codec_total_upsample(s2s_codec* m);       /* samples per frame (1920) */
+
+/* ---- Qwen3-TTS talker + code predictor: text -> codebook ids, 12.5 frames per second of speech ------------------
+ * Replaces the autoregressive half of faster-qwen3-tts' `generate_custom_voice_streaming(text, speaker, language,
+ * instruct, chunk_size, max_new_tokens, non_streaming_mode)` (S/TTS/qwen3_tts_handler.py:946-978; warm-up :555-572).
+ * The package is absent everywhere; the arithmetic is pinned to the published cousin, the Qwen3-Omni talker in
+ * transformers (modeling_qwen3_omni_moe.py: talker :3029-3281, code predictor :2550-2731, prompt layout :3842-3905) with
+ * a dense talker MLP and greedy selection (oracle/qwen3tts_ref.py) -- UNPINNED against the real Qwen3-TTS.
+ * One frame = 1 talker step (first codebook, special ids suppressed) + n_groups code-predictor steps (residual
+ * codebooks) + the next talker input (sum of the frame's code embeddings + the next text embedding / tts_pad). */
+typedef struct {
+  /* talker (Qwen3-style decoder over the codec vocabulary) */
+  int32_t d_model, layers, heads, kv_heads, head_dim, ffn, vocab;
+  /* code predictor (same width; one embedding table and one head per residual codebook) */
+  int32_t cp_layers, cp_heads, cp_kv_heads, cp_head_dim, cp_ffn, cp_vocab;
+  int32_t n_groups;                      /* codebooks per frame (16) */
+  int32_t text_vocab, text_hidden;       /* text-side embedding table and its width (thinker_hidden_size) */
+  float rope_theta, rms_eps;
+  int32_t compute_dtype;                 /* S2S_BF16 / S2S_F16 for the decoder weights; projections / glue fp32 */
+  int32_t max_sessions, max_positions, max_text;
+  int32_t codec_eos, codec_nothink, codec_think_bos, codec_think_eos, codec_pad, codec_bos;
+  int32_t tts_bos, tts_eos, tts_pad, im_start, assistant, newline;
+  s2s_codec_config codec;                /* the waveform decoder owned by the same model object */
+} s2s_qwen3tts_config;
+typedef struct s2s_qwen3tts s2s_qwen3tts;
+int s2s_qwen3tts_create(s2s_ctx* ctx, const s2s_qwen3tts_config* cfg, s2s_qwen3tts** out);
+int s2s_qwen3tts_destroy(s2s_qwen3tts* m);
+/* names: the cousin's talker state dict ("model.layers.0.self_attn.q_proj.weight", "model.codec_embedding.weight",
+ * "codec_head.weight", "text_projection.linear_fc1.weight", "code_predictor.model.layers...",
+ * "code_predictor.model.codec_embedding.<i>.weight", "code_predictor.lm_head.<i>.weight"), "text_embedding.weight", and
+ * the codec decoder's names prefixed with "code2wav.". */
+int s2s_qwen3tts_bind_tensor(s2s_qwen3tts* m, const char* name, const void* data_h, const int64_t* shape, int32_t ndim,
+                             int32_t dtype);
+int s2s_qwen3tts_init_random(s2s_qwen3tts* m, uint64_t seed);
+int s2s_qwen3tts_finalize(s2s_qwen3tts* m);
+/* Start an utterance in `slot`: builds the prompt ([im_start, assistant, newline] + text, codec prefix with the speaker
+ * id), prefills the talker and stages the first frame's input.  text_ids_h: >= 1 text token ids. */
+int s2s_qwen3tts_prefill(s2s_qwen3tts* m, int32_t slot, const int32_t* text_ids_h, int32_t n_text, int32_t speaker_id,
+                         void* stream);
+/* Generate n_frames frames for the B (<= s2s_qwen3tts_max_batch) sessions slots_h[B] in lock step: 3 persistent
+ * launches per frame serve all of them.  codes_out_d [B][n_frames][n_groups] i32.  A session whose first code is
+ * codec_eos has finished: the caller drops that frame and everything after it (frames_done is not advanced past it).
+ * Asynchronous on `stream`. */
+int s2s_qwen3tts_decode_frames(s2s_qwen3tts* m, const int32_t* slots_h, int32_t B, int32_t n_frames,
+                               int32_t* codes_out_d, void* stream);
+/* Waveform of the newest `n_new` frames of `slot` (codes kept by the library since prefill), decoded behind up to
+ * `left_context` frames of history (Qwen3OmniMoeCode2Wav.chunked_decode); wav_out_d f32 [n_new * 1920 (max)]. */
+int s2s_qwen3tts_decode_audio(s2s_qwen3tts* m, int32_t slot, int32_t n_new, int32_t left_context, float* wav_out_d,
+                              int32_t* n_out_h, void* stream);
+/* Tell the library how many frames of `slot` are valid (after the caller saw codec_eos inside a chunk). */
+int s2s_qwen3tts_set_frames(s2s_qwen3tts* m, int32_t slot, int32_t n_frames);
+int32_t s2s_qwen3tts_frames(s2s_qwen3tts* m, int32_t slot);
+int32_t s2s_qwen3tts_max_batch(s2s_qwen3tts* m);
+s2s_codec* s2s_qwen3tts_codec(s2s_qwen3tts* m);
+
 /* ---- TTS post-processing (Qwen3TTSHandler._stream) -------------------------------------
  * wav24k_d f32[n] -> polyphase resample 24k->16k (scipy.signal.resample_poly(x, 2, 3) taps supplied by
  * the host mirror) -> clip(x*32768) -> int16.  out16k_d must hold ceil(n*2/3) samples.          */

@@ -21,6 +21,11 @@ EXPORTED = [
     "s2s_llama_create", "s2s_llama_destroy", "s2s_llama_bind_tensor", "s2s_llama_init_random",
     "s2s_llama_finalize", "s2s_llama_session_reset", "s2s_llama_prefill", "s2s_llama_decode", "s2s_llama_generate", "s2s_llama_set_trace", "s2s_llama_max_decode_batch",
     "s2s_tts_postproc",
+    "s2s_codec_create", "s2s_codec_destroy", "s2s_codec_bind_tensor", "s2s_codec_init_random", "s2s_codec_finalize",
+    "s2s_codec_decode", "s2s_codec_samples", "s2s_codec_total_upsample",
+    "s2s_qwen3tts_create", "s2s_qwen3tts_destroy", "s2s_qwen3tts_bind_tensor", "s2s_qwen3tts_init_random",
+    "s2s_qwen3tts_finalize", "s2s_qwen3tts_prefill", "s2s_qwen3tts_decode_frames", "s2s_qwen3tts_decode_audio",
+    "s2s_qwen3tts_set_frames", "s2s_qwen3tts_frames", "s2s_qwen3tts_max_batch", "s2s_qwen3tts_codec",
 ]
 
 
@@ -46,6 +51,24 @@ class LlamaConfig(C.Structure):
         ("compute_dtype", C.c_int32), ("max_sessions", C.c_int32), ("max_positions", C.c_int32),
         ("max_prefill", C.c_int32), ("qk_norm", C.c_int32), ("n_tables", C.c_int32),
     ]
+
+
+class CodecConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("codebook_size", "hidden", "heads", "kv_heads", "inter", "layers", "quantizers")] + [
+        ("n_upsample_rates", C.c_int32), ("upsample_rates", C.c_int32 * 8),
+        ("n_upsampling_ratios", C.c_int32), ("upsampling_ratios", C.c_int32 * 4),
+        ("decoder_dim", C.c_int32), ("sliding_window", C.c_int32), ("rope_theta", C.c_float), ("rms_eps", C.c_float),
+        ("max_frames", C.c_int32)]
+
+
+class Qwen3TTSConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "d_model", "layers", "heads", "kv_heads", "head_dim", "ffn", "vocab",
+        "cp_layers", "cp_heads", "cp_kv_heads", "cp_head_dim", "cp_ffn", "cp_vocab", "n_groups", "text_vocab", "text_hidden")] + [
+        ("rope_theta", C.c_float), ("rms_eps", C.c_float)] + [(n, C.c_int32) for n in (
+            "compute_dtype", "max_sessions", "max_positions", "max_text",
+            "codec_eos", "codec_nothink", "codec_think_bos", "codec_think_eos", "codec_pad", "codec_bos",
+            "tts_bos", "tts_eos", "tts_pad", "im_start", "assistant", "newline")] + [("codec", CodecConfig)]
 
 
 class S2SError(RuntimeError):
@@ -101,6 +124,31 @@ def load() -> C.CDLL:
     lib.s2s_llama_max_decode_batch.argtypes = [vp]
     lib.s2s_llama_max_decode_batch.restype = i32
     lib.s2s_tts_postproc.argtypes = [vp, vp, i32, vp, i32, vp, C.POINTER(i32), vp]
+    lib.s2s_codec_create.argtypes = [vp, C.POINTER(CodecConfig), C.POINTER(vp)]
+    lib.s2s_codec_destroy.argtypes = [vp]
+    lib.s2s_codec_bind_tensor.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32, i32]
+    lib.s2s_codec_init_random.argtypes = [vp, C.c_uint64]
+    lib.s2s_codec_finalize.argtypes = [vp]
+    lib.s2s_codec_decode.argtypes = [vp, vp, i32, i32, vp, C.POINTER(i32), vp, vp]
+    lib.s2s_codec_samples.argtypes = [vp, i32]
+    lib.s2s_codec_samples.restype = i32
+    lib.s2s_codec_total_upsample.argtypes = [vp]
+    lib.s2s_codec_total_upsample.restype = i32
+    lib.s2s_qwen3tts_create.argtypes = [vp, C.POINTER(Qwen3TTSConfig), C.POINTER(vp)]
+    lib.s2s_qwen3tts_destroy.argtypes = [vp]
+    lib.s2s_qwen3tts_bind_tensor.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32, i32]
+    lib.s2s_qwen3tts_init_random.argtypes = [vp, C.c_uint64]
+    lib.s2s_qwen3tts_finalize.argtypes = [vp]
+    lib.s2s_qwen3tts_prefill.argtypes = [vp, i32, C.POINTER(i32), i32, i32, vp]
+    lib.s2s_qwen3tts_decode_frames.argtypes = [vp, C.POINTER(i32), i32, i32, vp, vp]
+    lib.s2s_qwen3tts_decode_audio.argtypes = [vp, i32, i32, i32, vp, C.POINTER(i32), vp]
+    lib.s2s_qwen3tts_set_frames.argtypes = [vp, i32, i32]
+    lib.s2s_qwen3tts_frames.argtypes = [vp, i32]
+    lib.s2s_qwen3tts_frames.restype = i32
+    lib.s2s_qwen3tts_max_batch.argtypes = [vp]
+    lib.s2s_qwen3tts_max_batch.restype = i32
+    lib.s2s_qwen3tts_codec.argtypes = [vp]
+    lib.s2s_qwen3tts_codec.restype = vp
     _lib = lib
     return lib
 

@@ -389,6 +389,11 @@ __device__ __forceinline__ unsigned int cluster_id_x() {
   asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ unsigned int cluster_nctaid_x() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(r));
+  return r;
+}
 // all threads of all CTAs of the cluster; release/acquire at cluster scope covers the global-memory hand-offs
 // ONE thread publishes the CTA's writes (bar.sync + fence by thread 0: cumulative, like grid_arrive); the hardware barrier
 // itself is relaxed -- barrier.cluster.arrive.release makes EVERY thread execute MEMBAR.ALL.GPU, which serialises
@@ -589,7 +594,12 @@ whisper_decode_cluster_kernel(const WhisperDecParams p, int step_begin, int step
   __shared__ GemvArgs s_args[3];   // [0] prepared for the next projection, [1] built in-phase, [2] out-projection slice
   __shared__ GemvRing s_rings[DEC_WARPS];
   WdcCtx cx;
-  cx.cid = (int)cluster_id_x(); cx.rank = (int)cluster_ctarank(); cx.cs = p.cluster_size;
+  // Cluster identity comes from the hardware registers only: whatever cluster shape the launch really got (a tool that
+  // intercepts the launch may drop or change the cluster attribute -- round 1's ncu-wrapped run returned wrong ids
+  // because the size was taken from the parameter block), rank / size / id stay mutually consistent and the head -> cluster
+  // assignment stays correct; a shape with fewer clusters than heads is caught below.
+  cx.cid = (int)cluster_id_x(); cx.rank = (int)cluster_ctarank(); cx.cs = (int)cluster_nctaid_x();
+  if ((int)(gridDim.x / cx.cs) < p.heads) __trap();
   if (threadIdx.x < 6) {
     const int i = threadIdx.x;
     const bool has_head = cx.cid < p.heads;

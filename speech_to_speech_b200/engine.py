@@ -11,7 +11,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import S2S_BF16, S2S_F16, S2S_F32, DTYPE_CODES, LlamaConfig, S2SError, WhisperConfig, WhisperDecodeOpts, check
+from ._lib import (S2S_BF16, S2S_F16, S2S_F32, DTYPE_CODES, CodecConfig, LlamaConfig, Qwen3TTSConfig, S2SError, WhisperConfig,
+                   WhisperDecodeOpts, check)
 
 _ctx_lock = threading.Lock()
 _ctx_by_device: dict[int, C.c_void_p] = {}
@@ -307,6 +308,172 @@ class LlamaEngine:
     def close(self) -> None:
         if self.handle:
             self.lib.s2s_llama_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _bind_all(lib_fn, handle, weights: Mapping[str, "np.ndarray | torch.Tensor"], what: str, prefix: str = "") -> None:
+    for name, w in weights.items():
+        if isinstance(w, torch.Tensor):
+            w = w.detach().to("cpu", torch.float32).numpy()
+        a = np.ascontiguousarray(w)
+        if a.dtype not in (np.float32, np.float16):
+            a = a.astype(np.float32)
+        shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+        check(lib_fn(handle, (prefix + name).encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim, _np_dtype_code(a)),
+              f"{what} bind_tensor({prefix}{name})")
+
+
+def codec_config(g: Mapping, max_frames: int = 40) -> CodecConfig:
+    """CodecConfig from a geometry mapping (oracle.code2wav_ref.Code2WavGeometry.to_dict() field names)."""
+    cfg = CodecConfig()
+    cfg.codebook_size, cfg.hidden, cfg.heads, cfg.kv_heads = int(g["codebook_size"]), int(g["hidden"]), int(g["heads"]), int(g["kv_heads"])
+    cfg.inter, cfg.layers, cfg.quantizers = int(g["inter"]), int(g["layers"]), int(g["quantizers"])
+    rates, ratios = list(g["upsample_rates"]), list(g["upsampling_ratios"])
+    cfg.n_upsample_rates, cfg.n_upsampling_ratios = len(rates), len(ratios)
+    for i, r in enumerate(rates):
+        cfg.upsample_rates[i] = int(r)
+    for i, r in enumerate(ratios):
+        cfg.upsampling_ratios[i] = int(r)
+    cfg.decoder_dim, cfg.sliding_window = int(g["decoder_dim"]), int(g["sliding_window"])
+    cfg.rope_theta, cfg.rms_eps = float(g.get("rope_theta", 10000.0)), float(g.get("rms_eps", 1e-5))
+    cfg.max_frames = int(max_frames)
+    return cfg
+
+
+class CodecEngine:
+    """Codebook ids -> 24 kHz waveform on one B200 (the codec-decoder half of the TTS slot; csrc/codec_decode.cu)."""
+
+    def __init__(self, geometry: Mapping, max_frames: int = 40, device: int = 0, _handle=None, _owner=None):
+        self.lib = _lib.load()
+        self.device = device
+        self.ctx = get_context(device)
+        self.geometry = dict(geometry)
+        self._owner = _owner            # a Qwen3TTSEngine that owns the handle
+        if _handle is not None:
+            self.handle = _handle
+            return
+        self.cfg = codec_config(self.geometry, max_frames)
+        self.handle = C.c_void_p()
+        check(self.lib.s2s_codec_create(self.ctx, C.byref(self.cfg), C.byref(self.handle)), "s2s_codec_create")
+
+    def load_state_dict(self, weights) -> None:
+        _bind_all(self.lib.s2s_codec_bind_tensor, self.handle, weights, "codec")
+        check(self.lib.s2s_codec_finalize(self.handle), "s2s_codec_finalize")
+
+    def init_random(self, seed: int = 0) -> None:
+        check(self.lib.s2s_codec_init_random(self.handle, seed), "s2s_codec_init_random")
+        check(self.lib.s2s_codec_finalize(self.handle), "s2s_codec_finalize")
+
+    def samples(self, T: int) -> int:
+        return int(self.lib.s2s_codec_samples(self.handle, T))
+
+    @property
+    def total_upsample(self) -> int:
+        return int(self.lib.s2s_codec_total_upsample(self.handle))
+
+    def decode(self, codes: torch.Tensor, ctx_frames: int = 0, return_hidden: bool = False):
+        """codes int32 cuda [T, quantizers] (frame-major) -> wav f32 cuda [samples of frames ctx_frames..T)."""
+        T = int(codes.shape[0])
+        dev = f"cuda:{self.device}"
+        wav = torch.empty((self.samples(T),), dtype=torch.float32, device=dev)
+        hid = torch.empty((T, self.geometry["hidden"]), dtype=torch.float32, device=dev) if return_hidden else None
+        n = C.c_int32(0)
+        check(self.lib.s2s_codec_decode(self.handle, _ptr(codes.contiguous()), T, ctx_frames, _ptr(wav), C.byref(n), _ptr(hid),
+                                        _stream_ptr(self.device)), "s2s_codec_decode")
+        return (wav[: n.value], hid) if return_hidden else wav[: n.value]
+
+    def close(self) -> None:
+        if self.handle and self._owner is None:
+            self.lib.s2s_codec_destroy(self.handle)
+        self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Qwen3TTSEngine:
+    """Talker + code predictor + codec decoder of the TTS slot on one B200 (csrc/qwen3tts.cu).  Geometry mapping =
+    oracle.qwen3tts_ref.TTSGeometry.to_dict(); codec geometry = oracle.code2wav_ref.Code2WavGeometry.to_dict()."""
+
+    def __init__(self, geometry: Mapping, codec_geometry: Mapping, dtype: str = "bfloat16", max_sessions: int = 4,
+                 max_positions: int = 1024, max_text: int = 256, codec_max_frames: int = 40, device: int = 0):
+        self.lib = _lib.load()
+        self.device = device
+        self.ctx = get_context(device)
+        self.geometry = dict(geometry)
+        g, t, p = self.geometry, dict(geometry["talker"]), dict(geometry["predictor"])
+        cfg = Qwen3TTSConfig()
+        cfg.d_model, cfg.layers, cfg.heads, cfg.kv_heads = int(t["d_model"]), int(t["layers"]), int(t["heads"]), int(t["kv_heads"])
+        cfg.head_dim, cfg.ffn, cfg.vocab = int(t["head_dim"]), int(t["ffn"]), int(t["vocab"])
+        assert int(p["d_model"]) == cfg.d_model, "talker and code predictor share the hidden width"
+        cfg.cp_layers, cfg.cp_heads, cfg.cp_kv_heads = int(p["layers"]), int(p["heads"]), int(p["kv_heads"])
+        cfg.cp_head_dim, cfg.cp_ffn, cfg.cp_vocab = int(p["head_dim"]), int(p["ffn"]), int(p["vocab"])
+        cfg.n_groups, cfg.text_vocab, cfg.text_hidden = int(g["n_groups"]), int(g["text_vocab"]), int(g["text_hidden"])
+        cfg.rope_theta, cfg.rms_eps = float(t["rope_theta"]), float(t["rms_eps"])
+        cfg.compute_dtype = DTYPE_CODES[dtype]
+        cfg.max_sessions, cfg.max_positions, cfg.max_text = max_sessions, max_positions, max_text
+        for k in ("codec_eos", "codec_nothink", "codec_think_bos", "codec_think_eos", "codec_pad", "codec_bos",
+                  "tts_bos", "tts_eos", "tts_pad", "im_start", "assistant", "newline"):
+            setattr(cfg, k, int(g[k]))
+        cfg.codec = codec_config(codec_geometry, codec_max_frames)
+        self.cfg = cfg
+        self.n_groups = cfg.n_groups
+        self.codec_eos = cfg.codec_eos
+        self.handle = C.c_void_p()
+        check(self.lib.s2s_qwen3tts_create(self.ctx, C.byref(cfg), C.byref(self.handle)), "s2s_qwen3tts_create")
+        self.codec = CodecEngine(codec_geometry, device=device, _handle=C.c_void_p(self.lib.s2s_qwen3tts_codec(self.handle)), _owner=self)
+
+    def load_state_dict(self, weights, codec_weights) -> None:
+        _bind_all(self.lib.s2s_qwen3tts_bind_tensor, self.handle, weights, "qwen3tts")
+        _bind_all(self.lib.s2s_qwen3tts_bind_tensor, self.handle, codec_weights, "qwen3tts", prefix="code2wav.")
+        check(self.lib.s2s_qwen3tts_finalize(self.handle), "s2s_qwen3tts_finalize")
+
+    def init_random(self, seed: int = 0) -> None:
+        check(self.lib.s2s_qwen3tts_init_random(self.handle, seed), "s2s_qwen3tts_init_random")
+        check(self.lib.s2s_qwen3tts_finalize(self.handle), "s2s_qwen3tts_finalize")
+
+    def max_batch(self) -> int:
+        return int(self.lib.s2s_qwen3tts_max_batch(self.handle))
+
+    def prefill(self, slot: int, text_ids: Sequence[int], speaker_id: int) -> None:
+        arr, n = _lib.i32_array(text_ids)
+        check(self.lib.s2s_qwen3tts_prefill(self.handle, slot, arr, n, int(speaker_id), _stream_ptr(self.device)), "s2s_qwen3tts_prefill")
+
+    def decode_frames(self, slots: Sequence[int], n_frames: int) -> torch.Tensor:
+        """-> codes int32 cuda [B, n_frames, n_groups] (asynchronous)."""
+        sl, B = _lib.i32_array(slots)
+        codes = torch.empty((B, n_frames, self.n_groups), dtype=torch.int32, device=f"cuda:{self.device}")
+        check(self.lib.s2s_qwen3tts_decode_frames(self.handle, sl, B, n_frames, _ptr(codes), _stream_ptr(self.device)),
+              "s2s_qwen3tts_decode_frames")
+        return codes
+
+    def frames(self, slot: int) -> int:
+        return int(self.lib.s2s_qwen3tts_frames(self.handle, slot))
+
+    def set_frames(self, slot: int, n: int) -> None:
+        check(self.lib.s2s_qwen3tts_set_frames(self.handle, slot, n), "s2s_qwen3tts_set_frames")
+
+    def decode_audio(self, slot: int, n_new: int, left_context: int = 25) -> torch.Tensor:
+        """Waveform (f32 cuda, 24 kHz) of the newest n_new frames of the slot."""
+        cap = self.codec.samples(min(n_new + left_context, self.cfg.codec.max_frames))
+        wav = torch.empty((cap,), dtype=torch.float32, device=f"cuda:{self.device}")
+        n = C.c_int32(0)
+        check(self.lib.s2s_qwen3tts_decode_audio(self.handle, slot, n_new, left_context, _ptr(wav), C.byref(n), _stream_ptr(self.device)),
+              "s2s_qwen3tts_decode_audio")
+        return wav[: n.value]
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.s2s_qwen3tts_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):

@@ -1,7 +1,7 @@
 """Developer aid (not a test): A/B of the 8-phase decode kernel and the cluster kernel (S2S_WHISPER_CLUSTER=0/1)."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from oracle import weights as W
 from speech_to_speech_b200 import engine as E
 import bench

@@ -1,6 +1,6 @@
 """Developer bring-up script (NOT collected by pytest): runs every CUDA stage against the oracle and prints
 per-stage errors instead of stopping at the first failure.  Usage on the GPU box:
-    python tests/dev_gpu_check.py [stage ...]      stages: gemm attn logmel encode decode e2e
+    python tests/dev/dev_gpu_check.py [stage ...]      stages: gemm attn logmel encode decode e2e
 """
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ import traceback
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import weights as W, whisper_ref as R  # noqa: E402

@@ -1,7 +1,7 @@
 """Developer bring-up (not collected): Llama path error levels per dtype."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from oracle import weights as W, llama_ref as R
 from speech_to_speech_b200 import engine as E
 GOLD = os.path.join(ROOT, "tests", "golden")

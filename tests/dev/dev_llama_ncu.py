@@ -1,5 +1,5 @@
 import os, sys, numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from oracle import weights as W
 from speech_to_speech_b200 import engine as E
 g = W.LLAMA_GEOMETRIES["llama-3-8b-2l"]

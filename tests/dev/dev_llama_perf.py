@@ -1,7 +1,7 @@
 """Developer aid: Llama-3-8B prefill/decode timing on one B200 (random-init weights)."""
 import os, sys, time, json
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from oracle import weights as W
 from speech_to_speech_b200 import engine as E
 name = sys.argv[1] if len(sys.argv) > 1 else "llama-3-8b"

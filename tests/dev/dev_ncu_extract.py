@@ -1,7 +1,7 @@
 """Developer aid (not a test): turn the ncu captures under gpurun_out/ into the committed summaries under profiles/.
 
-  python tests/dev_ncu_extract.py launches gpurun_out/launches_r1.csv profiles/launches_r1_summary.txt
-  python tests/dev_ncu_extract.py reps profiles/ncu_summary_r1.md gpurun_out/prof_a.ncu-rep [gpurun_out/prof_b.ncu-rep ...]
+  python tests/dev/dev_ncu_extract.py launches gpurun_out/launches_r1.csv profiles/launches_r1_summary.txt
+  python tests/dev/dev_ncu_extract.py reps profiles/ncu_summary_r1.md gpurun_out/prof_a.ncu-rep [gpurun_out/prof_b.ncu-rep ...]
 The second form also writes profiles/ncu_decode_traffic.json (DRAM bytes per launch of the decode kernels, read by
 bench.py for roofline.traffic)."""
 import csv, io, json, os, subprocess, sys
@@ -63,7 +63,7 @@ def reps(dst, files):
                 v = float(v.replace(",", ""))
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
             if "whisper_decode" in name:
-                key = "cluster_b1" if "cluster" in name else "grid_b16"   # the captures of tests/dev_ncu_decode.py 1 / 16
+                key = "cluster_b1" if "cluster" in name else "grid_b16"   # the captures of tests/dev/dev_ncu_decode.py 1 / 16
                 traffic[key] = {"kernel": name.split("(")[0], "dram_bytes_per_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
                                 "source": os.path.basename(fpath)}
         out.append("")

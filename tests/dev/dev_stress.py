@@ -2,7 +2,7 @@
 Every repetition of the same launch must give bit-identical ids and logits."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from oracle import weights as W
 from speech_to_speech_b200 import engine as E
 import bench

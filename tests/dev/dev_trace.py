@@ -1,7 +1,7 @@
 """Developer aid (not a test): per-phase timeline of the persistent decode kernel from %globaltimer stamps."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from oracle import weights as W
 from speech_to_speech_b200 import engine as E
 import bench

@@ -2,7 +2,7 @@
 # Developer aid: reproduce the round-1 driver failure (ncu-wrapped smoke returned wrong ids) and run the sanitizers.
 cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out/diag; mkdir -p $O
-export S2S_LIB_PATH=$PWD/tests/dev/libs2s_b200_diag.so
+
 SMOKE='import __graft_entry__ as g; g.smoke(); print("__SMOKE_OK__")'
 run() { name=$1; shift; echo "=== $name"; ( "$@" ) > $O/$name.log 2>&1; echo "rc=$? $(grep -c __SMOKE_OK__ $O/$name.log) ok; $(grep -h 'smoke:' $O/$name.log | tail -1 | cut -c1-200)"; }
 run plain python -c "$SMOKE"

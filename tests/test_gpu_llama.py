@@ -141,3 +141,51 @@ def test_llama3_8b_layer_geometry_two_layers(E):
     forced = torch.tensor([ref_ids[1:]], dtype=torch.int32, device="cuda")
     ids, lens, lg = eng.decode([0], first, 2, forced=forced, return_logits=True)
     assert np.abs(lg[:, 0].cpu().numpy() - ref_lg[1:]).max() < LOGIT_TOL
+
+
+# ---- Qwen3 family (qk_norm): the reference's DEFAULT LLM is Qwen/Qwen3-4B-Instruct-2507 (language_model_base_arguments.py:6-9)
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_qwen3_qk_norm_prefill_and_decode_match_golden(E, golden_dir, dtype):
+    """Per-head RMSNorm(head_dim) on q and k before RoPE (transformers modeling_qwen3.py Qwen3Attention), golden pinned
+    to Qwen3ForCausalLM: prefill logits, teacher-forced decode logits, ids where the margin allows."""
+    g, w, eng = _engine(E, "qwen3-micro", dtype)
+    tol = TOL[dtype]
+    G = np.load(os.path.join(golden_dir, "llama_qwen3-micro.npz"))
+    gold = G["gen_ids"]
+    nxt, logits = eng.prefill(0, G["prompt"].tolist(), return_logits=True)
+    lg = logits.cpu().numpy()
+    assert np.abs(lg[-1][G["col_idx"]] - G["prefill_last_cols"]).max() < tol
+    assert np.abs(lg[len(G["prompt"]) // 2][G["col_idx"]] - G["prefill_mid_cols"]).max() < tol
+    first = torch.tensor([int(gold[0])], dtype=torch.int32, device="cuda")
+    forced = torch.from_numpy(np.ascontiguousarray(gold[None, 1:])).cuda().int()
+    ids, lens, dlog = eng.decode([0], first, len(gold) - 1, forced=forced, return_logits=True)
+    dl = dlog[:, 0].cpu().numpy()
+    tv = np.take_along_axis(dl, G["top_idx"][1:], 1)
+    assert np.abs(tv - G["top_val"][1:]).max() < tol
+    safe = (G["top_val"][1:, 0] - G["top_val"][1:, 1]) > 4 * tol
+    assert (ids[0].cpu().numpy()[safe] == gold[1:][safe]).all()
+
+
+def test_qwen3_decode_matches_debug_phases_and_oracle_batch(E, monkeypatch):
+    """Qwen3 geometry, 3 sessions of different lengths in one launch vs the oracle; the persistent launch and the
+    one-launch-per-phase debug mode must agree bit for bit (the grid barrier is the only difference)."""
+    g = W.LLAMA_GEOMETRIES["qwen3-micro"]
+    w = W.make_llama_weights(g, 0)
+    rng = np.random.default_rng(21)
+    prompts = [rng.integers(0, g.vocab, n) for n in (5, 33, 70)]
+    refs = [R.greedy_generate(w, g, p, 6, return_logits=True) for p in prompts]
+    outs = []
+    for dbg in ("0", "1"):
+        monkeypatch.setenv("S2S_DEBUG_PHASES", dbg)
+        eng = E.LlamaEngine(g.to_dict(), dtype="float16", max_sessions=3, max_positions=128, max_prefill=128)
+        eng.load_state_dict(w)
+        for s, p in enumerate(prompts):
+            eng.prefill(s, p.tolist())
+        first = torch.tensor([r[0][0] for r in refs], dtype=torch.int32, device="cuda")
+        forced = torch.tensor([r[0][1:] for r in refs], dtype=torch.int32, device="cuda")
+        ids, lens, logits = eng.decode([0, 1, 2], first, 5, forced=forced, return_logits=True)
+        outs.append((ids.cpu().numpy().copy(), logits.cpu().numpy().copy()))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for s in range(3):
+        assert np.abs(outs[0][1][:, s] - refs[s][1][1:]).max() < TOL["float16"], s

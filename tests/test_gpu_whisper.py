@@ -298,3 +298,137 @@ def test_bad_arguments_raise(E):
     eng2 = E.WhisperEngine(g.to_dict())
     with pytest.raises(S2SError):
         eng2.encode(1)  # not finalized
+
+
+# ------------------------------------------------------------------------------------------ the benchmarked configuration
+# Whisper-small, 4-token prompt + 128 generated tokens (131 decoder steps: 5 self-attention key blocks), the real 88-entry
+# suppress list of the bench, at 1 session (cluster kernel and 8-phase kernel) and 16 sessions per launch.
+def _bench_opts(E, n=128):
+    import bench
+    return E.WhisperDecodeOptions(prefix=bench.PREFIX, eos_id=-1, max_new_tokens=n, suppress=bench.SUPPRESS,
+                                  begin_suppress=bench.BEGIN_SUPPRESS)
+
+
+def _check_session_against_oracle(w, g, enc_f32, opts, ids_free, ids_forced_run, lg_gpu, tol):
+    """ids_free: the engine's free-running ids; lg_gpu [n, vocab]: its logits when teacher-forced with ids_free."""
+    n = opts.max_new_tokens
+    ref_ids, lg_ref = R.greedy_decode(w, g, enc_f32, list(opts.prefix), n, -1, list(opts.suppress), list(opts.begin_suppress),
+                                      forced=[int(t) for t in ids_free], return_logits=True)
+    fin = np.isfinite(lg_ref)
+    assert (np.isfinite(lg_gpu) == fin).all()                     # same ids suppressed at every step
+    err = float(np.abs(lg_gpu[fin] - lg_ref[fin]).max())
+    assert err < tol, err
+    srt = np.sort(lg_ref, axis=1)
+    safe = (srt[:, -1] - srt[:, -2]) > 4 * tol
+    ref_ids = np.asarray(ref_ids)
+    # teacher-forced argmax agrees wherever the oracle's margin is above the tolerance band ...
+    assert (np.asarray(ids_forced_run)[safe] == ref_ids[safe]).all()
+    # ... and the free run IS the oracle's greedy sequence up to the first sub-margin step (fed tokens identical until then)
+    k = int(np.argmin(safe)) if (~safe).any() else n
+    assert (np.asarray(ids_free)[:k] == ref_ids[:k]).all()
+    return err, int(safe.sum()), k
+
+
+@pytest.mark.parametrize("cluster", ["1", "0"])
+def test_small_128_tokens_single_session_vs_oracle(E, monkeypatch, cluster):
+    monkeypatch.setenv("S2S_WHISPER_CLUSTER", cluster)
+    g, w, eng = _engine(E, "small")
+    audio = W.synthetic_audio(3, 160000)
+    eng.logmel(torch.from_numpy(audio)[None].cuda(), [len(audio)])
+    enc = eng.encode(1, return_output=True)[0].cpu().numpy()
+    opts = _bench_opts(E)
+    ids, lens = eng.decode(1, opts)
+    ids_free = ids[0].cpu().numpy().copy()
+    assert int(lens[0]) == 128
+    ids_f, _, logits = eng.decode(1, opts, forced=ids.clone(), return_logits=True)
+    err, n_safe, k = _check_session_against_oracle(w, g, enc, opts, ids_free, ids_f[0].cpu().numpy(), logits[:, 0].cpu().numpy(),
+                                                   LOGIT_TOL)
+    assert n_safe >= 64
+
+
+def test_small_128_tokens_sixteen_sessions_vs_oracle(E):
+    nb = 16
+    g, w, eng = _engine(E, "small", max_batch=nb)
+    auds = [W.synthetic_audio(200 + i, 160000 if i % 4 else 96000) for i in range(nb)]
+    pcm = np.zeros((nb, 480000), np.float32)
+    for i, a in enumerate(auds):
+        pcm[i, : len(a)] = a
+    eng.logmel(torch.from_numpy(pcm).cuda(), [len(a) for a in auds])
+    enc = eng.encode(nb, return_output=True).cpu().numpy()
+    opts = _bench_opts(E)
+    ids, lens = eng.decode(nb, opts)
+    ids_free = ids.cpu().numpy().copy()
+    ids_f, _, logits = eng.decode(nb, opts, forced=ids.clone(), return_logits=True)
+    lg = logits.cpu().numpy()
+    for i in (0, 7, 15):   # the numpy oracle on three of the sixteen (lower half, upper half of the tensor-core tile, last)
+        _check_session_against_oracle(w, g, enc[i], opts, ids_free[i], ids_f[i].cpu().numpy(), lg[:, i], LOGIT_TOL)
+    # every session alone through the single-session path gives logits within the tolerance band of its batched run
+    eng1 = E.WhisperEngine(g.to_dict(), dtype="float16", max_batch=1)
+    eng1.load_state_dict(w)
+    for i in (3, 12):
+        eng1.logmel(torch.from_numpy(auds[i])[None].cuda(), [len(auds[i])])
+        eng1.encode(1)
+        _, _, l1 = eng1.decode(1, opts, forced=ids[i:i + 1].clone(), return_logits=True)
+        a, b = l1[:, 0].cpu().numpy(), lg[:, i]
+        fin = np.isfinite(a)
+        assert np.abs(a[fin] - b[fin]).max() < LOGIT_TOL
+
+
+@pytest.mark.parametrize("nb", [1, 16])
+def test_small_131_steps_persistent_equals_phase_by_phase(E, monkeypatch, nb):
+    """Timing-perturbed rerun of the benchmarked decode: the persistent launch (grid barriers) and one launch per phase
+    (kernel boundaries instead of barriers) must agree BIT FOR BIT on ids and logits -- a missing acquire/release or a
+    stale read shows up here.  Both single-session kernels and the 16-session kernel."""
+    g = W.WHISPER_GEOMETRIES["small"]
+    w = W.make_whisper_weights(g, 0)
+    auds = [W.synthetic_audio(300 + i, 160000) for i in range(nb)]
+    pcm = torch.from_numpy(np.stack(auds)).cuda()
+    opts = _bench_opts(E)
+    modes = [("0", "1"), ("1", "1")] + ([("0", "0"), ("1", "0")] if nb == 1 else [])
+    outs = {}
+    for dbg, cl in modes:
+        monkeypatch.setenv("S2S_DEBUG_PHASES", dbg)
+        monkeypatch.setenv("S2S_WHISPER_CLUSTER", cl)
+        eng = E.WhisperEngine(g.to_dict(), dtype="float16", max_batch=nb)
+        eng.load_state_dict(w)
+        eng.logmel(pcm, [160000] * nb)
+        eng.encode(nb)
+        ids, lens = eng.decode(nb, opts)
+        _, _, logits = eng.decode(nb, _bench_opts(E, 16), forced=ids[:, :16].contiguous(), return_logits=True)
+        outs[(dbg, cl)] = (ids.cpu().numpy().copy(), logits.cpu().numpy().copy())
+        eng.close()
+    for cl in {m[1] for m in modes}:
+        a, b = outs[("0", cl)], outs[("1", cl)]
+        assert np.array_equal(a[0], b[0]), f"ids differ between persistent and per-phase launches (cluster={cl})"
+        assert np.array_equal(a[1], b[1], equal_nan=True), f"logits differ (cluster={cl})"
+
+
+def test_large_v3_geometry_slice(E):
+    """Whisper-large-v3 layer shapes (d 1280, 20 heads, ffn 5120, 128 mels, vocab 51866) with 2 + 2 layers: encoder vs oracle
+    and 6 teacher-forced decoder steps (the 8-phase kernel with the reduced batch this geometry allows)."""
+    g0 = W.WHISPER_GEOMETRIES["large-v3"]
+    g = W.WhisperGeometry(g0.d_model, g0.heads, 2, 2, g0.ffn, g0.n_mels, g0.vocab, 1500, 448)
+    w = W.make_whisper_weights(g, 0)
+    eng = E.WhisperEngine(g.to_dict(), dtype="float16", max_batch=2)
+    eng.load_state_dict(w)
+    auds = [W.synthetic_audio(5, 160000), W.synthetic_audio(6, 480000)]
+    pcm = np.zeros((2, 480000), np.float32)
+    for i, a in enumerate(auds):
+        pcm[i, : len(a)] = a
+    mel = eng.logmel(torch.from_numpy(pcm).cuda(), [len(a) for a in auds], return_mel=True).cpu().numpy()
+    out = eng.encode(2, return_output=True).cpu().numpy()
+    prefix, eos = [50258, 50259, 50360, 50364], 50257
+    opts = E.WhisperDecodeOptions(prefix=prefix, eos_id=eos, max_new_tokens=6, suppress=[1, 2, 7], begin_suppress=[220, eos])
+    refs = []
+    for i, a in enumerate(auds):
+        mel_ref = R.log_mel_spectrogram(a, g.n_mels)
+        assert np.abs(mel[i] - mel_ref).max() < 1e-4
+        enc_ref = R.encoder_forward(w, g, mel_ref)
+        assert np.abs(out[i] - enc_ref).max() < 2 * ENC_TOL
+        refs.append(R.greedy_decode(w, g, enc_ref, prefix, 6, -1, [1, 2, 7], [220, eos], return_logits=True))
+    forced = torch.tensor(np.stack([np.asarray(r[0]) for r in refs]), dtype=torch.int32, device="cuda")
+    ids, lens, logits = eng.decode(2, opts, forced=forced, return_logits=True)
+    lg = logits.cpu().numpy()
+    for i, (rid, rlg) in enumerate(refs):
+        fin = np.isfinite(rlg)
+        assert np.abs(lg[:, i][fin] - rlg[fin]).max() < 2 * LOGIT_TOL, i
