@@ -25,6 +25,11 @@ logger = logging.getLogger(__name__)
 
 LLAMA_GEOMETRIES = {
     "micro": dict(d_model=256, layers=2, heads=2, kv_heads=1, head_dim=128, ffn=512, vocab=2048),
+    "qwen3-micro": dict(d_model=256, layers=2, heads=4, kv_heads=2, head_dim=64, ffn=512, vocab=2048, rope_theta=1000000.0,
+                        rms_eps=1e-6, qk_norm=True),
+    # the reference's default LLM (language_model_base_arguments.py:6-9): Qwen/Qwen3-4B-Instruct-2507
+    "qwen3-4b": dict(d_model=2560, layers=36, heads=32, kv_heads=8, head_dim=128, ffn=9728, vocab=151936, rope_theta=5000000.0,
+                     rms_eps=1e-6, qk_norm=True),
     "mini": dict(d_model=1024, layers=4, heads=8, kv_heads=2, head_dim=128, ffn=3584, vocab=32064),
     "llama-3-8b": dict(d_model=4096, layers=32, heads=32, kv_heads=8, head_dim=128, ffn=14336, vocab=128256,
                        rope_theta=500000.0, rms_eps=1e-5),
@@ -38,6 +43,7 @@ class TokenStreamer:
                  decode_chunk: Optional[Callable[[int, int, int, int], list]] = None, lock: Optional[Any] = None):
         self.engine, self.decode_text, self.eos_ids, self.chunk, self.slot = engine, decode_text, set(int(e) for e in eos_ids), max(1, chunk), slot
         self.generated: list[int] = []
+        self._po = self._ro = 0   # incremental detokenisation window
         # decode_chunk(slot, first_token, n, eos) -> ids: the shared-engine path routes it through the session batcher;
         # lock serialises prefill on a shared engine (one thread per engine handle at a time)
         self._decode_chunk = decode_chunk or self._decode_direct
@@ -51,9 +57,29 @@ class TokenStreamer:
             ids, lens = eng.decode([slot], first, n, eos_id=eos)
             return ids[0, : int(lens[0]) if int(lens[0]) > 0 else n].tolist()
 
+    def _fresh_text(self) -> str:
+        """Incremental detokenisation: decode only the window [previous chunk | new tokens] instead of the whole reply every
+        chunk (O(n * window), not O(n^2)); the previous chunk is context for correct spacing / byte merges."""
+        toks = self.generated
+        before = self.decode_text(toks[self._po:self._ro]) if self._ro > self._po else ""
+        now = self.decode_text(toks[self._po:])
+        if len(now) > len(before) and not now.endswith("\ufffd"):
+            self._po, self._ro = self._ro, len(toks)
+            return now[len(before):]
+        return ""
+
     def stream(self, prompt_ids: Sequence[int], max_new_tokens: int, should_stop: Callable[[], bool] = lambda: False) -> Iterator[str]:
         eng = self.engine
         max_prefill = eng.cfg.max_prefill
+        max_pos = int(getattr(eng, "max_positions", 1 << 30))
+        prompt_ids = list(prompt_ids) or [0]          # an empty prompt still needs one position to predict from
+        # one session must never make a shared launch fail (llama.cu rejects len + n_steps > max_positions for the whole batch):
+        # keep the tail of an over-long prompt and cap the reply at what the KV slot can still hold
+        room = max_pos - 2
+        if len(prompt_ids) > room - 1:
+            logger.warning("LLM prompt of %d tokens exceeds the %d-position KV slot: keeping the last %d", len(prompt_ids), max_pos, room - 1)
+            prompt_ids = prompt_ids[-(room - 1):]
+        max_new_tokens = max(1, min(int(max_new_tokens), room - len(prompt_ids)))
         nxt = None
         with self._lock:
             eng.reset(self.slot)
@@ -61,16 +87,15 @@ class TokenStreamer:
                 nxt, _ = eng.prefill(self.slot, list(prompt_ids[o:o + max_prefill]))
             tok = int(nxt[0])
         self.generated = []
-        emitted = ""
+        self._po = self._ro = 0
         eos_for_kernel = next(iter(self.eos_ids)) if len(self.eos_ids) == 1 else -1
         while len(self.generated) < max_new_tokens:
             if tok in self.eos_ids:
                 break
             self.generated.append(tok)
-            text = self.decode_text(self.generated)
-            if len(text) > len(emitted) and not text.endswith("�"):
-                yield text[len(emitted):]
-                emitted = text
+            piece = self._fresh_text()
+            if piece:
+                yield piece
             if should_stop() or len(self.generated) >= max_new_tokens:
                 break
             n = min(self.chunk, max_new_tokens - len(self.generated))
@@ -84,9 +109,11 @@ class TokenStreamer:
             if stop or not out:
                 break
             tok = out[-1]
-        text = self.decode_text(self.generated) if self.generated else ""
-        if len(text) > len(emitted):  # flush the tail (tokens appended by the last launch before EOS / budget end)
-            yield text[len(emitted):]
+        if self.generated:   # flush the tail (tokens appended by the last launch before EOS / budget end)
+            before = self.decode_text(self.generated[self._po:self._ro]) if self._ro > self._po else ""
+            now = self.decode_text(self.generated[self._po:])
+            if len(now) > len(before):
+                yield now[len(before):]
 
 
 class _LlamaBundle:
@@ -131,6 +158,31 @@ class _LlamaBundle:
         self.engine.close()
 
 
+def geometry_from_hf_config(c: Any, max_positions: int) -> dict:
+    """Engine geometry from a transformers config, REJECTING everything the kernels do not implement instead of loading
+    it and producing silently wrong logits: model families other than Llama / Mistral / Qwen3, RoPE scaling (Llama-3.1+
+    `rope_scaling={"rope_type": "llama3", ...}`, linear, dynamic, yarn), attention / MLP biases, a sliding window shorter than
+    the KV slot, MoE variants."""
+    mt = getattr(c, "model_type", None)
+    if mt not in ("llama", "mistral", "qwen3"):
+        raise ValueError(f"B200LanguageModelHandler supports Llama / Mistral / Qwen3 checkpoints (got model_type={mt!r})")
+    rope = getattr(c, "rope_parameters", None) or getattr(c, "rope_scaling", None) or {}
+    rtype = (rope.get("rope_type") or rope.get("type") or "default") if isinstance(rope, dict) else "default"
+    if rtype != "default":
+        raise ValueError(f"rope scaling {rtype!r} is not implemented by the sm_100a RoPE table (plain theta^(-2j/hd) only)")
+    theta = float((rope.get("rope_theta") if isinstance(rope, dict) else None) or getattr(c, "rope_theta", 10000.0))
+    for flag in ("attention_bias", "mlp_bias"):
+        if getattr(c, flag, False):
+            raise ValueError(f"{flag}=True is not implemented (projections are bias-free in the built path)")
+    sw = getattr(c, "sliding_window", None)
+    if sw is not None and getattr(c, "use_sliding_window", True) and int(sw) < int(max_positions):
+        raise ValueError(f"sliding_window={sw} < max_positions={max_positions}: windowed attention is not implemented")
+    heads = int(c.num_attention_heads)
+    return dict(d_model=int(c.hidden_size), layers=int(c.num_hidden_layers), heads=heads, kv_heads=int(c.num_key_value_heads),
+                head_dim=int(getattr(c, "head_dim", None) or c.hidden_size // heads), ffn=int(c.intermediate_size),
+                vocab=int(c.vocab_size), rope_theta=theta, rms_eps=float(c.rms_norm_eps), qk_norm=(mt == "qwen3"))
+
+
 def _reference_base():
     """The reference's BaseLanguageModelHandler when importable (nltk stubbed like the reference's own tests do)."""
     try:
@@ -163,6 +215,10 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
         from .. import engine as E
         dev = int(device.split(":")[1]) if ":" in device else 0
         self.gen_kwargs = dict(gen_kwargs)
+        if self.gen_kwargs.get("do_sample") or float(self.gen_kwargs.get("temperature") or 0.0) > 0.0:
+            logger.warning("B200LanguageModelHandler decodes greedily on the device: do_sample / temperature are ignored")
+        if int(self.gen_kwargs.get("min_new_tokens") or 0) > 0:
+            logger.warning("B200LanguageModelHandler: min_new_tokens is ignored (EOS always ends the reply)")
         self.stream_chunk_tokens = int(self.gen_kwargs.pop("stream_chunk_tokens", 8))
         max_pos = int(self.gen_kwargs.pop("max_positions", 4096))
         max_sessions = max(1, int(self.gen_kwargs.pop("max_sessions", 1)))
@@ -179,11 +235,7 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
             tokenizer = AutoTokenizer.from_pretrained(model_name)
             hf = AutoModelForCausalLM.from_pretrained(model_name)
             c = hf.config
-            if c.model_type not in ("llama", "mistral"):
-                raise ValueError(f"B200LanguageModelHandler supports Llama-family checkpoints (got model_type={c.model_type!r})")
-            geom = dict(d_model=c.hidden_size, layers=c.num_hidden_layers, heads=c.num_attention_heads, kv_heads=c.num_key_value_heads,
-                        head_dim=getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads, ffn=c.intermediate_size,
-                        vocab=c.vocab_size, rope_theta=float(getattr(c, "rope_theta", 10000.0)), rms_eps=float(c.rms_norm_eps))
+            geom = geometry_from_hf_config(c, max_pos)
             engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=max_sessions, max_positions=max_pos, max_prefill=512, device=dev)
             engine.load_state_dict(hf.state_dict())
             eos = hf.generation_config.eos_token_id
@@ -204,15 +256,34 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
         n = int(max_new_tokens or self.gen_kwargs.get("max_new_tokens", 1024))
         return self.streamer.stream(prompt_ids, n, should_stop)
 
+    def setup(self, **kwargs: Any) -> None:  # type: ignore[override]
+        """LanguageModelHandler.setup (S/LLM/language_model.py:795-798): base setup, then warm up so that the first user turn
+        does not pay for cudaFuncSetAttribute and the cooperative-launch cold start."""
+        super().setup(**kwargs)
+        self.warmup()
+
+    def _prompt_ids(self, chat_messages: Any) -> list:
+        """What the reference feeds the model (:846-848, :885): the chat template rendered with the generation prompt and
+        `enable_thinking=False`, then tokenised the way `pipeline("text-generation")` tokenises a string prompt."""
+        tok = self.tokenizer
+        if isinstance(tok, _IdTokenizer):
+            return list(tok.apply_chat_template(chat_messages, tokenize=True, add_generation_prompt=True))
+        text = tok.apply_chat_template(chat_messages, tokenize=False, add_generation_prompt=True, enable_thinking=False)
+        ids = tok(text)["input_ids"]
+        return list(ids[0]) if ids and isinstance(ids[0], (list, tuple)) else list(ids)
+
     # -- reference hook (S/LLM/language_model.py:832-892) -----------------------------------------
     def _generate(self, chat: Any, language_code: Optional[str], gen: Optional[int], ctx: Any, runtime_config: Any = None,
                   response: Any = None) -> Iterator[Any]:
         chat_messages = chat.to_transformers_chat()
-        prompt_ids = self.tokenizer.apply_chat_template(chat_messages, tokenize=True, add_generation_prompt=True)
-        if isinstance(prompt_ids, dict):
-            prompt_ids = prompt_ids["input_ids"]
-        ctx.input_tokens += len(prompt_ids)
-        stop = (lambda: self._check_stop(gen, ctx)) if hasattr(self, "_check_stop") else (lambda: False)
+        counted = self.tokenizer.apply_chat_template(chat_messages, tokenize=True)   # the reference's prompt-token count (:842-844)
+        ctx.input_tokens += len(counted if isinstance(counted, list) else counted["input_ids"])
+        prompt_ids = self._prompt_ids(chat_messages)
+        aborted = threading.Event()
+        if getattr(ctx, "prefetch_transaction", None) is not None:   # speculative prefetch discarded -> stop at the next chunk (:879-880)
+            ctx.prefetch_transaction.register_abort(aborted.set)
+        check = getattr(self, "_check_stop", None)
+        stop = (lambda: aborted.is_set() or bool(check(gen, ctx))) if check else aborted.is_set
         token_iter = self.generate_text_stream(prompt_ids, should_stop=stop)
         yield from self._stream_tokens(token_iter, gen, language_code, ctx, runtime_config, response)
 

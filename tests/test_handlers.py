@@ -215,6 +215,33 @@ def test_registers_in_the_reference_backend_registry():
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+def test_tts_spec_and_overrides_cover_all_three_slots():
+    """`b200-qwen3` reuses the reference's Qwen3TTSHandlerArguments / prefix; install_overrides() swaps the classes behind the
+    unchanged names whisper / transformers / qwen3 (the lazy factories resolve to our modules, nothing is imported yet)."""
+    import dataclasses
+    import speech_to_speech_b200.registry as r
+    import speech_to_speech.backend_registry as br
+    from speech_to_speech.arguments_classes.qwen3_tts_arguments import Qwen3TTSHandlerArguments
+    saved = (dict(br.STT_BACKENDS), dict(br.LLM_BACKENDS), dict(br.TTS_BACKENDS))
+    try:
+        specs = r.register()
+        tts = specs["b200-qwen3"]
+        assert br.TTS_BACKENDS["b200-qwen3"] is tts and tts.kind == "tts" and tts.config_type is Qwen3TTSHandlerArguments
+        cfg = tts.normalize(Qwen3TTSHandlerArguments(qwen3_tts_model_name="random:micro", qwen3_tts_speaker="Aiden"))
+        assert cfg["model_name"] == "random:micro" and cfg["speaker"] == "Aiden" and cfg["blocksize"] == 512
+        before = {k: br.TTS_BACKENDS[k].create_handler for k in ("qwen3",)}
+        r.install_overrides()
+        assert br.TTS_BACKENDS["qwen3"].create_handler is not before["qwen3"]
+        assert br.TTS_BACKENDS["qwen3"].config_type is Qwen3TTSHandlerArguments
+        assert br.LLM_BACKENDS["transformers"].name == "transformers" and br.STT_BACKENDS["whisper"].name == "whisper"
+        for spec in (br.STT_BACKENDS["whisper"], br.LLM_BACKENDS["transformers"], br.TTS_BACKENDS["qwen3"]):
+            assert dataclasses.is_dataclass(spec) and callable(spec.create_handler)
+    finally:
+        for d, s in zip((br.STT_BACKENDS, br.LLM_BACKENDS, br.TTS_BACKENDS), saved):
+            d.clear(); d.update(s)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
 def test_llm_handler_implements_the_reference_hooks():
     from speech_to_speech_b200.handlers import language_model_handler as LH
     from speech_to_speech.LLM.language_model import BaseLanguageModelHandler
