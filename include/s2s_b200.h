@@ -81,6 +81,8 @@ typedef struct {
   int32_t n_suppress;
   const int32_t* begin_suppress_h; /* SuppressTokensAtBeginLogitsProcessor */
   int32_t n_begin_suppress;
+  const int32_t* prefix_rows_h;    /* optional [B][n_prefix]: one prompt per utterance (per-utterance language after
+                                      detect_language on the SAME encoder output, whisper_stt_handler.py:236-241); NULL = prefix_h */
 } s2s_whisper_decode_opts;
 
 /* pcm_d: [B, pcm_stride] f32 mono 16 kHz, n_samples_h[b] valid samples each (rest ignored, padded
@@ -237,9 +239,10 @@ int s2s_qwen3tts_prefill(s2s_qwen3tts* m, int32_t slot, const int32_t* text_ids_
 /* Generate n_frames frames for the B (<= s2s_qwen3tts_max_batch) sessions slots_h[B] in lock step: 3 persistent
  * launches per frame serve all of them.  codes_out_d [B][n_frames][n_groups] i32.  A session whose first code is
  * codec_eos has finished: the caller drops that frame and everything after it (frames_done is not advanced past it).
- * Asynchronous on `stream`. */
+ * forced_codes_d (optional, [B][n_frames][n_groups]): teacher-forced feedback for parity tests -- the reported codes are
+ * still the models' own decisions, the given codes are what is fed forward and kept.  Asynchronous on `stream`. */
 int s2s_qwen3tts_decode_frames(s2s_qwen3tts* m, const int32_t* slots_h, int32_t B, int32_t n_frames,
-                               int32_t* codes_out_d, void* stream);
+                               int32_t* codes_out_d, const int32_t* forced_codes_d, void* stream);
 /* Waveform of the newest `n_new` frames of `slot` (codes kept by the library since prefill), decoded behind up to
  * `left_context` frames of history (Qwen3OmniMoeCode2Wav.chunked_decode); wav_out_d f32 [n_new * 1920 (max)]. */
 int s2s_qwen3tts_decode_audio(s2s_qwen3tts* m, int32_t slot, int32_t n_new, int32_t left_context, float* wav_out_d,

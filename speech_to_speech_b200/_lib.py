@@ -40,6 +40,7 @@ class WhisperDecodeOpts(C.Structure):
         ("prefix_h", C.POINTER(C.c_int32)), ("n_prefix", C.c_int32), ("max_new_tokens", C.c_int32),
         ("eos_id", C.c_int32), ("suppress_h", C.POINTER(C.c_int32)), ("n_suppress", C.c_int32),
         ("begin_suppress_h", C.POINTER(C.c_int32)), ("n_begin_suppress", C.c_int32),
+        ("prefix_rows_h", C.POINTER(C.c_int32)),
     ]
 
 
@@ -140,7 +141,7 @@ def load() -> C.CDLL:
     lib.s2s_qwen3tts_init_random.argtypes = [vp, C.c_uint64]
     lib.s2s_qwen3tts_finalize.argtypes = [vp]
     lib.s2s_qwen3tts_prefill.argtypes = [vp, i32, C.POINTER(i32), i32, i32, vp]
-    lib.s2s_qwen3tts_decode_frames.argtypes = [vp, C.POINTER(i32), i32, i32, vp, vp]
+    lib.s2s_qwen3tts_decode_frames.argtypes = [vp, C.POINTER(i32), i32, i32, vp, vp, vp]
     lib.s2s_qwen3tts_decode_audio.argtypes = [vp, i32, i32, i32, vp, C.POINTER(i32), vp]
     lib.s2s_qwen3tts_set_frames.argtypes = [vp, i32, i32]
     lib.s2s_qwen3tts_frames.argtypes = [vp, i32]

@@ -87,7 +87,9 @@ __global__ void frame_prepare_kernel(TtsBatch tb, int f, const float* __restrict
 // between talker and predictor: predictor input 0 = final-norm(talker hidden) (the cousin feeds hidden_states[-1], which
 // transformers ties to the post-norm last_hidden_state); predictor cache slot = batch index, position 0
 __global__ void frame_mid_kernel(const float* __restrict__ hidden, const float* __restrict__ norm_w, float eps, int d,
-                                 float* __restrict__ x_in_p, int* __restrict__ pslot_d, int* __restrict__ ppos_d) {
+                                 float* __restrict__ x_in_p, int* __restrict__ pslot_d, int* __restrict__ ppos_d,
+                                 const int* __restrict__ code0, const int* __restrict__ forced /*[B][n_frames][G] or null*/, int f,
+                                 int n_frames, int G, int* __restrict__ code0_feed, int* __restrict__ forced_frame /*[B][G]*/) {
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float* h = hidden + (long long)b * d;
@@ -101,22 +103,28 @@ __global__ void frame_mid_kernel(const float* __restrict__ hidden, const float* 
   const float r = 1.0f / sqrtf(tot / (float)d + eps);
   for (int i = threadIdx.x; i < d; i += blockDim.x) x_in_p[(long long)b * d + i] = norm_w[i] * (h[i] * r);
   if (threadIdx.x == 0) { pslot_d[b] = b; ppos_d[b] = 0; }
+  // teacher forcing (parity tests): the code predictor is fed the given codes of this frame, its own argmax is still reported
+  if (threadIdx.x < G) {
+    if (forced) forced_frame[b * G + threadIdx.x] = forced[((long long)b * n_frames + f) * G + threadIdx.x];
+    if (threadIdx.x == 0) code0_feed[b] = forced ? forced[((long long)b * n_frames + f) * G] : code0[b];
+  }
 }
 
 // after the predictor: record the frame's codes and build the next talker input
 //   xnext = E_talker[code0] + sum_{i >= 1} E_pred[i - 1][code_i] + (trailing[frame] | tts_pad)
 template <typename T>
 __global__ void frame_finish_kernel(TtsBatch tb, int f, int n_frames, int G, const int* __restrict__ pcodes /*[B][G]*/,
+                                    const int* __restrict__ code0 /*[B] talker argmax*/, const int* __restrict__ forced_frame /*[B][G] or null*/,
                                     const T* __restrict__ talker_embed, const T* __restrict__ pred_embed, long long pred_stride,
                                     int d, const float* __restrict__ trailing_all, long long trailing_stride,
                                     const float* __restrict__ pad_all, float* __restrict__ xnext_all,
                                     int* __restrict__ codes_out, int* __restrict__ history, long long history_stride) {
   const int b = blockIdx.x, slot = tb.slot[b], fa = tb.frames0[b] + f;
-  const int* pc = pcodes + b * G;
+  // reported: the models' own decisions (talker argmax, predictor argmaxes); fed forward / kept: the forced codes if given
+  const int* pc = forced_frame ? forced_frame + b * G : pcodes + b * G;
   if (threadIdx.x < G) {
-    const int c = pc[threadIdx.x];
-    codes_out[((long long)b * n_frames + f) * G + threadIdx.x] = c;
-    history[(long long)slot * history_stride + (long long)fa * G + threadIdx.x] = c;
+    codes_out[((long long)b * n_frames + f) * G + threadIdx.x] = threadIdx.x == 0 ? code0[b] : pcodes[b * G + threadIdx.x];
+    history[(long long)slot * history_stride + (long long)fa * G + threadIdx.x] = pc[threadIdx.x];
   }
   const float* extra = fa < tb.n_trailing[b] ? trailing_all + (long long)slot * trailing_stride + (long long)fa * d
                                               : pad_all + (long long)slot * d;
@@ -166,7 +174,7 @@ struct s2s_qwen3tts {
   // frame workspace
   float *x_in_t = nullptr, *hidden = nullptr, *x_in_p = nullptr;
   int *tslot_d = nullptr, *tpos_d = nullptr, *pslot_d = nullptr, *ppos_d = nullptr, *code0 = nullptr, *pcodes = nullptr,
-      *tlen = nullptr, *plen = nullptr;
+      *tlen = nullptr, *plen = nullptr, *code0_feed = nullptr, *forced_frame = nullptr;
   unsigned char* suppress = nullptr;
 };
 
@@ -257,6 +265,8 @@ int s2s_qwen3tts_create(s2s_ctx* ctx, const s2s_qwen3tts_config* cfg, s2s_qwen3t
     S2S_CHECK(talloc(m, &m->pcodes, (size_t)TTS_MAX_B * c.n_groups * 4));
     S2S_CHECK(talloc(m, &m->tlen, TTS_MAX_B * 4));
     S2S_CHECK(talloc(m, &m->plen, TTS_MAX_B * 4));
+    S2S_CHECK(talloc(m, &m->code0_feed, TTS_MAX_B * 4));
+    S2S_CHECK(talloc(m, &m->forced_frame, (size_t)TTS_MAX_B * c.n_groups * 4));
     S2S_CHECK(talloc(m, &m->suppress, (size_t)c.vocab));
     // transformers generate(): the last 1024 ids of the codec vocabulary except codec_eos are never predicted (TF:3954-3962)
     std::vector<unsigned char> mask((size_t)c.vocab, 0);
@@ -408,7 +418,7 @@ int s2s_qwen3tts_prefill(s2s_qwen3tts* m, int32_t slot, const int32_t* text_ids_
 }
 
 int s2s_qwen3tts_decode_frames(s2s_qwen3tts* m, const int32_t* slots_h, int32_t B, int32_t n_frames, int32_t* codes_out_d,
-                               void* stream) {
+                               const int32_t* forced_codes_d, void* stream) {
   S2S_REQUIRE(m && m->finalized && slots_h && codes_out_d, "qwen3tts decode_frames: null argument / not finalized");
   const auto& c = m->cfg;
   const int max_b = tts_max_batch(m);
@@ -439,20 +449,23 @@ int s2s_qwen3tts_decode_frames(s2s_qwen3tts* m, const int32_t* slots_h, int32_t 
       p.hidden_out = m->hidden; p.suppress = m->suppress;
       S2S_CHECK(llama_decode_launch(m->ctx, p, c.compute_dtype, m->talker->debug_phases, st));
     }
-    frame_mid_kernel<<<B, 256, 0, st>>>(m->hidden, m->talker->norm_f, c.rms_eps, d, m->x_in_p, m->pslot_d, m->ppos_d);
+    frame_mid_kernel<<<B, 256, 0, st>>>(m->hidden, m->talker->norm_f, c.rms_eps, d, m->x_in_p, m->pslot_d, m->ppos_d, m->code0,
+                                        forced_codes_d, f, n_frames, G, m->code0_feed, m->forced_frame);
     S2S_LAUNCH_CHECK();
     {   // code predictor: [hidden, embed(code0)] then one step per residual codebook, each with its own table / head
       LlamaDecParams p{};
       llama_fill_dec_params(m->pred, p);
       p.B = B; p.slot = m->pslot_d; p.pos = m->ppos_d; p.max_len = 1;
-      p.x_in = m->x_in_p; p.first_ids = m->code0; p.n_steps = G; p.eos = -1; p.out_ids = m->pcodes; p.out_len = m->plen;
+      p.x_in = m->x_in_p; p.first_ids = m->code0_feed; p.n_steps = G; p.eos = -1; p.out_ids = m->pcodes; p.out_len = m->plen;
+      p.forced = forced_codes_d ? m->forced_frame : nullptr;
       p.embed0 = m->talker->embed; p.embed_stride = (long long)m->pred->embed_table_elems; p.head_stride = (long long)m->pred->head_t_table_elems;
       S2S_CHECK(llama_decode_launch(m->ctx, p, c.compute_dtype, m->pred->debug_phases, st));
     }
-    if (bf) frame_finish_kernel<__nv_bfloat16><<<B, 256, 0, st>>>(tb, f, n_frames, G, m->pcodes, (const __nv_bfloat16*)m->talker->embed,
+    const int* ff = forced_codes_d ? m->forced_frame : nullptr;
+    if (bf) frame_finish_kernel<__nv_bfloat16><<<B, 256, 0, st>>>(tb, f, n_frames, G, m->pcodes, m->code0, ff, (const __nv_bfloat16*)m->talker->embed,
           (const __nv_bfloat16*)m->pred->embed, (long long)m->pred->embed_table_elems, d, m->trailing, m->trailing_stride, m->pad_embed,
           m->xnext, codes_out_d, m->history, m->history_stride);
-    else frame_finish_kernel<__half><<<B, 256, 0, st>>>(tb, f, n_frames, G, m->pcodes, (const __half*)m->talker->embed,
+    else frame_finish_kernel<__half><<<B, 256, 0, st>>>(tb, f, n_frames, G, m->pcodes, m->code0, ff, (const __half*)m->talker->embed,
           (const __half*)m->pred->embed, (long long)m->pred->embed_table_elems, d, m->trailing, m->trailing_stride, m->pad_embed,
           m->xnext, codes_out_d, m->history, m->history_stride);
     S2S_LAUNCH_CHECK();

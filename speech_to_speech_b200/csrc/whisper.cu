@@ -75,6 +75,9 @@ struct s2s_whisper {
   void* self_kv = nullptr;
   int *tokens = nullptr, *out_ids = nullptr, *out_len = nullptr, *done = nullptr, *n_done = nullptr, *cand_idx = nullptr;
   unsigned char *suppress = nullptr, *suppress_lang = nullptr;
+  std::vector<int> suppress_key[2];        // the id lists the device masks were built from (masks are static per options)
+  int* tok_stage = nullptr;                // pinned host staging of the prompt tokens
+  cudaEvent_t tok_event = nullptr;         // recorded after the staging buffer's last H2D copy
   unsigned int* sync_counter = nullptr;
   int s_max = 0;
   int last_B = 0;
@@ -362,6 +365,8 @@ int s2s_whisper_create(s2s_ctx* ctx, const s2s_whisper_config* cfg, s2s_whisper*
 int s2s_whisper_destroy(s2s_whisper* m) {
   if (!m) return S2S_OK;
   for (void* p : m->allocs) cudaFree(p);
+  if (m->tok_stage) cudaFreeHost(m->tok_stage);
+  if (m->tok_event) cudaEventDestroy(m->tok_event);
   delete m;
   return S2S_OK;
 }
@@ -553,7 +558,7 @@ int s2s_whisper_encode(s2s_whisper* m, const float* mel_in_d, int32_t B, float* 
   return S2S_OK;
 }
 
-static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, int max_new, int eos,
+static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, const int32_t* prefix_rows_h, int n_prefix, int max_new, int eos,
                        const unsigned char* suppress_d, int32_t B, int32_t* ids_out_d, int32_t* len_out_d,
                        const int32_t* forced_d, float* logits_out_d, cudaStream_t st) {
   const auto& c = m->cfg;
@@ -561,15 +566,23 @@ static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, in
   S2S_REQUIRE(B >= 1 && B <= m->last_B, "decode: B=%d but %d utterances are encoded", B, m->last_B);
   S2S_REQUIRE(n_prefix >= 1 && max_new >= 1 && n_prefix + max_new <= c.max_target_positions,
               "decode: n_prefix %d + max_new %d > %d", n_prefix, max_new, c.max_target_positions);
-  // prompt tokens for every row
-  std::vector<int> tok((size_t)B * c.max_target_positions, 0);
-  for (int b = 0; b < B; ++b)
+  // prompt tokens for every row, through a pinned staging buffer owned by the model: no stream synchronisation per call
+  // (the event only waits for the PREVIOUS call's copy, long finished in steady state)
+  if (!m->tok_stage) {
+    S2S_CHECK_CUDA(cudaHostAlloc(&m->tok_stage, (size_t)c.max_batch * c.max_target_positions * 4, cudaHostAllocDefault));
+    S2S_CHECK_CUDA(cudaEventCreateWithFlags(&m->tok_event, cudaEventDisableTiming));
+  } else {
+    S2S_CHECK_CUDA(cudaEventSynchronize(m->tok_event));
+  }
+  for (int b = 0; b < B; ++b) {
+    const int32_t* row = prefix_rows_h ? prefix_rows_h + (size_t)b * n_prefix : prefix_h;
     for (int i = 0; i < n_prefix; ++i) {
-      S2S_REQUIRE(prefix_h[i] >= 0 && prefix_h[i] < c.vocab, "decode: prefix token %d out of range", prefix_h[i]);
-      tok[(size_t)b * c.max_target_positions + i] = prefix_h[i];
+      S2S_REQUIRE(row[i] >= 0 && row[i] < c.vocab, "decode: prefix token %d out of range", row[i]);
+      m->tok_stage[(size_t)b * c.max_target_positions + i] = row[i];
     }
-  S2S_CHECK_CUDA(cudaMemcpyAsync(m->tokens, tok.data(), tok.size() * 4, cudaMemcpyHostToDevice, st));
-  S2S_CHECK_CUDA(cudaStreamSynchronize(st));  // tok is a stack-lifetime host buffer
+  }
+  S2S_CHECK_CUDA(cudaMemcpyAsync(m->tokens, m->tok_stage, (size_t)B * c.max_target_positions * 4, cudaMemcpyHostToDevice, st));
+  S2S_CHECK_CUDA(cudaEventRecord(m->tok_event, st));
   const int group = whisper_decode_max_batch(d, c.ffn);  // sessions per persistent launch (<= 16)
   for (int b0 = 0; b0 < B; b0 += group) {
     const int nb = (B - b0) < group ? (B - b0) : group;
@@ -604,6 +617,14 @@ static int decode_impl(s2s_whisper* m, const int32_t* prefix_h, int n_prefix, in
 
 static int upload_suppress(s2s_whisper* m, unsigned char* dst, const int32_t* always, int n_always, const int32_t* begin,
                            int n_begin, bool invert_always, cudaStream_t st) {
+  // the mask is a pure function of the id lists: rebuilt and uploaded only when they change (once per handler in practice)
+  std::vector<int>& key = m->suppress_key[dst == m->suppress ? 0 : 1];
+  std::vector<int> now;
+  now.reserve((size_t)n_always + n_begin + 2);
+  now.push_back(n_always); now.push_back(invert_always ? 1 : 0);
+  now.insert(now.end(), always, always + n_always);
+  now.insert(now.end(), begin, begin + n_begin);
+  if (now == key) return S2S_OK;
   std::vector<unsigned char> mask((size_t)m->cfg.vocab, invert_always ? 1 : 0);
   for (int i = 0; i < n_always; ++i) {
     S2S_REQUIRE(always[i] >= 0 && always[i] < m->cfg.vocab, "suppress id %d out of range", always[i]);
@@ -615,6 +636,7 @@ static int upload_suppress(s2s_whisper* m, unsigned char* dst, const int32_t* al
   }
   S2S_CHECK_CUDA(cudaMemcpyAsync(dst, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
   S2S_CHECK_CUDA(cudaStreamSynchronize(st));
+  key.swap(now);
   return S2S_OK;
 }
 
@@ -624,7 +646,7 @@ int s2s_whisper_decode(s2s_whisper* m, const s2s_whisper_decode_opts* o, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
   S2S_CHECK(upload_suppress(m, m->suppress, o->suppress_h, o->n_suppress, o->begin_suppress_h, o->n_begin_suppress, false, st));
-  return decode_impl(m, o->prefix_h, o->n_prefix, o->max_new_tokens, o->eos_id, m->suppress, B, ids_out_d, len_out_d,
+  return decode_impl(m, o->prefix_h, o->prefix_rows_h, o->n_prefix, o->max_new_tokens, o->eos_id, m->suppress, B, ids_out_d, len_out_d,
                      forced_d, logits_out_d, st);
 }
 
@@ -647,7 +669,7 @@ int s2s_whisper_detect_language(s2s_whisper* m, int32_t sot_id, const int32_t* l
   S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
   S2S_CHECK(upload_suppress(m, m->suppress_lang, lang_ids_h, n_lang, nullptr, 0, true, st));
   // eos = -1: never matches, so the single generated id is returned as is
-  return decode_impl(m, &sot_id, 1, 1, -1, m->suppress_lang, B, lang_out_d, m->out_len, nullptr, nullptr, st);
+  return decode_impl(m, &sot_id, nullptr, 1, 1, -1, m->suppress_lang, B, lang_out_d, m->out_len, nullptr, nullptr, st);
 }
 
 int s2s_whisper_transcribe(s2s_whisper* m, const s2s_whisper_decode_opts* o, const float* pcm_h, int64_t pcm_stride,

@@ -512,7 +512,9 @@ __device__ __forceinline__ void wdc_block(const WhisperDecParams& p, const WdcCt
                            cx.cs * DEC_WARPS, rec_s + warp * REC);
       __syncthreads();
       if (warp == 0)
-        attn_finish_item<T, HD>(rec_s, DEC_WARPS, p.part + (long long)(b * H + h) * p.s_max * REC, cx.rank, cx.cs, nullptr,
+        // always the record path (splits >= 2): with a 1-CTA cluster (a profiler that drops the cluster shape) the single
+        // record is merged below like any other, instead of attn_finish_item's splits == 1 shortcut writing a head output
+        attn_finish_item<T, HD>(rec_s, DEC_WARPS, p.part + (long long)(b * H + h) * p.s_max * REC, cx.rank, max(cx.cs, 2), nullptr,
                                 static_cast<T*>(nullptr));
       __syncthreads();
     }

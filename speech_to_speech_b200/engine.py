@@ -60,13 +60,21 @@ class WhisperDecodeOptions:
     max_new_tokens: int = 128
     suppress: Sequence[int] = ()
     begin_suppress: Sequence[int] = ()
+    prefix_rows: Optional[Sequence[Sequence[int]]] = None   # one prompt per utterance (same length as `prefix`)
 
     def to_c(self):
         pre, n_pre = _lib.i32_array(self.prefix)
         sup, n_sup = _lib.i32_array(self.suppress)
         beg, n_beg = _lib.i32_array(self.begin_suppress)
-        o = WhisperDecodeOpts(pre, n_pre, int(self.max_new_tokens), int(self.eos_id), sup, n_sup, beg, n_beg)
-        o._keep = (pre, sup, beg)  # keep the arrays alive
+        rows = None
+        if self.prefix_rows is not None:
+            flat = [int(t) for r in self.prefix_rows for t in r]
+            if any(len(r) != n_pre for r in self.prefix_rows):
+                raise ValueError("every row of prefix_rows must have len(prefix) tokens")
+            rows, _ = _lib.i32_array(flat)
+        o = WhisperDecodeOpts(pre, n_pre, int(self.max_new_tokens), int(self.eos_id), sup, n_sup, beg, n_beg,
+                              C.cast(rows, C.POINTER(C.c_int32)) if rows is not None else None)
+        o._keep = (pre, sup, beg, rows)  # keep the arrays alive
         return o
 
 
@@ -177,6 +185,25 @@ class WhisperEngine:
                                               ids.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(C.c_void_p),
                                               _stream_ptr(self.device)), "s2s_whisper_transcribe")
         return [ids[b, : lens[b]].tolist() for b in range(B)]
+
+    def transcribe_auto(self, audio: Sequence[np.ndarray], sot_id: int, lang_ids: Sequence[int], make_opts) -> tuple:
+        """Language detection and transcription on ONE encoder pass, like the reference (`_detect_language` hands its
+        `encoder_outputs` to `generate`, S/STT/whisper_stt_handler.py:166-197, 236-241): log-mel + encoder once, one masked
+        decoder step -> language token per utterance, then greedy decode with a per-utterance prompt.
+        make_opts(lang_tokens: list[int]) -> WhisperDecodeOptions with `prefix_rows` set.  -> (ids per utterance, language tokens)."""
+        B = len(audio)
+        n = [min(len(a), 480000) for a in audio]
+        dev = f"cuda:{self.device}"
+        pcm = torch.zeros((B, max(max(n), 1)), dtype=torch.float32, device=dev)
+        for i, a in enumerate(audio):
+            pcm[i, : n[i]] = torch.from_numpy(np.ascontiguousarray(a[: n[i]], dtype=np.float32)).to(dev, non_blocking=True)
+        self.logmel(pcm, n)
+        self.encode(B)
+        langs = self.detect_language(B, sot_id, lang_ids).cpu().tolist()
+        opts = make_opts(langs)
+        ids, lens = self.decode(B, opts)
+        ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+        return [ids[b, : lens[b]].tolist() for b in range(B)], langs
 
     def close(self) -> None:
         if self.handle:
@@ -448,11 +475,15 @@ class Qwen3TTSEngine:
         arr, n = _lib.i32_array(text_ids)
         check(self.lib.s2s_qwen3tts_prefill(self.handle, slot, arr, n, int(speaker_id), _stream_ptr(self.device)), "s2s_qwen3tts_prefill")
 
-    def decode_frames(self, slots: Sequence[int], n_frames: int) -> torch.Tensor:
-        """-> codes int32 cuda [B, n_frames, n_groups] (asynchronous)."""
+    def decode_frames(self, slots: Sequence[int], n_frames: int, forced: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-> codes int32 cuda [B, n_frames, n_groups] (asynchronous).  forced (int32 cuda, same shape): teacher-forced
+        feedback for parity tests; the returned codes are still the models' own decisions."""
         sl, B = _lib.i32_array(slots)
         codes = torch.empty((B, n_frames, self.n_groups), dtype=torch.int32, device=f"cuda:{self.device}")
-        check(self.lib.s2s_qwen3tts_decode_frames(self.handle, sl, B, n_frames, _ptr(codes), _stream_ptr(self.device)),
+        if forced is not None:
+            forced = forced.to(torch.int32).contiguous()
+            assert tuple(forced.shape) == (B, n_frames, self.n_groups)
+        check(self.lib.s2s_qwen3tts_decode_frames(self.handle, sl, B, n_frames, _ptr(codes), _ptr(forced), _stream_ptr(self.device)),
               "s2s_qwen3tts_decode_frames")
         return codes
 

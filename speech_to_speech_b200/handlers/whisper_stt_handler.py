@@ -77,6 +77,8 @@ class _EngineBundle:
         return (tuple(o.prefix), int(o.eos_id), int(o.max_new_tokens), tuple(o.suppress), tuple(o.begin_suppress))
 
     def _run_batch(self, key: tuple, audios: list) -> list:
+        if key and key[0] == "auto":
+            return self._run_auto_batch(key, audios)
         opts = self.E.WhisperDecodeOptions(prefix=list(key[0]), eos_id=key[1], max_new_tokens=key[2], suppress=list(key[3]),
                                            begin_suppress=list(key[4]))
         with self.lock:
@@ -91,6 +93,27 @@ class _EngineBundle:
     def detect_language(self, audio: np.ndarray, sot: int, lang_ids: list[int]) -> int:
         with self.lock:
             return int(self.engine.detect_language_host(audio, sot, lang_ids))
+
+    # auto-language mode: detection and decode share one encoder pass; concurrent sessions still share the launches.
+    # spec = (sot, language ids, fallback language id, prompt tail after the language token, eos, max_new, suppress,
+    # begin_suppress): hashable and identical for handlers with the same options, so their requests merge in the batcher.
+    def _run_auto_batch(self, key: tuple, audios: list) -> list:
+        _, sot, lang_ids, fallback, tail, eos, max_new, sup, beg = key
+        known = set(lang_ids)
+
+        def make_opts(langs: list) -> Any:
+            rows = [[sot, (t if t in known else fallback)] + list(tail) for t in langs]
+            return self.E.WhisperDecodeOptions(prefix=rows[0], eos_id=eos, max_new_tokens=max_new, suppress=list(sup),
+                                               begin_suppress=list(beg), prefix_rows=rows)
+        with self.lock:
+            ids, langs = self.engine.transcribe_auto(audios, sot, list(lang_ids), make_opts)
+        return list(zip(ids, langs))
+
+    def transcribe_auto(self, audio: np.ndarray, spec: tuple) -> tuple:
+        key = ("auto",) + tuple(spec)
+        if self.batcher is not None:
+            return self.batcher.call(key, audio)
+        return self._run_auto_batch(key, [audio])[0]
 
     def close(self) -> None:
         if self.batcher is not None:
@@ -134,6 +157,7 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         else:
             self.bundle = self._load(model_name)
         self.engine, self.tokens, self._decode_text = self.bundle.engine, self.bundle.tokens, self.bundle.decode_text
+        self.processor = getattr(self.bundle, "processor", None)
         self.warmup()
 
     # -- loading ---------------------------------------------------------------------------------
@@ -158,10 +182,11 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         engine.load_state_dict({k: v for k, v in hf.state_dict().items() if not k.startswith("proj_out")})
         tokens = TokenTable.from_generation_config(hf.generation_config)
         del hf
-        self.processor = processor
-        return _EngineBundle(E, engine, tokens,
-                             lambda ids: processor.batch_decode([ids], skip_special_tokens=True, decode_with_timestamps=False)[0],
-                             self.max_batch, self.batch_wait_s)
+        bundle = _EngineBundle(E, engine, tokens,
+                               lambda ids: processor.batch_decode([ids], skip_special_tokens=True, decode_with_timestamps=False)[0],
+                               self.max_batch, self.batch_wait_s)
+        bundle.processor = processor   # every handler sharing the engine sees the processor, not only the one that loaded it
+        return bundle
 
     def warmup(self) -> None:
         logger.info("Warming up %s", type(self).__name__)
@@ -174,12 +199,22 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         forced = self.gen_kwargs.get("language")
         return forced if isinstance(forced, str) and forced and forced != "auto" else None
 
+    def _prefix(self, lang_id: Optional[int]) -> list:
+        """Decoder prompt of `_retrieve_init_tokens` (TF generation_whisper.py:1455-1608): multilingual checkpoints get
+        [sot, language, task, notimestamps]; English-only ones (whisper-*.en, distil-*.en: no lang_to_id / task_to_id in
+        the generation config) get [sot, notimestamps] -- never invented language / task tokens."""
+        t = self.tokens
+        tail = [] if self.gen_kwargs.get("return_timestamps") else [t.no_timestamps]
+        if not t.lang_to_id or lang_id is None:
+            return [t.sot] + tail
+        task = t.translate if self.gen_kwargs.get("task") == "translate" else t.transcribe
+        return [t.sot, int(lang_id), task] + tail
+
     def _options(self, language: str):
         t = self.tokens
-        lang_id = t.lang_to_id.get(language, t.lang_to_id.get(DEFAULT_LANGUAGE, t.sot + 1))
-        task = t.translate if self.gen_kwargs.get("task") == "translate" else t.transcribe
-        prefix = [t.sot, lang_id, task] + ([] if self.gen_kwargs.get("return_timestamps") else [t.no_timestamps])
-        return self._E.WhisperDecodeOptions(prefix=prefix, eos_id=t.eos, max_new_tokens=int(self.gen_kwargs.get("max_new_tokens", 128)),
+        lang_id = t.lang_to_id.get(language, t.lang_to_id.get(DEFAULT_LANGUAGE)) if t.lang_to_id else None
+        return self._E.WhisperDecodeOptions(prefix=self._prefix(lang_id), eos_id=t.eos,
+                                            max_new_tokens=int(self.gen_kwargs.get("max_new_tokens", 128)),
                                             suppress=t.suppress, begin_suppress=t.begin_suppress)
 
     def _detect_language(self, audio: np.ndarray) -> Optional[str]:
@@ -205,9 +240,24 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         audio = np.asarray(vad_audio.audio, dtype=np.float32)
         forced = self._forced_language()
         language_code = forced
-        if forced is None:
-            language_code = self._detect_language(audio) or self.last_language or DEFAULT_LANGUAGE
-        ids = self._transcribe(audio, language_code)
+        ids = None
+        if forced is None and self.tokens.lang_to_id:
+            # detection and decode on one encoder pass (the reference reuses `encoder_outputs`, :236-241)
+            try:
+                t = self.tokens
+                fallback = t.lang_to_id.get(self.last_language or DEFAULT_LANGUAGE, t.lang_to_id.get(DEFAULT_LANGUAGE))
+                spec = (t.sot, tuple(t.lang_to_id.values()), fallback, tuple(self._prefix(fallback)[2:]), t.eos,
+                        int(self.gen_kwargs.get("max_new_tokens", 128)), tuple(t.suppress), tuple(t.begin_suppress))
+                raw, tok = self.bundle.transcribe_auto(np.ascontiguousarray(audio[:480000], dtype=np.float32), spec)
+                language_code = t.id_to_lang.get(int(tok)) or self.last_language or DEFAULT_LANGUAGE
+                ids = [i for i in raw if i != t.eos]
+            except Exception as e:  # the reference survives a failing detection and falls back (:188-197)
+                logger.warning("Whisper language detection failed (%s); falling back to the previous language", e)
+                language_code = self.last_language or DEFAULT_LANGUAGE
+        elif forced is None:
+            language_code = self.last_language or DEFAULT_LANGUAGE
+        if ids is None:
+            ids = self._transcribe(audio, language_code)
         if language_code in SUPPORTED_LANGUAGES:
             self.last_language = language_code
         else:

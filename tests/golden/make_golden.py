@@ -119,6 +119,40 @@ def whisper_golden(name: str):
     print(f"whisper_{name}: ids={gen_ids[:12]}... n={len(gen_ids)} mel[{mel.min():.3f},{mel.max():.3f}]")
 
 
+def whisper_langdetect_golden(name: str = "micro"):
+    """`WhisperGenerationMixin.detect_language` (TF generation_whisper.py:1610-1674) -- the call the reference's
+    `_detect_language` makes (S/STT/whisper_stt_handler.py:166-197) -- on the seeded random-init model, with `lang_to_id` set
+    on its generation_config (a random-init config has none).  Pins oracle.whisper_ref.detect_language."""
+    import torch
+    from transformers import WhisperFeatureExtractor
+
+    geom = W.WHISPER_GEOMETRIES[name]
+    weights = W.make_whisper_weights(geom, seed=0)
+    model = build_hf_whisper(geom, weights)
+    sot = geom.vocab - 96
+    codes = ["en", "zh", "de", "es", "fr", "ja", "ko", "ru"]
+    lang_to_id = {f"<|{c}|>": sot + 1 + i for i, c in enumerate(codes)}
+    model.generation_config.lang_to_id = lang_to_id
+    model.generation_config.decoder_start_token_id = sot
+    model.config.decoder_start_token_id = sot
+    fe = WhisperFeatureExtractor(feature_size=geom.n_mels)
+    seeds, lens, got, logits = [0, 21, 22, 23, 24, 25], [160000, 48000, 480000, 16000, 96000, 240000], [], []
+    for seed, n in zip(seeds, lens):
+        audio = W.synthetic_audio(seed, n)
+        feats = fe(audio, sampling_rate=16000, return_tensors="pt").input_features
+        with torch.no_grad():
+            enc = model.get_encoder()(feats)
+            lang = model.detect_language(encoder_outputs=enc, generation_config=model.generation_config)
+            dec = model(encoder_outputs=enc, decoder_input_ids=torch.tensor([[sot]])).logits[0, -1].numpy()
+        got.append(int(lang[0]))
+        logits.append(dec[list(lang_to_id.values())])
+    path = os.path.join(OUT, f"whisper_langdetect_{name}.npz")
+    np.savez_compressed(path, audio_seeds=np.asarray(seeds), n_samples=np.asarray(lens), sot=sot,
+                        lang_ids=np.asarray(list(lang_to_id.values()), np.int32), detected=np.asarray(got, np.int32),
+                        lang_logits=np.stack(logits).astype(np.float32))
+    print("wrote", path, got)
+
+
 def build_hf_llama(geom: W.LlamaGeometry, weights):
     import torch
     from transformers import LlamaConfig, LlamaForCausalLM
@@ -312,6 +346,8 @@ if __name__ == "__main__":
     if what in ("whisper", "all"):
         for n in WHISPER_CASES:
             whisper_golden(n)
+    if what in ("langdetect", "all"):
+        whisper_langdetect_golden("micro")
     if what in ("llama", "all"):
         for n in LLAMA_CASES:
             llama_golden(n)

@@ -83,5 +83,8 @@ def test_real_geometry_slice_vs_oracle(E):
     ref, hid_ref = C.code2wav_forward(w, g, codes, return_hidden=True)
     wav, hid = eng.decode(_codes_dev(codes), 0, return_hidden=True)
     assert eng.total_upsample == 1920
-    assert np.abs(hid.cpu().numpy() - hid_ref).max() < 5e-4
-    assert np.abs(wav.cpu().numpy() - ref).max() < WAV_TOL
+    he = float(np.abs(hid.cpu().numpy() - hid_ref).max())
+    got = wav.cpu().numpy()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    we = float(np.abs(got - ref).max())
+    assert he < 5e-4 and we < WAV_TOL, f"hidden err {he:.3e} (|ref| max {np.abs(hid_ref).max():.2f}), wav err {we:.3e}"

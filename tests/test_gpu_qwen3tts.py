@@ -28,17 +28,53 @@ def _engine(E, dtype="float16", **kw):
     return g, cg, w, cw, eng
 
 
+# logits tolerances of the 16-bit engines (the same figures as tests/test_gpu_llama.py); a decision is "safe" when the oracle's
+# top-1 margin exceeds 4x the tolerance.  Random-init heads give margins of O(1), so most -- not all -- decisions are safe.
+TOL = {"float16": 2.5e-2, "bfloat16": 0.2}
+
+
+def _margins(t_logits, p_logits):
+    """[F] talker margins and [F, G-1] predictor margins (top-1 minus top-2 of the processed logits)."""
+    def m(x):
+        s = np.sort(np.where(np.isfinite(x), x, -1e30), axis=-1)
+        return s[..., -1] - s[..., -2]
+    return m(t_logits), m(p_logits)
+
+
+def _check_forced(eng, slot_codes, slots, tol, min_safe_frac):
+    """Teacher-forced run along the oracle's codes: every one of the 16 x F decisions is compared where it is safe.
+    slot_codes: list of (codes [F, G], talker_logits [>=F, V], predictor_logits [F, G-1, Vp]) per slot."""
+    F = min(len(c[0]) for c in slot_codes)
+    forced = torch.tensor(np.stack([c[0][:F] for c in slot_codes]), dtype=torch.int32, device="cuda")
+    got = eng.decode_frames(slots, F, forced=forced).cpu().numpy()
+    n_safe = n_all = 0
+    for i, (codes, tl, pl) in enumerate(slot_codes):
+        mt, mp = _margins(tl[:F], pl[:F])
+        safe = np.concatenate([mt[:, None], mp], axis=1) > 4 * tol       # [F, G]
+        assert np.array_equal(got[i][safe], codes[:F][safe]), (i, np.argwhere(safe & (got[i] != codes[:F]))[:4])
+        n_safe += int(safe.sum()); n_all += safe.size
+    assert n_safe >= min_safe_frac * n_all, (n_safe, n_all)
+    return got
+
+
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 def test_codes_match_transformers_golden(E, golden_dir, dtype):
+    """Codes and margins from the transformers cousin (tests/golden/qwen3tts_micro.npz): teacher-forced along the golden
+    codes every safe decision is bit-exact; the free run equals the golden codes up to the first unsafe decision."""
     g, cg, w, cw, eng = _engine(E, dtype)
     G = np.load(os.path.join(golden_dir, "qwen3tts_micro.npz"))
-    F = int(G["max_frames"])
+    gold, tl, pl = G["codes"], G["talker_logits"], G["predictor_logits"]
+    F = len(gold)
     eng.prefill(0, G["text_ids"].tolist(), int(G["speaker"]))
-    codes = eng.decode_frames([0], F)[0].cpu().numpy()
-    # ids are compared up to the first frame whose decision margin is below the 16-bit operand noise (none in practice:
-    # make_weights gives the heads wide logits); the first codes of all F frames and the full F-1 golden frames
-    assert codes[:, 0].tolist() == G["code0_all"].tolist()
-    assert np.array_equal(codes[: F - 1], G["codes"])
+    _check_forced(eng, [(gold, tl, pl)], [0], TOL[dtype], 0.6 if dtype == "float16" else 0.2)
+    mt, mp = _margins(tl[:F], pl[:F])
+    safe = (np.concatenate([mt[:, None], mp], axis=1) > 4 * TOL[dtype]).all(axis=1)
+    k = int(np.argmin(safe)) if (~safe).any() else F
+    eng.prefill(0, G["text_ids"].tolist(), int(G["speaker"]))
+    free = eng.decode_frames([0], F)[0].cpu().numpy()
+    assert np.array_equal(free[:k], gold[:k])
+    if k < F:   # the first unsafe frame may differ only in its unsafe codebooks' suffix: its first code is safe or equal
+        assert free[k, 0] == gold[k, 0] or mt[k] <= 4 * TOL[dtype]
 
 
 def test_batched_sessions_equal_oracle_and_single_runs(E):
@@ -47,19 +83,30 @@ def test_batched_sessions_equal_oracle_and_single_runs(E):
     texts = [rng.integers(0, 400, n).tolist() for n in (1, 3, 9, 17)]
     speakers = [2301, 2302, 2301, 2400]
     F = 7
-    refs = [R.generate(w, g, t, s, F) for t, s in zip(texts, speakers)]
+    refs = [R.generate(w, g, t, s, F, return_logits=True) for t, s in zip(texts, speakers)]
+    for slot, (t, s) in enumerate(zip(texts, speakers)):
+        eng.prefill(slot, t, s)
+    _check_forced(eng, refs, [0, 1, 2, 3], TOL["float16"], 0.6)
+    # free run of the four sessions in one launch sequence == each session alone (same kernels, batch of 1): bit-exact
     for slot, (t, s) in enumerate(zip(texts, speakers)):
         eng.prefill(slot, t, s)
     got = eng.decode_frames([0, 1, 2, 3], F).cpu().numpy()
-    for slot in range(4):
-        assert np.array_equal(got[slot][: len(refs[slot])], refs[slot]), slot
-    # frames continue across calls (state lives in the library): 3 + 4 frames == 7 frames
+    for slot, (t, s) in enumerate(zip(texts, speakers)):
+        eng.prefill(slot, t, s)
+        alone = eng.decode_frames([slot], F)[0].cpu().numpy()
+        mt, mp = _margins(refs[slot][1][:F], refs[slot][2][:F])
+        safe = (np.concatenate([mt[:, None], mp], axis=1) > 4 * TOL["float16"]).all(axis=1)
+        k = int(np.argmin(safe)) if (~safe).any() else F
+        assert np.array_equal(got[slot][:k], refs[slot][0][:k]) and np.array_equal(alone[:k], refs[slot][0][:k]), slot
+    # frames continue across calls (state lives in the library): 3 + 4 frames == 7 frames in one call
     for slot, (t, s) in enumerate(zip(texts, speakers)):
         eng.prefill(slot, t, s)
     a = eng.decode_frames([3, 1], 3).cpu().numpy()
     b = eng.decode_frames([3, 1], 4).cpu().numpy()
-    assert np.array_equal(np.concatenate([a, b], 1)[0], got[3]) and np.array_equal(np.concatenate([a, b], 1)[1], got[1])
-    assert eng.frames(3) == 7 and eng.frames(0) == 0
+    eng.prefill(3, texts[3], speakers[3]); eng.prefill(1, texts[1], speakers[1])
+    whole = eng.decode_frames([3, 1], 7).cpu().numpy()
+    assert np.array_equal(np.concatenate([a, b], 1), whole)
+    assert eng.frames(3) == 7 and eng.frames(0) == 7
 
 
 def test_persistent_launch_equals_per_phase_launches(E, monkeypatch):
@@ -83,9 +130,10 @@ def test_streaming_audio_matches_the_oracle_chunked_decode(E):
     wav_ref = C.chunked_decode(cw, cg, codes_ref.T, chunk_size=chunk, left_context=left)
     eng.prefill(0, text, 2301)
     outs, done = [], 0
-    while done < F:
+    while done < F:   # teacher-forced along the oracle's codes: the library keeps the forced codes, the codec decodes those
         n = min(chunk, F - done)
-        eng.decode_frames([0], n)
+        forced = torch.tensor(codes_ref[None, done:done + n], dtype=torch.int32, device="cuda")
+        eng.decode_frames([0], n, forced=forced)
         outs.append(eng.decode_audio(0, n, left).cpu().numpy())
         done += n
     got = np.concatenate(outs)

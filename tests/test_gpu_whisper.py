@@ -432,3 +432,38 @@ def test_large_v3_geometry_slice(E):
     for i, (rid, rlg) in enumerate(refs):
         fin = np.isfinite(rlg)
         assert np.abs(lg[:, i][fin] - rlg[fin]).max() < 2 * LOGIT_TOL, i
+
+
+def test_detect_language_matches_transformers_golden_and_shares_the_encoder_pass(E, golden_dir):
+    """s2s_whisper_detect_language against the language tokens transformers' detect_language chose
+    (tests/golden/whisper_langdetect_micro.npz), six utterances in one batch; then transcribe_auto: detection and decode on
+    ONE encoder pass with a per-utterance prompt equal detect + transcribe done separately."""
+    G = np.load(os.path.join(golden_dir, "whisper_langdetect_micro.npz"))
+    g, w, eng = _engine(E, "micro", max_batch=6)
+    auds = [W.synthetic_audio(int(s), int(n)) for s, n in zip(G["audio_seeds"], G["n_samples"])]
+    pcm = np.zeros((6, 480000), np.float32)
+    for i, a in enumerate(auds):
+        pcm[i, : len(a)] = a
+    eng.logmel(torch.from_numpy(pcm).cuda(), [len(a) for a in auds])
+    eng.encode(6)
+    sot, lang = int(G["sot"]), G["lang_ids"].tolist()
+    got = eng.detect_language(6, sot, lang).cpu().tolist()
+    srt = np.sort(G["lang_logits"], axis=1)
+    safe = (srt[:, -1] - srt[:, -2]) > 4 * LOGIT_TOL
+    assert safe.sum() >= 3
+    assert [a for a, s in zip(got, safe) if s] == [int(b) for b, s in zip(G["detected"], safe) if s]
+    tail, eos = [sot + 20, sot + 21], g.vocab - 1
+    mk = lambda langs: E.WhisperDecodeOptions(prefix=[sot, langs[0]] + tail, eos_id=eos, max_new_tokens=6, suppress=[1, 2],
+                                              begin_suppress=[220], prefix_rows=[[sot, t] + tail for t in langs])
+    launches0 = E.launch_count(reset=True)
+    ids, langs = eng.transcribe_auto(auds, sot, lang, mk)
+    n_auto = E.launch_count()
+    assert langs == got
+    for i in (0, 3, 5):
+        o = E.WhisperDecodeOptions(prefix=[sot, langs[i]] + tail, eos_id=eos, max_new_tokens=6, suppress=[1, 2], begin_suppress=[220])
+        assert eng.transcribe([auds[i]], o)[0] == ids[i]
+    eng.logmel(torch.from_numpy(pcm).cuda(), [len(a) for a in auds]); eng.encode(6)
+    E.launch_count(reset=True)
+    eng.encode(6)
+    n_encode = E.launch_count()
+    assert n_auto < 2 * n_encode      # one encoder pass, not two (the round-1 handler encoded twice in auto mode)

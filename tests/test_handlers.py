@@ -38,6 +38,16 @@ class FakeEngine:
             return -1
         return lang_ids[2] if self.detect_result == "third" else self.detect_result
 
+    def transcribe_auto(self, audio, sot, lang_ids, make_opts):
+        """Detection + decode on one encoder pass (engine.WhisperEngine.transcribe_auto): a real engine always answers with
+        one of lang_ids; `None` models an id outside the handler's table."""
+        langs = [self.detect_language_host(a, sot, lang_ids) for a in audio]
+        opts = make_opts(langs)
+        rows = opts.prefix_rows
+        for a, row in zip(audio, rows):
+            self.calls.append(("transcribe", len(a), list(row), opts.max_new_tokens))
+        return [[11, 22, 33, opts.eos_id] for _ in audio], langs
+
     def close(self):
         self.calls.append(("close",))
 
@@ -69,6 +79,7 @@ def make_handler(language="en", gen_kwargs=None, max_batch=1, engine=None):
         max_new_tokens: int = 128
         suppress: tuple = ()
         begin_suppress: tuple = ()
+        prefix_rows: object = None
 
     h._E = SimpleNamespace(WhisperDecodeOptions=Opts)
     h.max_batch, h.batch_wait_s, h._shared_key = max_batch, 0.2, None

@@ -71,3 +71,19 @@ def test_detect_language_is_masked_argmax(case):
     lang = [5, 17, 33, 250]
     got = R.detect_language(w, g, case["enc"], int(case["G"]["prefix"][0]), lang)
     assert got in lang
+
+
+def test_detect_language_matches_transformers_detect_language(golden_dir):
+    """oracle.detect_language pinned to WhisperGenerationMixin.detect_language (TF generation_whisper.py:1610-1674) on six
+    utterances: the same language token, and the same language logits within 1e-4 (tests/golden/make_golden.py langdetect)."""
+    import os
+    G = np.load(os.path.join(golden_dir, "whisper_langdetect_micro.npz"))
+    g = W.WHISPER_GEOMETRIES["micro"]
+    w = W.make_whisper_weights(g, 0)
+    lang = G["lang_ids"].tolist()
+    for seed, n, want, lg in zip(G["audio_seeds"], G["n_samples"], G["detected"], G["lang_logits"]):
+        enc = R.encoder_forward(w, g, R.log_mel_spectrogram(W.synthetic_audio(int(seed), int(n)), g.n_mels))
+        assert R.detect_language(w, g, enc, int(G["sot"]), lang) == int(want)
+        st = R.DecoderState(g, R.cross_kv(w, g, enc))
+        logits = R.decoder_step(w, g, st, int(G["sot"]))
+        assert np.abs(logits[lang] - lg).max() < 1e-4
