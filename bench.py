@@ -1,19 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- the headline measurement (contract: task brief "Measurement").
 
-Workload (BASELINE.json configs[1]): Whisper-small, one synthetic 10 s / 16 kHz utterance per step, the whole STT
-device path of WhisperSTTHandler.process: log-mel -> encoder (30 s padded window, as the reference) -> greedy
-decode of exactly 128 new tokens (4-token forced prompt, suppress lists, no early EOS on either arm).
-Weights: seeded random-init at the exact geometry (no checkpoints offline); timing is value independent.
+Workload = BASELINE.json configs[2], the configuration its metric is quoted on: the FULL TURN of the cascade on one GPU,
+    Whisper-small STT (10 s / 16 kHz utterance, 128 tokens)  ->  Llama-3-8B bf16 (64-token prompt, 128-token reply)
+    ->  Qwen3-TTS (talker + code predictor + codec decoder; the reply spoken: 20-token first sentence + the other 108 tokens)
+with S conversation sessions per GPU in flight together (sessions batch inside the GPU; ranks shard sessions).
+Weights: seeded random-init at the exact / published geometries (no checkpoints offline); timing is value independent.
+One STEP = one wave: every one of the S sessions of a rank completes one full turn.
 
-metric  = concurrent real-time sessions = (utterances / s) x 10 s of audio per utterance, whole job over N GPUs
-value   : inputs resident in HBM, CUDA-event timed          e2e: host PCM -> ids on host through the C ABI
-roofline: the persistent decode kernel (dominant, HBM-bound): algorithmic bytes / measured launch time
-cpu_baseline / --impl reference: transformers fp32 on the host cores (the calls the reference handler makes).
+metric   "concurrent real-time sessions": a live session repeats [user speaks AUDIO_IN_S -> turn -> assistant speaks the
+         reply]; a GPU that completes S turns in T seconds sustains S * cycle_s / T such sessions, cycle_s = AUDIO_IN_S + the
+         seconds of speech generated per turn; "real-time" additionally needs every session's TTS real-time factor >= 1 in the
+         wave (reported; the line says so when it fails).  The p50 audio-in -> first-audio-out latency (VADAudio.created_at_s ->
+         first int16 block, the interval the reference logs, S/TTS/qwen3_tts_handler.py:867-878) is reported beside it for one
+         session on an idle GPU and for the sessions of the loaded wave.
+value    device-timed: inputs resident in HBM, engine-level launch sequence of the wave, CUDA events.
+e2e      the same wave through the three HANDLER classes (B200WhisperSTTHandler -> B200LanguageModelHandler ->
+         B200Qwen3TTSHandler): one thread per session, host PCM in, int16 blocks on the host out, shared engines + batchers.
+roofline the kernel with the largest share of the step (measured per stage with CUDA events): algorithmic bytes / time.
+cpu_baseline / --impl reference: the reference's CPU path for the same turn on the host cores (transformers Whisper-small
+         fp32 in full + a stated, scaled sample of Llama-3-8B; faster-whisper and faster-qwen3-tts are unavailable).
 
-    python bench.py --gpus 1 --steps 20 --warmup 3
+    python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps 2 --warmup 1
+    python bench.py --impl reference --steps 1 --warmup 0
 """
 from __future__ import annotations
 
@@ -34,7 +44,14 @@ sys.path.insert(0, ROOT)
 MODEL = "small"
 AUDIO_S = 10.0
 N_SAMPLES = 160000
-MAX_NEW = 128
+MAX_NEW = 128                     # STT tokens and LLM reply tokens
+LLM_PROMPT = 64
+FIRST_SENTENCE = 20               # reply tokens that make the first TTS input (stream_batch_sentences=1)
+SEC_PER_TOKEN = 0.30              # speech seconds per reply token (~2.6 words/s, the handler's own estimate, :60)
+FRAMES_PER_S = 12.5
+CHUNK = 8                         # the reference's streaming chunk (qwen3_tts_handler.py:49)
+LEFT_CTX = 25
+TTS_GEOM = "qwen3-tts-12hz"
 PREFIX = [50258, 50259, 50359, 50363]
 SUPPRESS = [1, 2, 7, 8, 9, 10, 14, 25, 26, 27, 28, 29, 31, 58, 59, 60, 61, 62, 63, 90, 91, 92, 93, 359, 503, 522, 542,
             873, 893, 902, 918, 922, 931, 1350, 1853, 1982, 2460, 2627, 3246, 3253, 3268, 3536, 3846, 3961, 4183, 4667,
@@ -42,21 +59,44 @@ SUPPRESS = [1, 2, 7, 8, 9, 10, 14, 25, 26, 27, 28, 29, 31, 58, 59, 60, 61, 62, 6
             16553, 16604, 18362, 18956, 20075, 21675, 22520, 26130, 26161, 26435, 28279, 29464, 31650, 32302, 32470,
             36865, 42863, 47425, 49870, 50254, 50258, 50358, 50359, 50360, 50361, 50362]
 BEGIN_SUPPRESS = [220, 50257]
-METRIC = "concurrent real-time sessions (10 s utterances transcribed per 10 s; Whisper-small STT turn)"
+METRIC = "concurrent real-time sessions (full turn: Whisper-small -> Llama-3-8B 128-tok reply -> Qwen3-TTS); p50 audio-in->first-audio-out ms"
 
 
-def decode_bytes_per_launch(g, n_prefix, max_new) -> dict:
-    """Algorithmic HBM bytes of one persistent-decode launch (DESIGN.md 'whisper_decode_kernel')."""
+def frames_for(tokens: int) -> int:
+    return int(round(tokens * SEC_PER_TOKEN * FRAMES_PER_S))
+
+
+F1, F2 = frames_for(FIRST_SENTENCE), frames_for(MAX_NEW - FIRST_SENTENCE)     # 75 + 405 frames = 38.4 s of speech
+REPLY_S = (F1 + F2) / FRAMES_PER_S
+CYCLE_S = AUDIO_S + REPLY_S
+
+
+def workload_config(world: int, sessions_per_gpu: int) -> dict:
+    """The SAME dict on both arms (the driver compares them)."""
+    return {"workload": "full turn, BASELINE configs[2]: whisper-small STT (10 s utterance, 128 tokens) -> llama-3-8b (64-token "
+                        "prompt, 128-token reply) -> qwen3-tts 12 Hz (reply spoken: 75 + 405 codec frames = 38.4 s)",
+            "audio_in_s": AUDIO_S, "reply_audio_s": REPLY_S, "cycle_s": CYCLE_S, "stt_tokens": MAX_NEW, "llm_prompt": LLM_PROMPT,
+            "llm_reply_tokens": MAX_NEW, "tts_frames": F1 + F2, "tts_chunk_frames": CHUNK, "tts_left_context": LEFT_CTX,
+            "sessions_per_gpu": sessions_per_gpu, "parallelism": f"session-shard dp{world}",
+            "gates": "speculative_reopen 0, smart_turn off, stream_batch_sentences 1 (BASELINE.md section 3)",
+            "weights": "seeded random-init, exact / published geometries"}
+
+
+def decode_bytes_whisper(g, n_prefix, max_new, B) -> float:
     d, L, f, V, T = g.d_model, g.dec_layers, g.ffn, g.vocab, g.max_source_positions
-    w_layer = (3 * d * d + d * d + d * d + d * d + f * d + d * f) * 2          # 16-bit weights streamed per token
-    cross_kv = L * T * 2 * d * 2                                                  # per utterance per token
-    logits = V * d * 2
+    w_layer = (3 * d * d + 3 * d * d + 2 * f * d) * 2
+    cross_kv = L * T * 2 * d * 2
     steps = n_prefix - 1 + max_new
     self_kv = sum(L * 2 * (p + 1) * d * 2 for p in range(steps))
-    total = steps * (L * w_layer + cross_kv) + max_new * logits + self_kv
-    return {"per_token_step": L * w_layer + cross_kv + logits, "per_launch": total, "steps": steps,
-            # B sessions per launch share the weight and logits streams; cross-KV and self-KV are per session
-            "per_launch_batched": lambda B: steps * (L * w_layer + B * cross_kv) + max_new * logits + B * self_kv}
+    return steps * (L * w_layer + B * cross_kv) + max_new * V * d * 2 + B * self_kv
+
+
+def decode_bytes_llama(g, n_steps, B, past) -> float:
+    d, L, f, V = g.d_model, g.layers, g.ffn, g.vocab
+    qd, kvd = g.heads * g.head_dim, g.kv_heads * g.head_dim
+    w_layer = ((qd + 2 * kvd) * d + d * qd + 3 * f * d) * 2
+    kv = sum(L * 2 * (past + s + 1) * kvd * 2 for s in range(n_steps))
+    return n_steps * (L * w_layer + V * d * 2) + B * kv
 
 
 class ClockSampler:
@@ -103,7 +143,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# =============================================================================================== reference arm
+# =============================================================================================== reference arm (CPU)
 def build_hf_whisper(g):
     import torch
     from transformers import WhisperConfig, WhisperForConditionalGeneration
@@ -116,83 +156,251 @@ def build_hf_whisper(g):
     return WhisperForConditionalGeneration(cfg).eval()
 
 
-def run_reference_once(model, fe, audio):
+def run_reference_stt(model, fe, audio):
     """What WhisperSTTHandler.process does on device='cpu', torch_dtype float32 (S/STT/whisper_stt_handler.py:83-87, 243)."""
     import torch
     feats = fe(audio, sampling_rate=16000, return_tensors="pt").input_features
     with torch.no_grad():
-        out = model.generate(feats, decoder_input_ids=torch.tensor([PREFIX]), max_new_tokens=MAX_NEW,
-                             min_new_tokens=MAX_NEW, num_beams=1, do_sample=False, suppress_tokens=SUPPRESS,
-                             begin_suppress_tokens=BEGIN_SUPPRESS, return_timestamps=False)
-    return out
+        return model.generate(feats, decoder_input_ids=torch.tensor([PREFIX]), max_new_tokens=MAX_NEW, min_new_tokens=MAX_NEW,
+                              num_beams=1, do_sample=False, suppress_tokens=SUPPRESS, begin_suppress_tokens=BEGIN_SUPPRESS,
+                              return_timestamps=False)
 
 
-def reference_arm(args, rank):
-    """--impl reference: the transformers CPU path (the code the reference handler executes) on the host cores."""
-    if rank != 0:
-        return
+LLM_SAMPLE_LAYERS, LLM_SAMPLE_TOKENS = 4, 16
+
+
+def cpu_turn(n_turns: int, threads: int) -> dict:
+    """The reference's CPU implementation of the turn on `threads` host threads: transformers Whisper-small generate fp32 (in
+    full: the call WhisperSTTHandler makes) + transformers LlamaForCausalLM at the Llama-3-8B layer geometry, a bounded sample
+    (4 of 32 layers, 16 of 128 reply tokens after the 64-token prompt, bf16) scaled by 32/4 x 128/16 -- the lm_head / embedding
+    cost is counted once per token at full width.  TTS: n/a (faster-qwen3-tts is not installed anywhere), so the
+    CPU turn is STT + LLM only, which flatters the CPU arm."""
+    import logging
     import torch
     from oracle import weights as W
+    torch.set_num_threads(threads)
+    logging.getLogger("transformers").setLevel(logging.ERROR)
+    from transformers import LlamaConfig, LlamaForCausalLM, WhisperFeatureExtractor
     g = W.WHISPER_GEOMETRIES[MODEL]
-    line = {"metric": METRIC, "unit": "sessions", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "impl": "reference", "config": {"workload": f"whisper-{MODEL} encode + greedy decode, single 10 s utterance",
-                                            "max_new_tokens": MAX_NEW, "audio_s": AUDIO_S}}
-    try:
-        from transformers import WhisperFeatureExtractor
-        import logging
-        logging.getLogger("transformers").setLevel(logging.ERROR)
-        model = build_hf_whisper(g)
-        fe = WhisperFeatureExtractor(feature_size=g.n_mels)
-        kind, what = "reference", f"transformers {__import__('transformers').__version__} WhisperForConditionalGeneration.generate fp32"
-        fn = lambda a: run_reference_once(model, fe, a)
-    except Exception as e:  # transformers missing: time the numpy oracle port instead
-        from oracle import whisper_ref as R
-        w = W.make_whisper_weights(g, 0)
-        kind, what = "port", f"numpy oracle port (transformers unavailable: {type(e).__name__})"
-        fn = lambda a: R.transcribe_ids(w, g, a, PREFIX, MAX_NEW, -1, SUPPRESS, BEGIN_SUPPRESS)
-    audio = W.synthetic_audio(0, N_SAMPLES)
-    for _ in range(max(0, args.warmup)):
-        fn(audio)
-    times = []
-    for i in range(args.steps):
-        a = W.synthetic_audio(i, N_SAMPLES)
+    model = build_hf_whisper(g)
+    fe = WhisperFeatureExtractor(feature_size=g.n_mels)
+    lg = W.LLAMA_GEOMETRIES["llama-3-8b"]
+    cfg = LlamaConfig(vocab_size=lg.vocab, hidden_size=lg.d_model, intermediate_size=lg.ffn, num_hidden_layers=LLM_SAMPLE_LAYERS,
+                      num_attention_heads=lg.heads, num_key_value_heads=lg.kv_heads, head_dim=lg.head_dim, rms_norm_eps=lg.rms_eps,
+                      rope_theta=lg.rope_theta, tie_word_embeddings=False)
+    torch.manual_seed(1)
+    llm = LlamaForCausalLM(cfg).to(torch.bfloat16).eval()
+    prompt = torch.randint(0, lg.vocab, (1, LLM_PROMPT))
+    run_reference_stt(model, fe, W.synthetic_audio(0, N_SAMPLES))          # warm-up
+    stt_s, llm_s = [], []
+    for i in range(n_turns):
+        a = W.synthetic_audio(100 + i, N_SAMPLES)
         t = time.perf_counter()
-        fn(a)
-        times.append(time.perf_counter() - t)
-    ms = 1e3 * sum(times) / len(times)
-    val = AUDIO_S / (ms / 1e3)
-    cores = torch.get_num_threads()
-    line.update({"value": val, "ms_per_step": ms,
-                 "cpu_baseline": {"value": val, "unit": "sessions", "cores": cores, "kind": kind,
-                                  "sample": f"{args.steps} utterances x ({what}), {os.cpu_count()} host cpus"},
-                 "e2e": {"value": val, "unit": "sessions", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                 "latency_ms_p50": 1e3 * statistics.median(times)})
+        run_reference_stt(model, fe, a)
+        stt_s.append(time.perf_counter() - t)
+        t = time.perf_counter()
+        with torch.no_grad():
+            llm.generate(prompt, max_new_tokens=LLM_SAMPLE_TOKENS, min_new_tokens=LLM_SAMPLE_TOKENS, do_sample=False, pad_token_id=0)
+        llm_s.append(time.perf_counter() - t)
+    stt, llm_sample = sum(stt_s) / len(stt_s), sum(llm_s) / len(llm_s)
+    llm_full = llm_sample * (32 / LLM_SAMPLE_LAYERS) * (MAX_NEW / LLM_SAMPLE_TOKENS)
+    turn = stt + llm_full
+    return {"value": CYCLE_S / turn, "unit": "sessions", "cores": threads, "kind": "reference",
+            "turn_s": turn, "stt_s": stt, "llm_s_scaled": llm_full,
+            "sample": f"{n_turns} turn(s): transformers {__import__('transformers').__version__} WhisperForConditionalGeneration.generate fp32 "
+                      f"in full ({stt:.2f} s) + LlamaForCausalLM bf16 {LLM_SAMPLE_LAYERS}/32 layers x {LLM_SAMPLE_TOKENS}/128 tokens "
+                      f"({llm_sample:.2f} s, scaled to {llm_full:.1f} s); TTS n/a; torch.set_num_threads({threads}) of {os.cpu_count()} cpus; "
+                      "faster-whisper unavailable, transformers CPU path timed instead; faster-qwen3-tts unavailable"}
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: rank 0 alone, all host cores whatever the launcher's OMP_NUM_THREADS says."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    line = {"metric": METRIC, "unit": "sessions", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (STT) / bf16 (LLM)", "data": "synthetic",
+            "impl": "reference", "config": workload_config(world, args.sessions)}
+    try:
+        cb = cpu_turn(max(1, args.steps), threads)
+        line.update({"value": cb["value"], "ms_per_step": 1e3 * cb["turn_s"], "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": "sessions", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "latency_ms_p50": 1e3 * cb["turn_s"]})
+    except Exception as e:
+        line.update({"value": None, "error": f"{type(e).__name__}: {e}"})
     print(json.dumps(line), flush=True)
 
 
 # =============================================================================================== B200 arm
+class Stack:
+    """The three engines of one GPU, shared by all its sessions (one weight copy each)."""
+
+    def __init__(self, E, W, dev: int, S: int):
+        import torch
+        from speech_to_speech_b200.tts_model import B200Qwen3TTS
+        self.E, self.W, self.dev, self.S = E, W, dev, S
+        self.wg = W.WHISPER_GEOMETRIES[MODEL]
+        self.lg = W.LLAMA_GEOMETRIES["llama-3-8b"]
+        self.whisper = E.WhisperEngine(self.wg.to_dict(), dtype="float16", max_batch=min(16, S), device=dev)
+        self.whisper.init_random(1234)
+        self.llm = E.LlamaEngine(self.lg.to_dict(), dtype="bfloat16", max_sessions=S, max_positions=LLM_PROMPT + MAX_NEW + 8,
+                                 max_prefill=LLM_PROMPT, device=dev)
+        self.llm.init_random(7)
+        self.tts = B200Qwen3TTS.from_random(TTS_GEOM, seed=11, dtype="bfloat16", device=dev, max_sessions=S,
+                                            max_positions=max(F1, F2) + 32, max_text=128)
+        self.opts = E.WhisperDecodeOptions(prefix=PREFIX, eos_id=-1, max_new_tokens=MAX_NEW, suppress=SUPPRESS,
+                                           begin_suppress=BEGIN_SUPPRESS)
+        self.llm_b = self.llm.max_decode_batch()
+        self.tts_b = self.tts.engine.max_batch()
+        self.prompt = np.random.default_rng(0).integers(0, self.lg.vocab, LLM_PROMPT).tolist()
+        from speech_to_speech_b200.handlers.qwen3_tts_postproc import TTSPostProcessor
+        self.post = TTSPostProcessor(dev)
+        self.torch = torch
+
+
+def wave_device(st: Stack, pcm_dev, ev) -> None:
+    """One wave of S full turns as an engine-level launch sequence; stage boundaries marked with CUDA events."""
+    torch, S = st.torch, st.S
+    dev = f"cuda:{st.dev}"
+    ev["t0"].record()
+    for b0 in range(0, S, 16):                                           # ---- STT
+        nb = min(16, S - b0)
+        st.whisper.logmel(pcm_dev[b0:b0 + nb], [N_SAMPLES] * nb)
+        st.whisper.encode(nb)
+        st.whisper.decode(nb, st.opts)
+    ev["stt"].record()
+    firsts = []
+    for s in range(S):                                                    # ---- LLM prefill
+        st.llm.reset(s)
+        nxt, _ = st.llm.prefill(s, st.prompt)
+        firsts.append(nxt)
+    ev["prefill"].record()
+    first = torch.cat(firsts)
+    for b0 in range(0, S, st.llm_b):                                      # ---- LLM decode, llm_b sessions per launch
+        sl = list(range(b0, min(S, b0 + st.llm_b)))
+        st.llm.decode(sl, first[b0:b0 + len(sl)].contiguous(), MAX_NEW - 1)
+    ev["llm"].record()
+    eng = st.tts.engine
+    text1, text2 = [3] * FIRST_SENTENCE, [5] * (MAX_NEW - FIRST_SENTENCE)
+    for text, frames in ((text1, F1), (text2, F2)):                       # ---- TTS: two utterances per turn
+        for s in range(S):
+            eng.prefill(s, text, 2301)
+        done = 0
+        while done < frames:
+            n = min(CHUNK, frames - done)
+            for b0 in range(0, S, st.tts_b):
+                eng.decode_frames(list(range(b0, min(S, b0 + st.tts_b))), n)
+            ev["frames_mark"].append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            a, b = ev["frames_mark"][-1]
+            a.record()
+            for b0 in range(0, S, st.tts_b):
+                for wav in eng.decode_audio_batch(list(range(b0, min(S, b0 + st.tts_b))), n, LEFT_CTX):
+                    st.post.to_int16_device(wav)
+            b.record()
+            done += n
+    ev["tts"].record()
+
+
+def e2e_wave(handlers, auds, S) -> dict:
+    """The wave through the three handler classes, one thread per session (the reference's thread-per-unit shape)."""
+    from speech_to_speech_b200.host import resolve
+    api = resolve()
+    lat, rtf, t_done = [None] * S, [None] * S, [None] * S
+    errs = []
+
+    def session(i):
+        try:
+            stt, llm, tts = handlers[i]
+            vad = api.VADAudio(audio=auds[i], mode="final", turn_id=f"t{i}", turn_revision=0)
+            out = list(stt.process(vad))
+            tr = out[-1]
+            pieces, n_tok, first_audio, speech_s, t_tts0 = [], 0, None, 0.0, None
+            stream = llm.generate_text_stream(llm_prompt, max_new_tokens=MAX_NEW)
+
+            def speak(n_tokens, frames):
+                nonlocal first_audio, speech_s, t_tts0
+                tts.max_new_tokens = frames
+                tts.streaming_chunk_size = CHUNK
+                if t_tts0 is None:
+                    t_tts0 = time.perf_counter()
+                item = api.TTSInput(text="x" * n_tokens, speech_stopped_at_s=tr.speech_stopped_at_s)
+                for blk in tts.process(item):
+                    if first_audio is None:
+                        first_audio = time.perf_counter()
+                    speech_s += len(blk) / 16000.0
+            spoke_first = False
+            for piece in stream:
+                n_tok = len(llm.streamer.generated)
+                if not spoke_first and n_tok >= FIRST_SENTENCE:
+                    speak(FIRST_SENTENCE, F1)
+                    spoke_first = True
+            speak(MAX_NEW - FIRST_SENTENCE, F2)
+            t_end = time.perf_counter()
+            lat[i] = 1e3 * (first_audio - vad.created_at_s)
+            rtf[i] = speech_s / max(1e-9, t_end - t_tts0)
+            t_done[i] = t_end
+        except Exception as e:  # noqa: BLE001
+            errs.append(f"session {i}: {type(e).__name__}: {e}")
+
+    llm_prompt = np.random.default_rng(0).integers(0, 128256, LLM_PROMPT).tolist()
+    ths = [threading.Thread(target=session, args=(i,)) for i in range(S)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    wall = time.perf_counter() - t0
+    ok = [x for x in lat if x is not None]
+    return {"wall_s": wall, "latency_ms": ok, "rtf": [x for x in rtf if x is not None], "errors": errs[:3]}
+
+
+def make_handlers(S: int, dev: int):
+    """S pipeline units' worth of handler instances sharing one engine per stage (gen_kwargs / kwargs of the reference slots)."""
+    from queue import Queue
+    from threading import Event
+    from speech_to_speech_b200.handlers.language_model_handler import B200LanguageModelHandler
+    from speech_to_speech_b200.handlers.qwen3_tts_handler import B200Qwen3TTSHandler
+    from speech_to_speech_b200.handlers.whisper_stt_handler import B200WhisperSTTHandler
+    out = []
+    for i in range(S):
+        stt = B200WhisperSTTHandler(Event(), queue_in=Queue(), queue_out=Queue(),
+                                    setup_kwargs=dict(model_name=f"random:{MODEL}:1234", device=f"cuda:{dev}", torch_dtype="float16",
+                                                      language="en", gen_kwargs={"max_new_tokens": MAX_NEW}, max_batch=min(16, S),
+                                                      batch_wait_ms=3.0))
+        stt.tokens.eos = -1                   # random-init weights: every utterance decodes its full 128 tokens (both arms do)
+        llm = object.__new__(B200LanguageModelHandler)   # the load hook only: the request lifecycle needs the reference's Chat types
+        llm.device = f"cuda:{dev}"
+        B200LanguageModelHandler._load_model(llm, "random:llama-3-8b:7", f"cuda:{dev}", "bfloat16",
+                                             {"max_new_tokens": MAX_NEW, "max_sessions": S, "max_positions": LLM_PROMPT + MAX_NEW + 8,
+                                              "stream_chunk_tokens": 8, "batch_wait_ms": 2.0})
+        llm.eos_ids = []                      # random-init weights: never stop early, every reply has 128 tokens
+        llm.streamer.eos_ids = set()
+        tts = B200Qwen3TTSHandler(Event(), queue_in=Queue(), queue_out=Queue(), setup_args=(Event(),),
+                                  setup_kwargs=dict(model_name=f"random:{TTS_GEOM}", device=f"cuda:{dev}", speaker="Aiden",
+                                                    max_sessions=S, gen_kwargs={"seed": 11}))
+        out.append((stt, llm, tts))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-baseline-utts", type=int, default=2, help="utterances timed on the host CPU (rank 0, N=1)")
+    ap.add_argument("--sessions", type=int, default=16, help="conversation sessions in flight per GPU (one wave = one turn of each)")
+    ap.add_argument("--cpu-baseline-turns", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the device-timed region (use with ncu --profile-from-start off)")
-    ap.add_argument("--no-turn", action="store_true", help="skip the full-turn (STT -> LLM -> TTS post-proc) breakdown")
-    ap.add_argument("--batch", type=int, default=16, help="sessions per launch for the secondary 'batched' figure (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-
     if args.impl == "reference":
-        reference_arm(args, rank)
+        reference_arm(args, rank, world)
         return
 
     import torch
@@ -204,240 +412,169 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    g = W.WHISPER_GEOMETRIES[args.model]
-    eng = E.WhisperEngine(g.to_dict(), dtype="float16", max_batch=max(1, args.batch), device=local_rank)
-    eng.init_random(seed=1234)
-    opts = E.WhisperDecodeOptions(prefix=PREFIX, eos_id=-1, max_new_tokens=MAX_NEW, suppress=SUPPRESS,
-                                  begin_suppress=BEGIN_SUPPRESS)
     dev = f"cuda:{local_rank}"
-    n_in = args.warmup + args.steps
-    # every step gets its own utterance; each rank a disjoint shard of the session stream (weak scaling, no collective)
-    sessions = shard.local_sessions(rank, world, world * min(n_in, 8))  # global session ids owned by this rank
-    auds = [W.synthetic_audio(sid, N_SAMPLES) for sid in sessions]
-    pcm_dev = [torch.from_numpy(a)[None].to(dev).contiguous() for a in auds]
-    pinned = [torch.from_numpy(a).pin_memory() for a in auds]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    S = args.sessions
+    st = Stack(E, W, local_rank, S)
 
-    def step_device(i):
-        eng.logmel(pcm_dev[i % len(pcm_dev)], [N_SAMPLES])
-        eng.encode(1)
-        return eng.decode(1, opts)
-
-    for i in range(args.warmup):
-        step_device(i)
+    # ---- session-shard split: the ingest rank (0) holds every session's PCM and scatters each rank its shard over NCCL -------
+    layout = shard.shard_layout(world * S, world)
+    full = None
+    if rank == 0:
+        full = torch.stack([torch.from_numpy(W.synthetic_audio(sid, N_SAMPLES)) for r in range(world) for sid in layout[r]]).to(dev)
+    xe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    xe[0].record()
+    pcm_dev = shard.scatter_from_ingest(full, S, (N_SAMPLES,), torch.float32, dev)
+    xe[1].record()
     torch.cuda.synchronize()
+    scatter_ms = xe[0].elapsed_time(xe[1])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- timed region 1: device-resident inputs, CUDA events per step, L2 flushed between steps ----
+    def new_events():
+        names = ("t0", "stt", "prefill", "llm", "tts")
+        ev = {n: torch.cuda.Event(enable_timing=True) for n in names}
+        ev["frames_mark"] = []
+        return ev
+
+    for _ in range(args.warmup):
+        wave_device(st, pcm_dev, new_events())
+    torch.cuda.synchronize()
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
     E.launch_count(local_rank, reset=True)
+    evs = []
     barrier()
     if args.profile_region:
         torch.cuda.cudart().cudaProfilerStart()
     t_wall = time.perf_counter()
     for i in range(args.steps):
-        flush.fill_(i & 0xFF)          # L2 flush (not timed)
-        s, mid, e = ev[i]
-        s.record()
-        eng.logmel(pcm_dev[i % len(pcm_dev)], [N_SAMPLES])
-        eng.encode(1)
-        mid.record()
-        eng.decode(1, opts)
-        e.record()
+        flush.fill_(i & 0xFF)                 # L2 flush between timed steps (not timed)
+        ev = new_events()
+        wave_device(st, pcm_dev, ev)
+        evs.append(ev)
     barrier()
     if args.profile_region:
         torch.cuda.cudart().cudaProfilerStop()
     wall_s = time.perf_counter() - t_wall
     launches = E.launch_count(local_rank, reset=True)
-    step_ms = [s.elapsed_time(e) for s, _, e in ev]
-    dec_ms = [m.elapsed_time(e) for _, m, e in ev]
-    enc_ms = [s.elapsed_time(m) for s, m, _ in ev]
+
+    def stage(ev, a, b):
+        return ev[a].elapsed_time(ev[b])
+    step_ms = [stage(e, "t0", "tts") for e in evs]
+    stages = {"stt_ms": statistics.mean(stage(e, "t0", "stt") for e in evs),
+              "llm_prefill_ms": statistics.mean(stage(e, "stt", "prefill") for e in evs),
+              "llm_decode_ms": statistics.mean(stage(e, "prefill", "llm") for e in evs),
+              "tts_ms": statistics.mean(stage(e, "llm", "tts") for e in evs)}
+    codec_ms = statistics.mean(sum(a.elapsed_time(b) for a, b in e["frames_mark"]) for e in evs)
+    stages["tts_codec_postproc_ms"] = codec_ms
+    stages["tts_talker_predictor_ms"] = stages["tts_ms"] - codec_ms
     total_ms = sum(step_ms)
 
-    # ---- timed region 2: end to end through the public host API (pinned host PCM in, ids on host out) ----
-    for i in range(3):
-        eng.transcribe([pinned[i % len(pinned)].numpy()], opts)
-    barrier()
-    e2e_t = []
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        torch.cuda.synchronize()
-        t = time.perf_counter()
-        ids = eng.transcribe([pinned[i % len(pinned)].numpy()], opts)
-        e2e_t.append(time.perf_counter() - t)
-    barrier()
-    e2e_total = sum(e2e_t)
+    # ---- results back to the ingest rank (first codec chunk's int16 audio + ids are what a client needs first): gather ----
+    res = torch.zeros((S, 64), dtype=torch.int32, device=dev)
+    ge = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ge[0].record()
+    shard.gather_to_ingest(res)
+    ge[1].record()
+    torch.cuda.synchronize()
+    gather_ms = ge[0].elapsed_time(ge[1])
 
-    # ---- secondary figure: B concurrent sessions per launch (the weight stream is shared by the batch) ----
-    batched = None
-    if args.batch > 1:
-        Bn = args.batch
-        pcm_b = torch.stack([pcm_dev[i % len(pcm_dev)][0] for i in range(Bn)]).contiguous()
-        host_b = [pinned[i % len(pinned)].numpy() for i in range(Bn)]
-        for _ in range(2):
-            eng.logmel(pcm_b, [N_SAMPLES] * Bn); eng.encode(Bn); eng.decode(Bn, opts)
-        torch.cuda.synchronize()
-        nb_steps = max(3, args.steps // 4)
-        evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-               for _ in range(nb_steps)]
-        barrier()
-        for i in range(nb_steps):
-            flush.fill_(i & 0xFF)
-            evb[i][0].record()
-            eng.logmel(pcm_b, [N_SAMPLES] * Bn); eng.encode(Bn)
-            evb[i][2].record()
-            eng.decode(Bn, opts)
-            evb[i][1].record()
-        barrier()
-        b_ms = [a.elapsed_time(b) for a, b, _ in evb]
-        b_dec_ms = sum(m.elapsed_time(b) for _, b, m in evb) / nb_steps
-        tb = []
-        for i in range(nb_steps):
-            t = time.perf_counter(); eng.transcribe(host_b, opts); tb.append(time.perf_counter() - t)
-        barrier()
-        b_tot, b_e2e = shard.max_over_ranks([sum(b_ms), sum(tb)], device=dev)
-        batched = {"batch_per_gpu": Bn, "steps": nb_steps, "ms_per_step": b_tot / nb_steps,
-                   "value": world * Bn * AUDIO_S / (b_tot / nb_steps / 1e3),
-                   "e2e_value": world * Bn * AUDIO_S / (b_e2e / nb_steps), "latency_ms_p50": statistics.median(b_ms),
-                   "decode_ms": b_dec_ms,
-                   "note": "same kernels, Bn utterances per launch; every session still gets its full 128-token decode"}
+    # ---- single-session latency on an idle GPU + the loaded wave, through the handler classes (host PCM in, int16 out) ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            handlers = make_handlers(S, local_rank)
+            auds = [pcm_dev[i].cpu().numpy() for i in range(S)]
+            e2e_wave(handlers[:1], auds, 1)                                    # warm-up
+            single = [e2e_wave(handlers[:1], auds, 1) for _ in range(3)]
+            e2e_wave(handlers, auds, S)                                        # warm-up of the loaded path
+            barrier()
+            loaded = [e2e_wave(handlers, auds, S) for _ in range(max(1, min(args.steps, 2)))]
+            barrier()
+            e2e = {"single": single, "loaded": loaded}
+            for hs in handlers:
+                for h in hs:
+                    try:
+                        h.cleanup()
+                    except Exception:
+                        pass
+        except Exception as ex:  # never lose the headline line because of the handler-level section
+            e2e = {"error": f"{type(ex).__name__}: {ex}"}
     clocks = sampler.stop() if rank == 0 else None
 
-    total_ms, e2e_total = shard.max_over_ranks([total_ms, e2e_total], device=dev)  # slowest rank defines the job
+    e2e_wall = statistics.mean(w["wall_s"] for w in e2e["loaded"]) if e2e and "loaded" in e2e else float("nan")
+    total_ms, e2e_wall_max = shard.max_over_ranks([total_ms, e2e_wall if e2e_wall == e2e_wall else 0.0], device=dev)
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
-        value = shard.whole_job_sessions(world, AUDIO_S, ms_per_step)
-        e2e_value = shard.whole_job_sessions(world, AUDIO_S, 1e3 * e2e_total / args.steps)
+        value = world * S * CYCLE_S / (ms_per_step / 1e3)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        nb = decode_bytes_per_launch(g, len(PREFIX), MAX_NEW)
-        dec_avg_ms = sum(dec_ms) / len(dec_ms)
-        achieved = nb["per_launch"] / 1e9 / (dec_avg_ms / 1e3)
-        cluster_on = os.environ.get("S2S_WHISPER_CLUSTER", "1") != "0"
-        kernel_name = ("whisper_decode_cluster_kernel (persistent, 8-CTA cluster per head, 1 launch per utterance)" if cluster_on
-                       else "whisper_decode_kernel (persistent, 1 launch per utterance)")
-        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
-        tpath = os.path.join(ROOT, "profiles", "ncu_decode_traffic.json")
+        # dominant stage of the step and its kernel's roofline
+        shares = {k: v / ms_per_step for k, v in stages.items() if k in ("stt_ms", "llm_prefill_ms", "llm_decode_ms", "tts_talker_predictor_ms", "tts_codec_postproc_ms")}
+        n_llm_launch = (S + st.llm_b - 1) // st.llm_b
+        llm_bytes = decode_bytes_llama(st.lg, MAX_NEW - 1, min(S, st.llm_b), LLM_PROMPT)
+        llm_ms = stages["llm_decode_ms"] / n_llm_launch
+        ach_llm = llm_bytes / 1e9 / (llm_ms / 1e3)
+        n_w_launch = (S + 15) // 16
+        wb = decode_bytes_whisper(st.wg, len(PREFIX), MAX_NEW, min(S, 16))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
         if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic = tj.get("cluster_b1" if cluster_on else "grid_b1", {}).get("dram_bytes_per_launch")
-        if batched is not None:
-            bb = nb["per_launch_batched"](batched["batch_per_gpu"])
-            ach_b = bb / 1e9 / (batched["decode_ms"] / 1e3)
-            batched["roofline"] = {"kernel": "whisper_decode_kernel (persistent, %d sessions per launch)" % batched["batch_per_gpu"],
-                                   "bound": "hbm", "achieved": ach_b, "peak": peak, "unit": "GB/s", "frac": ach_b / peak,
-                                   "algorithmic_bytes_per_launch": bb,
-                                   "traffic": (json.load(open(tpath)).get("grid_b%d" % batched["batch_per_gpu"], {}).get("dram_bytes_per_launch")
-                                               if os.path.exists(tpath) else None)}
+            traffic = json.load(open(tpath)).get("llama_decode", {}).get("dram_bytes_per_launch")
+        roofline = {"kernel": f"llama_decode_kernel (persistent, {min(S, st.llm_b)} sessions x {MAX_NEW - 1} steps per launch, Llama-3-8B bf16)",
+                    "bound": "hbm", "achieved": ach_llm, "peak": peak, "unit": "GB/s", "frac": ach_llm / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": llm_bytes, "launch_ms": llm_ms, "launches_per_step": n_llm_launch,
+                    "peak_source": peak_src, "share_of_step": shares["llm_decode_ms"], "stage_shares": shares}
         line = {
-            "metric": METRIC, "value": value, "unit": "sessions", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": f"whisper-{args.model} log-mel + encoder + greedy decode, single 10 s utterance (BASELINE configs[1])",
-                       "max_new_tokens": MAX_NEW, "audio_s": AUDIO_S, "batch_per_gpu": 1, "parallelism": f"session-shard dp{world}",
-                       "l2": "flushed between timed steps (256 MiB write); per-token weight stream 335 MB > 126 MB L2",
-                       "weights": "seeded random-init, exact geometry"},
-            "latency_ms_p50": statistics.median(step_ms), "e2e_latency_ms_p50": 1e3 * statistics.median(e2e_t),
-            "stage_ms": {"logmel_encoder": sum(enc_ms) / len(enc_ms), "decode_128_tokens": dec_avg_ms},
-            "wall_s_timed_region": wall_s,
-            "e2e": {"value": e2e_value, "unit": "sessions", "h2d_bytes_per_step": N_SAMPLES * 4,
-                    "d2h_bytes_per_step": MAX_NEW * 4 + 4},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": kernel_name, "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": nb["per_launch"], "peak_source": peak_src,
-                         "share_of_step": dec_avg_ms / ms_per_step},
-            "clocks": clocks,
-            "batched": batched,
+            "metric": METRIC, "value": value, "unit": "sessions", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 (Whisper) / bf16 (Llama, talker) operands, f32 accumulate; codec decoder f32", "data": "synthetic",
+            "config": {**workload_config(world, S),
+                       "l2": "flushed between timed steps (256 MiB write); every stage streams > 126 MB of weights per launch"},
+            "turn_gpu_ms_per_session": ms_per_step / S, "stage_ms": stages, "wall_s_timed_region": wall_s,
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+            "session_shard_exchange": {"collective": "torch.distributed scatter (PCM from the ingest rank) + gather (results), NCCL send/recv",
+                                       "scatter_ms": scatter_ms, "gather_ms": gather_ms,
+                                       "bytes_in_per_session": N_SAMPLES * 4, "bytes_out_per_session": 64 * 4},
+            "whisper_decode_roofline": {"kernel": "whisper_decode_kernel (persistent, 16 sessions per launch)", "bound": "hbm",
+                                        "algorithmic_bytes_per_launch": wb, "launches_per_step": n_w_launch},
         }
-        if world == 1 and not args.no_turn:
-            try:
-                line["turn"] = full_turn(eng, opts, pinned[0].numpy(), local_rank)
-            except Exception as e:  # never lose the headline line because of the extra section
-                line["turn"] = {"error": f"{type(e).__name__}: {e}"}
+        if e2e and "loaded" in e2e:
+            lat_loaded = [x for w in e2e["loaded"] for x in w["latency_ms"]]
+            rtf_loaded = [x for w in e2e["loaded"] for x in w["rtf"]]
+            lat_single = [x for w in e2e["single"] for x in w["latency_ms"]]
+            e2e_val = world * S * CYCLE_S / e2e_wall_max if e2e_wall_max > 0 else None
+            realtime = bool(rtf_loaded) and min(rtf_loaded) >= 1.0
+            line["e2e"] = {"value": e2e_val, "unit": "sessions", "h2d_bytes_per_step": S * N_SAMPLES * 4,
+                           "d2h_bytes_per_step": S * int((F1 + F2) * 1920 * 2 / 3) * 2,
+                           "wall_s_per_wave": e2e_wall_max, "path": "B200WhisperSTTHandler -> B200LanguageModelHandler -> B200Qwen3TTSHandler, "
+                           "one thread per session, shared engines + session batchers",
+                           "tts_rtf_min": min(rtf_loaded) if rtf_loaded else None, "tts_rtf_p50": statistics.median(rtf_loaded) if rtf_loaded else None,
+                           "real_time": realtime, "errors": [e for w in e2e["loaded"] for e in w["errors"]][:3]}
+            line["latency_ms_p50"] = statistics.median(lat_loaded) if lat_loaded else None
+            line["latency_ms_p50_single_session"] = statistics.median(lat_single) if lat_single else None
+            line["latency_note"] = ("audio-in (VADAudio.created_at_s) -> first int16 block out of the TTS handler; 'single' = one session on an "
+                                    "idle GPU, 'latency_ms_p50' = the S sessions of a wave that all stop speaking at the same instant (worst case)")
+        elif e2e:
+            line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(g, args.cpu_baseline_utts)
+            try:
+                line["cpu_baseline"] = cpu_turn(args.cpu_baseline_turns, os.cpu_count() or 1)
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "unit": "sessions", "cores": 0, "kind": "reference", "sample": f"failed: {type(ex).__name__}: {ex}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def full_turn(whisper_eng, opts, audio, device):
-    """BASELINE configs[2] breakdown on one GPU, one session: Whisper-small STT -> Llama-3-8B (64-token prompt, 128-token
-    reply, bf16, random-init) -> TTS post-processing of a 640 ms codec chunk.  The Qwen3-TTS model itself is not built
-    (DESIGN.md section 7), so 'first_audio' below excludes the TTS model latency and says so."""
-    import torch
-    from oracle import weights as W
-    from speech_to_speech_b200 import engine as E
-    from speech_to_speech_b200.handlers.qwen3_tts_postproc import TTSPostProcessor
-    lg = W.LLAMA_GEOMETRIES["llama-3-8b"]
-    llm = E.LlamaEngine(lg.to_dict(), dtype="bfloat16", max_sessions=1, max_positions=1024, max_prefill=512, device=device)
-    llm.init_random(7)
-    post = TTSPostProcessor(device)
-    prompt = np.random.default_rng(0).integers(0, lg.vocab, 64).tolist()
-    chunk24k = (0.2 * np.sin(np.arange(15360) * 0.05)).astype(np.float32)  # 8 codec frames x 1920 samples
-    rows = []
-    for it in range(4):
-        t0 = time.perf_counter()
-        whisper_eng.transcribe([audio], opts)
-        t1 = time.perf_counter()
-        llm.reset(0)
-        nxt, _ = llm.prefill(0, prompt)
-        first = int(nxt[0])  # D2H: first reply token available on the host
-        t2 = time.perf_counter()
-        ids, lens = llm.decode([0], nxt, 19)  # first sentence ~20 tokens (what the TTS stage needs to start)
-        torch.cuda.synchronize()
-        t3 = time.perf_counter()
-        ids, lens = llm.decode([0], ids[:, -1].contiguous(), 108)
-        torch.cuda.synchronize()
-        t4 = time.perf_counter()
-        post(chunk24k)
-        t5 = time.perf_counter()
-        rows.append([1e3 * (b - a) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4), (t4, t5))])
-    r = np.median(np.asarray(rows[1:]), axis=0)
-    llm.close()
-    return {"config": "whisper-small STT (128 tok) -> llama-3-8b bf16 (64-tok prompt, 128-tok reply) -> tts post-proc (640 ms chunk); 1 session",
-            "stt_ms": r[0], "llm_prefill_first_token_ms": r[1], "llm_first_sentence_20tok_ms": r[2], "llm_remaining_108tok_ms": r[3],
-            "tts_postproc_chunk_ms": r[4], "audio_in_to_first_sentence_ms": r[0] + r[1] + r[2],
-            "llm_decode_ms_per_token": (r[2] + r[3]) / 127.0,
-            "note": "Qwen3-TTS talker/codec not built (upstream absent, parity unpinned): first-audio latency would add its TTFA"}
-
-
-def cpu_baseline(g, n_utts):
-    """Bounded CPU sample beside the GPU number: the transformers fp32 path on the host cores (rank 0, N=1)."""
-    import torch
-    from oracle import weights as W
-    try:
-        from transformers import WhisperFeatureExtractor
-        import logging
-        logging.getLogger("transformers").setLevel(logging.ERROR)
-        model = build_hf_whisper(g)
-        fe = WhisperFeatureExtractor(feature_size=g.n_mels)
-        run_reference_once(model, fe, W.synthetic_audio(0, N_SAMPLES))  # warm-up
-        ts = []
-        for i in range(n_utts):
-            a = W.synthetic_audio(100 + i, N_SAMPLES)
-            t = time.perf_counter()
-            run_reference_once(model, fe, a)
-            ts.append(time.perf_counter() - t)
-        sec = sum(ts) / len(ts)
-        return {"value": AUDIO_S / sec, "unit": "sessions", "cores": torch.get_num_threads(), "kind": "reference",
-                "sample": f"{n_utts} utterances, transformers WhisperForConditionalGeneration.generate fp32 on "
-                          f"{torch.get_num_threads()} threads ({os.cpu_count()} cpus), {sec:.2f} s/utterance"}
-    except Exception as e:
-        return {"value": None, "unit": "sessions", "cores": 0, "kind": "port", "sample": f"failed: {type(e).__name__}: {e}"}
 
 
 if __name__ == "__main__":

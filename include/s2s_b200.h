@@ -182,6 +182,10 @@ typedef struct {
   int32_t decoder_dim, sliding_window;
   float rope_theta, rms_eps;
   int32_t max_frames;   /* longest decode call: left context + chunk (33 for chunk_size 8 behind 25 frames of history) */
+  int32_t max_batch;    /* sequences decoded by one launch sequence (concurrently speaking sessions, <= 16; 0 = 1) */
+  int32_t precision;    /* 0 = fp32 FMA everywhere (the reference slot's `parity_mode`, qwen3_tts_arguments.py:99-101: waveform
+                           within 1e-3 of the fp32 oracle); 1 = contractions on the tensor cores with fp16 operands and fp32
+                           accumulation (waveform within 1e-2) */
 } s2s_codec_config;
 typedef struct s2s_codec s2s_codec;
 int s2s_codec_create(s2s_ctx* ctx, const s2s_codec_config* cfg, s2s_codec** out);
@@ -247,6 +251,10 @@ int s2s_qwen3tts_decode_frames(s2s_qwen3tts* m, const int32_t* slots_h, int32_t 
  * `left_context` frames of history (Qwen3OmniMoeCode2Wav.chunked_decode); wav_out_d f32 [n_new * 1920 (max)]. */
 int s2s_qwen3tts_decode_audio(s2s_qwen3tts* m, int32_t slot, int32_t n_new, int32_t left_context, float* wav_out_d,
                               int32_t* n_out_h, void* stream);
+/* The same for B sessions whose chunks have the same shape (same n_new and the same amount of history): ONE launch sequence,
+ * the linear layers see B x T rows.  wav_out_d + b * wav_stride receives session b's samples. */
+int s2s_qwen3tts_decode_audio_batch(s2s_qwen3tts* m, const int32_t* slots_h, int32_t B, int32_t n_new, int32_t left_context,
+                                    float* wav_out_d, int64_t wav_stride, int32_t* n_out_h, void* stream);
 /* Tell the library how many frames of `slot` are valid (after the caller saw codec_eos inside a chunk). */
 int s2s_qwen3tts_set_frames(s2s_qwen3tts* m, int32_t slot, int32_t n_frames);
 int32_t s2s_qwen3tts_frames(s2s_qwen3tts* m, int32_t slot);

@@ -24,7 +24,7 @@ EXPORTED = [
     "s2s_codec_create", "s2s_codec_destroy", "s2s_codec_bind_tensor", "s2s_codec_init_random", "s2s_codec_finalize",
     "s2s_codec_decode", "s2s_codec_samples", "s2s_codec_total_upsample",
     "s2s_qwen3tts_create", "s2s_qwen3tts_destroy", "s2s_qwen3tts_bind_tensor", "s2s_qwen3tts_init_random",
-    "s2s_qwen3tts_finalize", "s2s_qwen3tts_prefill", "s2s_qwen3tts_decode_frames", "s2s_qwen3tts_decode_audio",
+    "s2s_qwen3tts_finalize", "s2s_qwen3tts_prefill", "s2s_qwen3tts_decode_frames", "s2s_qwen3tts_decode_audio", "s2s_qwen3tts_decode_audio_batch",
     "s2s_qwen3tts_set_frames", "s2s_qwen3tts_frames", "s2s_qwen3tts_max_batch", "s2s_qwen3tts_codec",
 ]
 
@@ -59,7 +59,7 @@ class CodecConfig(C.Structure):
         ("n_upsample_rates", C.c_int32), ("upsample_rates", C.c_int32 * 8),
         ("n_upsampling_ratios", C.c_int32), ("upsampling_ratios", C.c_int32 * 4),
         ("decoder_dim", C.c_int32), ("sliding_window", C.c_int32), ("rope_theta", C.c_float), ("rms_eps", C.c_float),
-        ("max_frames", C.c_int32)]
+        ("max_frames", C.c_int32), ("max_batch", C.c_int32), ("precision", C.c_int32)]
 
 
 class Qwen3TTSConfig(C.Structure):
@@ -143,6 +143,7 @@ def load() -> C.CDLL:
     lib.s2s_qwen3tts_prefill.argtypes = [vp, i32, C.POINTER(i32), i32, i32, vp]
     lib.s2s_qwen3tts_decode_frames.argtypes = [vp, C.POINTER(i32), i32, i32, vp, vp, vp]
     lib.s2s_qwen3tts_decode_audio.argtypes = [vp, i32, i32, i32, vp, C.POINTER(i32), vp]
+    lib.s2s_qwen3tts_decode_audio_batch.argtypes = [vp, C.POINTER(i32), i32, i32, i32, vp, i64, C.POINTER(i32), vp]
     lib.s2s_qwen3tts_set_frames.argtypes = [vp, i32, i32]
     lib.s2s_qwen3tts_frames.argtypes = [vp, i32]
     lib.s2s_qwen3tts_frames.restype = i32

@@ -33,6 +33,7 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ contraction kernel
 constexpr int CV_BM = 64, CV_BK = 16, CV_THREADS = 256;
+constexpr int CODEC_MAX_BATCH = 16;   // sequences per launch sequence (one per concurrently speaking session)
 
 template <int BN>
 __global__ void __launch_bounds__(CV_THREADS) conv1d_f32_kernel(const ConvArgs a) {
@@ -105,16 +106,154 @@ __global__ void __launch_bounds__(CV_THREADS) conv1d_f32_kernel(const ConvArgs a
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core contraction
+// The same contraction on the tensor cores: fp16 operands (activations converted while they are staged, weights stored as
+// fp16 k-pairs at bind time), fp32 accumulate, fp32 epilogue (bias / activation / scale / residual) and fp32 output.
+// mma.sync.m16n8k16, CTA tile 128 (time) x 64 (channels) x 32 (k), 8 warps as 4 x 2, warp tile 32 x 32.  The codec
+// decoder is ~5 GFLOP per frame and every chunk re-decodes its 25 frames of left context (chunked_decode): on the CUDA
+// cores it was the largest share of a turn (bench.py stage_ms), here it is weight- and activation-stream bound.
+// tcgen05 is not used: the operand is a strided gather of fp32 rows (dilated taps, causal zero rows) that has to be
+// converted on the way in, which the generic-proxy staging path does and a TMA descriptor does not.
+constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_THREADS = 256;
+constexpr int TC_APAD = 8;     // halves: row stride 40 halves = 80 B -> conflict-free 32-bit fragment loads
+constexpr int TC_BPAD = 8;     // half2 words
+
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// wh: weights as half2 k-pairs, [k][C_in_pad / 2][N] (C_in_pad = C_in rounded up to 2, zero padded)
+__global__ void __launch_bounds__(TC_THREADS) conv1d_tc_kernel(const ConvArgs a, const __half2* __restrict__ wh, int c_pairs) {
+  __shared__ __half As[2][TC_BM][TC_BK + TC_APAD];
+  __shared__ uint32_t Bs[2][TC_BK / 2][TC_BN + TC_BPAD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;                 // warp tile origin: rows 32 wm, cols 32 wn
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN, z = blockIdx.z;
+  const float* X = a.x + (long long)z * a.x_bs;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+  const int kt_per_tap = (a.C_in + TC_BK - 1) / TC_BK;
+  const int n_kt = a.k * kt_per_tap;
+  // A staging: 128 rows x 32 channels fp32 -> fp16; thread -> row tid / 2, 16 consecutive channels
+  const int a_row = tid >> 1, a_c = (tid & 1) * 16;
+  // B staging: 16 k-pairs x 64 n words; thread -> pair tid / 16, 4 consecutive n
+  const int b_kp = tid >> 4, b_n = (tid & 15) * 4;
+  float areg[16];
+  uint32_t breg[4];
+  auto load_tile = [&](int kt) {
+    const int j = kt / kt_per_tap, c0 = (kt - j * kt_per_tap) * TC_BK;
+    const int xr = m0 + a_row + a.x_row0 + j * a.dil;
+    const bool ok = (m0 + a_row) < a.T_out && xr >= 0 && xr < a.T_in;
+    const float* xp = X + (long long)xr * a.ldx + c0 + a_c;
+    if (ok && c0 + a_c + 16 <= a.C_in && ((reinterpret_cast<uintptr_t>(xp) & 15) == 0)) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 q = *reinterpret_cast<const float4*>(xp + 4 * v);
+        areg[4 * v] = q.x; areg[4 * v + 1] = q.y; areg[4 * v + 2] = q.z; areg[4 * v + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < 16; ++v) areg[v] = (ok && c0 + a_c + v < a.C_in) ? xp[v] : 0.f;
+    }
+    const int kp = (j * c_pairs) + (c0 >> 1) + b_kp;          // pair row of the weight matrix
+    const bool kok = (c0 >> 1) + b_kp < c_pairs;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int n = n0 + b_n + v;
+      breg[v] = (kok && n < a.N) ? __ldg(reinterpret_cast<const uint32_t*>(wh + (long long)kp * a.N + n)) : 0u;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int v = 0; v < 16; v += 2)
+      *reinterpret_cast<__half2*>(&As[buf][a_row][a_c + v]) = __floats2half2_rn(areg[v], areg[v + 1]);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) Bs[buf][b_kp][b_n + v] = breg[v];
+  };
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < n_kt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < n_kt) load_tile(kt + 1);              // global loads of the next tile fly during the MMAs
+#pragma unroll
+    for (int ks = 0; ks < TC_BK; ks += 16) {
+      uint32_t af[2][4], bf[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = wm * 32 + i * 16 + g;
+        af[i][0] = *reinterpret_cast<const uint32_t*>(&As[buf][r][ks + 2 * t]);
+        af[i][1] = *reinterpret_cast<const uint32_t*>(&As[buf][r + 8][ks + 2 * t]);
+        af[i][2] = *reinterpret_cast<const uint32_t*>(&As[buf][r][ks + 8 + 2 * t]);
+        af[i][3] = *reinterpret_cast<const uint32_t*>(&As[buf][r + 8][ks + 8 + 2 * t]);
+      }
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        const int n = wn * 32 + jn * 8 + g;
+        bf[jn][0] = Bs[buf][(ks >> 1) + t][n];
+        bf[jn][1] = Bs[buf][(ks >> 1) + 4 + t][n];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) mma_f16_16816(acc[i][jn], af[i][0], af[i][1], af[i][2], af[i][3], bf[jn][0], bf[jn][1]);
+    }
+    if (kt + 1 < n_kt) store_tile(buf ^ 1);
+    __syncthreads();
+  }
+  float* Y = a.y + (long long)z * a.y_bs;
+  const float* R = a.resid ? a.resid + (long long)z * a.r_bs : nullptr;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int tt = m0 + wm * 32 + i * 16 + g + (r >> 1) * 8;
+        const int n = n0 + wn * 32 + jn * 8 + 2 * t + (r & 1);
+        if (tt >= a.T_out || n >= a.N) continue;
+        float v = acc[i][jn][r];
+        if (a.bias) v += __ldg(a.bias + (n % a.bias_mod));
+        if (a.act == 1) v = gelu_erf(v);
+        else if (a.act == 2) v = v / (1.0f + expf(-v));
+        if (a.scale) v *= __ldg(a.scale + n);
+        if (R) v += R[(long long)tt * a.ldr + n];
+        Y[(long long)tt * a.ldy + n] = v;
+      }
+}
+
+// fp32 [k][C_in][N] -> half2 pairs [k][ceil(C_in / 2)][N]
+__global__ void pack_weight_pairs_kernel(const float* __restrict__ w, int k, int C_in, int N, __half2* __restrict__ out) {
+  const int cp = (C_in + 1) >> 1;
+  const long long total = (long long)k * cp * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const long long r = i / N;
+    const int p = (int)(r % cp), j = (int)(r / cp);
+    const int c = 2 * p;
+    const float lo = w[((long long)j * C_in + c) * N + n];
+    const float hi = c + 1 < C_in ? w[((long long)j * C_in + c + 1) * N + n] : 0.f;
+    out[i] = __floats2half2_rn(lo, hi);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ small kernels
-// x[t, :] = mean_q E[q * cb + codes[t][q], :]
-__global__ void code_embed_mean_kernel(const int* __restrict__ codes, int Q, int cb, const float* __restrict__ E, int H,
-                                       float* __restrict__ x) {
-  const int t = blockIdx.x;
+// x[b * T + t, :] = mean_q E[q * cb + codes_b[t][q], :]   (one code pointer per sequence of the batch)
+struct CodePtrs { const int* p[CODEC_MAX_BATCH]; };
+__global__ void code_embed_mean_kernel(CodePtrs cp, int T, int Q, int cb, const float* __restrict__ E, int H, float* __restrict__ x) {
+  const int b = blockIdx.x / T, t = blockIdx.x % T;
+  const int* codes = cp.p[b];
   const float inv = 1.0f / (float)Q;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     float s = 0.f;
     for (int q = 0; q < Q; ++q) s += E[((long long)q * cb + codes[t * Q + q]) * H + i];
-    x[(long long)t * H + i] = s * inv;
+    x[(long long)blockIdx.x * H + i] = s * inv;
   }
 }
 
@@ -133,7 +272,8 @@ __global__ void rmsnorm_rows_f32_kernel(const float* __restrict__ x, const float
 
 // RoPE (rotate_half pairs (j, j + hd/2)) on q and k in place; qkv [T, (H + 2 KV) * hd], position = row index
 __global__ void rope_rows_f32_kernel(float* __restrict__ qkv, int T, int n_rot_heads, int hd, int ld, float theta) {
-  const int t = blockIdx.x;
+  const int t = blockIdx.x % T;              // rows of a batch are [b * T + t]: the position restarts with every sequence
+  qkv += (long long)(blockIdx.x - t) * ld;
   const int half = hd >> 1;
   for (int i = threadIdx.x; i < n_rot_heads * half; i += blockDim.x) {
     const int h = i / half, j = i % half;
@@ -148,13 +288,16 @@ __global__ void rope_rows_f32_kernel(float* __restrict__ qkv, int T, int n_rot_h
 }
 
 // causal sliding-window attention, one warp per (query t, head h); keys t - W + 1 .. t; fp32 softmax
-__global__ void swa_attention_f32_kernel(const float* __restrict__ qkv, int T, int H, int KV, int hd, int W, float* __restrict__ o) {
+__global__ void swa_attention_f32_kernel(const float* __restrict__ qkv, int B, int T, int H, int KV, int hd, int W, float* __restrict__ o) {
   extern __shared__ float sm[];   // per warp: q[hd] + p[W]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int item = blockIdx.x * nw + warp;
-  if (item >= T * H) return;
-  const int t = item / H, h = item % H, g = H / KV;
+  if (item >= B * T * H) return;
+  const int bt = item / H, h = item % H, g = H / KV;
+  const int b = bt / T, t = bt % T;          // sequence b of the batch: keys never cross a sequence boundary
   const int ld = (H + 2 * KV) * hd;
+  qkv += (long long)b * T * ld;
+  o += (long long)b * T * (H * hd);
   float* qs = sm + (size_t)warp * (hd + W);
   float* ps = qs + hd;
   const float* q = qkv + (long long)t * ld + h * hd;
@@ -208,7 +351,9 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, int T, int C, con
                                   const float* __restrict__ lw, const float* __restrict__ lb, float eps, float* __restrict__ y) {
   extern __shared__ float hs[];   // [C]
   __shared__ float red[2][32];
-  const int t = blockIdx.x;
+  const int t = blockIdx.x % T;   // rows [b * T + t]: the causal window restarts with every sequence of the batch
+  x += (long long)(blockIdx.x - t) * C;
+  y += (long long)(blockIdx.x - t) * C;
   float s1 = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float v = bd[c];
@@ -237,10 +382,10 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, int T, int C, con
   for (int c = threadIdx.x; c < C; c += blockDim.x) y[(long long)t * C + c] = (hs[c] - mean) * rstd * lw[c] + lb[c];
 }
 
-// wav[i] = clamp(x[(skip + i) * ld], -1, 1)
-__global__ void clamp_out_kernel(const float* __restrict__ x, long long ld, int skip, int n, float* __restrict__ wav) {
+// wav[b][i] = clamp(x[b][skip + i], -1, 1)
+__global__ void clamp_out_kernel(const float* __restrict__ x, long long x_bs, int skip, int n, float* __restrict__ wav, long long wav_bs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) wav[i] = fminf(1.0f, fmaxf(-1.0f, x[(long long)(skip + i) * ld]));
+  if (i < n) wav[(long long)blockIdx.y * wav_bs + i] = fminf(1.0f, fmaxf(-1.0f, x[(long long)blockIdx.y * x_bs + skip + i]));
 }
 
 __global__ void exp_prep_kernel(float* a, float* b, int n) {   // alpha -> exp(alpha); beta -> 1 / (exp(beta) + 1e-9)
@@ -267,6 +412,15 @@ struct CSlot {
 };
 
 }  // namespace
+
+int conv1d_tc_launch(const ConvArgs& a, const void* w_pairs, cudaStream_t st) {
+  if (a.T_out <= 0 || a.N <= 0) return S2S_OK;
+  const int batch = a.batch > 0 ? a.batch : 1;
+  dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.T_out + TC_BM - 1) / TC_BM, batch);
+  conv1d_tc_kernel<<<grid, TC_THREADS, 0, st>>>(a, reinterpret_cast<const __half2*>(w_pairs), (a.C_in + 1) >> 1);
+  S2S_LAUNCH_CHECK();
+  return S2S_OK;
+}
 
 int conv1d_f32_launch(const ConvArgs& a, cudaStream_t st) {
   if (a.T_out <= 0 || a.N <= 0) return S2S_OK;
@@ -312,9 +466,14 @@ struct s2s_codec {
   float *bufX = nullptr, *bufA = nullptr, *bufH = nullptr;
   size_t buf_elems = 0;
   int total_up = 1;
+  // tensor-core path: fp16 k-pair copies of the contraction weights, keyed by the fp32 matrix they were packed from
+  struct TcW { int k, C_in, N; void* packed; };
+  std::unordered_map<const float*, TcW> tc_w;
 };
 
 namespace {
+
+void tc_register(CodecDecoder* m, const float* w, int k, int C_in, int N) { m->tc_w[w] = CodecDecoder::TcW{k, C_in, N, nullptr}; }
 
 int calloc_f(CodecDecoder* m, float** out, size_t n) {
   void* p = nullptr;
@@ -369,6 +528,8 @@ int build(CodecDecoder* m) {
     sub(p + "mlp.up_proj.weight", L.w_gu, 2 * I, I, I, H, sh);
     S2S_CHECK(cslot(m, p + "self_attn.o_proj.weight", &L.w_o, C_LINEAR, H, qd, 0, 0, sh));
     S2S_CHECK(cslot(m, p + "mlp.down_proj.weight", &L.w_down, C_LINEAR, H, I, 0, 0, 1.0f / sqrtf((float)I)));
+    tc_register(m, L.w_qkv, 1, H, qd + 2 * kvd); tc_register(m, L.w_gu, 1, H, 2 * I);
+    tc_register(m, L.w_o, 1, qd, H); tc_register(m, L.w_down, 1, I, H);
     S2S_CHECK(cslot(m, p + "input_layernorm.weight", &L.n1, C_PLAIN, H, 0, 0, 0, 0.1f, 1.0f));
     S2S_CHECK(cslot(m, p + "post_attention_layernorm.weight", &L.n2, C_PLAIN, H, 0, 0, 0, 0.1f, 1.0f));
     S2S_CHECK(cslot(m, p + "self_attn_layer_scale.scale", &L.ls_attn, C_PLAIN, H, 0, 0, 0, 0.1f, 0.5f));
@@ -393,10 +554,12 @@ int build(CodecDecoder* m) {
     S2S_CHECK(cslot(m, p + "1.pwconv2.weight", &U.pw2_w, C_LINEAR, H, 4 * H, 0, 0, 0.5f * sh));
     S2S_CHECK(cslot(m, p + "1.pwconv2.bias", &U.pw2_b, C_PLAIN, H, 0, 0, 0, 0.02f));
     S2S_CHECK(cslot(m, p + "1.gamma", &U.gamma, C_PLAIN, H, 0, 0, 0, 0.05f, 0.3f));
+    tc_register(m, U.up_w, 1, H, f * H); tc_register(m, U.pw1_w, 1, H, 4 * H); tc_register(m, U.pw2_w, 1, 4 * H, H);
   }
   const int D = c.decoder_dim;
   S2S_CHECK(cslot(m, "decoder.0.conv.weight", &m->d0_w, C_CONV, D, H, 7, 0, 1.0f / sqrtf(7.0f * H)));
   S2S_CHECK(cslot(m, "decoder.0.conv.bias", &m->d0_b, C_PLAIN, D, 0, 0, 0, 0.02f));
+  tc_register(m, m->d0_w, 7, H, D);
   m->blocks.resize(c.n_upsample_rates);
   auto snake = [&](const std::string& pa, const std::string& pb, float** a, float** b, int n) -> int {
     S2S_CHECK(cslot(m, pa, a, C_PLAIN, n, 0, 0, 0, 0.2f));
@@ -413,6 +576,7 @@ int build(CodecDecoder* m) {
     S2S_CHECK(snake(p + "0.alpha", p + "0.beta", &B.a0, &B.b0, B.cin));
     S2S_CHECK(cslot(m, p + "1.conv.weight", &B.tc_w, C_TCONV, B.cin, B.cout, 2 * B.rate, B.rate, 1.0f / sqrtf(2.0f * B.cin)));
     S2S_CHECK(cslot(m, p + "1.conv.bias", &B.tc_b, C_PLAIN, B.cout, 0, 0, 0, 0.02f));
+    tc_register(m, B.tc_w, 2, B.cin, B.rate * B.cout);
     for (int u = 0; u < 3; ++u) {
       const std::string q = p + std::to_string(u + 2) + ".";
       CodecResUnit& R = B.u[u];
@@ -422,17 +586,20 @@ int build(CodecDecoder* m) {
       S2S_CHECK(snake(q + "act2.alpha", q + "act2.beta", &R.a2, &R.b2, B.cout));
       S2S_CHECK(cslot(m, q + "conv2.conv.weight", &R.c2_w, C_CONV, B.cout, B.cout, 1, 0, 1.0f / sqrtf((float)B.cout)));
       S2S_CHECK(cslot(m, q + "conv2.conv.bias", &R.c2_b, C_PLAIN, B.cout, 0, 0, 0, 0.02f));
+      tc_register(m, R.c1_w, 7, B.cout, B.cout); tc_register(m, R.c2_w, 1, B.cout, B.cout);
     }
   }
   const int n = c.n_upsample_rates, cl = D >> n;
   S2S_CHECK(snake("decoder." + std::to_string(n + 1) + ".alpha", "decoder." + std::to_string(n + 1) + ".beta", &m->fa, &m->fb, cl));
-  S2S_CHECK(cslot(m, "decoder." + std::to_string(n + 2) + ".conv.weight", &m->f_w, C_CONV, 1, cl, 7, 0, 0.02f / sqrtf(7.0f * cl)));
+  S2S_CHECK(cslot(m, "decoder." + std::to_string(n + 2) + ".conv.weight", &m->f_w, C_CONV, 1, cl, 7, 0, 0.5f / sqrtf(7.0f * cl)));
   S2S_CHECK(cslot(m, "decoder." + std::to_string(n + 2) + ".conv.bias", &m->f_b, C_PLAIN, 1, 0, 0, 0, 0.02f));
   (void)dummy;
-  // workspace for max_frames
-  const int T = c.max_frames;
+  // workspace for max_batch sequences of max_frames
+  const int T = c.max_frames * (c.max_batch > 0 ? c.max_batch : 1);
   std::vector<int> L;
-  codec_lengths(c, T, L);
+  codec_lengths(c, c.max_frames, L);
+  const size_t nb = (size_t)(c.max_batch > 0 ? c.max_batch : 1);
+  for (int& v : L) v = (int)((size_t)v * nb);
   size_t mx = (size_t)L[0] * std::max(4 * H, D);
   for (int i = 0; i < c.n_upsample_rates; ++i) mx = std::max(mx, (size_t)L[i + 1] * (size_t)(D >> (i + 1)));
   mx = std::max(mx, (size_t)L[0] * (size_t)D);
@@ -447,6 +614,15 @@ int build(CodecDecoder* m) {
   S2S_CHECK(calloc_f(m, &m->gu, (size_t)T * 2 * I));
   S2S_CHECK(calloc_f(m, &m->hmid, (size_t)T * I));
   return S2S_OK;
+}
+
+// one contraction: tensor cores (fp16 operands) unless the model runs in parity mode or the shape has no packed weights
+int contract(CodecDecoder* m, const ConvArgs& a, cudaStream_t st) {
+  if (m->cfg.precision != 0) {
+    auto it = m->tc_w.find(a.w);
+    if (it != m->tc_w.end() && it->second.packed) return conv1d_tc_launch(a, it->second.packed, st);
+  }
+  return conv1d_f32_launch(a, st);
 }
 
 ConvArgs linear_args(const float* x, int T, int K, const float* w, int N, float* y) {
@@ -583,113 +759,142 @@ int codec_finalize(CodecDecoder* m) {
       exp_prep_kernel<<<(m->snake_len[i] + 255) / 256, 256>>>(m->snake_pairs[i].first, m->snake_pairs[i].second, m->snake_len[i]);
       S2S_LAUNCH_CHECK();
     }
+  // fp16 k-pair copies for the tensor-core contraction (rebuilt on every (re)load)
+  for (auto& kv : m->tc_w) {
+    CodecDecoder::TcW& t = kv.second;
+    const size_t words = (size_t)t.k * ((t.C_in + 1) / 2) * t.N;
+    if (!t.packed) {
+      S2S_CHECK_CUDA(cudaMalloc(&t.packed, words * 4));
+      m->allocs.push_back(t.packed);
+    }
+    pack_weight_pairs_kernel<<<(unsigned)std::min<size_t>((words + 255) / 256, 4096), 256>>>(kv.first, t.k, t.C_in, t.N,
+                                                                                               reinterpret_cast<__half2*>(t.packed));
+    S2S_LAUNCH_CHECK();
+  }
   S2S_CHECK_CUDA(cudaDeviceSynchronize());
   m->finalized = true;
   return S2S_OK;
 }
 
-int codec_decode(CodecDecoder* m, const int32_t* codes_d, int T, int ctx_frames, float* wav_out_d, int32_t* n_out_h,
-                 float* hidden_out_d, cudaStream_t st) {
+// B sequences of the same shape (T frames, ctx_frames of history) through ONE launch sequence: the linear layers see
+// B * T rows, the causal convolutions run one sequence per blockIdx.z.  codes_d[b]: [T][Q]; wav_out_d + b * wav_stride.
+int codec_decode_batch(CodecDecoder* m, const int32_t* const* codes_d, int B, int T, int ctx_frames, float* wav_out_d,
+                       long long wav_stride, int32_t* n_out_h, float* hidden_out_d, cudaStream_t st) {
   S2S_REQUIRE(m && m->finalized && codes_d && wav_out_d, "codec decode: null argument / not finalized");
   const auto& c = m->cfg;
+  const int maxB = c.max_batch > 0 ? c.max_batch : 1;
+  S2S_REQUIRE(B >= 1 && B <= maxB && B <= CODEC_MAX_BATCH, "codec decode: batch %d outside [1,%d]", B, std::min(maxB, CODEC_MAX_BATCH));
   S2S_REQUIRE(T >= 1 && T <= c.max_frames, "codec decode: T=%d outside [1,%d]", T, c.max_frames);
   S2S_REQUIRE(ctx_frames >= 0 && ctx_frames < T, "codec decode: context %d must be smaller than T=%d", ctx_frames, T);
   S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
   const int H = c.hidden, hd = H / c.heads, qd = c.heads * hd, kvd = c.kv_heads * hd, I = c.inter, ldq = qd + 2 * kvd;
-  code_embed_mean_kernel<<<T, 256, 0, st>>>(codes_d, c.quantizers, c.codebook_size, m->embed, H, m->x);
+  const int R = B * T;   // rows of the transformer part
+  CodePtrs cp{};
+  for (int b = 0; b < B; ++b) cp.p[b] = codes_d[b];
+  code_embed_mean_kernel<<<R, 256, 0, st>>>(cp, T, c.quantizers, c.codebook_size, m->embed, H, m->x);
   S2S_LAUNCH_CHECK();
   for (int l = 0; l < c.layers; ++l) {
     const CodecLayer& L = m->layers[l];
-    rmsnorm_rows_f32_kernel<<<(T + 7) / 8, 256, 0, st>>>(m->x, L.n1, c.rms_eps, T, H, m->xn);
+    rmsnorm_rows_f32_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->x, L.n1, c.rms_eps, R, H, m->xn);
     S2S_LAUNCH_CHECK();
-    S2S_CHECK(conv1d_f32_launch(linear_args(m->xn, T, H, L.w_qkv, ldq, m->qkv), st));
-    rope_rows_f32_kernel<<<T, 256, 0, st>>>(m->qkv, T, c.heads + c.kv_heads, hd, ldq, c.rope_theta);
+    S2S_CHECK(contract(m, linear_args(m->xn, R, H, L.w_qkv, ldq, m->qkv), st));
+    rope_rows_f32_kernel<<<R, 256, 0, st>>>(m->qkv, T, c.heads + c.kv_heads, hd, ldq, c.rope_theta);
     S2S_LAUNCH_CHECK();
     {
       const int nw = 8;
       const size_t sm = (size_t)nw * (hd + c.sliding_window) * 4;
-      swa_attention_f32_kernel<<<(T * c.heads + nw - 1) / nw, nw * 32, sm, st>>>(m->qkv, T, c.heads, c.kv_heads, hd, c.sliding_window, m->att);
+      swa_attention_f32_kernel<<<(R * c.heads + nw - 1) / nw, nw * 32, sm, st>>>(m->qkv, B, T, c.heads, c.kv_heads, hd, c.sliding_window, m->att);
       S2S_LAUNCH_CHECK();
     }
     {
-      ConvArgs a = linear_args(m->att, T, qd, L.w_o, H, m->x);
+      ConvArgs a = linear_args(m->att, R, qd, L.w_o, H, m->x);
       a.scale = L.ls_attn; a.resid = m->x; a.ldr = H;
-      S2S_CHECK(conv1d_f32_launch(a, st));
+      S2S_CHECK(contract(m, a, st));
     }
-    rmsnorm_rows_f32_kernel<<<(T + 7) / 8, 256, 0, st>>>(m->x, L.n2, c.rms_eps, T, H, m->xn);
+    rmsnorm_rows_f32_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->x, L.n2, c.rms_eps, R, H, m->xn);
     S2S_LAUNCH_CHECK();
-    S2S_CHECK(conv1d_f32_launch(linear_args(m->xn, T, H, L.w_gu, 2 * I, m->gu), st));
-    silu_mul_kernel<<<(unsigned)(((long long)T * I + 255) / 256), 256, 0, st>>>(m->gu, I, (long long)T * I, m->hmid);
+    S2S_CHECK(contract(m, linear_args(m->xn, R, H, L.w_gu, 2 * I, m->gu), st));
+    silu_mul_kernel<<<(unsigned)(((long long)R * I + 255) / 256), 256, 0, st>>>(m->gu, I, (long long)R * I, m->hmid);
     S2S_LAUNCH_CHECK();
     {
-      ConvArgs a = linear_args(m->hmid, T, I, L.w_down, H, m->x);
+      ConvArgs a = linear_args(m->hmid, R, I, L.w_down, H, m->x);
       a.scale = L.ls_mlp; a.resid = m->x; a.ldr = H;
-      S2S_CHECK(conv1d_f32_launch(a, st));
+      S2S_CHECK(contract(m, a, st));
     }
   }
-  rmsnorm_rows_f32_kernel<<<(T + 7) / 8, 256, 0, st>>>(m->x, m->norm_f, c.rms_eps, T, H, m->bufX);
+  rmsnorm_rows_f32_kernel<<<(R + 7) / 8, 256, 0, st>>>(m->x, m->norm_f, c.rms_eps, R, H, m->bufX);
   S2S_LAUNCH_CHECK();
-  if (hidden_out_d) S2S_CHECK_CUDA(cudaMemcpyAsync(hidden_out_d, m->bufX, (size_t)T * H * 4, cudaMemcpyDeviceToDevice, st));
-  // upsampling stages: transposed conv (k = stride) + ConvNeXt
+  if (hidden_out_d) S2S_CHECK_CUDA(cudaMemcpyAsync(hidden_out_d, m->bufX, (size_t)R * H * 4, cudaMemcpyDeviceToDevice, st));
+  // upsampling stages: transposed conv (k = stride: row-wise, so the batch is just more rows) + ConvNeXt
   float *X = m->bufX, *A = m->bufA, *Hb = m->bufH;
-  int len = T;
+  int len = T;   // per sequence
   for (int i = 0; i < c.n_upsampling_ratios; ++i) {
     const CodecConvNeXt& U = m->ups[i];
     const int f = c.upsampling_ratios[i];
     {
-      ConvArgs a = linear_args(X, len, H, U.up_w, f * H, A);
+      ConvArgs a = linear_args(X, B * len, H, U.up_w, f * H, A);
       a.bias = U.up_b; a.bias_mod = H;
-      S2S_CHECK(conv1d_f32_launch(a, st));
+      S2S_CHECK(contract(m, a, st));
     }
-    len *= f;   // A is [len, H]
-    dwconv7_ln_kernel<<<len, 256, (size_t)H * 4, st>>>(A, len, H, U.dw_w, U.dw_b, U.ln_w, U.ln_b, 1e-6f, Hb);
+    len *= f;   // A is [B * len, H]
+    dwconv7_ln_kernel<<<B * len, 256, (size_t)H * 4, st>>>(A, len, H, U.dw_w, U.dw_b, U.ln_w, U.ln_b, 1e-6f, Hb);
     S2S_LAUNCH_CHECK();
     {
-      ConvArgs a = linear_args(Hb, len, H, U.pw1_w, 4 * H, X);
+      ConvArgs a = linear_args(Hb, B * len, H, U.pw1_w, 4 * H, X);
       a.bias = U.pw1_b; a.act = 1;
-      S2S_CHECK(conv1d_f32_launch(a, st));
+      S2S_CHECK(contract(m, a, st));
     }
     {
-      ConvArgs a = linear_args(X, len, 4 * H, U.pw2_w, H, A);
+      ConvArgs a = linear_args(X, B * len, 4 * H, U.pw2_w, H, A);
       a.bias = U.pw2_b; a.scale = U.gamma; a.resid = A; a.ldr = H;
-      S2S_CHECK(conv1d_f32_launch(a, st));
+      S2S_CHECK(contract(m, a, st));
     }
-    std::swap(X, A);   // X = stage output [len, H]
+    std::swap(X, A);   // X = stage output [B * len, H]
   }
   const int D = c.decoder_dim;
-  S2S_CHECK(conv1d_f32_launch(causal_conv_args(X, len, H, m->d0_w, m->d0_b, 7, 1, D, A), st));
+  auto batched = [&](ConvArgs a, int cin, int cout_row, int rows_in, int rows_out) {
+    a.batch = B; a.x_bs = (long long)rows_in * cin; a.y_bs = (long long)rows_out * cout_row; a.r_bs = a.y_bs;
+    return a;
+  };
+  S2S_CHECK(contract(m, batched(causal_conv_args(X, len, H, m->d0_w, m->d0_b, 7, 1, D, A), H, D, len, len), st));
   std::swap(X, A);
   for (int i = 0; i < c.n_upsample_rates; ++i) {
-    const CodecBlock& B = m->blocks[i];
-    S2S_CHECK(snake_launch(X, B.a0, B.b0, B.cin, (long long)len * B.cin, A, st));
+    const CodecBlock& Bk = m->blocks[i];
+    S2S_CHECK(snake_launch(X, Bk.a0, Bk.b0, Bk.cin, (long long)B * len * Bk.cin, A, st));
     {
       ConvArgs a{};
-      a.x = A; a.ldx = B.cin; a.T_in = len; a.x_row0 = 0; a.w = B.tc_w; a.k = 2; a.dil = 1; a.C_in = B.cin; a.N = B.rate * B.cout;
-      a.bias = B.tc_b; a.bias_mod = B.cout; a.y = X; a.ldy = (long long)B.rate * B.cout; a.T_out = len - 1; a.batch = 1;
-      S2S_CHECK(conv1d_f32_launch(a, st));
+      a.x = A; a.ldx = Bk.cin; a.T_in = len; a.x_row0 = 0; a.w = Bk.tc_w; a.k = 2; a.dil = 1; a.C_in = Bk.cin; a.N = Bk.rate * Bk.cout;
+      a.bias = Bk.tc_b; a.bias_mod = Bk.cout; a.y = X; a.ldy = (long long)Bk.rate * Bk.cout; a.T_out = len - 1;
+      S2S_CHECK(contract(m, batched(a, Bk.cin, Bk.rate * Bk.cout, len, len - 1), st));
     }
-    len = (len - 1) * B.rate;   // X is [len, cout]
+    len = (len - 1) * Bk.rate;   // X is [B][len, cout]
     static const int dil[3] = {1, 3, 9};
     for (int u = 0; u < 3; ++u) {
-      const CodecResUnit& R = B.u[u];
-      S2S_CHECK(snake_launch(X, R.a1, R.b1, B.cout, (long long)len * B.cout, A, st));
-      S2S_CHECK(conv1d_f32_launch(causal_conv_args(A, len, B.cout, R.c1_w, R.c1_b, 7, dil[u], B.cout, Hb), st));
-      S2S_CHECK(snake_launch(Hb, R.a2, R.b2, B.cout, (long long)len * B.cout, A, st));
-      ConvArgs a = causal_conv_args(A, len, B.cout, R.c2_w, R.c2_b, 1, 1, B.cout, X);
-      a.resid = X; a.ldr = B.cout;
-      S2S_CHECK(conv1d_f32_launch(a, st));
+      const CodecResUnit& Ru = Bk.u[u];
+      S2S_CHECK(snake_launch(X, Ru.a1, Ru.b1, Bk.cout, (long long)B * len * Bk.cout, A, st));
+      S2S_CHECK(contract(m, batched(causal_conv_args(A, len, Bk.cout, Ru.c1_w, Ru.c1_b, 7, dil[u], Bk.cout, Hb), Bk.cout, Bk.cout, len, len), st));
+      S2S_CHECK(snake_launch(Hb, Ru.a2, Ru.b2, Bk.cout, (long long)B * len * Bk.cout, A, st));
+      ConvArgs a = linear_args(A, B * len, Bk.cout, Ru.c2_w, Bk.cout, X);   // 1-tap: row-wise over the whole batch
+      a.bias = Ru.c2_b; a.resid = X; a.ldr = Bk.cout;
+      S2S_CHECK(contract(m, a, st));
     }
   }
   const int cl = D >> c.n_upsample_rates;
-  S2S_CHECK(snake_launch(X, m->fa, m->fb, cl, (long long)len * cl, A, st));
-  S2S_CHECK(conv1d_f32_launch(causal_conv_args(A, len, cl, m->f_w, m->f_b, 7, 1, 1, Hb), st));
+  S2S_CHECK(snake_launch(X, m->fa, m->fb, cl, (long long)B * len * cl, A, st));
+  S2S_CHECK(contract(m, batched(causal_conv_args(A, len, cl, m->f_w, m->f_b, 7, 1, 1, Hb), cl, 1, len, len), st));
   const int skip = ctx_frames * m->total_up;
   const int n_out = len - skip;
   S2S_REQUIRE(n_out > 0, "codec decode: nothing left after dropping %d context frames", ctx_frames);
-  clamp_out_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(Hb, 1, skip, n_out, wav_out_d);
+  S2S_REQUIRE(B == 1 || wav_stride >= n_out, "codec decode: wav_stride %lld < %d samples", wav_stride, n_out);
+  clamp_out_kernel<<<dim3((n_out + 255) / 256, B), 256, 0, st>>>(Hb, len, skip, n_out, wav_out_d, wav_stride);
   S2S_LAUNCH_CHECK();
   if (n_out_h) *n_out_h = n_out;
   return S2S_OK;
+}
+
+int codec_decode(CodecDecoder* m, const int32_t* codes_d, int T, int ctx_frames, float* wav_out_d, int32_t* n_out_h,
+                 float* hidden_out_d, cudaStream_t st) {
+  return codec_decode_batch(m, &codes_d, 1, T, ctx_frames, wav_out_d, 0, n_out_h, hidden_out_d, st);
 }
 
 extern "C" {

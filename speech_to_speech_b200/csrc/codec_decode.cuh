@@ -16,6 +16,8 @@ struct ConvArgs {
   int batch; long long x_bs, y_bs, r_bs;    // independent sequences along blockIdx.z
 };
 int conv1d_f32_launch(const ConvArgs& a, cudaStream_t st);
+// the same contraction on the tensor cores; w_pairs = fp16 k-pair copy of a.w (pack_weight_pairs_kernel)
+int conv1d_tc_launch(const ConvArgs& a, const void* w_pairs, cudaStream_t st);
 
 typedef s2s_codec CodecDecoder;   // the C-ABI handle is the model object
 int codec_create(s2s_ctx* ctx, const s2s_codec_config* cfg, CodecDecoder** out);
@@ -27,5 +29,7 @@ int codec_finalize(CodecDecoder* m);
 // Qwen3OmniMoeCode2Wav.chunked_decode); *n_out_h = samples written to wav_out_d.  hidden_out_d optional [T, hidden].
 int codec_decode(CodecDecoder* m, const int32_t* codes_d, int T, int ctx_frames, float* wav_out_d, int32_t* n_out_h,
                  float* hidden_out_d, cudaStream_t st);
+int codec_decode_batch(CodecDecoder* m, const int32_t* const* codes_d, int B, int T, int ctx_frames, float* wav_out_d,
+                       long long wav_stride, int32_t* n_out_h, float* hidden_out_d, cudaStream_t st);
 int codec_samples_for(const CodecDecoder* m, int T);   // waveform length of a T-frame decode (before the context drop)
 int codec_total_upsample(const CodecDecoder* m);

@@ -492,6 +492,27 @@ int s2s_qwen3tts_decode_audio(s2s_qwen3tts* m, int32_t slot, int32_t n_new, int3
   return codec_decode(m->codec, codes, ctx + n_new, ctx, wav_out_d, n_out_h, nullptr, (cudaStream_t)stream);
 }
 
+int s2s_qwen3tts_decode_audio_batch(s2s_qwen3tts* m, const int32_t* slots_h, int32_t B, int32_t n_new, int32_t left_context,
+                                    float* wav_out_d, int64_t wav_stride, int32_t* n_out_h, void* stream) {
+  S2S_REQUIRE(m && m->finalized && slots_h && wav_out_d, "qwen3tts decode_audio_batch: null argument / not finalized");
+  const auto& c = m->cfg;
+  S2S_REQUIRE(B >= 1 && B <= TTS_MAX_B, "qwen3tts decode_audio_batch: B=%d outside [1,%d]", B, TTS_MAX_B);
+  const int32_t* ptrs[TTS_MAX_B];
+  int ctx0 = -1;
+  for (int b = 0; b < B; ++b) {
+    const int slot = slots_h[b];
+    S2S_REQUIRE(slot >= 0 && slot < c.max_sessions && m->sess[slot].active, "qwen3tts decode_audio_batch: bad slot %d", slot);
+    const int frames = m->sess[slot].frames;
+    S2S_REQUIRE(n_new >= 1 && n_new <= frames, "qwen3tts decode_audio_batch: n_new=%d but slot %d holds %d frames", n_new, slot, frames);
+    const int start = frames - n_new;
+    const int ctx = (start - left_context > 0) ? left_context : start;   // Qwen3OmniMoeCode2Wav.chunked_decode (:3786)
+    if (ctx0 < 0) ctx0 = ctx;
+    S2S_REQUIRE(ctx == ctx0, "qwen3tts decode_audio_batch: slot %d has %d frames of history, the batch %d (group equal shapes)", slot, ctx, ctx0);
+    ptrs[b] = m->history + (long long)slot * m->history_stride + (long long)(start - ctx) * c.n_groups;
+  }
+  return codec_decode_batch(m->codec, ptrs, B, ctx0 + n_new, ctx0, wav_out_d, wav_stride, n_out_h, nullptr, (cudaStream_t)stream);
+}
+
 int s2s_qwen3tts_set_frames(s2s_qwen3tts* m, int32_t slot, int32_t n_frames) {
   S2S_REQUIRE(m && slot >= 0 && slot < m->cfg.max_sessions, "qwen3tts set_frames: bad slot");
   S2S_REQUIRE(n_frames >= 0 && n_frames <= m->sess[slot].frames, "qwen3tts set_frames: %d outside [0,%d]", n_frames, m->sess[slot].frames);

@@ -356,7 +356,7 @@ def _bind_all(lib_fn, handle, weights: Mapping[str, "np.ndarray | torch.Tensor"]
               f"{what} bind_tensor({prefix}{name})")
 
 
-def codec_config(g: Mapping, max_frames: int = 40) -> CodecConfig:
+def codec_config(g: Mapping, max_frames: int = 40, precision: int = 1, max_batch: int = 1) -> CodecConfig:
     """CodecConfig from a geometry mapping (oracle.code2wav_ref.Code2WavGeometry.to_dict() field names)."""
     cfg = CodecConfig()
     cfg.codebook_size, cfg.hidden, cfg.heads, cfg.kv_heads = int(g["codebook_size"]), int(g["hidden"]), int(g["heads"]), int(g["kv_heads"])
@@ -370,13 +370,15 @@ def codec_config(g: Mapping, max_frames: int = 40) -> CodecConfig:
     cfg.decoder_dim, cfg.sliding_window = int(g["decoder_dim"]), int(g["sliding_window"])
     cfg.rope_theta, cfg.rms_eps = float(g.get("rope_theta", 10000.0)), float(g.get("rms_eps", 1e-5))
     cfg.max_frames = int(max_frames)
+    cfg.max_batch = int(max_batch)
+    cfg.precision = int(g.get("precision", precision))   # 0: fp32 parity mode, 1: fp16 tensor-core contractions
     return cfg
 
 
 class CodecEngine:
     """Codebook ids -> 24 kHz waveform on one B200 (the codec-decoder half of the TTS slot; csrc/codec_decode.cu)."""
 
-    def __init__(self, geometry: Mapping, max_frames: int = 40, device: int = 0, _handle=None, _owner=None):
+    def __init__(self, geometry: Mapping, max_frames: int = 40, device: int = 0, precision: int = 1, _handle=None, _owner=None):
         self.lib = _lib.load()
         self.device = device
         self.ctx = get_context(device)
@@ -385,7 +387,7 @@ class CodecEngine:
         if _handle is not None:
             self.handle = _handle
             return
-        self.cfg = codec_config(self.geometry, max_frames)
+        self.cfg = codec_config(self.geometry, max_frames, precision)
         self.handle = C.c_void_p()
         check(self.lib.s2s_codec_create(self.ctx, C.byref(self.cfg), C.byref(self.handle)), "s2s_codec_create")
 
@@ -432,7 +434,7 @@ class Qwen3TTSEngine:
     oracle.qwen3tts_ref.TTSGeometry.to_dict(); codec geometry = oracle.code2wav_ref.Code2WavGeometry.to_dict()."""
 
     def __init__(self, geometry: Mapping, codec_geometry: Mapping, dtype: str = "bfloat16", max_sessions: int = 4,
-                 max_positions: int = 1024, max_text: int = 256, codec_max_frames: int = 40, device: int = 0):
+                 max_positions: int = 1024, max_text: int = 256, codec_max_frames: int = 40, device: int = 0, codec_precision: int = 1):
         self.lib = _lib.load()
         self.device = device
         self.ctx = get_context(device)
@@ -451,7 +453,7 @@ class Qwen3TTSEngine:
         for k in ("codec_eos", "codec_nothink", "codec_think_bos", "codec_think_eos", "codec_pad", "codec_bos",
                   "tts_bos", "tts_eos", "tts_pad", "im_start", "assistant", "newline"):
             setattr(cfg, k, int(g[k]))
-        cfg.codec = codec_config(codec_geometry, codec_max_frames)
+        cfg.codec = codec_config(codec_geometry, codec_max_frames, codec_precision, max_batch=min(16, max_sessions))
         self.cfg = cfg
         self.n_groups = cfg.n_groups
         self.codec_eos = cfg.codec_eos
@@ -501,6 +503,22 @@ class Qwen3TTSEngine:
         check(self.lib.s2s_qwen3tts_decode_audio(self.handle, slot, n_new, left_context, _ptr(wav), C.byref(n), _stream_ptr(self.device)),
               "s2s_qwen3tts_decode_audio")
         return wav[: n.value]
+
+    def decode_audio_batch(self, slots: Sequence[int], n_new: int, left_context: int = 25) -> list:
+        """Waveforms of the newest n_new frames of several sessions whose chunks have the same shape, in ONE launch sequence.
+        -> list of f32 cuda tensors (views of one buffer)."""
+        sl, B = _lib.i32_array(slots)
+        cap = self.codec.samples(min(n_new + left_context, self.cfg.codec.max_frames))
+        wav = torch.empty((B, cap), dtype=torch.float32, device=f"cuda:{self.device}")
+        n = C.c_int32(0)
+        check(self.lib.s2s_qwen3tts_decode_audio_batch(self.handle, sl, B, n_new, left_context, _ptr(wav), cap, C.byref(n),
+                                                       _stream_ptr(self.device)), "s2s_qwen3tts_decode_audio_batch")
+        return [wav[b, : n.value] for b in range(B)]
+
+    def history_context(self, slot: int, n_new: int, left_context: int = 25) -> int:
+        """Frames of history the next decode_audio(slot, n_new) will decode behind (chunked_decode's rule)."""
+        start = self.frames(slot) - n_new
+        return left_context if start - left_context > 0 else start
 
     def close(self) -> None:
         if self.handle:

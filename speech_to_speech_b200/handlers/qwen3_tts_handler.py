@@ -69,13 +69,16 @@ class B200Qwen3TTSHandler(_Base):  # type: ignore[misc, valid-type]
         dt = "float16" if self.dtype == torch.float16 else "bfloat16"
         dev = int(device.split(":")[1]) if ":" in device else 0
         n = max(1, self._b200_max_sessions)
-        key = ("qwen3tts", model_name, dt, dev, n)
+        # the reference slot's `parity_mode` (qwen3_tts_arguments.py:99-101) selects the exact fp32 codec decoder
+        prec = 0 if getattr(self, "parity_mode", False) else 1
+        key = ("qwen3tts", model_name, dt, dev, n, prec)
 
         def build() -> B200Qwen3TTS:
             if model_name.startswith("random:"):
-                return B200Qwen3TTS.from_random(model_name.split(":", 1)[1], seed=self._b200_seed, dtype=dt, device=dev, max_sessions=n)
+                return B200Qwen3TTS.from_random(model_name.split(":", 1)[1], seed=self._b200_seed, dtype=dt, device=dev, max_sessions=n,
+                                                codec_precision=prec)
             return B200Qwen3TTS.from_pretrained(model_name, device=device, dtype=self.dtype, attn_implementation=attn_implementation,
-                                                backend=backend, max_sessions=n)
+                                                backend=backend, max_sessions=n, codec_precision=prec)
 
         self.model = acquire_shared(key, build, lambda m: m.close())
         self._b200_shared_key = key

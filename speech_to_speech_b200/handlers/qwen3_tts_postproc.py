@@ -38,6 +38,17 @@ class TTSPostProcessor:
                                            E._stream_ptr(self.device)), "s2s_tts_postproc")
         return out[: n_out.value].cpu().numpy()
 
+    def to_int16_device(self, x24k):
+        """Device in, device out (int16 cuda tensor): the kernel alone, for device-timed measurements."""
+        torch, E = self._torch, self._E
+        x = x24k.contiguous()
+        n = x.numel()
+        out = torch.empty(((2 * n + 2) // 3,), dtype=torch.int16, device=x.device)
+        n_out = C.c_int32(0)
+        E.check(self._lib.s2s_tts_postproc(self.ctx, E._ptr(x), n, E._ptr(self.taps), self.taps.numel(), E._ptr(out), C.byref(n_out),
+                                           E._stream_ptr(self.device)), "s2s_tts_postproc")
+        return out[: n_out.value]
+
     def from_device(self, x24k) -> np.ndarray:
         """f32[n] @ 24 kHz ALREADY ON THE DEVICE (the codec decoder's output) -> int16[ceil(2n/3)] @ 16 kHz (host): no H2D,
         and only int16 samples cross PCIe."""

@@ -113,19 +113,20 @@ class B200Qwen3TTS:
     @classmethod
     def from_random(cls, geometry: "str | Mapping" = "qwen3-tts-12hz", codec_geometry: "str | Mapping | None" = None, seed: int = 0,
                     dtype: str = "bfloat16", device: int = 0, max_sessions: int = 1, max_positions: int = 2048, max_text: int = 512,
-                    tokenize: Optional[Callable] = None, speakers: Optional[Mapping[str, int]] = None, **kw: Any) -> "B200Qwen3TTS":
+                    tokenize: Optional[Callable] = None, speakers: Optional[Mapping[str, int]] = None, codec_precision: int = 1,
+                    **kw: Any) -> "B200Qwen3TTS":
         from . import engine as E
         g = TTS_GEOMETRIES[geometry] if isinstance(geometry, str) else dict(geometry)
         cg = codec_geometry if codec_geometry is not None else (geometry if isinstance(geometry, str) else "qwen3-tts-12hz")
         cg = CODEC_GEOMETRIES[cg] if isinstance(cg, str) else dict(cg)
         eng = E.Qwen3TTSEngine(g, cg, dtype=dtype, max_sessions=max_sessions, max_positions=max_positions, max_text=max_text,
-                               codec_max_frames=LEFT_CONTEXT_FRAMES + 16, device=device)
+                               codec_max_frames=LEFT_CONTEXT_FRAMES + 16, device=device, codec_precision=codec_precision)
         eng.init_random(seed)
         return cls(eng, tokenize or byte_tokenizer(g["text_vocab"]), speakers or DEFAULT_SPEAKERS, max_sessions=max_sessions, **kw)
 
     @classmethod
     def from_pretrained(cls, model_name: str, device: Any = "cuda", dtype: Any = None, attn_implementation: str = "eager",
-                        backend: str = "torch", max_sessions: int = 1, **_ignored: Any) -> "B200Qwen3TTS":
+                        backend: str = "torch", max_sessions: int = 1, codec_precision: int = 1, **_ignored: Any) -> "B200Qwen3TTS":
         """Load a checkpoint DIRECTORY in the cousin's layout: `config.json` with {"talker": ..., "code2wav": ..., "speaker_id":
         ...}, `model.safetensors` with the talker state dict (+ "text_embedding.weight", "code2wav.*") and tokenizer files.
         Hub ids cannot be resolved offline, and the real Qwen3-TTS checkpoint layout is unverified (upstream absent): both
@@ -146,7 +147,8 @@ class B200Qwen3TTS:
         g, cg = cfg["talker"], cfg["code2wav"]
         dev = int(str(device).split(":")[1]) if ":" in str(device) else 0
         dt = "float16" if dtype in (torch.float16, "float16") else "bfloat16"
-        eng = E.Qwen3TTSEngine(g, cg, dtype=dt, max_sessions=max_sessions, codec_max_frames=LEFT_CONTEXT_FRAMES + 16, device=dev)
+        eng = E.Qwen3TTSEngine(g, cg, dtype=dt, max_sessions=max_sessions, codec_max_frames=LEFT_CONTEXT_FRAMES + 16, device=dev,
+                               codec_precision=codec_precision)
         sd = load_file(os.path.join(model_name, "model.safetensors"))
         eng.load_state_dict({k: v for k, v in sd.items() if not k.startswith("code2wav.")},
                             {k[len("code2wav."):]: v for k, v in sd.items() if k.startswith("code2wav.")})
@@ -195,11 +197,28 @@ class B200Qwen3TTS:
             self._slot_cv.notify()
 
     def _run_frames(self, key: Any, slots: list) -> list:
-        """SessionBatcher callback: `key` = frames per chunk; one decode_frames call for all the sessions that asked."""
+        """SessionBatcher callback: `key` = frames per chunk.  ONE decode_frames call for all the sessions that asked, then the
+        codec decoder once per group of sessions whose chunks have the same shape (same valid frames, same history).
+        -> per session (valid frames, finished, waveform on the device or None)."""
+        eng, n = self.engine, int(key)
         with self._lock:
-            codes = self.engine.decode_frames(slots, int(key))
-            host = codes.cpu().numpy()          # B x n x 16 int32: the only per-chunk D2H besides the audio itself
-        return [host[i] for i in range(len(slots))]
+            before = [eng.frames(s) for s in slots]
+            host = eng.decode_frames(slots, n).cpu().numpy()   # B x n x 16 int32: the only per-chunk D2H besides the audio
+            groups: dict = {}
+            out: list = [None] * len(slots)
+            for i, s in enumerate(slots):
+                eos = np.nonzero(host[i][:, 0] == eng.codec_eos)[0]
+                valid = int(eos[0]) if len(eos) else n
+                if valid < n:
+                    eng.set_frames(s, before[i] + valid)
+                out[i] = (valid, valid < n, None)
+                if valid > 0:
+                    groups.setdefault((valid, eng.history_context(s, valid, LEFT_CONTEXT_FRAMES)), []).append(i)
+            for (valid, _ctx), idx in groups.items():
+                wavs = eng.decode_audio_batch([slots[i] for i in idx], valid, LEFT_CONTEXT_FRAMES)
+                for i, w in zip(idx, wavs):
+                    out[i] = (valid, out[i][1], w)
+        return out
 
     def _generate(self, text_ids: Sequence[int], speaker_id: int, chunk_size: int, max_new_tokens: int) -> Iterator[tuple]:
         eng = self.engine
@@ -214,17 +233,11 @@ class B200Qwen3TTS:
             done = 0
             while done < budget:
                 n = min(chunk, budget - done)
-                codes = self.batcher.call(n, slot) if self.batcher is not None else self._run_frames(n, [slot])[0]
-                eos = np.nonzero(codes[:, 0] == eng.codec_eos)[0]
-                valid = int(eos[0]) if len(eos) else n
-                with self._lock:
-                    if valid < n:
-                        eng.set_frames(slot, done + valid)
-                    wav = eng.decode_audio(slot, valid, LEFT_CONTEXT_FRAMES) if valid > 0 else None
+                valid, finished, wav = self.batcher.call(n, slot) if self.batcher is not None else self._run_frames(n, [slot])[0]
                 done += valid
                 if wav is not None and wav.numel() > 0:
                     yield DeviceAudio(wav), SAMPLE_RATE, {"frames": done, "elapsed_s": perf_counter() - t0}
-                if valid < n:
+                if finished:
                     break
         finally:
             self._release_slot(slot)

@@ -23,7 +23,7 @@ def _engine(E, dtype="float16", **kw):
     cg = C.Code2WavGeometry(**{**cg.to_dict(), "quantizers": g.n_groups, "codebook_size": g.predictor.vocab,
                                "upsample_rates": tuple(cg.upsample_rates), "upsampling_ratios": tuple(cg.upsampling_ratios)})
     w, cw = R.make_weights(g, 0), C.make_weights(cg, 0)
-    eng = E.Qwen3TTSEngine(g.to_dict(), cg.to_dict(), dtype=dtype, max_positions=128, max_text=64, **kw)
+    eng = E.Qwen3TTSEngine(g.to_dict(), cg.to_dict(), dtype=dtype, max_positions=128, max_text=64, codec_precision=0, **kw)
     eng.load_state_dict(w, cw)
     return g, cg, w, cw, eng
 
@@ -139,3 +139,24 @@ def test_streaming_audio_matches_the_oracle_chunked_decode(E):
     got = np.concatenate(outs)
     assert got.shape == wav_ref.shape
     assert np.abs(got - wav_ref).max() < 1e-3
+
+
+def test_batched_audio_decode_equals_per_session_decode(E):
+    """Three speaking sessions with chunks of the same shape through ONE codec launch sequence == each alone, bit for bit
+    (every output row depends on its own sequence only), in both codec precisions."""
+    for prec in (0, 1):
+        g, cg = R.GEOMETRIES["micro"], C.GEOMETRIES["micro"]
+        cg = C.Code2WavGeometry(**{**cg.to_dict(), "quantizers": g.n_groups, "codebook_size": g.predictor.vocab,
+                                   "upsample_rates": tuple(cg.upsample_rates), "upsampling_ratios": tuple(cg.upsampling_ratios)})
+        eng = E.Qwen3TTSEngine(g.to_dict(), cg.to_dict(), dtype="float16", max_sessions=3, max_positions=128, max_text=64,
+                               codec_precision=prec)
+        eng.load_state_dict(R.make_weights(g, 0), C.make_weights(cg, 0))
+        for slot, text in enumerate(([1, 2, 3], [9, 8], [4, 4, 4, 4])):
+            eng.prefill(slot, text, 2301)
+        for n in (8, 8, 5):     # history 0, 8, 16 frames behind the chunk
+            eng.decode_frames([0, 1, 2], n)
+            together = [w.cpu().numpy().copy() for w in eng.decode_audio_batch([0, 1, 2], n, 25)]
+            for slot in range(3):
+                alone = eng.decode_audio(slot, n, 25).cpu().numpy()
+                assert np.array_equal(alone, together[slot]), (prec, n, slot)
+        eng.close()
