@@ -106,7 +106,7 @@ def test_batched_sessions_equal_oracle_and_single_runs(E):
     eng.prefill(3, texts[3], speakers[3]); eng.prefill(1, texts[1], speakers[1])
     whole = eng.decode_frames([3, 1], 7).cpu().numpy()
     assert np.array_equal(np.concatenate([a, b], 1), whole)
-    assert eng.frames(3) == 7 and eng.frames(0) == 7
+    assert eng.frames(3) == 7 and eng.frames(1) == 7 and eng.frames(0) == 0   # slot 0 was re-prefilled and not decoded since
 
 
 def test_persistent_launch_equals_per_phase_launches(E, monkeypatch):
