@@ -166,31 +166,31 @@ def run_reference_stt(model, fe, audio):
                               return_timestamps=False)
 
 
-LLM_SAMPLE_LAYERS, LLM_SAMPLE_TOKENS = 4, 16
+LLM_SAMPLE_LAYERS, LLM_SAMPLE_TOKENS = 2, 8
 
 
 def cpu_turn(n_turns: int, threads: int) -> dict:
     """The reference's CPU implementation of the turn on `threads` host threads: transformers Whisper-small generate fp32 (in
-    full: the call WhisperSTTHandler makes) + transformers LlamaForCausalLM at the Llama-3-8B layer geometry, a bounded sample
-    (4 of 32 layers, 16 of 128 reply tokens after the 64-token prompt, bf16) scaled by 32/4 x 128/16 -- the lm_head / embedding
-    cost is counted once per token at full width.  TTS: n/a (faster-qwen3-tts is not installed anywhere), so the
-    CPU turn is STT + LLM only, which flatters the CPU arm."""
+    full: the call WhisperSTTHandler makes) + the transformers Llama decoder stack at the Llama-3-8B layer geometry, a bounded
+    sample (2 of 32 layers, the 64-token prompt + 8 of 128 reply tokens through the KV cache, fp32) scaled by 32/2 x 128/8;
+    embedding and lm_head are left out of the sample, which flatters the CPU arm.  TTS: n/a (faster-qwen3-tts is not installed
+    anywhere), so the CPU turn is STT + LLM only -- again in the CPU arm's favour."""
     import logging
     import torch
     from oracle import weights as W
     torch.set_num_threads(threads)
     logging.getLogger("transformers").setLevel(logging.ERROR)
-    from transformers import LlamaConfig, LlamaForCausalLM, WhisperFeatureExtractor
+    from transformers import LlamaConfig, LlamaModel, WhisperFeatureExtractor
     g = W.WHISPER_GEOMETRIES[MODEL]
     model = build_hf_whisper(g)
     fe = WhisperFeatureExtractor(feature_size=g.n_mels)
     lg = W.LLAMA_GEOMETRIES["llama-3-8b"]
-    cfg = LlamaConfig(vocab_size=lg.vocab, hidden_size=lg.d_model, intermediate_size=lg.ffn, num_hidden_layers=LLM_SAMPLE_LAYERS,
+    cfg = LlamaConfig(vocab_size=1024, hidden_size=lg.d_model, intermediate_size=lg.ffn, num_hidden_layers=LLM_SAMPLE_LAYERS,
                       num_attention_heads=lg.heads, num_key_value_heads=lg.kv_heads, head_dim=lg.head_dim, rms_norm_eps=lg.rms_eps,
-                      rope_theta=lg.rope_theta, tie_word_embeddings=False)
+                      rope_theta=lg.rope_theta)
     torch.manual_seed(1)
-    llm = LlamaForCausalLM(cfg).to(torch.bfloat16).eval()
-    prompt = torch.randint(0, lg.vocab, (1, LLM_PROMPT))
+    llm = LlamaModel(cfg).eval()
+    prompt = torch.randint(0, 1024, (1, LLM_PROMPT))
     run_reference_stt(model, fe, W.synthetic_audio(0, N_SAMPLES))          # warm-up
     stt_s, llm_s = [], []
     for i in range(n_turns):
@@ -198,19 +198,23 @@ def cpu_turn(n_turns: int, threads: int) -> dict:
         t = time.perf_counter()
         run_reference_stt(model, fe, a)
         stt_s.append(time.perf_counter() - t)
-        t = time.perf_counter()
         with torch.no_grad():
-            llm.generate(prompt, max_new_tokens=LLM_SAMPLE_TOKENS, min_new_tokens=LLM_SAMPLE_TOKENS, do_sample=False, pad_token_id=0)
-        llm_s.append(time.perf_counter() - t)
+            out = llm(prompt, use_cache=True)                               # prefill (not timed: the GPU arm's prefill is small too)
+            kv, tok = out.past_key_values, prompt[:, -1:]
+            t = time.perf_counter()
+            for _ in range(LLM_SAMPLE_TOKENS):
+                out = llm(tok, past_key_values=kv, use_cache=True)
+                kv = out.past_key_values
+            llm_s.append(time.perf_counter() - t)
     stt, llm_sample = sum(stt_s) / len(stt_s), sum(llm_s) / len(llm_s)
     llm_full = llm_sample * (32 / LLM_SAMPLE_LAYERS) * (MAX_NEW / LLM_SAMPLE_TOKENS)
     turn = stt + llm_full
     return {"value": CYCLE_S / turn, "unit": "sessions", "cores": threads, "kind": "reference",
             "turn_s": turn, "stt_s": stt, "llm_s_scaled": llm_full,
             "sample": f"{n_turns} turn(s): transformers {__import__('transformers').__version__} WhisperForConditionalGeneration.generate fp32 "
-                      f"in full ({stt:.2f} s) + LlamaForCausalLM bf16 {LLM_SAMPLE_LAYERS}/32 layers x {LLM_SAMPLE_TOKENS}/128 tokens "
-                      f"({llm_sample:.2f} s, scaled to {llm_full:.1f} s); TTS n/a; torch.set_num_threads({threads}) of {os.cpu_count()} cpus; "
-                      "faster-whisper unavailable, transformers CPU path timed instead; faster-qwen3-tts unavailable"}
+                      f"in full ({stt:.2f} s) + LlamaModel fp32 decode {LLM_SAMPLE_LAYERS}/32 layers x {LLM_SAMPLE_TOKENS}/128 tokens "
+                      f"({llm_sample:.2f} s, scaled to {llm_full:.1f} s; embedding / lm_head not counted); TTS n/a; torch.set_num_threads({threads}) "
+                      f"of {os.cpu_count()} cpus; faster-whisper unavailable, transformers CPU path timed instead; faster-qwen3-tts unavailable"}
 
 
 def reference_arm(args, rank, world):
@@ -232,6 +236,14 @@ def reference_arm(args, rank, world):
 
 
 # =============================================================================================== B200 arm
+_T0 = time.perf_counter()
+
+
+def log(msg: str) -> None:
+    """Progress on stderr (the JSON line is the only thing on stdout)."""
+    print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 class Stack:
     """The three engines of one GPU, shared by all its sessions (one weight copy each)."""
 
@@ -415,6 +427,7 @@ def main():
     dev = f"cuda:{local_rank}"
     S = args.sessions
     st = Stack(E, W, local_rank, S)
+    log(f"engines built: llm max batch {st.llm_b}, tts max batch {st.tts_b}")
 
     # ---- session-shard split: the ingest rank (0) holds every session's PCM and scatters each rank its shard over NCCL -------
     layout = shard.shard_layout(world * S, world)
@@ -440,9 +453,10 @@ def main():
         ev["frames_mark"] = []
         return ev
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         wave_device(st, pcm_dev, new_events())
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        log(f"warm-up wave {i} done")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -463,6 +477,7 @@ def main():
         torch.cuda.cudart().cudaProfilerStop()
     wall_s = time.perf_counter() - t_wall
     launches = E.launch_count(local_rank, reset=True)
+    log(f"timed region done: {wall_s:.2f} s for {args.steps} wave(s), {launches} launches")
 
     def stage(ev, a, b):
         return ev[a].elapsed_time(ev[b])
@@ -490,14 +505,18 @@ def main():
     if not args.no_e2e:
         try:
             handlers = make_handlers(S, local_rank)
+            log("handler instances built and warmed up")
             auds = [pcm_dev[i].cpu().numpy() for i in range(S)]
             e2e_wave(handlers[:1], auds, 1)                                    # warm-up
-            single = [e2e_wave(handlers[:1], auds, 1) for _ in range(3)]
+            single = [e2e_wave(handlers[:1], auds, 1) for _ in range(2)]
+            log(f"single-session e2e: {[round(w['wall_s'], 2) for w in single]} s, errors {single[-1]['errors']}")
             e2e_wave(handlers, auds, S)                                        # warm-up of the loaded path
+            log("loaded e2e warm-up wave done")
             barrier()
-            loaded = [e2e_wave(handlers, auds, S) for _ in range(max(1, min(args.steps, 2)))]
+            loaded = [e2e_wave(handlers, auds, S) for _ in range(2 if args.steps >= 4 else 1)]
             barrier()
             e2e = {"single": single, "loaded": loaded}
+            log(f"loaded e2e waves: {[round(w['wall_s'], 2) for w in loaded]} s")
             for hs in handlers:
                 for h in hs:
                     try:

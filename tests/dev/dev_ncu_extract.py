@@ -31,7 +31,7 @@ def launches(src, dst):
         agg[name] = (n + 1, t + v)
     tot = sum(t for _, t in agg.values())
     with open(dst, "w") as f:
-        f.write("# ncu launch list of the device-timed region of `bench.py --steps 2 --warmup 3 --profile-region --batch 0 --no-turn --no-cpu-baseline`\n"
+        f.write("# ncu launch list of the device-timed region of `bench.py --steps 1 --warmup 3 --profile-region --no-e2e --no-cpu-baseline`\n"
                 "# ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off ; cold-cache + serialised: compare SHARES\n")
         f.write(f"{'kernel':64s} {'launches':>8s} {'total_us':>11s} {'share':>7s}\n")
         for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -40,7 +40,7 @@ def launches(src, dst):
 
 
 def reps(dst, files):
-    out = ["# ncu summaries, round 1 (final)\n",
+    out = [f"# ncu summaries ({os.path.basename(dst)})\n",
            "Captured on a B200 with `ncu --set full --clock-control none --import-source on -k regex:<kernel>` (the .ncu-rep files stay in",
            "gpurun_out/, which is scratch); extracted with `ncu -i <rep> --page raw --csv`.  Durations under ncu are NOT bench numbers.\n"]
     traffic = {}
@@ -62,14 +62,20 @@ def reps(dst, files):
                 v, u = vals.get(k, ("0", "byte"))
                 v = float(v.replace(",", ""))
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
+            key = None
             if "whisper_decode" in name:
-                key = "cluster_b1" if "cluster" in name else "grid_b16"   # the captures of tests/dev/dev_ncu_decode.py 1 / 16
+                key = "whisper_decode_cluster" if "cluster" in name else "whisper_decode"
+            elif "llama_decode_kernel" in name:
+                key = "llama_decode"
+            elif "conv1d_tc" in name:
+                key = "conv1d_tc"
+            if key and key not in traffic:
                 traffic[key] = {"kernel": name.split("(")[0], "dram_bytes_per_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
-                                "source": os.path.basename(fpath)}
+                                "duration_under_ncu": vals.get("gpu__time_duration.sum"), "source": os.path.basename(fpath)}
         out.append("")
     open(dst, "w").write("\n".join(out) + "\n")
     if traffic:
-        json.dump(traffic, open(os.path.join(os.path.dirname(dst), "ncu_decode_traffic.json"), "w"), indent=1)
+        json.dump(traffic, open(os.path.join(os.path.dirname(dst), "ncu_traffic_r2.json"), "w"), indent=1)
     print("\n".join(out))
 
 
