@@ -128,11 +128,15 @@ struct DecSmem {
   unsigned int aux_off;    // sv
   unsigned int si_off, red_s_off, wb_off, redbuf_off, ring_off;
 };
-__host__ __device__ inline DecSmem dec_smem_layout(int B, int d, int kmax, int wb_floats) {
+// rg: rows of the fp32 statistics copy that are resident at a time (stage_rows_norm walks the B rows in groups of rg; rg = B
+// = everything in one memory round trip, the default); kmax: widest activation operand that is staged WHOLE (a wider one is
+// staged in K-chunks of kmax columns, gemv_mma_chunked).
+__host__ __device__ inline DecSmem dec_smem_layout(int B, int d, int kmax, int wb_floats, int rg = 0) {
   DecSmem L;
+  if (rg <= 0 || rg > B) rg = B;
   const unsigned int xh_small = (((unsigned)B * (unsigned)(d + GV_XPAD) * 2u) + 15u) & ~15u;
   unsigned int xh_bytes = (unsigned)B * (unsigned)(kmax + GV_XPAD) * 2u;
-  const unsigned int with_stats = xh_small + (unsigned)B * (unsigned)d * 4u;
+  const unsigned int with_stats = xh_small + (unsigned)rg * (unsigned)d * 4u;
   if (with_stats > xh_bytes) xh_bytes = with_stats;
   xh_bytes = (xh_bytes + 127u) & ~127u;
   L.xs_off = xh_small;
@@ -232,15 +236,21 @@ static __device__ __forceinline__ void norm_from_smem(const float* xs, int B, in
 
 template <typename T>
 static __device__ __noinline__ void stage_rows_norm(const float* x, int B, int d, float* xs, T* xh, int mode, const float* w,
-                                                    const float* bias, float eps, float* s_red, float* wb, int wb_ready) {
-  const int n = B * d;
+                                                    const float* bias, float eps, float* s_red, float* wb, int wb_ready, int rg = 0) {
+  if (rg <= 0 || rg > B) rg = B;
   const uint32_t xs_s = smem_u32(xs);
+  // rows in groups of rg (all of them at once unless the fp32 copy of B rows does not fit next to the 16-bit operand)
+#pragma unroll 1
+  for (int r0 = 0; r0 < B; r0 += rg) {
+    const int rows = min(rg, B - r0), n = rows * d;
+    const float* src = x + (long long)r0 * d;
 #pragma unroll 4
-  for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 4) cp_async16(xs_s + (uint32_t)i * 4, x + i);
-  if (!wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
-  cp_async_wait_all();
-  __syncthreads();
-  norm_from_smem<T>(xs, B, d, xh, mode, eps, s_red, wb);
+    for (int i = threadIdx.x * 4; i < n; i += DEC_THREADS * 4) cp_async16(xs_s + (uint32_t)i * 4, src + i);
+    if (r0 == 0 && !wb_ready) stage_norm_weights(w, mode == 1 ? bias : nullptr, d, wb);
+    cp_async_wait_all();
+    __syncthreads();
+    norm_from_smem<T>(xs, rows, d, xh + (long long)r0 * (d + GV_XPAD), mode, eps, s_red, wb);   // ends with a __syncthreads()
+  }
 }
 
 // Same, for a residual stream that is still in pieces: x_eff = x + add_bias + sum_p parts[p] (fixed order ->
@@ -336,6 +346,9 @@ struct GemvArgs {
   float* kraw;                 // Qwen3 (qk_norm): non-null -> q and k are stored RAW (fp32: q -> out, k -> kraw[b][k_rows]); the
                                // per-head RMSNorm + RoPE + cache append run in the following phase (llama_decode.cu ld_qknorm)
   int plan_id;                 // index into GemvRing::plans_s (>= 0) or -1: plan on the fly
+  // K-chunked operand (gemv_mma_chunked): kc > 0 -> the 16-bit activation [B, K] is NOT staged by the caller; it is staged
+  // here kc columns at a time from xsrc (row stride xsrc_ld), so a K wider than shared memory allows serves large batches
+  const void* xsrc; int xsrc_ld; int kc;
 };
 
 // epilogue of the row pair (row0, row0 + 1), row0 even, for session b.  v already carries the bias.
@@ -662,6 +675,138 @@ __device__ __noinline__ void gemv_mma(const GemvArgs& a, uint32_t xh_s, int B, f
       if (lo) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g, c[0] + bias0, c[1] + bias1, rl0, rl1, sup0, sup1, best_v[0], best_i[0]);
       if (hi) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g + 8, c[2] + bias0, c[3] + bias1, rh0, rh1, sup0, sup1, best_v[1], best_i[1]);
     }
+  }
+  ring.slot = cslot;
+  ring.parity = cpar;
+}
+
+// ---- the same projection with a K-chunked activation operand ----------------------------------------------------------
+// For K wider than the shared-memory operand region (Llama-3-8B down-projection: K = 14336 at 8+ sessions) the activation
+// [B, K] is staged kc columns at a time while the weights keep streaming through the ring.  The CTA -> tile assignment is
+// fixed over the chunks (every warp owns ONE (tile, K-slice) item: the plan of a [N, kc] projection), the accumulator
+// fragments live in registers across the chunks, and the K-split reduction + epilogue run once at the end -- so the result
+// is the same sum in a different association from the unchunked routine, and deterministic.
+// Host side: gemv_chunk_ok() says whether a shape satisfies the one-item-per-warp requirement.
+__host__ __device__ inline bool gemv_chunk_ok(int N, int K, int kc, int grid) {
+  if (kc <= 0 || (kc & 255) != 0 || K <= kc) return false;
+  GemvPlan pl;
+  gemv_make_plan_ex((N + GV_ROWS - 1) >> 3, kc, grid, 0, pl);
+  if (pl.main_rounds != 0) return false;
+  const int tail = pl.n_tiles, per_round = grid * (DEC_WARPS >> pl.ks_log);
+  if (tail > per_round) return false;                       // more than one item per warp
+  const int last = K % kc == 0 ? kc : K % kc;
+  return (last % (32 << pl.ks_log)) == 0;                   // the short last chunk still splits into whole k-windows
+}
+
+template <typename T, bool LLAMA>
+__device__ __noinline__ void gemv_mma_chunked(const GemvArgs& a, T* xh, int B, float (&best_v)[2], int (&best_i)[2], GemvRing& ring,
+                                              float4* red_s) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const T* __restrict__ W = reinterpret_cast<const T*>(a.W);
+  const T* __restrict__ X = reinterpret_cast<const T*>(a.xsrc);
+  const int N = a.N, K = a.K, KC = a.kc, mode = a.mode;
+  const int n_chunks = (K + KC - 1) / KC;
+  if (ring.pre_valid) __trap();                            // chunked projections are never prefetched across the barrier
+  GemvPlan pl;
+  gemv_make_plan(N, KC, pl);
+  if (pl.main_rounds != 0 || pl.tail_rounds > 1) __trap();  // gemv_chunk_ok() was not honoured by the launcher
+  const int ks = 1 << pl.ks_log, sl = warp & (ks - 1);
+  int tile, k0_full, klen_full;
+  const bool valid = pl.tail_rounds == 1 && gemv_item(pl, KC, 0, warp, tile, k0_full, klen_full);
+  const bool owner = valid && sl == 0;
+  const int row0 = tile * GV_ROWS + 2 * t;
+  const bool rows_ok = owner && row0 < N;
+  float bias0 = 0.f, bias1 = 0.f, rl0 = 0.f, rl1 = 0.f, rh0 = 0.f, rh1 = 0.f;
+  const bool lo = g < B, hi = g + 8 < B;
+  if (rows_ok) {
+    if (a.bias) { const float2 bb = __ldg(reinterpret_cast<const float2*>(a.bias + row0)); bias0 = bb.x; bias1 = bb.y; }
+    if (mode == EPI_RESID) {
+      if (lo) { const float2 r = __ldcg(reinterpret_cast<const float2*>(a.out + (long long)g * a.ldo + row0)); rl0 = r.x; rl1 = r.y; }
+      if (hi) { const float2 r = __ldcg(reinterpret_cast<const float2*>(a.out + (long long)(g + 8) * a.ldo + row0)); rh0 = r.x; rh1 = r.y; }
+    }
+  }
+  // producer cursor over this warp's unit stream: chunk pc, unit pu inside the chunk's slice
+  auto slice_of = [&](int c) { const int kcc = min(KC, K - c * KC); return kcc >> pl.ks_log; };
+  int pc = 0, pu = 0;
+  unsigned int pslot = ring.slot;
+  auto issue_next = [&](uint32_t dst, uint32_t bar) {
+    const int slice = slice_of(pc);
+    const int kb = pc * KC + sl * slice + pu * GV_UK;
+    const int len = min(GV_UK, slice - pu * GV_UK);
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(GV_ROWS * len * 2);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      bulk_g2s(dst, W + ((long long)tile * K + kb) * GV_ROWS, bytes, bar);
+    }
+    if (++pu * GV_UK >= slice) { pu = 0; ++pc; }
+  };
+  if (valid)
+    for (int n = 0; n < ring.slots && pc < n_chunks; ++n) {
+      issue_next(ring.base_s + pslot * GV_SLOT_BYTES, ring.bars_s + pslot * 8);
+      if (++pslot == (unsigned)ring.slots) pslot = 0;
+    }
+  unsigned int cslot = ring.slot, cpar = ring.parity;
+  const uint32_t xh_s = smem_u32(xh);
+  const uint32_t row_bytes = (uint32_t)(KC + GV_XPAD) * 2;
+  const uint32_t xrow_lo = xh_s + (uint32_t)g * row_bytes + (uint32_t)t * 16;
+  const uint32_t xrow_hi = xrow_lo + 8u * row_bytes;
+  const uint32_t wlane = (uint32_t)lane * 16;
+  float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int kcc = min(KC, K - ch * KC);
+    if (ch > 0) __syncthreads();                           // every warp is done with the previous chunk's operand
+    {   // stage columns [ch * KC, ch * KC + kcc) of the B rows
+      const int vpr = kcc >> 3, n = B * vpr;
+      int row = threadIdx.x / vpr, col = threadIdx.x - row * vpr;
+#pragma unroll 2
+      for (int i = threadIdx.x; i < n; i += DEC_THREADS) {
+        cp_async16(xh_s + row * row_bytes + (uint32_t)col * 16, reinterpret_cast<const uint4*>(X + (long long)row * a.xsrc_ld + ch * KC) + col);
+        col += DEC_THREADS;
+        while (col >= vpr) { col -= vpr; ++row; }
+      }
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    if (valid) {
+      const int slice = kcc >> pl.ks_log, k0 = sl * slice, upi = (slice + GV_UK - 1) >> 8;
+#pragma unroll 1
+      for (int u = 0; u < upi; ++u) {
+        mbar_wait_s(ring.bars_s + cslot * 8, cpar);
+        const uint32_t wsrc = ring.base_s + cslot * GV_SLOT_BYTES + wlane;
+        const int len = min(GV_UK, slice - u * GV_UK);
+        const uint32_t xk = (uint32_t)(k0 + u * GV_UK) * 2;
+#pragma unroll 4
+        for (int kk = 0; kk < len; kk += 32) {
+          const uint4 w = lds16(wsrc + kk * (GV_WIN_BYTES / 32));
+          uint4 xl = make_uint4(0u, 0u, 0u, 0u), xu = make_uint4(0u, 0u, 0u, 0u);
+          if (lo) xl = lds16(xrow_lo + xk + kk * 2);
+          if (hi) xu = lds16(xrow_hi + xk + kk * 2);
+          mma16816<T>(c, xl.x, xu.x, xl.y, xu.y, w.x, w.y);
+          mma16816<T>(e, xl.z, xu.z, xl.w, xu.w, w.z, w.w);
+        }
+        __syncwarp();
+        if (pc < n_chunks) issue_next(ring.base_s + cslot * GV_SLOT_BYTES, ring.bars_s + cslot * 8);   // refill the slot just drained
+        if (++cslot == (unsigned)ring.slots) { cslot = 0; cpar ^= 1u; }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] += e[i];
+  if (ks > 1) {
+    red_s[threadIdx.x] = make_float4(c[0], c[1], c[2], c[3]);
+    __syncthreads();
+    if (owner)
+#pragma unroll 1
+      for (int s = 1; s < ks; ++s) {
+        const float4 o = red_s[threadIdx.x + s * 32];
+        c[0] += o.x; c[1] += o.y; c[2] += o.z; c[3] += o.w;
+      }
+  }
+  if (rows_ok) {
+    if (lo) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g, c[0] + bias0, c[1] + bias1, rl0, rl1, 0, 0, best_v[0], best_i[0]);
+    if (hi) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g + 8, c[2] + bias0, c[3] + bias1, rh0, rh1, 0, 0, best_v[1], best_i[1]);
   }
   ring.slot = cslot;
   ring.parity = cpar;

@@ -186,6 +186,7 @@ __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, 
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
   a.pos = p.pos; a.slot = p.slot; a.kv_slot = p.kv_slot_stride; a.kv_ld = kvd; a.rope = p.rope; a.hd = p.hd;
   a.q_rows = qd; a.k_rows = kvd; a.q_scale = rsqrtf((float)p.hd); a.kraw = nullptr; a.plan_id = -1;
+  a.xsrc = nullptr; a.xsrc_ld = 0; a.kc = 0;
   const int kind = ld_kind(p, ph);
   if (kind < 6) {
     const int layer = ph / ld_nsub(p);
@@ -198,7 +199,10 @@ __device__ __forceinline__ bool ld_gemv_args(const LlamaDecParams& p, int step, 
         return true;
       case 2: a.W = w.w_o; a.N = d; a.K = qd; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; a.plan_id = 1; return true;
       case 3: a.W = w.w_gu; a.N = 2 * p.ffn; a.mode = EPI_SWIGLU; a.out_h = p.h; a.ldh = p.ffn; a.plan_id = 2; return true;
-      case 4: a.W = w.w_down; a.N = d; a.K = p.ffn; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; a.plan_id = 3; return true;
+      case 4:
+        a.W = w.w_down; a.N = d; a.K = p.ffn; a.mode = EPI_RESID; a.out = p.x; a.ldo = d; a.plan_id = 3;
+        if (p.down_kc > 0) { a.xsrc = p.h; a.xsrc_ld = p.ffn; a.kc = p.down_kc; a.plan_id = -1; }
+        return true;
       default: return false;
     }
   }
@@ -235,7 +239,7 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
     const int layer = ph / ld_nsub(p);
     const LlamaDecLayer& w = p.lw[layer];
     switch (kind) {
-      case 0: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm1, nullptr, p.eps, sm.s_red, sm.wb, wb_ready); break;
+      case 0: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm1, nullptr, p.eps, sm.s_red, sm.wb, wb_ready, p.norm_rg); break;
       case 1:
         if (p.hd == 128) ld_attn<T, 128>(p, layer, step, reinterpret_cast<float*>(sm.red));
         else ld_attn<T, 64>(p, layer, step, reinterpret_cast<float*>(sm.red));
@@ -244,8 +248,10 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
         if (p.hd == 128) ld_qknorm<T, 128>(p, layer); else ld_qknorm<T, 64>(p, layer);
         return;
       case 2: stage_rows_copy<T>(reinterpret_cast<const T*>(p.attn16), B, p.heads * p.hd, sm.xh); break;
-      case 3: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm2, nullptr, p.eps, sm.s_red, sm.wb, wb_ready); break;
-      default: stage_rows_copy<T>(reinterpret_cast<const T*>(p.h), B, p.ffn, sm.xh); break;
+      case 3: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm2, nullptr, p.eps, sm.s_red, sm.wb, wb_ready, p.norm_rg); break;
+      default:
+        if (a.kc > 0) { gemv_mma_chunked<T, true>(a, sm.xh, B, best_v, best_i, ring, sm.red); return; }
+        stage_rows_copy<T>(reinterpret_cast<const T*>(p.h), B, p.ffn, sm.xh); break;
     }
     gemv_mma<T, true>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     return;
@@ -253,7 +259,7 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
   if (kind == 6) {
     if (p.hidden_out && blockIdx.x == 0)  // the residual stream before the final norm (Qwen3-TTS: input of the code predictor)
       for (int i = threadIdx.x; i < B * d; i += DEC_THREADS) p.hidden_out[(long long)step * B * d + i] = __ldcg(p.x + i);
-    stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, p.norm_f, nullptr, p.eps, sm.s_red, sm.wb, wb_ready);
+    stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, p.norm_f, nullptr, p.eps, sm.s_red, sm.wb, wb_ready, p.norm_rg);
     gemv_mma<T, true>(a, smem_u32(sm.xh), B, best_v, best_i, ring, sm.red);
     gemv_argmax_candidates(best_v, best_i, B, sm.sv, sm.si, p.cand_val, p.cand_idx);
   } else {
@@ -277,7 +283,8 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   if (threadIdx.x == 0) { sp = p; sp.lw = s_layers; }
   for (int i = threadIdx.x; i < p.layers; i += DEC_THREADS) s_layers[i] = p.lw[i];
   __syncthreads();
-  const DecSmem lay = dec_smem_layout(p.B, p.d, ld_kmax(p.d, p.ffn, p.heads * p.hd), p.d);
+  const int kmax_whole = p.down_kc > 0 ? ld_kmax(p.d, p.down_kc, p.heads * p.hd) : ld_kmax(p.d, p.ffn, p.heads * p.hd);
+  const DecSmem lay = dec_smem_layout(p.B, p.d, kmax_whole, p.d, p.norm_rg);
   LdSmem<T> sm;
   sm.xh = reinterpret_cast<T*>(smem_raw);
   sm.xs = reinterpret_cast<float*>(smem_raw + lay.xs_off);
@@ -330,7 +337,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
             if (ld_has_gemv(sp, nstep, nph)) {
               if (threadIdx.x < 32) ld_gemv_args<T>(sp, nstep, nph, pre_args);  // one warp writes the shared struct
               __syncthreads();
-              gemv_prefetch<T>(pre_args, ring);
+              if (pre_args.kc == 0) gemv_prefetch<T>(pre_args, ring);   // a K-chunked projection starts its own stream
               pre_tag = nstep * n_ph + nph;
               const float* nw = nullptr;
               const int nk = ld_kind(sp, nph);
@@ -373,11 +380,13 @@ __global__ void llama_decode_init_kernel(const LlamaDecParams p) {
 
 template <typename T>
 int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
-  const DecSmem lay = dec_smem_layout(p.B, p.d, ld_kmax(p.d, p.ffn, p.heads * p.hd), p.d);
+  int kmax = 0, rg = 0, kc = 0, slots = 0;
+  S2S_REQUIRE(llama_decode_plan(p.B, p.d, p.ffn, p.heads * p.hd, ctx->num_sms, &kmax, &rg, &kc, &slots),
+              "llama decode: batch %d does not fit shared memory for d %d, ffn %d", p.B, p.d, p.ffn);
+  const DecSmem lay = dec_smem_layout(p.B, p.d, kmax, p.d, rg);
   LlamaDecParams pr = p;
   pr.sync_relaxed = dec_sync_relaxed_env();
-  pr.ring_slots = dec_ring_slots(lay);
-  S2S_REQUIRE(pr.ring_slots >= 2, "llama decode: batch %d x K %d does not fit shared memory", p.B, ld_kmax(p.d, p.ffn, p.heads * p.hd));
+  pr.ring_slots = slots; pr.norm_rg = rg; pr.down_kc = kc;
   const size_t smem = (size_t)lay.ring_off + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
   auto kern = llama_decode_kernel<T>;
   S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -416,8 +425,30 @@ int llama_decode_launch(s2s_ctx* ctx, const LlamaDecParams& p, int dtype, int de
   return S2S_ERR_UNSUPPORTED;
 }
 
+// Shared-memory plan of a batch.  Preferred: everything staged whole in one round trip (rg = B, kc = 0).  When that does not
+// leave two ring slots per warp: stage the ffn-wide down-projection operand in K-chunks of max(d, qd) columns and walk the
+// fp32 statistics copy in row groups (largest power of two that fits) -- Llama-3-8B: 4 sessions whole, 8 with chunks.
+bool llama_decode_plan(int B, int d, int ffn, int qd, int grid, int* kmax, int* rg, int* kc, int* ring_slots) {
+  {
+    const int km = ld_kmax(d, ffn, qd);
+    const int s = dec_ring_slots(dec_smem_layout(B, d, km, d, B));
+    if (s >= 2) { *kmax = km; *rg = B; *kc = 0; *ring_slots = s; return true; }
+  }
+  const int lim = ((std::max(d, qd) + 255) / 256) * 256;     // chunk = the widest operand that is staged whole anyway
+  if (ffn <= lim || !gemv_chunk_ok(d, ffn, lim, grid)) return false;
+  const int km = ld_kmax(d, lim, qd);
+  for (int g = B; g >= 2; g >>= 1) {
+    int gg = 1;
+    while (gg * 2 <= g) gg *= 2;
+    const int s = dec_ring_slots(dec_smem_layout(B, d, km, d, gg));
+    if (s >= 2) { *kmax = km; *rg = gg; *kc = lim; *ring_slots = s; return true; }
+  }
+  return false;
+}
+
 int llama_decode_max_batch(int d, int ffn, int qd) {
+  int kmax, rg, kc, slots;
   for (int B = DEC_MAX_B; B >= 1; --B)
-    if (dec_ring_slots(dec_smem_layout(B, d, ld_kmax(d, ffn, qd), d)) >= 2) return B;
+    if (llama_decode_plan(B, d, ffn, qd, 148, &kmax, &rg, &kc, &slots)) return B;
   return 0;
 }

@@ -181,7 +181,7 @@ __device__ __forceinline__ bool wd_gemv_args(const WhisperDecParams& p, int step
   const int L = p.layers, pos = step, d = p.d, B = p.B;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
-  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.kraw = nullptr; a.plan_id = 1;
+  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.kraw = nullptr; a.xsrc = nullptr; a.xsrc_ld = 0; a.kc = 0; a.plan_id = 1;
   if (ph < 8 * L) {
     const int layer = ph >> 3;
     const WhisperDecLayer& w = p.lw[layer];
@@ -421,7 +421,7 @@ __device__ __forceinline__ bool wdc_gemv_args(const WhisperDecParams& p, const W
   const int L = p.layers, pos = step, d = p.d, B = p.B;
   a.K = d; a.mode = EPI_STORE; a.out = p.q; a.ldo = d; a.out_h = nullptr; a.ldh = 0; a.d = d; a.kv0 = nullptr; a.kv_which = 0; a.kv_batch = 0;
   a.suppress = nullptr; a.first_step = 0; a.logits_out = nullptr; a.logits_ld = 0; a.bias = nullptr; a.W = nullptr; a.N = 0;
-  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.kraw = nullptr; a.plan_id = -1;
+  a.pos = nullptr; a.slot = nullptr; a.kv_slot = 0; a.kv_ld = 0; a.rope = nullptr; a.hd = HD; a.q_rows = 0; a.k_rows = 0; a.q_scale = 1.f; a.kraw = nullptr; a.xsrc = nullptr; a.xsrc_ld = 0; a.kc = 0; a.plan_id = -1;
   if (ph < 4 * L) {
     const int layer = ph >> 2;
     const WhisperDecLayer& w = p.lw[layer];
