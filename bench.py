@@ -262,7 +262,8 @@ class Stack:
                                             max_positions=max(F1, F2) + 32, max_text=128)
         self.opts = E.WhisperDecodeOptions(prefix=PREFIX, eos_id=-1, max_new_tokens=MAX_NEW, suppress=SUPPRESS,
                                            begin_suppress=BEGIN_SUPPRESS)
-        self.llm_b = self.llm.max_decode_batch()
+        mb = self.llm.max_decode_batch()
+        self.llm_b = -(-S // (-(-S // mb)))          # balanced launches: 16 sessions, 12 per launch at most -> 8 + 8
         self.tts_b = self.tts.engine.max_batch()
         self.prompt = np.random.default_rng(0).integers(0, self.lg.vocab, LLM_PROMPT).tolist()
         from speech_to_speech_b200.handlers.qwen3_tts_postproc import TTSPostProcessor

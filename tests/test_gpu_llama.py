@@ -189,3 +189,35 @@ def test_qwen3_decode_matches_debug_phases_and_oracle_batch(E, monkeypatch):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     for s in range(3):
         assert np.abs(outs[0][1][:, s] - refs[s][1][1:]).max() < TOL["float16"], s
+
+
+def test_llama3_8b_geometry_eight_sessions_k_chunked_down_projection(E):
+    """Llama-3-8B layer shapes, 2 layers, EIGHT sessions of different lengths in one launch: beyond 4 sessions the ffn-wide
+    (14336) down-projection operand is staged in K-chunks of 4096 columns and the RMSNorm statistics copy in row groups
+    (llama_decode_plan).  fp16 operands for a tight tolerance; every session's logits against the oracle, and the chunked
+    launch against the same sessions decoded 4 + 4 through the unchunked path."""
+    g = W.LLAMA_GEOMETRIES["llama-3-8b-2l"]
+    w = W.make_llama_weights(g, 0)
+    eng = E.LlamaEngine(g.to_dict(), dtype="float16", max_sessions=8, max_positions=128, max_prefill=64)
+    eng.load_state_dict(w)
+    assert eng.max_decode_batch() >= 8
+    rng = np.random.default_rng(31)
+    prompts = [rng.integers(0, g.vocab, 4 + 5 * s) for s in range(8)]
+    refs = [R.greedy_generate(w, g, p, 4, return_logits=True) for p in prompts]
+    first = torch.tensor([r[0][0] for r in refs], dtype=torch.int32, device="cuda")
+    forced = torch.tensor([r[0][1:] for r in refs], dtype=torch.int32, device="cuda")
+
+    def prefill_all():
+        for s, p in enumerate(prompts):
+            eng.reset(s)
+            eng.prefill(s, p.tolist())
+    prefill_all()
+    ids8, _, lg8 = eng.decode(list(range(8)), first, 3, forced=forced, return_logits=True)
+    lg8 = lg8.cpu().numpy()
+    for s in range(8):
+        assert np.abs(lg8[:, s] - refs[s][1][1:]).max() < TOL["float16"], s
+    prefill_all()
+    _, _, a = eng.decode([0, 1, 2, 3], first[:4].contiguous(), 3, forced=forced[:4].contiguous(), return_logits=True)
+    _, _, b = eng.decode([4, 5, 6, 7], first[4:].contiguous(), 3, forced=forced[4:].contiguous(), return_logits=True)
+    lg44 = np.concatenate([a.cpu().numpy(), b.cpu().numpy()], axis=1)
+    assert np.abs(lg8 - lg44).max() < 2e-3     # same sums, different association across the K-chunks
