@@ -74,6 +74,41 @@ int main() {
         const int p = attn_plan(BH, nb, smax, 148), S = p & 0x7f;
         if (S < 1 || S > nb || S > smax || S > ((p & ATTN_WARP_LEVEL) ? 32 : 16)) { printf("attn_plan(%d,%d,%d) = %d\n", BH, nb, smax, p); ++bad; }
       }
+  // K-chunked projections (gemv_mma_chunked): for every accepted shape each (tile, k) of every chunk is covered exactly once by
+  // the one-item-per-warp plan of a [N, kc] projection, including the short last chunk
+  {
+    const int cases[][3] = {{4096, 14336, 4096}, {2560, 9728, 4096}, {1024, 3584, 1024}, {4096, 14336, 2048}, {256, 1536, 256}};
+    for (auto& cse : cases)
+      for (int grid : {148, 132}) {
+        const int N = cse[0], K = cse[1], kc = cse[2];
+        if (!gemv_chunk_ok(N, K, kc, grid)) continue;
+        const int n_tiles = (N + 7) / 8, n_chunks = (K + kc - 1) / kc;
+        std::map<int, std::vector<std::pair<int, int>>> cover;
+        for (int bid = 0; bid < grid; ++bid) {
+          GemvPlan pl;
+          gemv_make_plan_ex(n_tiles, kc, grid, bid, pl);
+          if (pl.main_rounds != 0 || pl.tail_rounds > 1) { printf("chunk [%d,%d] kc %d: more than one item per warp\n", N, K, kc); ++bad; break; }
+          for (int w = 0; w < DEC_WARPS && pl.tail_rounds == 1; ++w) {
+            int tile, k0, klen;
+            if (!gemv_item(pl, kc, 0, w, tile, k0, klen)) continue;
+            const int sl = w & ((1 << pl.ks_log) - 1);
+            for (int c = 0; c < n_chunks; ++c) {
+              const int kcc = std::min(kc, K - c * kc), slice = kcc >> pl.ks_log;
+              if (slice % 32) { printf("chunk [%d,%d] kc %d: slice %d\n", N, K, kc, slice); ++bad; }
+              cover[tile].push_back({c * kc + sl * slice, slice});
+            }
+          }
+        }
+        if ((int)cover.size() != n_tiles) { printf("chunk [%d,%d] kc %d grid %d: %zu of %d tiles\n", N, K, kc, grid, cover.size(), n_tiles); ++bad; }
+        for (auto& kv : cover) {
+          std::sort(kv.second.begin(), kv.second.end());
+          int pos = 0;
+          for (auto& seg : kv.second) { if (seg.first != pos) { printf("chunk tile %d gap at %d\n", kv.first, pos); ++bad; break; } pos += seg.second; }
+          if (pos != K) { printf("chunk tile %d covers %d of %d\n", kv.first, pos, K); ++bad; }
+        }
+      }
+    if (!gemv_chunk_ok(4096, 14336, 4096, 148)) { printf("Llama-3-8B down-projection must be chunkable\n"); ++bad; }
+  }
   printf(bad ? "FAILED %d\n" : "OK\n", bad);
   return bad ? 1 : 0;
 }
