@@ -551,7 +551,11 @@ __host__ __device__ __forceinline__ int gemv_units_of(const GemvPlan& pl, int K,
 template <typename T>
 __device__ __forceinline__ void gemv_prefetch(const GemvArgs& a, GemvRing& ring) {
   static_assert(GV_UK == 256, "gemv_units_of shifts by 8");
-  if (a.plan_id >= 0) ring.plan = ring.plans_s[a.plan_id]; else gemv_make_plan(a.N, a.K, ring.plan);
+  // the ring state is ONE copy per warp in shared memory: lane 0 writes it, __syncwarp publishes it to the other lanes
+  // (every lane writing the same values is the same hardware behaviour but a data race on paper -- racecheck flags it)
+  const int lane0 = (threadIdx.x & 31) == 0;
+  if (lane0) { if (a.plan_id >= 0) ring.plan = ring.plans_s[a.plan_id]; else gemv_make_plan(a.N, a.K, ring.plan); }
+  __syncwarp();
   const GemvPlan& pl = ring.plan;
   const int warp = threadIdx.x >> 5;
   int nv = pl.main_rounds;
@@ -561,7 +565,6 @@ __device__ __forceinline__ void gemv_prefetch(const GemvArgs& a, GemvRing& ring)
     if (!gemv_item(pl, a.K, pl.main_rounds + r, warp, tile, k0, klen)) break;
     ++nv;
   }
-  ring.pre_nvalid = nv; ring.pre_valid = 1; ring.pre_W = a.W;
   int pj = 0, pu = 0;
   unsigned int pslot = ring.slot;
 #pragma unroll 1
@@ -570,13 +573,14 @@ __device__ __forceinline__ void gemv_prefetch(const GemvArgs& a, GemvRing& ring)
     if (++pu == gemv_units_of(pl, a.K, pj)) { pu = 0; ++pj; }
     if (++pslot == (unsigned)ring.slots) pslot = 0;
   }
-  ring.pre_pj = pj; ring.pre_pu = pu;
+  __syncwarp();
+  if (lane0) { ring.pre_nvalid = nv; ring.pre_valid = 1; ring.pre_W = a.W; ring.pre_pj = pj; ring.pre_pu = pu; }
+  __syncwarp();
 }
 
 // Wait for prefetched units that will never be consumed (early exit) so no bulk copy is in flight at CTA exit.
 __device__ __forceinline__ void gemv_drain(int K, GemvRing& ring) {
   if (!ring.pre_valid) return;
-  ring.pre_valid = 0;
   const GemvPlan& pl = ring.plan;
   int total = 0;
   for (int j = 0; j < ring.pre_nvalid && total < ring.slots; ++j) total += gemv_units_of(pl, K, j);
@@ -586,7 +590,9 @@ __device__ __forceinline__ void gemv_drain(int K, GemvRing& ring) {
     mbar_wait_s(ring.bars_s + cslot * 8, cpar);
     if (++cslot == (unsigned)ring.slots) { cslot = 0; cpar ^= 1u; }
   }
-  ring.slot = cslot; ring.parity = cpar;
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) { ring.pre_valid = 0; ring.slot = cslot; ring.parity = cpar; }
+  __syncwarp();
 }
 
 // best_v / best_i: running argmax of this lane for sessions g and g + 8 (EPI_LOGITS).
@@ -600,12 +606,14 @@ __device__ __noinline__ void gemv_mma(const GemvArgs& a, uint32_t xh_s, int B, f
   if (ring.pre_valid && ring.pre_W != a.W) __trap();  // prefetch bookkeeping bug: the ring holds another matrix
   if (!ring.pre_valid) gemv_prefetch<T>(a, ring);
   const GemvPlan pl = ring.plan;
-  ring.pre_valid = 0;
   int pj = ring.pre_pj, pu = ring.pre_pu;  // producer cursor (uniform over the warp)
   const int n_valid = ring.pre_nvalid;
+  const unsigned int slot_in = ring.slot, parity_in = ring.parity;
+  __syncwarp();                            // every lane has read the ring state before lane 0 updates it
+  if (lane == 0) ring.pre_valid = 0;
   const int n_items = pl.main_rounds + pl.tail_rounds;
   const int ks = 1 << pl.ks_log;
-  unsigned int cslot = ring.slot, cpar = ring.parity;
+  unsigned int cslot = slot_in, cpar = parity_in;
   const uint32_t xrow_lo = xh_s + (uint32_t)(g * (K + GV_XPAD) + t * 8) * 2;
   const uint32_t xrow_hi = xrow_lo + (uint32_t)(8 * (K + GV_XPAD)) * 2;
   const bool lo = g < B, hi = g + 8 < B;
@@ -676,8 +684,9 @@ __device__ __noinline__ void gemv_mma(const GemvArgs& a, uint32_t xh_s, int B, f
       if (hi) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g + 8, c[2] + bias0, c[3] + bias1, rh0, rh1, sup0, sup1, best_v[1], best_i[1]);
     }
   }
-  ring.slot = cslot;
-  ring.parity = cpar;
+  __syncwarp();
+  if (lane == 0) { ring.slot = cslot; ring.parity = cpar; }
+  __syncwarp();
 }
 
 // ---- the same projection with a K-chunked activation operand ----------------------------------------------------------
@@ -728,7 +737,8 @@ __device__ __noinline__ void gemv_mma_chunked(const GemvArgs& a, T* xh, int B, f
   // producer cursor over this warp's unit stream: chunk pc, unit pu inside the chunk's slice
   auto slice_of = [&](int c) { const int kcc = min(KC, K - c * KC); return kcc >> pl.ks_log; };
   int pc = 0, pu = 0;
-  unsigned int pslot = ring.slot;
+  const unsigned int slot_in = ring.slot, parity_in = ring.parity;
+  unsigned int pslot = slot_in;
   auto issue_next = [&](uint32_t dst, uint32_t bar) {
     const int slice = slice_of(pc);
     const int kb = pc * KC + sl * slice + pu * GV_UK;
@@ -746,7 +756,7 @@ __device__ __noinline__ void gemv_mma_chunked(const GemvArgs& a, T* xh, int B, f
       issue_next(ring.base_s + pslot * GV_SLOT_BYTES, ring.bars_s + pslot * 8);
       if (++pslot == (unsigned)ring.slots) pslot = 0;
     }
-  unsigned int cslot = ring.slot, cpar = ring.parity;
+  unsigned int cslot = slot_in, cpar = parity_in;
   const uint32_t xh_s = smem_u32(xh);
   const uint32_t row_bytes = (uint32_t)(KC + GV_XPAD) * 2;
   const uint32_t xrow_lo = xh_s + (uint32_t)g * row_bytes + (uint32_t)t * 16;
@@ -808,8 +818,9 @@ __device__ __noinline__ void gemv_mma_chunked(const GemvArgs& a, T* xh, int B, f
     if (lo) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g, c[0] + bias0, c[1] + bias1, rl0, rl1, 0, 0, best_v[0], best_i[0]);
     if (hi) gemv_pair_epilogue<T, LLAMA>(a, mode, row0, g + 8, c[2] + bias0, c[3] + bias1, rh0, rh1, 0, 0, best_v[1], best_i[1]);
   }
-  ring.slot = cslot;
-  ring.parity = cpar;
+  __syncwarp();
+  if (lane == 0) { ring.slot = cslot; ring.parity = cpar; }
+  __syncwarp();
 }
 
 // Per-CTA argmax candidates after an EPI_LOGITS gemv: merge the lanes of a session (t = 0..3), then the warps.

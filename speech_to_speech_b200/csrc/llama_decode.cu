@@ -231,7 +231,7 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
   // argument struct and ring state live in shared memory (all threads write identical values), not on the stack
   const int kind = ld_kind(p, ph);
   if (!ready && ld_has_gemv(p, step, ph)) {
-    if (threadIdx.x < 32) ld_gemv_args<T>(p, step, ph, a_scratch);  // one warp writes the shared struct
+    if (threadIdx.x == 0) ld_gemv_args<T>(p, step, ph, a_scratch);  // one thread writes the shared struct
     __syncthreads();
   }
   GemvArgs& a = ready ? *ready : a_scratch;
@@ -297,14 +297,15 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   {
     unsigned char* rb = smem_raw + lay.ring_off;
     const int warp = threadIdx.x >> 5;
-    ring.slots = p.ring_slots;
-    ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(rb + (size_t)DEC_WARPS * p.ring_slots * GV_SLOT_BYTES) + warp * p.ring_slots;
-    ring.bars_s = smem_u32(bars);
-    ring.slot = 0;
-    ring.parity = 0;
-    ring.plans_s = s_plans;
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0) {   // lane 0 owns the warp's ring state in shared memory
+      ring.slots = p.ring_slots;
+      ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
+      ring.bars_s = smem_u32(bars);
+      ring.slot = 0;
+      ring.parity = 0;
+      ring.plans_s = s_plans;
+      ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
       for (int i = 0; i < p.ring_slots; ++i) mbar_init(bars + i, 1);
       fence_barrier_init();
     }
@@ -313,9 +314,8 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
   unsigned int epoch = 0;
   int trace_i = 0;
   GemvArgs& pre_args = s_args[0];
-  pre_args.K = p.d;
+  if (threadIdx.x == 0) pre_args.K = p.d;
   int pre_tag = -1, wb_tag = -1;
-  ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
   const int n_ph = ld_nsub(p) * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
@@ -335,7 +335,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
 #pragma unroll 1
           for (int look = 0; look < 3 && nstep < step_end; ++look) {
             if (ld_has_gemv(sp, nstep, nph)) {
-              if (threadIdx.x < 32) ld_gemv_args<T>(sp, nstep, nph, pre_args);  // one warp writes the shared struct
+              if (threadIdx.x == 0) ld_gemv_args<T>(sp, nstep, nph, pre_args);  // one thread writes the shared struct
               __syncthreads();
               if (pre_args.kc == 0) gemv_prefetch<T>(pre_args, ring);   // a K-chunked projection starts its own stream
               pre_tag = nstep * n_ph + nph;
@@ -343,7 +343,7 @@ llama_decode_kernel(const LlamaDecParams p, int step_begin, int step_end, int ph
               const int nk = ld_kind(sp, nph);
               if (nk == 0) nw = sp.lw[nph / ld_nsub(sp)].norm1; else if (nk == 3) nw = sp.lw[nph / ld_nsub(sp)].norm2;
               else if (nk == 6) nw = sp.norm_f;
-              if (nw) { stage_norm_weights(nw, nullptr, sp.d, sm.wb); wb_tag = pre_tag; }
+              if (nw && wb_tag != pre_tag) { stage_norm_weights(nw, nullptr, sp.d, sm.wb); wb_tag = pre_tag; }
               break;
             }
             if (++nph == n_ph) { nph = 0; ++nstep; }

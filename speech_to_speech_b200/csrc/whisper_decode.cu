@@ -228,7 +228,7 @@ __device__ __forceinline__ void wd_phase(const WhisperDecParams& p, int step, in
   if (!ready) {
     has_gemv = wd_has_gemv(p, step, ph);
     if (has_gemv) {
-      if (threadIdx.x < 32) wd_gemv_args<T>(p, step, ph, a_scratch);  // one warp writes, everybody reads after the barrier
+      if (threadIdx.x == 0) wd_gemv_args<T>(p, step, ph, a_scratch);  // one thread writes, everybody reads after the barrier
       __syncthreads();
     }
   }
@@ -291,14 +291,15 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
   {
     unsigned char* rb = smem_raw + lay.ring_off;
     const int warp = threadIdx.x >> 5;
-    ring.slots = p.ring_slots;
-    ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(rb + (size_t)DEC_WARPS * p.ring_slots * GV_SLOT_BYTES) + warp * p.ring_slots;
-    ring.bars_s = smem_u32(bars);
-    ring.slot = 0;
-    ring.parity = 0;
-    ring.plans_s = s_plans;
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0) {   // lane 0 owns the warp's ring state in shared memory
+      ring.slots = p.ring_slots;
+      ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
+      ring.bars_s = smem_u32(bars);
+      ring.slot = 0;
+      ring.parity = 0;
+      ring.plans_s = s_plans;
+      ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
       for (int i = 0; i < p.ring_slots; ++i) mbar_init(bars + i, 1);
       fence_barrier_init();
     }
@@ -307,9 +308,8 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
   unsigned int epoch = 0;
   int trace_i = 0;
   GemvArgs& pre_args = s_args[0];
-  pre_args.K = p.d;
+  if (threadIdx.x == 0) pre_args.K = p.d;
   int pre_tag = -1, wb_tag = -1;  // (step, phase) the prepared arguments / staged norm weights belong to
-  ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
   const int n_ph = 8 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
@@ -334,7 +334,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
 #pragma unroll 1
           for (int look = 0; look < 3 && nstep < step_end; ++look) {
             if (wd_has_gemv(sp, nstep, nph)) {
-              if (threadIdx.x < 32) wd_gemv_args<T>(sp, nstep, nph, pre_args);  // one warp writes the shared struct
+              if (threadIdx.x == 0) wd_gemv_args<T>(sp, nstep, nph, pre_args);  // one thread writes the shared struct
               __syncthreads();
               gemv_prefetch<T>(pre_args, ring);  // plan + first weight units of the next projection -> shared memory
               pre_tag = nstep * n_ph + nph;
@@ -346,7 +346,7 @@ whisper_decode_kernel(const WhisperDecParams p, int step_begin, int step_end, in
                 if (sub == 0) { nw = w.ln1_w; nb = w.ln1_b; } else if (sub == 3) { nw = w.ln2_w; nb = w.ln2_b; }
                 else if (sub == 6) { nw = w.ln3_w; nb = w.ln3_b; }
               } else { nw = sp.lnf_w; nb = sp.lnf_b; }
-              if (nw) { stage_norm_weights(nw, nb, sp.d, sm.wb); wb_tag = pre_tag; }
+              if (nw && wb_tag != pre_tag) { stage_norm_weights(nw, nb, sp.d, sm.wb); wb_tag = pre_tag; }
               break;
             }
             if (++nph == n_ph) { nph = 0; ++nstep; }
@@ -474,12 +474,12 @@ __device__ __forceinline__ void wdc_block(const WhisperDecParams& p, const WdcCt
                            w.ln2_w, w.ln2_b, 1e-5f, sm.s_red, sm.wb, wb_ready);
   }
   if (tr) tr[1] = globaltimer_ns();
-  if (cx.cid >= H) { ring.pre_valid = 0; return; }  // no head for this cluster (nothing was prefetched: empty plan)
+  if (cx.cid >= H) return;  // no head for this cluster (nothing was prefetched for it: wdc_has_gemv)
   const int h = cx.cid;
   // B. the head's q (k, v) rows
   GemvArgs& a = ready ? *ready : scratch[0];
   GemvArgs& ao = scratch[1];
-  if (threadIdx.x < 32) {  // one warp writes the shared argument structs; the barrier publishes them
+  if (threadIdx.x == 0) {  // ONE thread writes the shared argument structs; the barrier publishes them
     if (!ready) wdc_gemv_args<T>(p, cx, step, layer * 4 + (cross ? 1 : 0), scratch[0]);
     ao = a;
     wdc_out_args(p, cx, layer, cross, ao);
@@ -542,7 +542,7 @@ __device__ __forceinline__ void wdc_phase(const WhisperDecParams& p, const WdcCt
     if (sub < 2) { wdc_block<T>(p, cx, step, layer, sub == 1, sm, ring, ready, scratch, wb_ready, tr); return; }
     const WhisperDecLayer& w = p.lw[layer];
     if (!ready) {
-      if (threadIdx.x < 32) wdc_gemv_args<T>(p, cx, step, ph, scratch[0]);
+      if (threadIdx.x == 0) wdc_gemv_args<T>(p, cx, step, ph, scratch[0]);
       __syncthreads();
     }
     GemvArgs& a = ready ? *ready : scratch[0];
@@ -559,7 +559,7 @@ __device__ __forceinline__ void wdc_phase(const WhisperDecParams& p, const WdcCt
   if (ph == 4 * L) {
     if (!ready) {
       if (!wdc_has_gemv(p, cx.cid, step, ph)) return;
-      if (threadIdx.x < 32) wdc_gemv_args<T>(p, cx, step, ph, scratch[0]);
+      if (threadIdx.x == 0) wdc_gemv_args<T>(p, cx, step, ph, scratch[0]);
       __syncthreads();
     }
     GemvArgs& a = ready ? *ready : scratch[0];
@@ -635,14 +635,15 @@ whisper_decode_cluster_kernel(const WhisperDecParams p, int step_begin, int step
   {
     unsigned char* rb = smem_raw + lay.ring_off;
     const int warp = threadIdx.x >> 5;
-    ring.slots = p.ring_slots;
-    ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(rb + (size_t)DEC_WARPS * p.ring_slots * GV_SLOT_BYTES) + warp * p.ring_slots;
-    ring.bars_s = smem_u32(bars);
-    ring.slot = 0;
-    ring.parity = 0;
-    ring.plans_s = s_plans;
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0) {   // lane 0 owns the warp's ring state in shared memory
+      ring.slots = p.ring_slots;
+      ring.base_s = smem_u32(rb + (size_t)warp * p.ring_slots * GV_SLOT_BYTES);
+      ring.bars_s = smem_u32(bars);
+      ring.slot = 0;
+      ring.parity = 0;
+      ring.plans_s = s_plans;
+      ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
       for (int i = 0; i < p.ring_slots; ++i) mbar_init(bars + i, 1);
       fence_barrier_init();
     }
@@ -651,9 +652,8 @@ whisper_decode_cluster_kernel(const WhisperDecParams p, int step_begin, int step
   unsigned int epoch = 0;
   int trace_i = 0;
   GemvArgs& pre_args = s_args[0];
-  pre_args.K = p.d;
+  if (threadIdx.x == 0) pre_args.K = p.d;
   int pre_tag = -1, wb_tag = -1;
-  ring.pre_valid = 0; ring.pre_pj = 0; ring.pre_pu = 0; ring.pre_nvalid = 0; ring.pre_W = nullptr;
   const int n_ph = 4 * p.layers + 2;
   for (int step = step_begin; step < step_end; ++step) {
     const int pb = coop ? 0 : ph_begin, pe = coop ? n_ph : ph_end;
@@ -684,9 +684,9 @@ whisper_decode_cluster_kernel(const WhisperDecParams p, int step_begin, int step
                 if (sub == 0) { nw = w.ln1_w; nb = w.ln1_b; } else if (sub == 1) { nw = w.ln2_w; nb = w.ln2_b; }
                 else if (sub == 2) { nw = w.ln3_w; nb = w.ln3_b; }
               } else { nw = sp.lnf_w; nb = sp.lnf_b; }
-              if (nw) { stage_norm_weights(nw, nb, sp.d, sm.wb); wb_tag = nstep * n_ph + nph; }
+              if (nw && wb_tag != nstep * n_ph + nph) { stage_norm_weights(nw, nb, sp.d, sm.wb); wb_tag = nstep * n_ph + nph; }   // once per target phase
               if (wdc_has_gemv(sp, cx.cid, nstep, nph)) {
-                if (threadIdx.x < 32) wdc_gemv_args<T>(sp, cx, nstep, nph, pre_args);
+                if (threadIdx.x == 0) wdc_gemv_args<T>(sp, cx, nstep, nph, pre_args);
                 __syncthreads();
                 gemv_prefetch<T>(pre_args, ring);
                 pre_tag = nstep * n_ph + nph;
