@@ -356,12 +356,16 @@ def e2e_wave(handlers, auds, S) -> dict:
             errs.append(f"session {i}: {type(e).__name__}: {e}")
 
     llm_prompt = np.random.default_rng(0).integers(0, 128256, LLM_PROMPT).tolist()
-    ths = [threading.Thread(target=session, args=(i,)) for i in range(S)]
+    ths = [threading.Thread(target=session, args=(i,), daemon=True) for i in range(S)]
     t0 = time.perf_counter()
     for t in ths:
         t.start()
+    deadline = t0 + 240.0                      # a stuck session must not hang the bench: report it instead
     for t in ths:
-        t.join()
+        t.join(max(0.0, deadline - time.perf_counter()))
+    stuck = sum(t.is_alive() for t in ths)
+    if stuck:
+        errs.append(f"{stuck} session thread(s) still running after 240 s")
     wall = time.perf_counter() - t0
     ok = [x for x in lat if x is not None]
     return {"wall_s": wall, "latency_ms": ok, "rtf": [x for x in rtf if x is not None], "errors": errs[:3]}
