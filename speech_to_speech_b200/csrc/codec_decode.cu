@@ -140,26 +140,30 @@ __global__ void __launch_bounds__(TC_THREADS) conv1d_tc_kernel(const ConvArgs a,
       for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
   const int kt_per_tap = (a.C_in + TC_BK - 1) / TC_BK;
   const int n_kt = a.k * kt_per_tap;
-  // A staging: 128 rows x 32 channels fp32 -> fp16; thread -> row tid / 2, 16 consecutive channels
-  const int a_row = tid >> 1, a_c = (tid & 1) * 16;
+  // A staging: 128 rows x 32 channels fp32 -> fp16.  8 consecutive lanes read one row's 128 contiguous bytes (fully coalesced
+  // float4 loads); a thread handles rows a_row + 32 v, v = 0..3, channels a_c .. a_c + 3
+  const int a_row = tid >> 3, a_c = (tid & 7) * 4;
   // B staging: 16 k-pairs x 64 n words; thread -> pair tid / 16, 4 consecutive n
   const int b_kp = tid >> 4, b_n = (tid & 15) * 4;
-  float areg[16];
+  float4 areg[4];
   uint32_t breg[4];
   auto load_tile = [&](int kt) {
     const int j = kt / kt_per_tap, c0 = (kt - j * kt_per_tap) * TC_BK;
-    const int xr = m0 + a_row + a.x_row0 + j * a.dil;
-    const bool ok = (m0 + a_row) < a.T_out && xr >= 0 && xr < a.T_in;
-    const float* xp = X + (long long)xr * a.ldx + c0 + a_c;
-    if (ok && c0 + a_c + 16 <= a.C_in && ((reinterpret_cast<uintptr_t>(xp) & 15) == 0)) {
+    const bool vec = (c0 + a_c + 4 <= a.C_in) && ((a.ldx & 3) == 0);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const float4 q = *reinterpret_cast<const float4*>(xp + 4 * v);
-        areg[4 * v] = q.x; areg[4 * v + 1] = q.y; areg[4 * v + 2] = q.z; areg[4 * v + 3] = q.w;
+    for (int v = 0; v < 4; ++v) {
+      const int r = a_row + 32 * v;
+      const int xr = m0 + r + a.x_row0 + j * a.dil;
+      const bool ok = (m0 + r) < a.T_out && xr >= 0 && xr < a.T_in;
+      const float* xp = X + (long long)xr * a.ldx + c0 + a_c;
+      if (ok && vec && ((reinterpret_cast<uintptr_t>(xp) & 15) == 0)) {
+        areg[v] = *reinterpret_cast<const float4*>(xp);
+      } else {
+        float t4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t4[e] = (ok && c0 + a_c + e < a.C_in) ? xp[e] : 0.f;
+        areg[v] = make_float4(t4[0], t4[1], t4[2], t4[3]);
       }
-    } else {
-#pragma unroll
-      for (int v = 0; v < 16; ++v) areg[v] = (ok && c0 + a_c + v < a.C_in) ? xp[v] : 0.f;
     }
     const int kp = (j * c_pairs) + (c0 >> 1) + b_kp;          // pair row of the weight matrix
     const bool kok = (c0 >> 1) + b_kp < c_pairs;
@@ -171,8 +175,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv1d_tc_kernel(const ConvArgs a,
   };
   auto store_tile = [&](int buf) {
 #pragma unroll
-    for (int v = 0; v < 16; v += 2)
-      *reinterpret_cast<__half2*>(&As[buf][a_row][a_c + v]) = __floats2half2_rn(areg[v], areg[v + 1]);
+    for (int v = 0; v < 4; ++v) {
+      __half2* dst = reinterpret_cast<__half2*>(&As[buf][a_row + 32 * v][a_c]);
+      dst[0] = __floats2half2_rn(areg[v].x, areg[v].y);
+      dst[1] = __floats2half2_rn(areg[v].z, areg[v].w);
+    }
 #pragma unroll
     for (int v = 0; v < 4; ++v) Bs[buf][b_kp][b_n + v] = breg[v];
   };
