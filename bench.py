@@ -280,7 +280,11 @@ def wave_device(st: Stack, pcm_dev, ev) -> None:
         nb = min(16, S - b0)
         st.whisper.logmel(pcm_dev[b0:b0 + nb], [N_SAMPLES] * nb)
         st.whisper.encode(nb)
+        wa, wb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wa.record()
         st.whisper.decode(nb, st.opts)
+        wb_.record()
+        ev["whisper_mark"].append((wa, wb_))
     ev["stt"].record()
     firsts = []
     for s in range(S):                                                    # ---- LLM prefill
@@ -456,6 +460,7 @@ def main():
         names = ("t0", "stt", "prefill", "llm", "tts")
         ev = {n: torch.cuda.Event(enable_timing=True) for n in names}
         ev["frames_mark"] = []
+        ev["whisper_mark"] = []
         return ev
 
     for i in range(args.warmup):
@@ -493,6 +498,7 @@ def main():
               "tts_ms": statistics.mean(stage(e, "llm", "tts") for e in evs)}
     codec_ms = statistics.mean(sum(a.elapsed_time(b) for a, b in e["frames_mark"]) for e in evs)
     stages["tts_codec_postproc_ms"] = codec_ms
+    stages["stt_decode_ms"] = statistics.mean(sum(a.elapsed_time(b) for a, b in e["whisper_mark"]) for e in evs)
     stages["tts_talker_predictor_ms"] = stages["tts_ms"] - codec_ms
     total_ms = sum(step_ms)
 
@@ -570,8 +576,11 @@ def main():
             "session_shard_exchange": {"collective": "torch.distributed scatter (PCM from the ingest rank) + gather (results), NCCL send/recv",
                                        "scatter_ms": scatter_ms, "gather_ms": gather_ms,
                                        "bytes_in_per_session": N_SAMPLES * 4, "bytes_out_per_session": 64 * 4},
-            "whisper_decode_roofline": {"kernel": "whisper_decode_kernel (persistent, 16 sessions per launch)", "bound": "hbm",
-                                        "algorithmic_bytes_per_launch": wb, "launches_per_step": n_w_launch},
+            "whisper_decode_roofline": {"kernel": f"whisper_decode_kernel (persistent, {min(S, 16)} sessions per launch)", "bound": "hbm",
+                                        "algorithmic_bytes_per_launch": wb, "launches_per_step": n_w_launch,
+                                        "achieved": wb / 1e9 / (stages["stt_decode_ms"] / n_w_launch / 1e3), "peak": peak, "unit": "GB/s",
+                                        "frac": wb / 1e9 / (stages["stt_decode_ms"] / n_w_launch / 1e3) / peak},
+            "stt_only_sessions": world * S * AUDIO_S / (stages["stt_ms"] / 1e3),
         }
         if e2e and "loaded" in e2e:
             lat_loaded = [x for w in e2e["loaded"] for x in w["latency_ms"]]
