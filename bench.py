@@ -217,11 +217,44 @@ def cpu_turn(n_turns: int, threads: int) -> dict:
                       f"of {os.cpu_count()} cpus; faster-whisper unavailable, transformers CPU path timed instead; faster-qwen3-tts unavailable"}
 
 
+def host_threads() -> int:
+    """CPU threads of the reference arm: the cores this process may run on (affinity / cgroup aware), at most 64 -- the same
+    count whatever the launcher's OMP_NUM_THREADS says (torchrun sets it to 1) and without oversubscribing a box whose
+    os.cpu_count() exceeds its quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, os.cpu_count() or n, 64))
+
+
+def cpu_baseline_subprocess(turns: int, timeout_s: float = 240.0) -> dict:
+    """The CPU turn in a child process (fresh OpenMP runtime, no CUDA context, hard time limit): `bench.py --impl reference`."""
+    import subprocess as sp
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        r = sp.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(max(1, turns)), "--warmup", "0"],
+                   capture_output=True, text=True, timeout=timeout_s, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                line = json.loads(ln)
+                if line.get("cpu_baseline"):
+                    return line["cpu_baseline"]
+                return {"value": None, "unit": "sessions", "cores": 0, "kind": "reference", "sample": "failed: " + str(line.get("error"))}
+        return {"value": None, "unit": "sessions", "cores": 0, "kind": "reference", "sample": "failed: no output; " + r.stderr[-300:]}
+    except sp.TimeoutExpired:
+        return {"value": None, "unit": "sessions", "cores": host_threads(), "kind": "reference",
+                "sample": f"not finished within {timeout_s:.0f} s on this host (bounded sample aborted)"}
+
+
 def reference_arm(args, rank, world):
-    """--impl reference: rank 0 alone, all host cores whatever the launcher's OMP_NUM_THREADS says."""
+    """--impl reference: rank 0 alone, a fixed thread count whatever the launcher's OMP_NUM_THREADS says."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     line = {"metric": METRIC, "unit": "sessions", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (STT) / bf16 (LLM)", "data": "synthetic",
             "impl": "reference", "config": workload_config(world, args.sessions)}
@@ -601,10 +634,8 @@ def main():
         elif e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            try:
-                line["cpu_baseline"] = cpu_turn(args.cpu_baseline_turns, os.cpu_count() or 1)
-            except Exception as ex:
-                line["cpu_baseline"] = {"value": None, "unit": "sessions", "cores": 0, "kind": "reference", "sample": f"failed: {type(ex).__name__}: {ex}"}
+            log("cpu baseline (child process)")
+            line["cpu_baseline"] = cpu_baseline_subprocess(args.cpu_baseline_turns)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -259,6 +259,8 @@ int s2s_qwen3tts_decode_audio_batch(s2s_qwen3tts* m, const int32_t* slots_h, int
 int s2s_qwen3tts_set_frames(s2s_qwen3tts* m, int32_t slot, int32_t n_frames);
 int32_t s2s_qwen3tts_frames(s2s_qwen3tts* m, int32_t slot);
 int32_t s2s_qwen3tts_max_batch(s2s_qwen3tts* m);
+/* Profiling aid (see s2s_llama_set_trace): phase stamps of the talker (which = 0) or code-predictor (1) launches. */
+int s2s_qwen3tts_set_trace(s2s_qwen3tts* m, int32_t which, uint64_t* trace_d, int32_t capacity);
 s2s_codec* s2s_qwen3tts_codec(s2s_qwen3tts* m);
 
 /* ---- TTS post-processing (Qwen3TTSHandler._stream) -------------------------------------

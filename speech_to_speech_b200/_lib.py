@@ -25,7 +25,7 @@ EXPORTED = [
     "s2s_codec_decode", "s2s_codec_samples", "s2s_codec_total_upsample",
     "s2s_qwen3tts_create", "s2s_qwen3tts_destroy", "s2s_qwen3tts_bind_tensor", "s2s_qwen3tts_init_random",
     "s2s_qwen3tts_finalize", "s2s_qwen3tts_prefill", "s2s_qwen3tts_decode_frames", "s2s_qwen3tts_decode_audio", "s2s_qwen3tts_decode_audio_batch",
-    "s2s_qwen3tts_set_frames", "s2s_qwen3tts_frames", "s2s_qwen3tts_max_batch", "s2s_qwen3tts_codec",
+    "s2s_qwen3tts_set_frames", "s2s_qwen3tts_frames", "s2s_qwen3tts_max_batch", "s2s_qwen3tts_codec", "s2s_qwen3tts_set_trace",
 ]
 
 
@@ -149,6 +149,7 @@ def load() -> C.CDLL:
     lib.s2s_qwen3tts_frames.restype = i32
     lib.s2s_qwen3tts_max_batch.argtypes = [vp]
     lib.s2s_qwen3tts_max_batch.restype = i32
+    lib.s2s_qwen3tts_set_trace.argtypes = [vp, i32, vp, i32]
     lib.s2s_qwen3tts_codec.argtypes = [vp]
     lib.s2s_qwen3tts_codec.restype = vp
     _lib = lib

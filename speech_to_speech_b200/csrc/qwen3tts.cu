@@ -524,6 +524,13 @@ int32_t s2s_qwen3tts_frames(s2s_qwen3tts* m, int32_t slot) {
   return m->sess[slot].frames;
 }
 int32_t s2s_qwen3tts_max_batch(s2s_qwen3tts* m) { return m ? tts_max_batch(m) : 0; }
+int s2s_qwen3tts_set_trace(s2s_qwen3tts* m, int32_t which, uint64_t* trace_d, int32_t capacity) {
+  S2S_REQUIRE(m && (which == 0 || which == 1), "qwen3tts set_trace: which = 0 (talker) or 1 (code predictor)");
+  s2s_llama* t = which == 0 ? m->talker : m->pred;
+  t->trace = reinterpret_cast<unsigned long long*>(trace_d);
+  t->trace_cap = trace_d ? capacity : 0;
+  return S2S_OK;
+}
 s2s_codec* s2s_qwen3tts_codec(s2s_qwen3tts* m) { return m ? m->codec : nullptr; }
 
 }  // extern "C"
