@@ -13,6 +13,7 @@ struct ConvArgs {
   const float* scale;                       // [N] or null (LayerScale / ConvNeXt gamma), applied after act
   const float* resid; long long ldr;        // [T_out, N] or null, added last (may alias y)
   float* y; long long ldy; int T_out;
+  int t0;                                   // first output row computed (rows below it are never read downstream: causal trimming)
   int batch; long long x_bs, y_bs, r_bs;    // independent sequences along blockIdx.z
 };
 int conv1d_f32_launch(const ConvArgs& a, cudaStream_t st);

@@ -381,7 +381,12 @@ __global__ void llama_decode_init_kernel(const LlamaDecParams p) {
 template <typename T>
 int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
   int kmax = 0, rg = 0, kc = 0, slots = 0;
-  S2S_REQUIRE(llama_decode_plan(p.B, p.d, p.ffn, p.heads * p.hd, ctx->num_sms, &kmax, &rg, &kc, &slots),
+  int grid = ctx->num_sms;
+  if (const char* e = getenv("S2S_DECODE_CTAS")) {   // developer knob: a smaller cooperative grid (SM-partition experiments)
+    const int v = atoi(e);
+    if (v >= 8 && v < grid) grid = v;
+  }
+  S2S_REQUIRE(llama_decode_plan(p.B, p.d, p.ffn, p.heads * p.hd, grid, &kmax, &rg, &kc, &slots),
               "llama decode: batch %d does not fit shared memory for d %d, ffn %d", p.B, p.d, p.ffn);
   const DecSmem lay = dec_smem_layout(p.B, p.d, kmax, p.d, rg);
   LlamaDecParams pr = p;
@@ -393,7 +398,6 @@ int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream
   llama_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
   S2S_LAUNCH_CHECK();
   const int n_ph = ld_nsub(p) * p.layers + 2;
-  const int grid = ctx->num_sms;
   if (!debug_phases) {
     int sb = 0, se = p.n_steps, pb = 0, pe = n_ph, coop = 1;
     LlamaDecParams pp = pr;
