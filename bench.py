@@ -278,21 +278,22 @@ def log(msg: str) -> None:
 
 
 class Stack:
-    """The three engines of one GPU, shared by all its sessions (one weight copy each)."""
+    """The three engines of one lane of one GPU, shared by the lane's sessions.  A lane is an SM partition (engine.get_context):
+    with L lanes the persistent decode kernels of lane i run on num_sms // L CTAs, concurrently with the other lanes'."""
 
-    def __init__(self, E, W, dev: int, S: int):
+    def __init__(self, E, W, dev: int, S: int, lane: int = 0, lanes: int = 1):
         import torch
         from speech_to_speech_b200.tts_model import B200Qwen3TTS
-        self.E, self.W, self.dev, self.S = E, W, dev, S
+        self.E, self.W, self.dev, self.S, self.lane, self.lanes = E, W, dev, S, lane, lanes
         self.wg = W.WHISPER_GEOMETRIES[MODEL]
         self.lg = W.LLAMA_GEOMETRIES["llama-3-8b"]
-        self.whisper = E.WhisperEngine(self.wg.to_dict(), dtype="float16", max_batch=min(16, S), device=dev)
+        self.whisper = E.WhisperEngine(self.wg.to_dict(), dtype="float16", max_batch=min(16, S), device=dev, lane=lane, lanes=lanes)
         self.whisper.init_random(1234)
         self.llm = E.LlamaEngine(self.lg.to_dict(), dtype="bfloat16", max_sessions=S, max_positions=LLM_PROMPT + MAX_NEW + 8,
-                                 max_prefill=LLM_PROMPT, device=dev)
+                                 max_prefill=LLM_PROMPT, device=dev, lane=lane, lanes=lanes)
         self.llm.init_random(7)
         self.tts = B200Qwen3TTS.from_random(TTS_GEOM, seed=11, dtype="bfloat16", device=dev, max_sessions=S,
-                                            max_positions=max(F1, F2) + 32, max_text=128)
+                                            max_positions=max(F1, F2) + 32, max_text=128, lane=lane, lanes=lanes)
         self.opts = E.WhisperDecodeOptions(prefix=PREFIX, eos_id=-1, max_new_tokens=MAX_NEW, suppress=SUPPRESS,
                                            begin_suppress=BEGIN_SUPPRESS)
         mb = self.llm.max_decode_batch()
@@ -349,6 +350,41 @@ def wave_device(st: Stack, pcm_dev, ev) -> None:
             b.record()
             done += n
     ev["tts"].record()
+
+
+def run_wave(stacks, pcm_dev, evs):
+    """One wave on every lane at once: a host thread per lane issues the lane's launch sequence on the lane's stream; the step is
+    timed on the calling stream, from an event every lane waits for to an event that waits for every lane."""
+    torch = stacks[0].torch
+    cur = torch.cuda.current_stream()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(cur)
+    if len(stacks) == 1:
+        wave_device(stacks[0], pcm_dev, evs[0])
+    else:
+        errs, Sl = [], stacks[0].S
+
+        def run(i):
+            try:
+                st = stacks[i]
+                torch.cuda.set_device(st.dev)
+                with st.E.lane_context(st.dev, st.lane, st.lanes):
+                    torch.cuda.current_stream().wait_event(start)
+                    wave_device(st, pcm_dev[i * Sl:(i + 1) * Sl], evs[i])
+                    evs[i]["done"].record()
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=run, args=(i,), daemon=True) for i in range(len(stacks))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+        for e in evs:
+            cur.wait_event(e["done"])
+    end.record(cur)
+    return start, end
 
 
 def e2e_wave(handlers, auds, S) -> dict:
@@ -408,30 +444,33 @@ def e2e_wave(handlers, auds, S) -> dict:
     return {"wall_s": wall, "latency_ms": ok, "rtf": [x for x in rtf if x is not None], "errors": errs[:3]}
 
 
-def make_handlers(S: int, dev: int):
-    """S pipeline units' worth of handler instances sharing one engine per stage (gen_kwargs / kwargs of the reference slots)."""
+def make_handlers(S: int, dev: int, lanes: int = 1):
+    """S pipeline units' worth of handler instances; the units of a lane share one engine per stage (gen_kwargs / kwargs of the
+    reference slots)."""
     from queue import Queue
     from threading import Event
     from speech_to_speech_b200.handlers.language_model_handler import B200LanguageModelHandler
     from speech_to_speech_b200.handlers.qwen3_tts_handler import B200Qwen3TTSHandler
     from speech_to_speech_b200.handlers.whisper_stt_handler import B200WhisperSTTHandler
     out = []
+    Sl = S // lanes
     for i in range(S):
+        lane = i // Sl
         stt = B200WhisperSTTHandler(Event(), queue_in=Queue(), queue_out=Queue(),
                                     setup_kwargs=dict(model_name=f"random:{MODEL}:1234", device=f"cuda:{dev}", torch_dtype="float16",
-                                                      language="en", gen_kwargs={"max_new_tokens": MAX_NEW}, max_batch=min(16, S),
-                                                      batch_wait_ms=3.0))
+                                                      language="en", gen_kwargs={"max_new_tokens": MAX_NEW}, max_batch=min(16, Sl),
+                                                      batch_wait_ms=3.0, lane=lane, lanes=lanes))
         stt.tokens.eos = -1                   # random-init weights: every utterance decodes its full 128 tokens (both arms do)
         llm = object.__new__(B200LanguageModelHandler)   # the load hook only: the request lifecycle needs the reference's Chat types
         llm.device = f"cuda:{dev}"
         B200LanguageModelHandler._load_model(llm, "random:llama-3-8b:7", f"cuda:{dev}", "bfloat16",
-                                             {"max_new_tokens": MAX_NEW, "max_sessions": S, "max_positions": LLM_PROMPT + MAX_NEW + 8,
-                                              "stream_chunk_tokens": 8, "batch_wait_ms": 2.0})
+                                             {"max_new_tokens": MAX_NEW, "max_sessions": Sl, "max_positions": LLM_PROMPT + MAX_NEW + 8,
+                                              "stream_chunk_tokens": 8, "batch_wait_ms": 2.0, "lane": lane, "lanes": lanes})
         llm.eos_ids = []                      # random-init weights: never stop early, every reply has 128 tokens
         llm.streamer.eos_ids = set()
         tts = B200Qwen3TTSHandler(Event(), queue_in=Queue(), queue_out=Queue(), setup_args=(Event(),),
                                   setup_kwargs=dict(model_name=f"random:{TTS_GEOM}", device=f"cuda:{dev}", speaker="Aiden",
-                                                    max_sessions=S, gen_kwargs={"seed": 11}))
+                                                    max_sessions=Sl, lane=lane, lanes=lanes, gen_kwargs={"seed": 11}))
         out.append((stt, llm, tts))
     return out
 
@@ -442,7 +481,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sessions", type=int, default=16, help="conversation sessions in flight per GPU (one wave = one turn of each)")
+    ap.add_argument("--sessions", type=int, default=32, help="conversation sessions in flight per GPU (one wave = one turn of each)")
+    ap.add_argument("--lanes", type=int, default=2,
+                    help="SM partitions per GPU: each lane runs sessions/lanes sessions through its own engines; the lanes' persistent "
+                         "decode launches run concurrently on num_sms/lanes CTAs each")
     ap.add_argument("--cpu-baseline-turns", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -467,9 +509,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = f"cuda:{local_rank}"
-    S = args.sessions
-    st = Stack(E, W, local_rank, S)
-    log(f"engines built: llm max batch {st.llm_b}, tts max batch {st.tts_b}")
+    S, L = args.sessions, max(1, args.lanes)
+    assert S % L == 0, "--sessions must be a multiple of --lanes"
+    stacks = [Stack(E, W, local_rank, S // L, lane, L) for lane in range(L)]
+    st = stacks[0]
+    log(f"engines built: {L} lane(s) x {S // L} sessions, llm max batch {st.llm_b}, tts max batch {st.tts_b}")
 
     # ---- session-shard split: the ingest rank (0) holds every session's PCM and scatters each rank its shard over NCCL -------
     layout = shard.shard_layout(world * S, world)
@@ -490,14 +534,17 @@ def main():
         torch.cuda.synchronize()
 
     def new_events():
-        names = ("t0", "stt", "prefill", "llm", "tts")
-        ev = {n: torch.cuda.Event(enable_timing=True) for n in names}
-        ev["frames_mark"] = []
-        ev["whisper_mark"] = []
-        return ev
+        names = ("t0", "stt", "prefill", "llm", "tts", "done")
+        out = []
+        for _ in range(L):
+            ev = {n: torch.cuda.Event(enable_timing=True) for n in names}
+            ev["frames_mark"] = []
+            ev["whisper_mark"] = []
+            out.append(ev)
+        return out
 
     for i in range(args.warmup):
-        wave_device(st, pcm_dev, new_events())
+        run_wave(stacks, pcm_dev, new_events())
         torch.cuda.synchronize()
         log(f"warm-up wave {i} done")
 
@@ -505,7 +552,7 @@ def main():
     if rank == 0:
         sampler.start()
     E.launch_count(local_rank, reset=True)
-    evs = []
+    evs, spans = [], []
     barrier()
     if args.profile_region:
         torch.cuda.cudart().cudaProfilerStart()
@@ -513,8 +560,8 @@ def main():
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                 # L2 flush between timed steps (not timed)
         ev = new_events()
-        wave_device(st, pcm_dev, ev)
-        evs.append(ev)
+        spans.append(run_wave(stacks, pcm_dev, ev))
+        evs.append(ev[0])                     # stage boundaries: lane 0's (the lanes run the same sequence side by side)
     barrier()
     if args.profile_region:
         torch.cuda.cudart().cudaProfilerStop()
@@ -524,7 +571,7 @@ def main():
 
     def stage(ev, a, b):
         return ev[a].elapsed_time(ev[b])
-    step_ms = [stage(e, "t0", "tts") for e in evs]
+    step_ms = [a.elapsed_time(b) for a, b in spans]
     stages = {"stt_ms": statistics.mean(stage(e, "t0", "stt") for e in evs),
               "llm_prefill_ms": statistics.mean(stage(e, "stt", "prefill") for e in evs),
               "llm_decode_ms": statistics.mean(stage(e, "prefill", "llm") for e in evs),
@@ -548,7 +595,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
-            handlers = make_handlers(S, local_rank)
+            handlers = make_handlers(S, local_rank, L)
             log("handler instances built and warmed up")
             auds = [pcm_dev[i].cpu().numpy() for i in range(S)]
             e2e_wave(handlers[:1], auds, 1)                                    # warm-up
@@ -584,35 +631,62 @@ def main():
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         # dominant stage of the step and its kernel's roofline
         shares = {k: v / ms_per_step for k, v in stages.items() if k in ("stt_ms", "llm_prefill_ms", "llm_decode_ms", "tts_talker_predictor_ms", "tts_codec_postproc_ms")}
-        n_llm_launch = (S + st.llm_b - 1) // st.llm_b
-        llm_bytes = decode_bytes_llama(st.lg, MAX_NEW - 1, min(S, st.llm_b), LLM_PROMPT)
+        Sl = S // L                                                   # sessions of one lane
+        n_llm_launch = (Sl + st.llm_b - 1) // st.llm_b                # per lane; the L lanes' launches run side by side
+        llm_bytes = decode_bytes_llama(st.lg, MAX_NEW - 1, min(Sl, st.llm_b), LLM_PROMPT)
         llm_ms = stages["llm_decode_ms"] / n_llm_launch
-        ach_llm = llm_bytes / 1e9 / (llm_ms / 1e3)
-        n_w_launch = (S + 15) // 16
-        wb = decode_bytes_whisper(st.wg, len(PREFIX), MAX_NEW, min(S, 16))
+        ach_llm_launch = llm_bytes / 1e9 / (llm_ms / 1e3)
+        ach_llm = L * ach_llm_launch
+        n_w_launch = (Sl + 15) // 16
+        wb = decode_bytes_whisper(st.wg, len(PREFIX), MAX_NEW, min(Sl, 16))
+        ach_w = L * wb / 1e9 / (stages["stt_decode_ms"] / n_w_launch / 1e3)
+        lane_ctas = torch.cuda.get_device_properties(local_rank).multi_processor_count // L
+        # the TTS frame loop: the same persistent kernel on the talker (1 step) and the code predictor (15 steps) per frame
+        from speech_to_speech_b200.tts_model import TTS_GEOMETRIES
+        tg = TTS_GEOMETRIES[TTS_GEOM]
+
+        def _w(g):   # bf16 weight bytes of one decode step (all layers + one output head)
+            qd, kvd = g["heads"] * g["head_dim"], g["kv_heads"] * g["head_dim"]
+            return (g["layers"] * ((qd + 2 * kvd) * g["d_model"] + g["d_model"] * qd + 3 * g["ffn"] * g["d_model"]) + g["vocab"] * g["d_model"]) * 2
+        frame_bytes = _w(tg["talker"]) + (tg["n_groups"] - 1) * _w(tg["predictor"])
+        n_frame_launch = (Sl + st.tts_b - 1) // st.tts_b
+        frame_ms = stages["tts_talker_predictor_ms"] / (F1 + F2) / n_frame_launch
+        ach_tts = L * frame_bytes / 1e9 / (frame_ms / 1e3)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("llama_decode", {}).get("dram_bytes_per_launch")
-        roofline = {"kernel": f"llama_decode_kernel (persistent, {min(S, st.llm_b)} sessions x {MAX_NEW - 1} steps per launch, Llama-3-8B bf16)",
+        roofline = {"kernel": f"llama_decode_kernel (persistent, {min(Sl, st.llm_b)} sessions x {MAX_NEW - 1} steps per launch, Llama-3-8B bf16; "
+                              f"{L} launch(es) run concurrently, one per lane of {lane_ctas} CTAs)",
                     "bound": "hbm", "achieved": ach_llm, "peak": peak, "unit": "GB/s", "frac": ach_llm / peak, "traffic": traffic,
-                    "algorithmic_bytes_per_launch": llm_bytes, "launch_ms": llm_ms, "launches_per_step": n_llm_launch,
+                    "achieved_note": f"sum over the {L} concurrent launches (each streams its own copy of the weights): "
+                                     f"{L} x algorithmic_bytes_per_launch / launch_ms; achieved_per_launch is one launch alone",
+                    "achieved_per_launch": ach_llm_launch, "concurrent_launches": L,
+                    "algorithmic_bytes_per_launch": llm_bytes, "launch_ms": llm_ms, "launches_per_step": L * n_llm_launch,
                     "peak_source": peak_src, "share_of_step": shares["llm_decode_ms"], "stage_shares": shares}
         line = {
             "metric": METRIC, "value": value, "unit": "sessions", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 (Whisper) / bf16 (Llama, talker) operands, f32 accumulate; codec decoder f32", "data": "synthetic",
-            "config": {**workload_config(world, S),
-                       "l2": "flushed between timed steps (256 MiB write); every stage streams > 126 MB of weights per launch"},
+            "config": workload_config(world, S),
+            "l2": "flushed between timed steps (256 MiB write); every stage streams > 126 MB of weights per launch",
+            "lanes": {"per_gpu": L, "ctas_per_lane": lane_ctas, "sessions_per_lane": Sl,
+                      "note": "SM partitions with their own engines and CUDA streams; stage_ms are lane 0's (all lanes run the same "
+                              "sequence side by side), ms_per_step spans all lanes"},
             "turn_gpu_ms_per_session": ms_per_step / S, "stage_ms": stages, "wall_s_timed_region": wall_s,
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
             "session_shard_exchange": {"collective": "torch.distributed scatter (PCM from the ingest rank) + gather (results), NCCL send/recv",
                                        "scatter_ms": scatter_ms, "gather_ms": gather_ms,
                                        "bytes_in_per_session": N_SAMPLES * 4, "bytes_out_per_session": 64 * 4},
-            "whisper_decode_roofline": {"kernel": f"whisper_decode_kernel (persistent, {min(S, 16)} sessions per launch)", "bound": "hbm",
-                                        "algorithmic_bytes_per_launch": wb, "launches_per_step": n_w_launch,
-                                        "achieved": wb / 1e9 / (stages["stt_decode_ms"] / n_w_launch / 1e3), "peak": peak, "unit": "GB/s",
-                                        "frac": wb / 1e9 / (stages["stt_decode_ms"] / n_w_launch / 1e3) / peak},
+            "whisper_decode_roofline": {"kernel": f"whisper_decode_kernel (persistent, {min(Sl, 16)} sessions per launch, {L} concurrent)",
+                                        "bound": "hbm", "algorithmic_bytes_per_launch": wb, "launches_per_step": L * n_w_launch,
+                                        "achieved": ach_w, "peak": peak, "unit": "GB/s", "frac": ach_w / peak},
+            "tts_frame_roofline": {"kernel": f"llama_decode_kernel on the talker (1 step) + code predictor ({tg['n_groups'] - 1} steps), "
+                                             f"{min(Sl, st.tts_b)} sessions per launch, {L} concurrent", "bound": "hbm",
+                                   "algorithmic_bytes_per_frame": frame_bytes, "ms_per_frame": frame_ms, "achieved": ach_tts, "peak": peak,
+                                   "unit": "GB/s", "frac": ach_tts / peak,
+                                   "note": "latency-bound: ~630 grid-barrier phases of 5-10 us per frame (profiles/r2/tts_phase_trace.txt); "
+                                           "weights are KV-free attention-light (<= 512 positions), KV bytes not counted"},
             "stt_only_sessions": world * S * AUDIO_S / (stages["stt_ms"] / 1e3),
         }
         if e2e and "loaded" in e2e:

@@ -45,8 +45,14 @@ typedef struct s2s_llama s2s_llama;
 /* ---- context ------------------------------------------------------------------------- */
 int s2s_init(int device, s2s_ctx** out);
 int s2s_destroy(s2s_ctx* ctx);
+/* SM partition ("lane") of a context: the persistent cooperative decode kernels of the models created on `ctx` use `ctas`
+ * CTAs (0 = one per SM, the default).  Contexts with disjoint partitions (e.g. two of 74 CTAs on a 148-SM B200), driven
+ * from different CUDA streams, run their decode launches concurrently; a decode step is a chain of latency-bound phases, so
+ * two half-grid launches take about as long as one whole-grid launch.  No reference counterpart (the reference runs one
+ * session per model call). */
+int s2s_set_sm_partition(s2s_ctx* ctx, int32_t ctas);
 const char* s2s_last_error(void);
-/* number of kernels this library launched on this thread's context since the last reset */
+/* number of kernels this library launched in this process (all contexts, all host threads) since the last reset */
 int64_t s2s_launch_count(s2s_ctx* ctx, int reset);
 
 /* ---- Whisper (STT) ---------------------------------------------------------------------

@@ -53,6 +53,32 @@ GEOMETRIES = {
 
 
 # --------------------------------------------------------------------------------------------------- building blocks
+# Operand rounding of the dense contractions (linears, convolutions with groups == 1, transposed convolutions).  None: fp32
+# throughout (the reference's arithmetic).  np.float16: both operands rounded to fp16, products summed in fp32 -- an emulation
+# of the CUDA library's default tensor-core mode (codec precision 1), used by the tests to tell operand-rounding error
+# (expected, bounded by this emulation) from a kernel bug.  Set with `operand_rounding(np.float16)`.
+_OPERAND = None
+
+
+class operand_rounding:
+    def __init__(self, dtype): self.dtype = dtype
+    def __enter__(self):
+        global _OPERAND
+        self.prev, _OPERAND = _OPERAND, self.dtype
+    def __exit__(self, *exc):
+        global _OPERAND
+        _OPERAND = self.prev
+
+
+def _q(a: np.ndarray) -> np.ndarray:
+    return a if _OPERAND is None else a.astype(_OPERAND).astype(np.float32)
+
+
+def _lin(h: np.ndarray, wt: np.ndarray) -> np.ndarray:
+    """h [T, K] @ wt[N, K].T"""
+    return _q(h) @ _q(wt).T
+
+
 def causal_conv1d(x: np.ndarray, w: np.ndarray, b: np.ndarray, dilation: int = 1, stride: int = 1, groups: int = 1) -> np.ndarray:
     """Qwen3OmniMoeCausalConvNet.forward (:3283-3316): left pad (k_eff - stride), right pad up to a whole frame, conv1d.
     x [C_in, T], w [C_out, C_in / groups, k] -> [C_out, T_out]."""
@@ -70,7 +96,10 @@ def causal_conv1d(x: np.ndarray, w: np.ndarray, b: np.ndarray, dilation: int = 1
     og = c_out // groups
     out = np.empty((c_out, t_out), np.float32)
     for g in range(groups):
-        out[g * og:(g + 1) * og] = np.einsum("ock,ctk->ot", w[g * og:(g + 1) * og], win[g * c_in_g:(g + 1) * c_in_g], optimize=True)
+        wg, xg = w[g * og:(g + 1) * og], win[g * c_in_g:(g + 1) * c_in_g]
+        if groups == 1:
+            wg, xg = _q(wg), _q(xg)                      # depthwise convolutions stay fp32 on the device as well
+        out[g * og:(g + 1) * og] = np.einsum("ock,ctk->ot", wg, xg, optimize=True)
     return (out + b[:, None]).astype(np.float32)
 
 
@@ -80,7 +109,7 @@ def causal_trans_conv1d(x: np.ndarray, w: np.ndarray, b: np.ndarray, stride: int
     c_in, c_out, k = w.shape
     T = x.shape[-1]
     full = np.zeros((c_out, (T - 1) * stride + k), np.float32)
-    contrib = np.einsum("ct,cok->otk", x, w, optimize=True)   # [C_out, T, k]
+    contrib = np.einsum("ct,cok->otk", _q(x), _q(w), optimize=True)   # [C_out, T, k]
     for j in range(k):
         full[:, j:j + (T - 1) * stride + 1:stride] += contrib[:, :, j]
     full += b[:, None]
@@ -118,8 +147,8 @@ def convnext_block(x: np.ndarray, w: dict, p: str) -> np.ndarray:
     dim = x.shape[0]
     h = causal_conv1d(x, w[p + "dwconv.conv.weight"], w[p + "dwconv.conv.bias"], groups=dim)
     h = layer_norm(h.T, w[p + "norm.weight"], w[p + "norm.bias"], 1e-6)
-    h = gelu(h @ w[p + "pwconv1.weight"].T + w[p + "pwconv1.bias"])
-    h = h @ w[p + "pwconv2.weight"].T + w[p + "pwconv2.bias"]
+    h = gelu(_lin(h, w[p + "pwconv1.weight"]) + w[p + "pwconv1.bias"])
+    h = _lin(h, w[p + "pwconv2.weight"]) + w[p + "pwconv2.bias"]
     return (x + (w[p + "gamma"] * h).T).astype(np.float32)
 
 
@@ -143,9 +172,9 @@ def transformer_layer(x: np.ndarray, w: dict, p: str, g: Code2WavGeometry, cos, 
     hd = g.hidden // g.heads
     grp = g.heads // g.kv_heads
     h = rms_norm(x, w[p + "input_layernorm.weight"], g.rms_eps)
-    q = (h @ w[p + "self_attn.q_proj.weight"].T).reshape(T, g.heads, hd).transpose(1, 0, 2)
-    k = (h @ w[p + "self_attn.k_proj.weight"].T).reshape(T, g.kv_heads, hd).transpose(1, 0, 2)
-    v = (h @ w[p + "self_attn.v_proj.weight"].T).reshape(T, g.kv_heads, hd).transpose(1, 0, 2)
+    q = _lin(h, w[p + "self_attn.q_proj.weight"]).reshape(T, g.heads, hd).transpose(1, 0, 2)
+    k = _lin(h, w[p + "self_attn.k_proj.weight"]).reshape(T, g.kv_heads, hd).transpose(1, 0, 2)
+    v = _lin(h, w[p + "self_attn.v_proj.weight"]).reshape(T, g.kv_heads, hd).transpose(1, 0, 2)
     q = q * cos[None] + _rotate_half(q) * sin[None]
     k = k * cos[None] + _rotate_half(k) * sin[None]
     k = np.repeat(k, grp, axis=0)
@@ -158,9 +187,9 @@ def transformer_layer(x: np.ndarray, w: dict, p: str, g: Code2WavGeometry, cos, 
     pr = np.exp(s)
     pr = pr / pr.sum(-1, keepdims=True)
     a = np.einsum("hts,hsd->thd", pr, v, optimize=True).reshape(T, g.heads * hd)
-    x = x + w[p + "self_attn_layer_scale.scale"] * (a @ w[p + "self_attn.o_proj.weight"].T)
+    x = x + w[p + "self_attn_layer_scale.scale"] * _lin(a, w[p + "self_attn.o_proj.weight"])
     h = rms_norm(x, w[p + "post_attention_layernorm.weight"], g.rms_eps)
-    m = (silu(h @ w[p + "mlp.gate_proj.weight"].T) * (h @ w[p + "mlp.up_proj.weight"].T)) @ w[p + "mlp.down_proj.weight"].T
+    m = _lin(silu(_lin(h, w[p + "mlp.gate_proj.weight"])) * _lin(h, w[p + "mlp.up_proj.weight"]), w[p + "mlp.down_proj.weight"])
     return (x + w[p + "mlp_layer_scale.scale"] * m).astype(np.float32)
 
 

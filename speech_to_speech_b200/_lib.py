@@ -13,7 +13,7 @@ DTYPE_CODES = {"float32": S2S_F32, "float16": S2S_F16, "bfloat16": S2S_BF16}
 
 # every symbol include/s2s_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = [
-    "s2s_init", "s2s_destroy", "s2s_last_error", "s2s_launch_count",
+    "s2s_init", "s2s_destroy", "s2s_set_sm_partition", "s2s_last_error", "s2s_launch_count",
     "s2s_whisper_create", "s2s_whisper_destroy", "s2s_whisper_bind_tensor", "s2s_whisper_init_random",
     "s2s_whisper_finalize", "s2s_whisper_logmel", "s2s_whisper_encode", "s2s_whisper_decode",
     "s2s_whisper_detect_language", "s2s_whisper_transcribe", "s2s_whisper_set_trace", "s2s_whisper_max_decode_batch",
@@ -96,6 +96,7 @@ def load() -> C.CDLL:
     lib.s2s_launch_count.argtypes = [C.c_void_p, C.c_int]
     lib.s2s_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.s2s_destroy.argtypes = [C.c_void_p]
+    lib.s2s_set_sm_partition.argtypes = [C.c_void_p, C.c_int32]
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     lib.s2s_whisper_create.argtypes = [vp, C.POINTER(WhisperConfig), C.POINTER(vp)]
     lib.s2s_whisper_destroy.argtypes = [vp]

@@ -29,7 +29,8 @@ from typing import Any, Callable, Hashable, List, Optional, Sequence, Tuple
 
 class SessionBatcher:
     def __init__(self, run_batch: Callable[[Hashable, List[Any]], Sequence[Any]], max_batch: int = 16,
-                 max_wait_s: float = 0.004, name: str = "s2s-batcher"):
+                 max_wait_s: float = 0.004, name: str = "s2s-batcher",
+                 thread_context: Optional[Callable[[], Any]] = None):
         if max_batch < 1:
             raise ValueError("max_batch must be >= 1")
         self._run_batch = run_batch
@@ -42,6 +43,9 @@ class SessionBatcher:
         self.batches_run = 0
         self.items_run = 0
         self.largest_batch = 0
+        # a context manager factory entered once by the engine thread for its whole life (e.g. the lane's CUDA stream)
+        self._thread_context = thread_context
+        self._fatal: Optional[BaseException] = None
         self._thread = threading.Thread(target=self._loop, name=name, daemon=True)
         self._thread.start()
 
@@ -81,6 +85,20 @@ class SessionBatcher:
                     self._cv.wait()
 
     def _loop(self) -> None:
+        if self._thread_context is None:
+            return self._serve()
+        try:
+            cm = self._thread_context()
+            cm.__enter__()
+        except BaseException as exc:   # the waiting handler threads must hear about it: every request fails with this error
+            self._fatal = exc
+            return self._serve()
+        try:
+            return self._serve()
+        finally:
+            cm.__exit__(None, None, None)
+
+    def _serve(self) -> None:
         while True:
             taken = self._take()
             if taken is None:
@@ -90,6 +108,8 @@ class SessionBatcher:
             if not live:
                 continue
             try:
+                if self._fatal is not None:
+                    raise RuntimeError(f"SessionBatcher engine thread could not enter its context: {self._fatal!r}")
                 results = self._run_batch(key, [it for it, _ in live])
                 if len(results) != len(live):
                     raise RuntimeError(f"run_batch returned {len(results)} results for {len(live)} items")

@@ -1,12 +1,14 @@
 // api.cu -- context, error reporting and the thin C-ABI wrappers around the stand-alone kernels.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
 static thread_local char g_err[1024] = "";
-static thread_local long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // process-wide: lanes launch from several host threads
 
 void s2s_set_error(const char* fmt, ...) {
   va_list ap;
@@ -21,9 +23,7 @@ extern "C" {
 const char* s2s_last_error(void) { return g_err; }
 
 int64_t s2s_launch_count(s2s_ctx*, int reset) {
-  const long long v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 int s2s_init(int device, s2s_ctx** out) {
@@ -42,6 +42,7 @@ int s2s_init(int device, s2s_ctx** out) {
   s2s_ctx* c = new s2s_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  c->decode_ctas = 0;
   c->encode_tiled = nullptr;
   cudaDriverEntryPointQueryResult q;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &c->encode_tiled, cudaEnableDefault, &q);
@@ -51,6 +52,14 @@ int s2s_init(int device, s2s_ctx** out) {
     return S2S_ERR_CUDA;
   }
   *out = c;
+  return S2S_OK;
+}
+
+int s2s_set_sm_partition(s2s_ctx* ctx, int32_t ctas) {
+  S2S_REQUIRE(ctx, "s2s_set_sm_partition: null context");
+  S2S_REQUIRE(ctas == 0 || (ctas >= 8 && ctas <= ctx->num_sms), "s2s_set_sm_partition: %d CTAs not in [8, %d] (0 = all SMs)", ctas,
+              ctx->num_sms);
+  ctx->decode_ctas = ctas;
   return S2S_OK;
 }
 

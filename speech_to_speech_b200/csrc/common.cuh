@@ -49,9 +49,15 @@ void s2s_count_launch(int n = 1);
 struct s2s_ctx {
   int device;
   int num_sms;
+  // SM partition ("lane"): the persistent cooperative decode kernels launched through this context use this many CTAs
+  // (0 = one per SM).  Two contexts of 74 CTAs each run their decode launches side by side on one GPU: the phases of a
+  // decode step are latency-bound, so two half-grid launches finish in about the time of one whole-grid launch.
+  int decode_ctas;
   // cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
   void* encode_tiled;
 };
+
+inline int dec_grid(const s2s_ctx* c) { return (c->decode_ctas > 0 && c->decode_ctas < c->num_sms) ? c->decode_ctas : c->num_sms; }
 
 // ------------------------------------------------------------------------------------------
 // dtype helpers

@@ -381,10 +381,10 @@ __global__ void llama_decode_init_kernel(const LlamaDecParams p) {
 template <typename T>
 int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream_t stream) {
   int kmax = 0, rg = 0, kc = 0, slots = 0;
-  int grid = ctx->num_sms;
-  if (const char* e = getenv("S2S_DECODE_CTAS")) {   // developer knob: a smaller cooperative grid (SM-partition experiments)
+  int grid = dec_grid(ctx);                          // the context's SM partition (s2s_set_sm_partition)
+  if (const char* e = getenv("S2S_DECODE_CTAS")) {   // developer knob: override for experiments (tests/dev/dev_lanes.py)
     const int v = atoi(e);
-    if (v >= 8 && v < grid) grid = v;
+    if (v >= 8 && v < ctx->num_sms) grid = v;
   }
   S2S_REQUIRE(llama_decode_plan(p.B, p.d, p.ffn, p.heads * p.hd, grid, &kmax, &rg, &kc, &slots),
               "llama decode: batch %d does not fit shared memory for d %d, ffn %d", p.B, p.d, p.ffn);

@@ -736,24 +736,25 @@ int launch_cluster_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, 
   S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // every head needs its own co-resident 8-CTA cluster (queried once per configuration)
   static thread_local size_t cached_smem = 0;
-  static thread_local int cached_heads = -1, cached_cs = 0, cached_n = 0;
+  static thread_local int cached_heads = -1, cached_cs = 0, cached_n = 0, cached_grid = 0;
+  const int lane_grid = dec_grid(ctx);
   int cs = 0, n_clusters = 0;
-  const bool cache_hit = cached_smem == smem && cached_heads == p.heads;
+  const bool cache_hit = cached_smem == smem && cached_heads == p.heads && cached_grid == lane_grid;
   if (cache_hit) { cs = cached_cs; n_clusters = cached_n; }
   // only the 8-CTA configuration is validated on hardware (12 heads of Whisper-small on 14-15 co-resident clusters);
   // geometries whose heads do not fit (large-v3: 20 heads) use the 8-phase kernel
   for (int cand = 8; cand >= 8 && !cs && !cache_hit; cand >>= 1) {
     cudaLaunchConfig_t qc{};
-    qc.gridDim = dim3((ctx->num_sms / cand) * cand); qc.blockDim = dim3(DEC_THREADS); qc.dynamicSmemBytes = smem;
+    qc.gridDim = dim3((lane_grid / cand) * cand); qc.blockDim = dim3(DEC_THREADS); qc.dynamicSmemBytes = smem;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = cand; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.attrs = qa; qc.numAttrs = 1;
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess) { cudaGetLastError(); continue; }
-    n = std::min(n, ctx->num_sms / cand);
+    n = std::min(n, lane_grid / cand);
     if (n >= p.heads) { cs = cand; n_clusters = n; }
   }
-  cached_smem = smem; cached_heads = p.heads; cached_cs = cs; cached_n = n_clusters;
+  cached_smem = smem; cached_heads = p.heads; cached_cs = cs; cached_n = n_clusters; cached_grid = lane_grid;
   if (!cs) return S2S_OK;
   WhisperDecParams pr = p;
   pr.sync_relaxed = dec_sync_relaxed_env();
@@ -799,7 +800,7 @@ int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStre
   pr.sync_relaxed = dec_sync_relaxed_env();
   pr.ring_slots = dec_ring_slots(lay);
   {
-    const int BH = p.B * p.heads, grid = ctx->num_sms;
+    const int BH = p.B * p.heads, grid = dec_grid(ctx);
     pr.cross_plan = attn_plan(BH, (p.n_ctx + ATT_BLK - 1) / ATT_BLK, p.s_max, grid);
     const int nb_max = (p.max_pos + ATT_BLK - 1) / ATT_BLK;
     S2S_REQUIRE(nb_max < (int)sizeof(pr.self_plan), "whisper decode: max_target_positions %d too large", p.max_pos);
@@ -813,7 +814,7 @@ int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStre
   S2S_LAUNCH_CHECK();
   const int total_steps = p.n_prefix - 1 + p.max_new;
   const int n_ph = 8 * p.layers + 2;
-  const int grid = ctx->num_sms;
+  const int grid = dec_grid(ctx);
   if (!debug_phases) {
     int sb = 0, se = total_steps, pb = 0, pe = n_ph, coop = 1;
     WhisperDecParams pp = pr;

@@ -15,20 +15,49 @@ from ._lib import (S2S_BF16, S2S_F16, S2S_F32, DTYPE_CODES, CodecConfig, LlamaCo
                    WhisperDecodeOpts, check)
 
 _ctx_lock = threading.Lock()
-_ctx_by_device: dict[int, C.c_void_p] = {}
+_ctx_by_device: dict[tuple, C.c_void_p] = {}
+_lane_streams: dict[tuple, "torch.cuda.Stream"] = {}
 
 
-def get_context(device: int = 0) -> C.c_void_p:
-    """One library context per CUDA device (created on first use)."""
+def get_context(device: int = 0, lane: int = 0, lanes: int = 1) -> C.c_void_p:
+    """One library context per CUDA device and lane (created on first use).  lanes > 1 partitions the SMs: the persistent
+    decode kernels of the engines built on lane i use num_sms // lanes CTAs (s2s_set_sm_partition), so the lanes' decode
+    launches -- issued from different CUDA streams (lane_stream) -- run side by side on one GPU."""
     if not torch.cuda.is_available():
         raise S2SError("speech_to_speech_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if not (lanes >= 1 and 0 <= lane < lanes):
+        raise ValueError(f"lane {lane} not in [0, {lanes})")
     lib = _lib.load()
+    key = (device, lane, lanes)
     with _ctx_lock:
-        if device not in _ctx_by_device:
+        if key not in _ctx_by_device:
             h = C.c_void_p()
             check(lib.s2s_init(device, C.byref(h)), "s2s_init")
-            _ctx_by_device[device] = h
-        return _ctx_by_device[device]
+            if lanes > 1:
+                sms = torch.cuda.get_device_properties(device).multi_processor_count
+                check(lib.s2s_set_sm_partition(h, sms // lanes), "s2s_set_sm_partition")
+            _ctx_by_device[key] = h
+        return _ctx_by_device[key]
+
+
+def lane_stream(device: int = 0, lane: int = 0, lanes: int = 1) -> "torch.cuda.Stream":
+    """The CUDA stream all work of a lane is issued on (engines take the calling thread's current stream: wrap the calls in
+    `with torch.cuda.stream(lane_stream(...))`).  One lane: the device's default stream, as before."""
+    if lanes <= 1:
+        return torch.cuda.default_stream(device)
+    key = (device, lane, lanes)
+    with _ctx_lock:
+        if key not in _lane_streams:
+            _lane_streams[key] = torch.cuda.Stream(device=device)
+        return _lane_streams[key]
+
+
+def lane_context(device: int = 0, lane: int = 0, lanes: int = 1):
+    """Context manager that makes the lane's stream the calling thread's current stream (a no-op for one lane).  Every thread
+    that touches a lane's engines -- handler threads, the session batchers' engine threads -- works inside it, so allocation
+    and use of every tensor of a lane happen on one stream."""
+    import contextlib
+    return contextlib.nullcontext() if lanes <= 1 else torch.cuda.stream(lane_stream(device, lane, lanes))
 
 
 def launch_count(device: int = 0, reset: bool = False) -> int:
@@ -81,10 +110,11 @@ class WhisperDecodeOptions:
 class WhisperEngine:
     """Whisper STT on one B200: log-mel -> encoder -> greedy decoder, batched over utterances."""
 
-    def __init__(self, geometry: Mapping[str, int], dtype: str = "float16", max_batch: int = 1, device: int = 0):
+    def __init__(self, geometry: Mapping[str, int], dtype: str = "float16", max_batch: int = 1, device: int = 0,
+                 lane: int = 0, lanes: int = 1):
         self.lib = _lib.load()
         self.device = device
-        self.ctx = get_context(device)
+        self.ctx = get_context(device, lane, lanes)
         self.geometry = dict(geometry)
         self.dtype = dtype
         self.max_batch = max_batch
@@ -258,10 +288,10 @@ class LlamaEngine:
     """Llama-family LLM on one B200: tcgen05 prefill + persistent greedy decode with a per-session KV cache."""
 
     def __init__(self, geometry: Mapping[str, float], dtype: str = "bfloat16", max_sessions: int = 1,
-                 max_positions: int = 2048, max_prefill: int = 512, device: int = 0):
+                 max_positions: int = 2048, max_prefill: int = 512, device: int = 0, lane: int = 0, lanes: int = 1):
         self.lib = _lib.load()
         self.device = device
-        self.ctx = get_context(device)
+        self.ctx = get_context(device, lane, lanes)
         self.geometry = dict(geometry)
         g = self.geometry
         self.cfg = LlamaConfig(
@@ -434,10 +464,11 @@ class Qwen3TTSEngine:
     oracle.qwen3tts_ref.TTSGeometry.to_dict(); codec geometry = oracle.code2wav_ref.Code2WavGeometry.to_dict()."""
 
     def __init__(self, geometry: Mapping, codec_geometry: Mapping, dtype: str = "bfloat16", max_sessions: int = 4,
-                 max_positions: int = 1024, max_text: int = 256, codec_max_frames: int = 40, device: int = 0, codec_precision: int = 1):
+                 max_positions: int = 1024, max_text: int = 256, codec_max_frames: int = 40, device: int = 0, codec_precision: int = 1,
+                 lane: int = 0, lanes: int = 1):
         self.lib = _lib.load()
         self.device = device
-        self.ctx = get_context(device)
+        self.ctx = get_context(device, lane, lanes)
         self.geometry = dict(geometry)
         g, t, p = self.geometry, dict(geometry["talker"]), dict(geometry["predictor"])
         cfg = Qwen3TTSConfig()

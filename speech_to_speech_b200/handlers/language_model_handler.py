@@ -14,6 +14,7 @@ concurrent sessions into one persistent launch through the SessionBatcher (`batc
 `engine.max_decode_batch()` sessions of different lengths per launch at the cost of one weight stream."""
 from __future__ import annotations
 
+import contextlib
 import logging
 import threading
 from typing import Any, Callable, Iterator, Optional, Sequence
@@ -40,7 +41,10 @@ class TokenStreamer:
     """Greedy generation as an iterator of text fragments (the role TextIteratorStreamer plays in the reference)."""
 
     def __init__(self, engine: Any, decode_text: Callable[[Sequence[int]], str], eos_ids: Sequence[int], chunk: int = 8, slot: int = 0,
-                 decode_chunk: Optional[Callable[[int, int, int, int], list]] = None, lock: Optional[Any] = None):
+                 decode_chunk: Optional[Callable[[int, int, int, int], list]] = None, lock: Optional[Any] = None,
+                 context: Optional[Callable[[], Any]] = None):
+        import contextlib
+        self._context = context or contextlib.nullcontext   # the lane's CUDA stream for this thread's GPU calls
         self.engine, self.decode_text, self.eos_ids, self.chunk, self.slot = engine, decode_text, set(int(e) for e in eos_ids), max(1, chunk), slot
         self.generated: list[int] = []
         self._po = self._ro = 0   # incremental detokenisation window
@@ -53,7 +57,7 @@ class TokenStreamer:
         import torch
         eng = self.engine
         first = torch.tensor([tok], dtype=torch.int32, device=f"cuda:{eng.device}")
-        with self._lock:
+        with self._lock, self._context():
             ids, lens = eng.decode([slot], first, n, eos_id=eos)
             return ids[0, : int(lens[0]) if int(lens[0]) > 0 else n].tolist()
 
@@ -81,7 +85,7 @@ class TokenStreamer:
             prompt_ids = prompt_ids[-(room - 1):]
         max_new_tokens = max(1, min(int(max_new_tokens), room - len(prompt_ids)))
         nxt = None
-        with self._lock:
+        with self._lock, self._context():
             eng.reset(self.slot)
             for o in range(0, len(prompt_ids), max_prefill):
                 nxt, _ = eng.prefill(self.slot, list(prompt_ids[o:o + max_prefill]))
@@ -120,12 +124,21 @@ class _LlamaBundle:
     """One engine shared by the handler instances of a process: KV-cache slots handed out per handler, prefill serialised
     by a lock, decode chunks of concurrent sessions merged into one launch by the SessionBatcher."""
 
-    def __init__(self, engine: Any, tokenizer: Any, eos_ids: list, max_sessions: int, batch_wait_s: float):
+    def __init__(self, engine: Any, tokenizer: Any, eos_ids: list, max_sessions: int, batch_wait_s: float, lane: int = 0, lanes: int = 1):
         self.engine, self.tokenizer, self.eos_ids = engine, tokenizer, eos_ids
+        self.lane, self.lanes = lane, lanes
         self.lock = threading.Lock()
         self._free = list(range(max_sessions))
         mb = max(1, min(int(engine.max_decode_batch()), max_sessions))
-        self.batcher = SessionBatcher(self._run_batch, mb, batch_wait_s, "s2s-llm-batcher") if max_sessions > 1 else None
+        self.batcher = SessionBatcher(self._run_batch, mb, batch_wait_s, "s2s-llm-batcher",
+                                      thread_context=self.lane_context) if max_sessions > 1 else None
+
+    def lane_context(self):
+        """The lane's CUDA stream as the calling thread's current stream (engine.lane_context; a no-op for one lane)."""
+        if self.lanes <= 1:
+            return contextlib.nullcontext()
+        from .. import engine as E
+        return E.lane_context(self.engine.device, self.lane, self.lanes)
 
     def acquire_slot(self) -> int:
         with self.lock:
@@ -141,8 +154,8 @@ class _LlamaBundle:
         import torch
         n, eos = key
         slots = [it[0] for it in items]
-        first = torch.tensor([it[1] for it in items], dtype=torch.int32, device=f"cuda:{self.engine.device}")
-        with self.lock:
+        with self.lock, self.lane_context():
+            first = torch.tensor([it[1] for it in items], dtype=torch.int32, device=f"cuda:{self.engine.device}")
             ids, lens = self.engine.decode(slots, first, n, eos_id=eos)
             ids, lens = ids.tolist(), lens.tolist()
         return [row[: (ln if ln > 0 else n)] for row, ln in zip(ids, lens)]
@@ -223,33 +236,36 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
         max_pos = int(self.gen_kwargs.pop("max_positions", 4096))
         max_sessions = max(1, int(self.gen_kwargs.pop("max_sessions", 1)))
         batch_wait_s = float(self.gen_kwargs.pop("batch_wait_ms", 2.0)) / 1000.0
+        # SM partition: the handler instances of lane i share lane i's engine (engine.get_context)
+        lanes = max(1, int(self.gen_kwargs.pop("lanes", 1)))
+        lane = int(self.gen_kwargs.pop("lane", 0)) % lanes
 
         def build() -> _LlamaBundle:
             if model_name.startswith("random:"):
                 parts = model_name.split(":")
                 geom = LLAMA_GEOMETRIES[parts[1]]
-                engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=max_sessions, max_positions=max_pos, max_prefill=512, device=dev)
+                engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=max_sessions, max_positions=max_pos, max_prefill=512, device=dev, lane=lane, lanes=lanes)
                 engine.init_random(int(parts[2]) if len(parts) > 2 else 0)
-                return _LlamaBundle(engine, _IdTokenizer(geom["vocab"]), [geom["vocab"] - 1], max_sessions, batch_wait_s)
+                return _LlamaBundle(engine, _IdTokenizer(geom["vocab"]), [geom["vocab"] - 1], max_sessions, batch_wait_s, lane, lanes)
             from transformers import AutoModelForCausalLM, AutoTokenizer
             tokenizer = AutoTokenizer.from_pretrained(model_name)
             hf = AutoModelForCausalLM.from_pretrained(model_name)
             c = hf.config
             geom = geometry_from_hf_config(c, max_pos)
-            engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=max_sessions, max_positions=max_pos, max_prefill=512, device=dev)
+            engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=max_sessions, max_positions=max_pos, max_prefill=512, device=dev, lane=lane, lanes=lanes)
             engine.load_state_dict(hf.state_dict())
             eos = hf.generation_config.eos_token_id
             eos_ids = list(eos) if isinstance(eos, (list, tuple)) else [int(eos)]
             del hf
-            return _LlamaBundle(engine, tokenizer, eos_ids, max_sessions, batch_wait_s)
+            return _LlamaBundle(engine, tokenizer, eos_ids, max_sessions, batch_wait_s, lane, lanes)
 
-        self._shared_key = ("llama", model_name, torch_dtype, dev, max_sessions, max_pos) if max_sessions > 1 else None
+        self._shared_key = ("llama", model_name, torch_dtype, dev, max_sessions, max_pos, lane, lanes) if max_sessions > 1 else None
         self.bundle = acquire_shared(self._shared_key, build, lambda b: b.close()) if self._shared_key else build()
         self.engine, self.tokenizer, self.eos_ids = self.bundle.engine, self.bundle.tokenizer, self.bundle.eos_ids
         self.slot = self.bundle.acquire_slot()
         self.streamer = TokenStreamer(self.engine, lambda ids: self.tokenizer.decode(list(ids), skip_special_tokens=True),
                                       self.eos_ids, self.stream_chunk_tokens, slot=self.slot, decode_chunk=self.bundle.decode_chunk,
-                                      lock=self.bundle.lock)
+                                      lock=self.bundle.lock, context=self.bundle.lane_context)
 
     def generate_text_stream(self, prompt_ids: Sequence[int], max_new_tokens: Optional[int] = None,
                              should_stop: Callable[[], bool] = lambda: False) -> Iterator[str]:

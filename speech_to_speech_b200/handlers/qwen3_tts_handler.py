@@ -47,9 +47,13 @@ class B200Qwen3TTSHandler(_Base):  # type: ignore[misc, valid-type]
     _b200_post: Any = None
     _b200_shared_key: Optional[tuple] = None
 
-    def setup(self, *args: Any, max_sessions: Optional[int] = None, **kwargs: Any) -> None:
+    def setup(self, *args: Any, max_sessions: Optional[int] = None, lane: Optional[int] = None, lanes: Optional[int] = None,
+              **kwargs: Any) -> None:
         gk = dict(kwargs.get("gen_kwargs") or {})
         self._b200_max_sessions = int(max_sessions if max_sessions is not None else gk.pop("max_sessions", 1))
+        # SM partition: the handler instances of lane i share lane i's engine (engine.get_context); see INTEGRATION.md section 4
+        self._b200_lanes = max(1, int(lanes if lanes is not None else gk.pop("lanes", 1)))
+        self._b200_lane = int(lane if lane is not None else gk.pop("lane", 0)) % self._b200_lanes
         self._b200_seed = int(gk.pop("seed", 0))
         kwargs["gen_kwargs"] = gk
         if "backend" in kwargs and kwargs["backend"] == "ggml":
@@ -71,19 +75,36 @@ class B200Qwen3TTSHandler(_Base):  # type: ignore[misc, valid-type]
         n = max(1, self._b200_max_sessions)
         # the reference slot's `parity_mode` (qwen3_tts_arguments.py:99-101) selects the exact fp32 codec decoder
         prec = 0 if getattr(self, "parity_mode", False) else 1
-        key = ("qwen3tts", model_name, dt, dev, n, prec)
+        lane, lanes = getattr(self, "_b200_lane", 0), getattr(self, "_b200_lanes", 1)
+        key = ("qwen3tts", model_name, dt, dev, n, prec, lane, lanes)
 
         def build() -> B200Qwen3TTS:
             if model_name.startswith("random:"):
                 return B200Qwen3TTS.from_random(model_name.split(":", 1)[1], seed=self._b200_seed, dtype=dt, device=dev, max_sessions=n,
-                                                codec_precision=prec)
+                                                codec_precision=prec, lane=lane, lanes=lanes)
             return B200Qwen3TTS.from_pretrained(model_name, device=device, dtype=self.dtype, attn_implementation=attn_implementation,
-                                                backend=backend, max_sessions=n, codec_precision=prec)
+                                                backend=backend, max_sessions=n, codec_precision=prec, lane=lane, lanes=lanes)
 
         self.model = acquire_shared(key, build, lambda m: m.close())
         self._b200_shared_key = key
         self._b200_device = dev
         logger.info("Qwen3-TTS model loaded (libs2s_b200, %s, %d session slot%s)", dt, n, "" if n == 1 else "s")
+
+    # ---- every GPU call of this handler's thread goes to its lane's stream ----------------------------------------------
+    def _b200_lane_context(self):
+        m = getattr(self, "model", None)
+        if isinstance(m, B200Qwen3TTS):
+            return m.lane_context()
+        import contextlib
+        return contextlib.nullcontext()
+
+    def process(self, *args: Any, **kwargs: Any):
+        with self._b200_lane_context():
+            yield from super().process(*args, **kwargs)
+
+    def warmup(self, *args: Any, **kwargs: Any):
+        with self._b200_lane_context():
+            return super().warmup(*args, **kwargs)
 
     # ---- per-chunk post-processing on the device --------------------------------------------------------------------------
     def _prepare_audio_chunk(self, item: Any):

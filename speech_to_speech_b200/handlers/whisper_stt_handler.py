@@ -12,6 +12,7 @@ process with the same (model, dtype, device) share ONE engine -- one copy of the
 (`batcher.py`): utterances of concurrent sessions that arrive within `batch_wait_ms` are transcribed by one launch."""
 from __future__ import annotations
 
+import contextlib
 import logging
 import re
 import threading
@@ -67,10 +68,19 @@ class TokenTable:
 class _EngineBundle:
     """An engine with what is needed to drive it; private to one handler or shared through the batcher."""
 
-    def __init__(self, E: Any, engine: Any, tokens: "TokenTable", decode_text: Any, max_batch: int, batch_wait_s: float):
+    def __init__(self, E: Any, engine: Any, tokens: "TokenTable", decode_text: Any, max_batch: int, batch_wait_s: float,
+                 lane: int = 0, lanes: int = 1):
         self.E, self.engine, self.tokens, self.decode_text = E, engine, tokens, decode_text
+        self.lane, self.lanes = lane, lanes
         self.lock = threading.Lock()  # the engine handle is used by one thread at a time (INTEGRATION.md)
-        self.batcher = SessionBatcher(self._run_batch, max_batch, batch_wait_s, "s2s-stt-batcher") if max_batch > 1 else None
+        self.batcher = SessionBatcher(self._run_batch, max_batch, batch_wait_s, "s2s-stt-batcher",
+                                      thread_context=self.lane_context) if max_batch > 1 else None
+
+    def lane_context(self):
+        """The lane's CUDA stream as the calling thread's current stream (engine.lane_context; a no-op for one lane)."""
+        if self.lanes <= 1:
+            return contextlib.nullcontext()
+        return self.E.lane_context(self.engine.device, self.lane, self.lanes)
 
     @staticmethod
     def _key(o: Any) -> tuple:
@@ -87,11 +97,11 @@ class _EngineBundle:
     def transcribe(self, audio: np.ndarray, opts: Any) -> list[int]:
         if self.batcher is not None:
             return self.batcher.call(self._key(opts), audio)
-        with self.lock:
+        with self.lock, self.lane_context():
             return self.engine.transcribe([audio], opts)[0]
 
     def detect_language(self, audio: np.ndarray, sot: int, lang_ids: list[int]) -> int:
-        with self.lock:
+        with self.lock, self.lane_context():
             return int(self.engine.detect_language_host(audio, sot, lang_ids))
 
     # auto-language mode: detection and decode share one encoder pass; concurrent sessions still share the launches.
@@ -105,7 +115,7 @@ class _EngineBundle:
             rows = [[sot, (t if t in known else fallback)] + list(tail) for t in langs]
             return self.E.WhisperDecodeOptions(prefix=rows[0], eos_id=eos, max_new_tokens=max_new, suppress=list(sup),
                                                begin_suppress=list(beg), prefix_rows=rows)
-        with self.lock:
+        with self.lock, self.lane_context():
             ids, langs = self.engine.transcribe_auto(audios, sot, list(lang_ids), make_opts)
         return list(zip(ids, langs))
 
@@ -131,7 +141,7 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
 
     def setup(self, model_name: str = "distil-whisper/distil-large-v3", device: str = "cuda", torch_dtype: str = "float16",
               compile_mode: Optional[str] = None, language: Optional[str] = None, gen_kwargs: dict[str, Any] = {},
-              max_batch: int = 1, batch_wait_ms: float = 4.0) -> None:
+              max_batch: int = 1, batch_wait_ms: float = 4.0, lane: int = 0, lanes: int = 1) -> None:
         if not str(device).startswith("cuda"):
             raise ValueError(f"B200WhisperSTTHandler runs on CUDA (sm_100a) only, got device={device!r}; there is no CPU fallback")
         from .. import engine as E  # raises ImportError if libs2s_b200.so is not built
@@ -150,9 +160,12 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         # one persistent decode launch carries up to 16 sessions; more concurrent sessions queue in the batcher
         self.max_batch = max(1, min(int(max_batch), 16))
         self.batch_wait_s = float(batch_wait_ms) / 1000.0
+        # SM partition: the handler instances of lane i share lane i's engine (engine.get_context)
+        self.lanes = max(1, int(lanes))
+        self.lane = int(lane) % self.lanes
         self._shared_key = None
         if self.max_batch > 1:
-            self._shared_key = ("whisper", model_name, torch_dtype, self.device_index, self.max_batch)
+            self._shared_key = ("whisper", model_name, torch_dtype, self.device_index, self.max_batch, self.lane, self.lanes)
             self.bundle = acquire_shared(self._shared_key, lambda: self._load(model_name), lambda b: b.close())
         else:
             self.bundle = self._load(model_name)
@@ -167,10 +180,11 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
             parts = model_name.split(":")
             geom = GEOMETRIES[parts[1]]
             seed = int(parts[2]) if len(parts) > 2 else 0
-            engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=self.max_batch, device=self.device_index)
+            engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=self.max_batch, device=self.device_index,
+                                     lane=self.lane, lanes=self.lanes)
             engine.init_random(seed)
             return _EngineBundle(E, engine, TokenTable.synthetic(geom["vocab"]), lambda ids: " ".join(f"<{i}>" for i in ids),
-                                 self.max_batch, self.batch_wait_s)
+                                 self.max_batch, self.batch_wait_s, self.lane, self.lanes)
         from transformers import AutoModelForSpeechSeq2Seq, AutoProcessor
         processor = AutoProcessor.from_pretrained(model_name)
         hf = AutoModelForSpeechSeq2Seq.from_pretrained(model_name)
@@ -178,13 +192,14 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         geom = dict(d_model=c.d_model, heads=c.encoder_attention_heads, enc_layers=c.encoder_layers, dec_layers=c.decoder_layers,
                     ffn=c.encoder_ffn_dim, n_mels=c.num_mel_bins, vocab=c.vocab_size,
                     max_source_positions=c.max_source_positions, max_target_positions=c.max_target_positions)
-        engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=self.max_batch, device=self.device_index)
+        engine = E.WhisperEngine(geom, dtype=self.torch_dtype, max_batch=self.max_batch, device=self.device_index,
+                                     lane=self.lane, lanes=self.lanes)
         engine.load_state_dict({k: v for k, v in hf.state_dict().items() if not k.startswith("proj_out")})
         tokens = TokenTable.from_generation_config(hf.generation_config)
         del hf
         bundle = _EngineBundle(E, engine, tokens,
                                lambda ids: processor.batch_decode([ids], skip_special_tokens=True, decode_with_timestamps=False)[0],
-                               self.max_batch, self.batch_wait_s)
+                               self.max_batch, self.batch_wait_s, self.lane, self.lanes)
         bundle.processor = processor   # every handler sharing the engine sees the processor, not only the one that loaded it
         return bundle
 

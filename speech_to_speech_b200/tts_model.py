@@ -18,6 +18,7 @@ Concurrent sessions: one engine per (checkpoint, dtype, device) is shared by all
 `s2s_qwen3tts_decode_frames` call -- 3 persistent launches per frame for up to 16 sessions."""
 from __future__ import annotations
 
+import contextlib
 import json
 import logging
 import os
@@ -95,8 +96,9 @@ def byte_tokenizer(text_vocab: int, reserved: int = 16) -> Callable[[str], list]
 
 class B200Qwen3TTS:
     def __init__(self, engine: Any, tokenize: Callable[[str], Sequence[int]], speakers: Mapping[str, int], max_sessions: int = 1,
-                 batch_wait_s: float = 0.002, tts_model_type: str = "custom_voice"):
+                 batch_wait_s: float = 0.002, tts_model_type: str = "custom_voice", lane: int = 0, lanes: int = 1):
         self.engine = engine
+        self.lane, self.lanes = int(lane), int(lanes)
         self.tokenize = tokenize
         self.speakers = {str(k).lower(): int(v) for k, v in speakers.items()}
         self.sample_rate = SAMPLE_RATE
@@ -104,29 +106,40 @@ class B200Qwen3TTS:
         self._free = list(range(max_sessions))
         self._slot_cv = threading.Condition()
         mb = max(1, min(int(engine.max_batch()), max_sessions))
-        self.batcher = SessionBatcher(self._run_frames, mb, batch_wait_s, "s2s-tts-batcher") if max_sessions > 1 else None
+        self.batcher = SessionBatcher(self._run_frames, mb, batch_wait_s, "s2s-tts-batcher",
+                                      thread_context=self.lane_context) if max_sessions > 1 else None
         # what the reference handler inspects: model.model.tts_model_type, get_supported_speakers (qwen3_tts_handler.py:574-593)
         inner = types.SimpleNamespace(tts_model_type=tts_model_type, get_supported_speakers=self.get_supported_speakers)
         self.model = types.SimpleNamespace(model=inner, get_supported_speakers=self.get_supported_speakers)
+
+    def lane_context(self):
+        """The lane's CUDA stream as the calling thread's current stream (no-op for one lane): engine.lane_context."""
+        if self.lanes <= 1:
+            return contextlib.nullcontext()
+        from . import engine as E
+        return E.lane_context(self.engine.device, self.lane, self.lanes)
 
     # ---- construction -------------------------------------------------------------------------------------------------
     @classmethod
     def from_random(cls, geometry: "str | Mapping" = "qwen3-tts-12hz", codec_geometry: "str | Mapping | None" = None, seed: int = 0,
                     dtype: str = "bfloat16", device: int = 0, max_sessions: int = 1, max_positions: int = 2048, max_text: int = 512,
                     tokenize: Optional[Callable] = None, speakers: Optional[Mapping[str, int]] = None, codec_precision: int = 1,
-                    **kw: Any) -> "B200Qwen3TTS":
+                    lane: int = 0, lanes: int = 1, **kw: Any) -> "B200Qwen3TTS":
         from . import engine as E
         g = TTS_GEOMETRIES[geometry] if isinstance(geometry, str) else dict(geometry)
         cg = codec_geometry if codec_geometry is not None else (geometry if isinstance(geometry, str) else "qwen3-tts-12hz")
         cg = CODEC_GEOMETRIES[cg] if isinstance(cg, str) else dict(cg)
         eng = E.Qwen3TTSEngine(g, cg, dtype=dtype, max_sessions=max_sessions, max_positions=max_positions, max_text=max_text,
-                               codec_max_frames=LEFT_CONTEXT_FRAMES + 16, device=device, codec_precision=codec_precision)
+                               codec_max_frames=LEFT_CONTEXT_FRAMES + 16, device=device, codec_precision=codec_precision,
+                               lane=lane, lanes=lanes)
         eng.init_random(seed)
-        return cls(eng, tokenize or byte_tokenizer(g["text_vocab"]), speakers or DEFAULT_SPEAKERS, max_sessions=max_sessions, **kw)
+        return cls(eng, tokenize or byte_tokenizer(g["text_vocab"]), speakers or DEFAULT_SPEAKERS, max_sessions=max_sessions,
+                   lane=lane, lanes=lanes, **kw)
 
     @classmethod
     def from_pretrained(cls, model_name: str, device: Any = "cuda", dtype: Any = None, attn_implementation: str = "eager",
-                        backend: str = "torch", max_sessions: int = 1, codec_precision: int = 1, **_ignored: Any) -> "B200Qwen3TTS":
+                        backend: str = "torch", max_sessions: int = 1, codec_precision: int = 1, lane: int = 0, lanes: int = 1,
+                        **_ignored: Any) -> "B200Qwen3TTS":
         """Load a checkpoint DIRECTORY in the cousin's layout: `config.json` with {"talker": ..., "code2wav": ..., "speaker_id":
         ...}, `model.safetensors` with the talker state dict (+ "text_embedding.weight", "code2wav.*") and tokenizer files.
         Hub ids cannot be resolved offline, and the real Qwen3-TTS checkpoint layout is unverified (upstream absent): both
@@ -148,13 +161,13 @@ class B200Qwen3TTS:
         dev = int(str(device).split(":")[1]) if ":" in str(device) else 0
         dt = "float16" if dtype in (torch.float16, "float16") else "bfloat16"
         eng = E.Qwen3TTSEngine(g, cg, dtype=dt, max_sessions=max_sessions, codec_max_frames=LEFT_CONTEXT_FRAMES + 16, device=dev,
-                               codec_precision=codec_precision)
+                               codec_precision=codec_precision, lane=lane, lanes=lanes)
         sd = load_file(os.path.join(model_name, "model.safetensors"))
         eng.load_state_dict({k: v for k, v in sd.items() if not k.startswith("code2wav.")},
                             {k[len("code2wav."):]: v for k, v in sd.items() if k.startswith("code2wav.")})
         tok = AutoTokenizer.from_pretrained(model_name)
         return cls(eng, lambda text: tok.encode(text, add_special_tokens=False), cfg.get("speaker_id") or DEFAULT_SPEAKERS,
-                   max_sessions=max_sessions)
+                   max_sessions=max_sessions, lane=lane, lanes=lanes)
 
     # ---- the calls the handler makes ------------------------------------------------------------------------------------
     def get_supported_speakers(self) -> list:

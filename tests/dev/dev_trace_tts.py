@@ -24,10 +24,7 @@ for which, name, L in ((0, "talker", eng.cfg.layers), (1, "predictor", eng.cfg.c
     body, wait = {}, {}
     n_ph = 6 * L + 2
     for i, row in enumerate(t):
-        ph = i % n_ph if which == 0 else None
-        if which == 1:   # step 0 skips the logits phase: n_ph - 1 phases, then n_ph per step
-            j = i if i < n_ph - 1 else (i - (n_ph - 1)) % n_ph
-            ph = j if i >= n_ph - 1 or j < 6 * L else j + 1
+        ph = i % n_ph     # the predictor's step 0 still records its (empty) logits phase: n_ph records per step for both
         k = kinds[ph % 6] if ph < 6 * L else ("logits" if ph == 6 * L else "select")
         body.setdefault(k, []).append((row[1] - row[0]) / 1e3)
         wait.setdefault(k, []).append((row[2] - row[1]) / 1e3)

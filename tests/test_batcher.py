@@ -257,3 +257,28 @@ def test_random_arrivals_keep_every_result_with_its_request():
         assert b.items_run == 240
     finally:
         b.close()
+
+
+def test_thread_context_is_entered_by_the_engine_thread_and_failures_reach_the_callers():
+    """The lane mechanism: the batcher's engine thread lives inside a context (the lane's CUDA stream in production); a context
+    that cannot be entered must fail the requests, not strand the handler threads."""
+    import contextlib
+    import threading
+    from speech_to_speech_b200.batcher import SessionBatcher
+    seen = []
+
+    @contextlib.contextmanager
+    def ctx():
+        seen.append(threading.current_thread().name)
+        yield
+
+    b = SessionBatcher(lambda key, items: [threading.current_thread().name for _ in items], 4, 0.001, "lane-thread", thread_context=ctx)
+    assert b.call("k", 1, timeout=5) == "lane-thread" and seen == ["lane-thread"]
+    b.close()
+
+    def broken():
+        raise AttributeError("no device")
+    b2 = SessionBatcher(lambda key, items: items, 4, 0.001, "lane-thread-2", thread_context=broken)
+    with pytest.raises(RuntimeError, match="could not enter"):
+        b2.call("k", 1, timeout=5)
+    b2.close()

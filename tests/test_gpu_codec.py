@@ -12,8 +12,9 @@ from oracle import code2wav_ref as C
 
 pytestmark = pytest.mark.gpu
 # precision 0 = fp32 FMA ("parity mode"): pre-transformer output 2e-4, waveform 1e-3.
-# precision 1 = fp16 tensor-core contractions with fp32 accumulation (the default): 2e-2 / 1e-2 (operands carry 11 significant
-# bits through ~45 contractions; waveform values lie in [-1, 1]).
+# precision 1 = fp16 tensor-core contractions with fp32 accumulation (the default): 2e-2 / 1e-2 at the micro geometry (operands
+# carry 11 significant bits through ~45 contractions; waveform values lie in [-1, 1]); at the real geometry the bound comes from
+# the oracle's fp16-operand emulation (test_real_geometry_slice_vs_oracle).
 HID_TOLS, WAV_TOLS = {0: 2e-4, 1: 2e-2}, {0: 1e-3, 1: 1e-2}
 
 
@@ -92,5 +93,19 @@ def test_real_geometry_slice_vs_oracle(E, precision):
     got = wav.cpu().numpy()
     assert got.shape == ref.shape, (got.shape, ref.shape)
     we = float(np.abs(got - ref).max())
-    # K up to 10752 per output at this geometry: fp32 summation-order differences reach 1.2e-3 on the waveform (measured)
-    assert he < (5e-4 if precision == 0 else 5e-2) and we < (2e-3 if precision == 0 else 1e-2), f"hidden err {he:.3e} (|ref| max {np.abs(hid_ref).max():.2f}), wav err {we:.3e}"
+    if precision == 0:
+        # K up to 10752 per output at this geometry: fp32 summation-order differences reach 1.2e-3 on the waveform (measured)
+        assert he < 5e-4 and we < 2e-3, f"hidden err {he:.3e} (|ref| max {np.abs(hid_ref).max():.2f}), wav err {we:.3e}"
+        return
+    # fp16 operands: with seeded random weights the decoder's output saturates the [-1, 1] clamp on ~45 % of the samples, so
+    # operand rounding alone moves the waveform by 0.17 (the oracle with both operands of every contraction rounded to fp16 and
+    # fp32 sums, `operand_rounding`).  The kernel must (a) agree with that emulation far more closely than the emulation agrees
+    # with fp32 -- they differ only in summation order and the rounding flips it causes -- and (b) stay within twice the
+    # emulation's own distance from the fp32 reference.
+    with C.operand_rounding(np.float16):
+        ref16, hid16 = C.code2wav_forward(w, g, codes, return_hidden=True)
+    inherent_h, inherent_w = float(np.abs(hid16 - hid_ref).max()), float(np.abs(ref16 - ref).max())
+    he16, we16 = float(np.abs(hid.cpu().numpy() - hid16).max()), float(np.abs(got - ref16).max())
+    msg = f"vs fp16 emulation: hidden {he16:.3e} wav {we16:.3e}; vs fp32: hidden {he:.3e} wav {we:.3e}; emulation vs fp32: {inherent_h:.3e} {inherent_w:.3e}"
+    assert he16 < 1e-3 and we16 < 3e-2, msg
+    assert he < 2 * inherent_h + 1e-3 and we < 2 * inherent_w + 1e-2, msg
