@@ -290,7 +290,7 @@ class Stack:
         self.whisper = E.WhisperEngine(self.wg.to_dict(), dtype="float16", max_batch=min(16, S), device=dev, lane=lane, lanes=lanes)
         self.whisper.init_random(1234)
         self.llm = E.LlamaEngine(self.lg.to_dict(), dtype="bfloat16", max_sessions=S, max_positions=LLM_PROMPT + MAX_NEW + 8,
-                                 max_prefill=LLM_PROMPT, device=dev, lane=lane, lanes=lanes)
+                                 max_prefill=LLM_PROMPT * 8, device=dev, lane=lane, lanes=lanes)
         self.llm.init_random(7)
         self.tts = B200Qwen3TTS.from_random(TTS_GEOM, seed=11, dtype="bfloat16", device=dev, max_sessions=S,
                                             max_positions=max(F1, F2) + 32, max_text=128, lane=lane, lanes=lanes)
@@ -321,10 +321,11 @@ def wave_device(st: Stack, pcm_dev, ev) -> None:
         ev["whisper_mark"].append((wa, wb_))
     ev["stt"].record()
     firsts = []
-    for s in range(S):                                                    # ---- LLM prefill
-        st.llm.reset(s)
-        nxt, _ = st.llm.prefill(s, st.prompt)
-        firsts.append(nxt)
+    for b0 in range(0, S, 8):                                             # ---- LLM prefill: 8 prompts per pass over the weights
+        sl = list(range(b0, min(S, b0 + 8)))
+        for s in sl:
+            st.llm.reset(s)
+        firsts.append(st.llm.prefill_batch(sl, [st.prompt] * len(sl)))
     ev["prefill"].record()
     first = torch.cat(firsts)
     for b0 in range(0, S, st.llm_b):                                      # ---- LLM decode, llm_b sessions per launch

@@ -161,6 +161,14 @@ int s2s_llama_session_reset(s2s_llama* m, int32_t slot);
  * next_id_d optional [1] i32 = argmax of the last position.                                 */
 int s2s_llama_prefill(s2s_llama* m, int32_t slot, const int32_t* ids_h, int32_t n, float* logits_out_d,
                       int32_t* next_id_d, void* stream);
+/* Prefill of B sessions in ONE pass over the weights (the reference prefills one request per pipeline call,
+ * LLM/language_model.py:883-888): ids_h holds the sessions' new prompt tokens back to back (n_h[b] tokens for slot slots_h[b],
+ * sum <= max_prefill, B <= 16); the projections and the MLP run over all rows at once, RoPE / KV append / causal attention per
+ * session.  next_ids_d [B] receives each session's greedy next token.  Rows of a session produce the same values as
+ * s2s_llama_prefill up to the tile shape the GEMM picks for the row count. */
+int s2s_llama_prefill_batch(s2s_llama* m, const int32_t* slots_h, int32_t B, const int32_t* ids_h, const int32_t* n_h,
+                            int32_t* next_ids_d, void* stream);
+
 /* Greedy decode for B (<= s2s_llama_max_decode_batch: 16, 4 for Llama-3-8B) sessions in one persistent launch.  slots_h[B]; first_ids_d[B] are the tokens to
  * feed first (the prefill argmax); ids_out_d [B, n_steps] receives the n_steps tokens generated AFTER them; eos stops
  * a row (eos_id < 0 disables); forced_d optional [B, n_steps] teacher-forced feedback; logits_out_d optional

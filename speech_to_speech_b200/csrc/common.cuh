@@ -57,6 +57,27 @@ struct s2s_ctx {
   void* encode_tiled;
 };
 
+// Opt a kernel in to the device's largest dynamic shared-memory size (227 KB minus its static shared memory) ONCE per process.
+// The attribute is per function, not per launch: host threads of different lanes launch the same kernel with different
+// sizes at the same time, and "set the size I need, then launch" races (a smaller size set by the other thread in between
+// makes the launch fail with cudaErrorLaunchOutOfResources).  The maximum is valid for every launch.
+template <typename K>
+inline cudaError_t s2s_opt_in_max_smem(K kern, int device, size_t need, const char** why) {
+  static thread_local const void* last_ok = nullptr;   // fast path: this thread already saw this kernel opted in
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)kern);
+  if (e != cudaSuccess) return e;
+  int optin = 0;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (e != cudaSuccess) return e;
+  const long long max_dyn = (long long)optin - (long long)fa.sharedSizeBytes;
+  if ((long long)need > max_dyn) { if (why) *why = "dynamic shared memory exceeds the device limit"; return cudaErrorInvalidValue; }
+  if (last_ok == (const void*)kern && fa.maxDynamicSharedSizeBytes >= max_dyn) return cudaSuccess;
+  e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn);
+  if (e == cudaSuccess) last_ok = (const void*)kern;
+  return e;
+}
+
 inline int dec_grid(const s2s_ctx* c) { return (c->decode_ctas > 0 && c->decode_ctas < c->num_sms) ? c->decode_ctas : c->num_sms; }
 
 // ------------------------------------------------------------------------------------------

@@ -227,6 +227,7 @@ int build(s2s_llama* m) {
   S2S_CHECK(lalloc(m, &m->attn, (size_t)P * qd * esz));
   S2S_CHECK(lalloc(m, &m->hbuf, (size_t)P * f * esz));
   S2S_CHECK(lalloc(m, &m->last_logits, (size_t)c.vocab * 4));
+  S2S_CHECK(lalloc(m, &m->batch_logits, (size_t)MAX_DEC_B * c.vocab * 4));
   m->vt_elems = attention_tc_scratch_elems(1, c.max_positions, c.kv_heads, hd);
   S2S_CHECK(lalloc(m, &m->vt, m->vt_elems * esz));
   // decode state
@@ -249,6 +250,7 @@ int build(s2s_llama* m) {
   S2S_CHECK(lalloc(m, &m->next_id, 16));
   S2S_CHECK(lalloc(m, &m->sync_counter, 16));
   S2S_CHECK(lalloc(m, &m->kraw, (size_t)MAX_DEC_B * kvd * 4));
+  S2S_CHECK(lalloc(m, &m->qn, (size_t)MAX_DEC_B * qd * 4));
   return S2S_OK;
 }
 
@@ -275,7 +277,69 @@ void llama_fill_dec_params(s2s_llama* m, LlamaDecParams& p) {
   p.part = m->part; p.s_max = m->s_max; p.attn16 = m->attn16; p.attn_cnt = m->attn_cnt;
   p.done = m->done; p.n_done = m->n_done; p.cand_val = m->cand_val; p.cand_idx = m->cand_idx; p.sync_counter = m->sync_counter;
   p.trace = m->trace; p.trace_cap = m->trace_cap;
-  p.qk_norm = c.qk_norm ? 1 : 0; p.kraw = m->kraw;
+  p.qk_norm = c.qk_norm ? 1 : 0; p.kraw = m->kraw; p.qn = m->qn;
+}
+
+// One pass of all decoder layers over R = sum of the segments' rows, already embedded in m->x.  A segment is the new rows of
+// one session (rows [off, off + n) of the buffers, positions [past, past + n) of its KV slot): the projections and the MLP
+// run over all R rows at once -- ONE pass over the weights for every session of a batched prefill -- while RoPE / cache
+// append and the causal attention run per segment against that session's cache.
+struct PrefillSeg { int slot, off, n, past; };
+
+static int prefill_layers(s2s_llama* m, const PrefillSeg* segs, int nseg, int R, cudaStream_t st) {
+  const auto& c = m->cfg;
+  const int d = c.d_model, f = c.ffn, hd = c.head_dim, qd = c.heads * hd, kvd = c.kv_heads * hd, dt = c.compute_dtype;
+  const int ldq = qd + 2 * kvd;
+  const bool bf = dt == S2S_BF16;
+  const size_t esz = 2;
+  for (int i = 0; i < c.layers; ++i) {
+    const LlamaDecLayer& L = m->layers_h[i];
+    S2S_CHECK(norm_rows_launch(m->x, L.norm1, nullptr, c.rms_eps, R, d, m->xn, nullptr, dt, st));
+    {
+      GemmProblem p = lgemm(m->xn, d, L.w_qkv, d, R, ldq, d);
+      p.out_h = m->qkv; p.ldo_h = ldq;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const PrefillSeg& sg = segs[sgi];
+      char* kc = reinterpret_cast<char*>(m->kv) + ((size_t)sg.slot * m->kv_slot_stride + (size_t)i * m->kv_layer_stride) * esz;
+      char* vc = kc + (size_t)m->kv_which_stride * esz;
+      char* qrow = reinterpret_cast<char*>(m->qkv) + (size_t)sg.off * ldq * esz;
+      const int n = sg.n, past = sg.past;
+      if (c.qk_norm) {
+#define S2S_QKN(T, HD) qknorm_rope_prefill_kernel<T, HD><<<n, 256, 0, st>>>((T*)qrow, c.heads, c.kv_heads, past, m->rope, \
+                                                                             L.q_norm, L.k_norm, c.rms_eps, (T*)kc, (T*)vc)
+        if (bf) { if (hd == 128) S2S_QKN(__nv_bfloat16, 128); else S2S_QKN(__nv_bfloat16, 64); }
+        else { if (hd == 128) S2S_QKN(__half, 128); else S2S_QKN(__half, 64); }
+#undef S2S_QKN
+      } else if (bf) {
+        rope_prefill_kernel<__nv_bfloat16><<<n, 256, 0, st>>>((__nv_bfloat16*)qrow, n, qd, kvd, hd, past, m->rope,
+                                                              (__nv_bfloat16*)kc, (__nv_bfloat16*)vc);
+      } else {
+        rope_prefill_kernel<__half><<<n, 256, 0, st>>>((__half*)qrow, n, qd, kvd, hd, past, m->rope, (__half*)kc, (__half*)vc);
+      }
+      S2S_LAUNCH_CHECK();
+      S2S_CHECK(attention_tc_launch(m->ctx, qrow, kc, vc, reinterpret_cast<char*>(m->attn) + (size_t)sg.off * qd * esz, 1, n, past + n,
+                                     c.heads, c.kv_heads, hd, ldq, kvd, kvd, qd, 1.0f / sqrtf((float)hd), 1, dt, m->vt, m->vt_elems, st));
+    }
+    {
+      GemmProblem p = lgemm(m->attn, qd, L.w_o, qd, R, d, qd);
+      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    S2S_CHECK(norm_rows_launch(m->x, L.norm2, nullptr, c.rms_eps, R, d, m->xn, nullptr, dt, st));
+    {
+      GemmProblem p = lgemm(m->xn, d, L.w_gu, d, R, 2 * f, d);
+      p.act = 2; p.out_h = m->hbuf; p.ldo_h = f;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+    {
+      GemmProblem p = lgemm(m->hbuf, f, L.w_down, f, R, d, f);
+      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
+      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+    }
+  }
+  return S2S_OK;
 }
 
 int llama_prefill_rows(s2s_llama* m, int slot, int n, float* logits_out_d, int32_t* next_id_d, float* hidden_out_d,
@@ -284,52 +348,9 @@ int llama_prefill_rows(s2s_llama* m, int slot, int n, float* logits_out_d, int32
   S2S_REQUIRE(n >= 1 && n <= c.max_prefill, "llama prefill: n=%d outside [1,%d]", n, c.max_prefill);
   const int past = m->len[slot];
   S2S_REQUIRE(past + n <= c.max_positions, "llama prefill: %d + %d tokens exceed max_positions %d", past, n, c.max_positions);
-  const int d = c.d_model, f = c.ffn, hd = c.head_dim, qd = c.heads * hd, kvd = c.kv_heads * hd, dt = c.compute_dtype;
-  const int ldq = qd + 2 * kvd;
-  const bool bf = dt == S2S_BF16;
-  char* kvb = reinterpret_cast<char*>(m->kv) + (size_t)slot * m->kv_slot_stride * 2;
-  for (int i = 0; i < c.layers; ++i) {
-    const LlamaDecLayer& L = m->layers_h[i];
-    char* kc = kvb + (size_t)i * m->kv_layer_stride * 2;
-    char* vc = kc + (size_t)m->kv_which_stride * 2;
-    S2S_CHECK(norm_rows_launch(m->x, L.norm1, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
-    {
-      GemmProblem p = lgemm(m->xn, d, L.w_qkv, d, n, ldq, d);
-      p.out_h = m->qkv; p.ldo_h = ldq;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-    }
-    if (c.qk_norm) {
-#define S2S_QKN(T, HD) qknorm_rope_prefill_kernel<T, HD><<<n, 256, 0, st>>>((T*)m->qkv, c.heads, c.kv_heads, past, m->rope, \
-                                                                             L.q_norm, L.k_norm, c.rms_eps, (T*)kc, (T*)vc)
-      if (bf) { if (hd == 128) S2S_QKN(__nv_bfloat16, 128); else S2S_QKN(__nv_bfloat16, 64); }
-      else { if (hd == 128) S2S_QKN(__half, 128); else S2S_QKN(__half, 64); }
-#undef S2S_QKN
-    } else if (bf) {
-      rope_prefill_kernel<__nv_bfloat16><<<n, 256, 0, st>>>((__nv_bfloat16*)m->qkv, n, qd, kvd, hd, past, m->rope,
-                                                            (__nv_bfloat16*)kc, (__nv_bfloat16*)vc);
-    } else {
-      rope_prefill_kernel<__half><<<n, 256, 0, st>>>((__half*)m->qkv, n, qd, kvd, hd, past, m->rope, (__half*)kc, (__half*)vc);
-    }
-    S2S_LAUNCH_CHECK();
-    S2S_CHECK(attention_tc_launch(m->ctx, m->qkv, kc, vc, m->attn, 1, n, past + n, c.heads, c.kv_heads, hd, ldq, kvd, kvd, qd,
-                                   1.0f / sqrtf((float)hd), 1, dt, m->vt, m->vt_elems, st));
-    {
-      GemmProblem p = lgemm(m->attn, qd, L.w_o, qd, n, d, qd);
-      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-    }
-    S2S_CHECK(norm_rows_launch(m->x, L.norm2, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
-    {
-      GemmProblem p = lgemm(m->xn, d, L.w_gu, d, n, 2 * f, d);
-      p.act = 2; p.out_h = m->hbuf; p.ldo_h = f;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-    }
-    {
-      GemmProblem p = lgemm(m->hbuf, f, L.w_down, f, n, d, f);
-      p.out_f = m->x; p.ldo_f = d; p.resid = m->x; p.ld_resid = d; p.resid_mode = 1;
-      S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
-    }
-  }
+  const int d = c.d_model, dt = c.compute_dtype;
+  const PrefillSeg seg{slot, 0, n, past};
+  S2S_CHECK(prefill_layers(m, &seg, 1, n, st));
   if (hidden_out_d)
     S2S_CHECK_CUDA(cudaMemcpyAsync(hidden_out_d, m->x + (size_t)(n - 1) * d, (size_t)d * 4, cudaMemcpyDeviceToDevice, st));
   S2S_CHECK(norm_rows_launch(m->x, m->norm_f, nullptr, c.rms_eps, n, d, m->xn, nullptr, dt, st));
@@ -352,6 +373,48 @@ int llama_prefill_rows(s2s_llama* m, int slot, int n, float* logits_out_d, int32
     S2S_LAUNCH_CHECK();
   }
   m->len[slot] = past + n;
+  return S2S_OK;
+}
+
+// last row of every segment -> consecutive 16-bit rows (input of the one lm_head GEMM of a batched prefill)
+template <typename T>
+__global__ void gather_last_rows_kernel(const T* __restrict__ xn, const int* __restrict__ last_row, int d, T* __restrict__ out) {
+  const T* src = xn + (long long)last_row[blockIdx.x] * d;
+  T* dst = out + (long long)blockIdx.x * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) dst[i] = src[i];
+}
+
+int llama_prefill_batch(s2s_llama* m, const int32_t* slots_h, int B, const int32_t* n_h, int32_t* next_ids_d, cudaStream_t st) {
+  const auto& c = m->cfg;
+  PrefillSeg segs[MAX_DEC_B];
+  int last_h[MAX_DEC_B], R = 0;
+  for (int b = 0; b < B; ++b) {
+    const int s = slots_h[b];
+    S2S_REQUIRE(m->len[s] + n_h[b] <= c.max_positions, "llama prefill_batch: slot %d: %d + %d tokens exceed max_positions %d", s, m->len[s],
+                n_h[b], c.max_positions);
+    segs[b] = PrefillSeg{s, R, n_h[b], m->len[s]};
+    R += n_h[b];
+    last_h[b] = R - 1;
+  }
+  const int d = c.d_model, dt = c.compute_dtype;
+  S2S_REQUIRE((size_t)c.max_prefill * c.heads * c.head_dim >= (size_t)B * d, "llama prefill_batch: scratch too small for %d sessions", B);
+  S2S_CHECK(prefill_layers(m, segs, B, R, st));
+  S2S_CHECK(norm_rows_launch(m->x, m->norm_f, nullptr, c.rms_eps, R, d, m->xn, nullptr, dt, st));
+  S2S_CHECK_CUDA(cudaMemcpyAsync(m->slot_d, last_h, (size_t)B * 4, cudaMemcpyHostToDevice, st));   // slot_d: free outside a decode launch
+  S2S_CHECK_CUDA(cudaStreamSynchronize(st));                                                        // last_h lives on this stack
+  if (dt == S2S_BF16) gather_last_rows_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)m->xn, m->slot_d, d, (__nv_bfloat16*)m->attn);
+  else gather_last_rows_kernel<__half><<<B, 256, 0, st>>>((const __half*)m->xn, m->slot_d, d, (__half*)m->attn);
+  S2S_LAUNCH_CHECK();
+  {
+    GemmProblem p = lgemm(m->attn, d, m->lm_head, d, B, c.vocab, d);
+    p.out_f = m->batch_logits; p.ldo_f = c.vocab;
+    S2S_CHECK(gemm_tc_launch(m->ctx, p, dt, st));
+  }
+  for (int b = 0; b < B; ++b) {
+    argmax_row_kernel<<<1, 1024, 0, st>>>(m->batch_logits + (size_t)b * c.vocab, c.vocab, next_ids_d + b);
+    S2S_LAUNCH_CHECK();
+  }
+  for (int b = 0; b < B; ++b) m->len[slots_h[b]] += n_h[b];
   return S2S_OK;
 }
 
@@ -522,6 +585,31 @@ int s2s_llama_prefill(s2s_llama* m, int32_t slot, const int32_t* ids_h, int32_t 
   else embed_gather_kernel<__half><<<n, 256, 0, st>>>(m->ids_d, (const __half*)m->embed, m->x, c.d_model);
   S2S_LAUNCH_CHECK();
   return llama_prefill_rows(m, slot, n, logits_out_d, next_id_d, nullptr, st);
+}
+
+int s2s_llama_prefill_batch(s2s_llama* m, const int32_t* slots_h, int32_t B, const int32_t* ids_h, const int32_t* n_h,
+                            int32_t* next_ids_d, void* stream) {
+  S2S_REQUIRE(m && m->finalized && slots_h && ids_h && n_h && next_ids_d, "llama prefill_batch: null argument / not finalized");
+  const auto& c = m->cfg;
+  S2S_REQUIRE(B >= 1 && B <= MAX_DEC_B, "llama prefill_batch: B=%d outside [1,%d]", B, MAX_DEC_B);
+  S2S_REQUIRE(m->n_tables == 1, "llama prefill_batch: multi-table models are driven by the TTS entry points");
+  int R = 0;
+  for (int b = 0; b < B; ++b) {
+    S2S_REQUIRE(slots_h[b] >= 0 && slots_h[b] < c.max_sessions, "llama prefill_batch: bad slot %d", slots_h[b]);
+    for (int b2 = 0; b2 < b; ++b2) S2S_REQUIRE(slots_h[b2] != slots_h[b], "llama prefill_batch: slot %d listed twice", slots_h[b]);
+    S2S_REQUIRE(n_h[b] >= 1, "llama prefill_batch: session %d has no rows", b);
+    R += n_h[b];
+  }
+  S2S_REQUIRE(R <= c.max_prefill, "llama prefill_batch: %d rows in total exceed max_prefill %d", R, c.max_prefill);
+  for (int i = 0; i < R; ++i) S2S_REQUIRE(ids_h[i] >= 0 && ids_h[i] < c.vocab, "llama prefill_batch: token %d out of range", ids_h[i]);
+  cudaStream_t st = (cudaStream_t)stream;
+  S2S_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+  S2S_CHECK_CUDA(cudaMemcpyAsync(m->ids_d, ids_h, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+  S2S_CHECK_CUDA(cudaStreamSynchronize(st));  // ids_h may be a temporary of the caller
+  if (c.compute_dtype == S2S_BF16) embed_gather_kernel<__nv_bfloat16><<<R, 256, 0, st>>>(m->ids_d, (const __nv_bfloat16*)m->embed, m->x, c.d_model);
+  else embed_gather_kernel<__half><<<R, 256, 0, st>>>(m->ids_d, (const __half*)m->embed, m->x, c.d_model);
+  S2S_LAUNCH_CHECK();
+  return llama_prefill_batch(m, slots_h, B, n_h, next_ids_d, st);
 }
 
 int s2s_llama_decode(s2s_llama* m, const int32_t* slots_h, int32_t B, const int32_t* first_ids_d, int32_t n_steps,

@@ -8,8 +8,9 @@
 //   0: RMSNorm + QKV projection + RoPE + KV append   1: GQA attention items (32-key blocks, last split merges)
 //   2: o_proj + residual                             3: RMSNorm + gate/up projection + SwiGLU     4: down + residual
 //   then 5L: final RMSNorm + lm_head + per-CTA argmax      5L+1: global argmax, EOS bookkeeping, next embedding
-// Qwen3 family (qk_norm, transformers modeling_qwen3.py Qwen3Attention): phase 0 stores RAW q / k, an extra phase applies
-// RMSNorm(head_dim) + RoPE per (session, head) and appends k to the cache: 6 phases per layer.
+// Qwen3 family (qk_norm, transformers modeling_qwen3.py Qwen3Attention): phase 0 stores RAW q / k; the per-head
+// RMSNorm(head_dim) + RoPE is folded into the attention items of phase 1 (ld_qk_prepare), so the phase count stays 5 per
+// layer (it was a sixth phase until round 2: ~10 us per layer and step of pure barrier latency in the TTS frame loop).
 // Projections are swap-AB tensor-core GEMVs (sessions on m) fed from per-warp bulk-copy rings of fragment-major weights
 // (decode_common.cuh, weight_tiles.cu); HBM-bound: 15.0 GB / token for Llama-3-8B.
 #include <algorithm>
@@ -25,6 +26,65 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
   return t;
 }
 
+// Qwen3: RMSNorm over head_dim of a raw q / k row (fp32 statistics, Qwen3RMSNorm), then RoPE.  One warp; rows are stored
+// pair-adjacent (2j, 2j+1) = rotate_half partners (j, j + hd/2), and so are the norm weights.  y: this lane's PER elements.
+template <int HD>
+__device__ __forceinline__ void ld_norm_rope_head(const float* src, const float* nw, const float2* rope_pos, float eps,
+                                                  float (&y)[HD / 32]) {
+  constexpr int PER = HD / 32;  // 2 or 4 consecutive elements per lane = 1 or 2 rotation pairs
+  const int lane = threadIdx.x & 31;
+  float v[PER], g[PER];
+  if (PER == 4) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(src + lane * 4));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    const float4 u = __ldg(reinterpret_cast<const float4*>(nw + lane * 4));
+    g[0] = u.x; g[1] = u.y; g[2] = u.z; g[3] = u.w;
+  } else {
+    const float2 t = __ldcg(reinterpret_cast<const float2*>(src + lane * 2));
+    v[0] = t.x; v[1] = t.y;
+    const float2 u = __ldg(reinterpret_cast<const float2*>(nw + lane * 2));
+    g[0] = u.x; g[1] = u.y;
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) ss = fmaf(v[i], v[i], ss);
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss * (1.0f / (float)HD) + eps);
+#pragma unroll
+  for (int i = 0; i < PER; i += 2) {
+    const float2 cs = rope_pos[(lane * PER + i) >> 1];
+    const float a0 = v[i] * rstd * g[i], a1 = v[i + 1] * rstd * g[i + 1];
+    y[i] = a0 * cs.x - a1 * cs.y;
+    y[i + 1] = a1 * cs.x + a0 * cs.y;
+  }
+}
+
+// Qwen3 (qk_norm), executed by ONE warp at the head of an attention item (session b, q head h): the normalised, rotated and
+// scaled q row goes to p.qn (the item's attend_blocks reads it from there); when the item's key range holds the step's own
+// key (`own_key`), the kv head's normalised + rotated k row is appended to the cache first.  Items that share a (session,
+// head) -- the key splits -- or a kv head write identical bytes, so no cross-CTA ordering is needed: every reader has
+// written the value itself (same warp: __syncwarp, same CTA: __syncthreads, issued by the caller).
+template <typename T, int HD>
+__device__ __forceinline__ void ld_qk_prepare(const LlamaDecParams& p, int layer, int b, int h, int pos, bool own_key) {
+  constexpr int PER = HD / 32;
+  const int H = p.heads, KV = p.kv_heads, lane = threadIdx.x & 31, g = h / (H / KV);
+  const LlamaDecLayer& w = p.lw[layer];
+  const float2* rp = p.rope + (long long)pos * (HD >> 1);
+  float y[PER];
+  ld_norm_rope_head<HD>(p.q + (long long)b * H * HD + h * HD, w.q_norm, rp, p.eps, y);
+  const float q_scale = rsqrtf((float)HD);
+  float* qd = p.qn + (long long)b * H * HD + h * HD + lane * PER;
+#pragma unroll
+  for (int i = 0; i < PER; i += 2) *reinterpret_cast<float2*>(qd + i) = make_float2(y[i] * q_scale, y[i + 1] * q_scale);
+  if (own_key) {
+    ld_norm_rope_head<HD>(p.kraw + (long long)b * KV * HD + g * HD, w.k_norm, rp, p.eps, y);
+    T* dst = reinterpret_cast<T*>(p.kv) + (long long)__ldg(p.slot + b) * p.kv_slot_stride + (long long)layer * p.kv_layer_stride +
+             (long long)pos * (KV * HD) + g * HD + lane * PER;
+#pragma unroll
+    for (int i = 0; i < PER; i += 2) *reinterpret_cast<uint32_t*>(dst + i) = DT<T>::pack2(y[i], y[i + 1]);
+  }
+}
+
 // GQA attention over each session's cached keys; items (session, q head, key split) per attn_plan (decode_common.cuh)
 template <typename T, int HD>
 __device__ __noinline__ void ld_attn(const LlamaDecParams& p, int layer, int step, float* rec_s) {
@@ -36,22 +96,27 @@ __device__ __noinline__ void ld_attn(const LlamaDecParams& p, int layer, int ste
   const int S = plan & 0x7f, bps = (n_blocks + S - 1) / S;
   const bool wl = plan & ATTN_WARP_LEVEL;
   const T* kv = reinterpret_cast<const T*>(p.kv);
+  const float* qbase = p.qk_norm ? p.qn : p.q;
 #pragma unroll 1
   for (int it = wl ? dec_first_item() : (int)blockIdx.x; it < BH * S; it += wl ? dec_item_stride() : (int)gridDim.x) {
     const int s = it % S, bh = it / S, h = bh % H, b = bh / H;
-    const int len = __ldcg(p.pos + b) + 1;  // this session's keys; splits past its end produce empty records
+    const int pos = __ldcg(p.pos + b), len = pos + 1;  // this session's keys; splits past its end produce empty records
     const int nb = (len + ATT_BLK - 1) / ATT_BLK;
     const T* Kb = kv + (long long)__ldg(p.slot + b) * p.kv_slot_stride + (long long)layer * p.kv_layer_stride + (h / grp) * HD;
     float* part_bh = p.part + (long long)bh * p.s_max * REC;
     T* out16 = reinterpret_cast<T*>(p.attn16) + (long long)b * H * HD + h * HD;
+    const float* q = qbase + (long long)b * H * HD + h * HD;
+    const int blk0 = s * bps, blk1 = min((s + 1) * bps, nb);
+    if (p.qk_norm && blk0 < blk1) {   // the split that holds the step's own key (the last block) appends it
+      if (wl || warp == 0) ld_qk_prepare<T, HD>(p, layer, b, h, pos, blk1 == nb);
+      if (wl) __syncwarp(); else __syncthreads();
+    }
     if (wl) {
-      attend_blocks<T, HD>(p.q + (long long)b * H * HD + h * HD, Kb, Kb + p.kv_which_stride, kvd, kvd, len, s * bps,
-                           min((s + 1) * bps, nb), 1, rec_s + warp * REC);
+      attend_blocks<T, HD>(q, Kb, Kb + p.kv_which_stride, kvd, kvd, len, blk0, blk1, 1, rec_s + warp * REC);
       attn_finish_item<T, HD>(rec_s + warp * REC, 1, part_bh, s, S, p.attn_cnt + bh, out16);
       __syncwarp();
     } else {
-      attend_blocks<T, HD>(p.q + (long long)b * H * HD + h * HD, Kb, Kb + p.kv_which_stride, kvd, kvd, len, s * bps + warp,
-                           min((s + 1) * bps, nb), DEC_WARPS, rec_s + warp * REC);
+      attend_blocks<T, HD>(q, Kb, Kb + p.kv_which_stride, kvd, kvd, len, blk0 + warp, blk1, DEC_WARPS, rec_s + warp * REC);
       __syncthreads();
       if (warp == 0) attn_finish_item<T, HD>(rec_s, DEC_WARPS, part_bh, s, S, p.attn_cnt + bh, out16);
       __syncthreads();
@@ -60,14 +125,11 @@ __device__ __noinline__ void ld_attn(const LlamaDecParams& p, int layer, int ste
 }
 
 
-// phase kinds: 0 qkv, 1 attention, 2 o_proj, 3 gate/up, 4 down, 5 q/k norm + RoPE (Qwen3), 6 logits, 7 select
-__host__ __device__ __forceinline__ int ld_nsub(const LlamaDecParams& p) { return p.qk_norm ? 6 : 5; }
+// phase kinds: 0 qkv, 1 attention (Qwen3: + q/k norm and RoPE), 2 o_proj, 3 gate/up, 4 down, 6 logits, 7 select
+__host__ __device__ __forceinline__ int ld_nsub(const LlamaDecParams&) { return 5; }
 __device__ __forceinline__ int ld_kind(const LlamaDecParams& p, int ph) {
-  const int ns = ld_nsub(p);
-  if (ph >= ns * p.layers) return ph == ns * p.layers ? 6 : 7;
-  const int sub = ph % ns;
-  if (!p.qk_norm || sub == 0) return sub;
-  return sub == 1 ? 5 : sub - 1;
+  if (ph >= 5 * p.layers) return ph == 5 * p.layers ? 6 : 7;
+  return ph % 5;
 }
 __device__ __forceinline__ bool ld_multi(const LlamaDecParams& p) { return p.head_stride != 0; }
 // output head of `step` (multi-table mode: step 0 predicts nothing)
@@ -75,60 +137,6 @@ __device__ __forceinline__ bool ld_has_head(const LlamaDecParams& p, int step) {
 __device__ __forceinline__ bool ld_has_gemv(const LlamaDecParams& p, int step, int ph) {
   const int k = ld_kind(p, ph);
   return k == 0 || k == 2 || k == 3 || k == 4 || (k == 6 && ld_has_head(p, step));
-}
-
-// Qwen3: per (session, head) RMSNorm over head_dim of the raw q / k rows (fp32 statistics, Qwen3RMSNorm), then RoPE;
-// q is scaled by head_dim^-0.5 and written back in place, k goes to the cache at the token's position.  One warp per
-// item; rows are stored pair-adjacent (2j, 2j+1) = rotate_half partners (j, j + hd/2), and so are the norm weights.
-template <typename T, int HD>
-__device__ __noinline__ void ld_qknorm(const LlamaDecParams& p, int layer) {
-  constexpr int PER = HD / 32;  // 2 or 4 consecutive elements per lane = 1 or 2 rotation pairs
-  const int H = p.heads, KV = p.kv_heads, lane = threadIdx.x & 31;
-  const int n_items = p.B * (H + KV);
-  const LlamaDecLayer& w = p.lw[layer];
-  const float q_scale = rsqrtf((float)HD);
-#pragma unroll 1
-  for (int it = dec_first_item(); it < n_items; it += dec_item_stride()) {
-    const int b = it / (H + KV), h = it % (H + KV);
-    const bool is_q = h < H;
-    float* src = is_q ? p.q + (long long)b * H * HD + h * HD : p.kraw + (long long)b * KV * HD + (h - H) * HD;
-    const float* nw = is_q ? w.q_norm : w.k_norm;
-    float v[PER], g[PER];
-    if (PER == 4) {
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(src + lane * 4));
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-      const float4 u = __ldg(reinterpret_cast<const float4*>(nw + lane * 4));
-      g[0] = u.x; g[1] = u.y; g[2] = u.z; g[3] = u.w;
-    } else {
-      const float2 t = __ldcg(reinterpret_cast<const float2*>(src + lane * 2));
-      v[0] = t.x; v[1] = t.y;
-      const float2 u = __ldg(reinterpret_cast<const float2*>(nw + lane * 2));
-      g[0] = u.x; g[1] = u.y;
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) ss = fmaf(v[i], v[i], ss);
-    ss = warp_sum(ss);
-    const float rstd = rsqrtf(ss * (1.0f / (float)HD) + p.eps);
-    const int pos = __ldcg(p.pos + b);
-    float y[PER];
-#pragma unroll
-    for (int i = 0; i < PER; i += 2) {
-      const float2 cs = p.rope[(long long)pos * (HD >> 1) + ((lane * PER + i) >> 1)];
-      const float a0 = v[i] * rstd * g[i], a1 = v[i + 1] * rstd * g[i + 1];
-      y[i] = a0 * cs.x - a1 * cs.y;
-      y[i + 1] = a1 * cs.x + a0 * cs.y;
-    }
-    if (is_q) {
-#pragma unroll
-      for (int i = 0; i < PER; i += 2) *reinterpret_cast<float2*>(src + lane * PER + i) = make_float2(y[i] * q_scale, y[i + 1] * q_scale);
-    } else {
-      T* dst = reinterpret_cast<T*>(p.kv) + (long long)__ldg(p.slot + b) * p.kv_slot_stride + (long long)layer * p.kv_layer_stride +
-               (long long)pos * (KV * HD) + (h - H) * HD + lane * PER;
-#pragma unroll
-      for (int i = 0; i < PER; i += 2) *reinterpret_cast<uint32_t*>(dst + i) = DT<T>::pack2(y[i], y[i + 1]);
-    }
-  }
 }
 
 template <typename T>
@@ -243,9 +251,6 @@ __device__ __forceinline__ void ld_phase(const LlamaDecParams& p, int step, int 
       case 1:
         if (p.hd == 128) ld_attn<T, 128>(p, layer, step, reinterpret_cast<float*>(sm.red));
         else ld_attn<T, 64>(p, layer, step, reinterpret_cast<float*>(sm.red));
-        return;
-      case 5:
-        if (p.hd == 128) ld_qknorm<T, 128>(p, layer); else ld_qknorm<T, 64>(p, layer);
         return;
       case 2: stage_rows_copy<T>(reinterpret_cast<const T*>(p.attn16), B, p.heads * p.hd, sm.xh); break;
       case 3: stage_rows_norm<T>(p.x, B, d, sm.xs, sm.xh, 2, w.norm2, nullptr, p.eps, sm.s_red, sm.wb, wb_ready, p.norm_rg); break;
@@ -394,7 +399,7 @@ int launch_t(s2s_ctx* ctx, const LlamaDecParams& p, int debug_phases, cudaStream
   pr.ring_slots = slots; pr.norm_rg = rg; pr.down_kc = kc;
   const size_t smem = (size_t)lay.ring_off + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
   auto kern = llama_decode_kernel<T>;
-  S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  S2S_CHECK_CUDA(s2s_opt_in_max_smem(kern, ctx->device, smem, nullptr));
   llama_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
   S2S_LAUNCH_CHECK();
   const int n_ph = ld_nsub(p) * p.layers + 2;

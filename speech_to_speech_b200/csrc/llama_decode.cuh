@@ -42,9 +42,10 @@ struct LlamaDecParams {
   int* done; int* n_done;
   float* cand_val; int* cand_idx;   // [B][grid]
   unsigned int* sync_counter;
-  // ---- Qwen3 family (qk_norm): 6 phases per layer, the extra one applies RMSNorm(head_dim) + RoPE to the raw q / k rows
+  // ---- Qwen3 family (qk_norm): the qkv phase stores raw q / k rows; the attention items apply RMSNorm(head_dim) + RoPE
   int qk_norm;
   float* kraw;                  // [B][KV*hd] fp32 raw k rows of the current token
+  float* qn;                    // [B][H*hd] fp32 normalised, rotated, scaled q rows (written and read inside the attention phase)
   // ---- embedding-driven use (Qwen3-TTS talker and code predictor, qwen3tts.cu) ----
   const float* x_in;            // [B][d] fp32 or null: the input of step 0 is this vector instead of embed[first_ids]
   float* hidden_out;            // [n_steps][B][d] fp32 or null: the residual stream BEFORE the final norm of every step

@@ -42,7 +42,7 @@ struct s2s_llama {
   std::vector<int> len;  // tokens in each slot
   // prefill workspace
   int* ids_d = nullptr;
-  float *x = nullptr, *last_logits = nullptr;
+  float *x = nullptr, *last_logits = nullptr, *batch_logits = nullptr;   // batch_logits: [MAX_DEC_B][vocab] (batched prefill)
   void *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *vt = nullptr;
   size_t vt_elems = 0;
   // decode state
@@ -57,6 +57,7 @@ struct s2s_llama {
   int trace_cap = 0;
   int n_tables = 1;                      // > 1: one embedding table and one output head per codebook (code predictor)
   size_t embed_table_elems = 0, head_table_elems = 0, head_t_table_elems = 0;
+  float* qn = nullptr;                   // qk_norm: normalised q rows of the decode step [B][H*hd]
   float* kraw = nullptr;                 // qk_norm: raw k rows of the decode step [B][KV*hd]
 };
 

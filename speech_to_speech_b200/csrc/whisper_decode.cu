@@ -733,7 +733,7 @@ int launch_cluster_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, 
   int slots = (int)std::min<long long>(4, avail / ((long long)DEC_WARPS * (GV_SLOT_BYTES + 8)));
   if (slots < 2) return S2S_OK;
   const size_t smem = (size_t)lay.ring_off + (size_t)DEC_WARPS * slots * (GV_SLOT_BYTES + 8) + 128;
-  S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  S2S_CHECK_CUDA(s2s_opt_in_max_smem(kern, ctx->device, smem, nullptr));
   // every head needs its own co-resident 8-CTA cluster (queried once per configuration)
   static thread_local size_t cached_smem = 0;
   static thread_local int cached_heads = -1, cached_cs = 0, cached_n = 0, cached_grid = 0;
@@ -809,7 +809,7 @@ int launch_t(s2s_ctx* ctx, const WhisperDecParams& p, int debug_phases, cudaStre
   S2S_REQUIRE(pr.ring_slots >= 2, "whisper decode: batch %d leaves no shared memory for the weight ring", p.B);
   const size_t smem = (size_t)lay.ring_off + (size_t)DEC_WARPS * pr.ring_slots * (GV_SLOT_BYTES + 8) + 128;
   auto kern = whisper_decode_kernel<T>;
-  S2S_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  S2S_CHECK_CUDA(s2s_opt_in_max_smem(kern, ctx->device, smem, nullptr));
   whisper_decode_init_kernel<T><<<p.B, 256, 0, stream>>>(pr);
   S2S_LAUNCH_CHECK();
   const int total_steps = p.n_prefix - 1 + p.max_new;

@@ -333,6 +333,17 @@ class LlamaEngine:
               "s2s_llama_prefill")
         return nxt, logits
 
+    def prefill_batch(self, slots: Sequence[int], prompts: Sequence[Sequence[int]]) -> torch.Tensor:
+        """Append prompts[i] to session slots[i], all sessions in ONE pass over the weights (total tokens <= max_prefill,
+        at most 16 sessions).  -> next ids, cuda int32[B] (asynchronous)."""
+        assert len(slots) == len(prompts) and len(slots) >= 1
+        sl, B = _lib.i32_array(slots)
+        flat, _ = _lib.i32_array([t for p in prompts for t in p])
+        ns, _ = _lib.i32_array([len(p) for p in prompts])
+        nxt = torch.empty((B,), dtype=torch.int32, device=f"cuda:{self.device}")
+        check(self.lib.s2s_llama_prefill_batch(self.handle, sl, B, flat, ns, _ptr(nxt), _stream_ptr(self.device)), "s2s_llama_prefill_batch")
+        return nxt
+
     def decode(self, slots: Sequence[int], first_ids: torch.Tensor, n_steps: int, eos_id: int = -1,
                forced: Optional[torch.Tensor] = None, return_logits: bool = False):
         B = len(slots)

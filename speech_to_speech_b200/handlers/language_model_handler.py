@@ -42,7 +42,7 @@ class TokenStreamer:
 
     def __init__(self, engine: Any, decode_text: Callable[[Sequence[int]], str], eos_ids: Sequence[int], chunk: int = 8, slot: int = 0,
                  decode_chunk: Optional[Callable[[int, int, int, int], list]] = None, lock: Optional[Any] = None,
-                 context: Optional[Callable[[], Any]] = None):
+                 context: Optional[Callable[[], Any]] = None, prefill: Optional[Callable[[int, Sequence[int]], int]] = None):
         import contextlib
         self._context = context or contextlib.nullcontext   # the lane's CUDA stream for this thread's GPU calls
         self.engine, self.decode_text, self.eos_ids, self.chunk, self.slot = engine, decode_text, set(int(e) for e in eos_ids), max(1, chunk), slot
@@ -51,6 +51,7 @@ class TokenStreamer:
         # decode_chunk(slot, first_token, n, eos) -> ids: the shared-engine path routes it through the session batcher;
         # lock serialises prefill on a shared engine (one thread per engine handle at a time)
         self._decode_chunk = decode_chunk or self._decode_direct
+        self._prefill = prefill   # shared engine: prompts of concurrent sessions are prefilled in one pass (bundle.prefill)
         self._lock = lock or threading.Lock()
 
     def _decode_direct(self, slot: int, tok: int, n: int, eos: int) -> list:
@@ -85,11 +86,14 @@ class TokenStreamer:
             prompt_ids = prompt_ids[-(room - 1):]
         max_new_tokens = max(1, min(int(max_new_tokens), room - len(prompt_ids)))
         nxt = None
-        with self._lock, self._context():
-            eng.reset(self.slot)
-            for o in range(0, len(prompt_ids), max_prefill):
-                nxt, _ = eng.prefill(self.slot, list(prompt_ids[o:o + max_prefill]))
-            tok = int(nxt[0])
+        if self._prefill is not None:
+            tok = int(self._prefill(self.slot, prompt_ids))
+        else:
+            with self._lock, self._context():
+                eng.reset(self.slot)
+                for o in range(0, len(prompt_ids), max_prefill):
+                    nxt, _ = eng.prefill(self.slot, list(prompt_ids[o:o + max_prefill]))
+                tok = int(nxt[0])
         self.generated = []
         self._po = self._ro = 0
         eos_for_kernel = next(iter(self.eos_ids)) if len(self.eos_ids) == 1 else -1
@@ -150,8 +154,53 @@ class _LlamaBundle:
         with self.lock:
             self._free.append(slot)
 
+    def _run_prefill(self, items: list) -> list:
+        """items: (slot, prompt ids).  Fresh prompts that fit one pass together are prefilled by ONE s2s_llama_prefill_batch
+        call (one pass over the weights for all of them); the rest go one by one, over-long prompts in max_prefill chunks."""
+        eng = self.engine
+        cap = int(eng.cfg.max_prefill)
+        out: list = [None] * len(items)
+        with self.lock, self.lane_context():
+            group: list = []
+            rows = 0
+
+            def flush() -> None:
+                nonlocal group, rows
+                if len(group) > 1:
+                    nxt = eng.prefill_batch([items[i][0] for i in group], [items[i][1] for i in group]).tolist()
+                    for i, t in zip(group, nxt):
+                        out[i] = int(t)
+                elif group:
+                    i = group[0]
+                    nx = None
+                    for o in range(0, len(items[i][1]), cap):
+                        nx, _ = eng.prefill(items[i][0], list(items[i][1][o:o + cap]))
+                    out[i] = int(nx[0])
+                group, rows = [], 0
+            for i, (slot, ids) in enumerate(items):
+                eng.reset(slot)
+                if len(ids) > cap:
+                    flush()
+                    group = [i]
+                    flush()
+                    continue
+                if rows + len(ids) > cap or len(group) >= 16:
+                    flush()
+                group.append(i)
+                rows += len(ids)
+            flush()
+        return out
+
+    def prefill(self, slot: int, ids: Sequence[int]) -> int:
+        """Reset the session and run its prompt; concurrent sessions' prompts share one pass over the weights."""
+        if self.batcher is None:
+            return self._run_prefill([(slot, list(ids))])[0]
+        return self.batcher.call(("prefill",), (slot, list(ids)))
+
     def _run_batch(self, key: tuple, items: list) -> list:
         import torch
+        if key and key[0] == "prefill":
+            return self._run_prefill(items)
         n, eos = key
         slots = [it[0] for it in items]
         with self.lock, self.lane_context():
@@ -265,7 +314,7 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
         self.slot = self.bundle.acquire_slot()
         self.streamer = TokenStreamer(self.engine, lambda ids: self.tokenizer.decode(list(ids), skip_special_tokens=True),
                                       self.eos_ids, self.stream_chunk_tokens, slot=self.slot, decode_chunk=self.bundle.decode_chunk,
-                                      lock=self.bundle.lock, context=self.bundle.lane_context)
+                                      lock=self.bundle.lock, context=self.bundle.lane_context, prefill=self.bundle.prefill)
 
     def generate_text_stream(self, prompt_ids: Sequence[int], max_new_tokens: Optional[int] = None,
                              should_stop: Callable[[], bool] = lambda: False) -> Iterator[str]:

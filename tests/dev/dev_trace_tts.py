@@ -20,12 +20,12 @@ for which, name, L in ((0, "talker", eng.cfg.layers), (1, "predictor", eng.cfg.c
     lib.s2s_qwen3tts_set_trace(eng.handle, which, None, 0)
     t = tr.cpu().numpy()
     t = t[t[:, 0] > 0]
-    kinds = ["qkv", "qknorm", "attn", "o_proj", "gate_up", "down"]
+    kinds = ["qkv", "attn", "o_proj", "gate_up", "down"]   # Qwen3 q/k norm runs inside the attention items
     body, wait = {}, {}
-    n_ph = 6 * L + 2
+    n_ph = 5 * L + 2
     for i, row in enumerate(t):
         ph = i % n_ph     # the predictor's step 0 still records its (empty) logits phase: n_ph records per step for both
-        k = kinds[ph % 6] if ph < 6 * L else ("logits" if ph == 6 * L else "select")
+        k = kinds[ph % 5] if ph < 5 * L else ("logits" if ph == 5 * L else "select")
         body.setdefault(k, []).append((row[1] - row[0]) / 1e3)
         wait.setdefault(k, []).append((row[2] - row[1]) / 1e3)
     total = (t[-1, 2] - t[0, 0]) / 1e3

@@ -210,3 +210,43 @@ def test_geometry_from_hf_config_rejects_what_the_kernels_do_not_implement():
         G(SimpleNamespace(**{**base, "model_type": "mistral", "sliding_window": 1024}), 4096)
     with pytest.raises(ValueError):
         G(SimpleNamespace(**{**base, "model_type": "gemma"}), 4096)
+
+
+def test_concurrent_prompts_share_one_batched_prefill_pass():
+    """_LlamaBundle._run_prefill: fresh prompts that fit max_prefill together go through ONE prefill_batch call (one pass over
+    the weights); a prompt longer than max_prefill is chunked on its own; every session is reset first."""
+    import types
+    from speech_to_speech_b200.handlers import language_model_handler as LH
+
+    class Eng:
+        cfg = types.SimpleNamespace(max_prefill=8)
+        device = 0
+
+        def __init__(self):
+            self.calls = []
+
+        def reset(self, slot):
+            self.calls.append(("reset", slot))
+
+        def prefill(self, slot, ids):
+            self.calls.append(("prefill", slot, len(ids)))
+            return [100 + slot], None
+
+        def prefill_batch(self, slots, prompts):
+            self.calls.append(("batch", tuple(slots), tuple(len(p) for p in prompts)))
+            return types.SimpleNamespace(tolist=lambda: [200 + s for s in slots])
+
+        def max_decode_batch(self):
+            return 4
+
+        def close(self):
+            pass
+
+    eng = Eng()
+    b = LH._LlamaBundle(eng, None, [0], 1, 0.001)
+    out = b._run_prefill([(0, [1, 2, 3]), (1, [4, 5, 6]), (2, list(range(20))), (3, [7, 8, 9, 10, 11]), (4, [1, 2, 3, 4])])
+    kinds = [c for c in eng.calls if c[0] != "reset"]
+    assert kinds == [("batch", (0, 1), (3, 3)), ("prefill", 2, 8), ("prefill", 2, 8), ("prefill", 2, 4), ("prefill", 3, 5), ("prefill", 4, 4)]
+    assert out == [200, 201, 102, 103, 104]
+    assert [c[1] for c in eng.calls if c[0] == "reset"] == [0, 1, 2, 3, 4]
+    assert b.prefill(1, [1, 2]) == 101          # no batcher (one session): straight through
