@@ -460,13 +460,13 @@ def make_handlers(S: int, dev: int, lanes: int = 1):
         stt = B200WhisperSTTHandler(Event(), queue_in=Queue(), queue_out=Queue(),
                                     setup_kwargs=dict(model_name=f"random:{MODEL}:1234", device=f"cuda:{dev}", torch_dtype="float16",
                                                       language="en", gen_kwargs={"max_new_tokens": MAX_NEW}, max_batch=min(16, Sl),
-                                                      batch_wait_ms=3.0, lane=lane, lanes=lanes))
+                                                      lane=lane, lanes=lanes))
         stt.tokens.eos = -1                   # random-init weights: every utterance decodes its full 128 tokens (both arms do)
         llm = object.__new__(B200LanguageModelHandler)   # the load hook only: the request lifecycle needs the reference's Chat types
         llm.device = f"cuda:{dev}"
         B200LanguageModelHandler._load_model(llm, "random:llama-3-8b:7", f"cuda:{dev}", "bfloat16",
                                              {"max_new_tokens": MAX_NEW, "max_sessions": Sl, "max_positions": LLM_PROMPT + MAX_NEW + 8,
-                                              "stream_chunk_tokens": 8, "batch_wait_ms": 2.0, "lane": lane, "lanes": lanes})
+                                              "stream_chunk_tokens": 8, "lane": lane, "lanes": lanes})
         llm.eos_ids = []                      # random-init weights: never stop early, every reply has 128 tokens
         llm.streamer.eos_ids = set()
         tts = B200Qwen3TTSHandler(Event(), queue_in=Queue(), queue_out=Queue(), setup_args=(Event(),),
@@ -605,9 +605,20 @@ def main():
             e2e_wave(handlers, auds, S)                                        # warm-up of the loaded path
             log("loaded e2e warm-up wave done")
             barrier()
+
+            def batcher_stats():
+                out = {}
+                for name, get in (("stt", lambda h: h[0].bundle.batcher), ("llm", lambda h: h[1].bundle.batcher), ("tts", lambda h: h[2].model.batcher)):
+                    bs = {id(get(h)): get(h) for h in handlers if get(h) is not None}
+                    out[name] = (sum(b.batches_run for b in bs.values()), sum(b.items_run for b in bs.values()))
+                return out
+            bs0 = batcher_stats()
             loaded = [e2e_wave(handlers, auds, S) for _ in range(2 if args.steps >= 4 else 1)]
+            bs1 = batcher_stats()
             barrier()
-            e2e = {"single": single, "loaded": loaded}
+            e2e = {"single": single, "loaded": loaded,
+                   "batching": {k: {"launch_groups": bs1[k][0] - bs0[k][0], "requests": bs1[k][1] - bs0[k][1],
+                                    "mean_batch": round((bs1[k][1] - bs0[k][1]) / max(1, bs1[k][0] - bs0[k][0]), 2)} for k in bs1}}
             log(f"loaded e2e waves: {[round(w['wall_s'], 2) for w in loaded]} s")
             for hs in handlers:
                 for h in hs:
@@ -701,7 +712,8 @@ def main():
                            "wall_s_per_wave": e2e_wall_max, "path": "B200WhisperSTTHandler -> B200LanguageModelHandler -> B200Qwen3TTSHandler, "
                            "one thread per session, shared engines + session batchers",
                            "tts_rtf_min": min(rtf_loaded) if rtf_loaded else None, "tts_rtf_p50": statistics.median(rtf_loaded) if rtf_loaded else None,
-                           "real_time": realtime, "errors": [e for w in e2e["loaded"] for e in w["errors"]][:3]}
+                           "real_time": realtime, "errors": [e for w in e2e["loaded"] for e in w["errors"]][:3],
+                           "batching": e2e.get("batching")}
             line["latency_ms_p50"] = statistics.median(lat_loaded) if lat_loaded else None
             line["latency_ms_p50_single_session"] = statistics.median(lat_single) if lat_single else None
             line["latency_note"] = ("audio-in (VADAudio.created_at_s) -> first int16 block out of the TTS handler; 'single' = one session on an "

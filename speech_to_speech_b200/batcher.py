@@ -13,6 +13,12 @@ against 121 one at a time.  The batcher is the host piece that makes that reacha
       ids = fut.result()                <------------------------------   most `max_wait_s` or until `max_batch`,
                                                                           run_batch(key, items) once, scatter
 
+Dispatch policy: a key's batch goes out when it is full (`max_batch`), when its oldest request has waited `max_wait_s`, or --
+with `idle_gap_s` set -- as soon as no further request has arrived for `idle_gap_s`.  Sessions that share launches resubmit in
+a burst (they all receive the previous launch's results at the same instant), so "the burst is over" is the signal that the
+batch is as full as it is going to get: a lone session waits one gap (a fraction of a millisecond) instead of the whole window,
+and under load the window can be long enough for every session's request without costing latency when they are all there.
+
 `key` groups requests that may share a launch (the decoder prompt / generation options are per launch in the C ABI:
 `s2s_whisper_transcribe` takes one `s2s_whisper_decode_opts`).  Requests with different keys are never mixed; they
 are served in arrival order of their first element.  Exceptions raised by `run_batch` are delivered to every future
@@ -30,12 +36,14 @@ from typing import Any, Callable, Hashable, List, Optional, Sequence, Tuple
 class SessionBatcher:
     def __init__(self, run_batch: Callable[[Hashable, List[Any]], Sequence[Any]], max_batch: int = 16,
                  max_wait_s: float = 0.004, name: str = "s2s-batcher",
-                 thread_context: Optional[Callable[[], Any]] = None):
+                 thread_context: Optional[Callable[[], Any]] = None, idle_gap_s: Optional[float] = None):
         if max_batch < 1:
             raise ValueError("max_batch must be >= 1")
         self._run_batch = run_batch
         self.max_batch = int(max_batch)
         self.max_wait_s = float(max_wait_s)
+        self.idle_gap_s = None if idle_gap_s is None else float(idle_gap_s)
+        self._last_arrival = 0.0
         self._cv = threading.Condition()
         # key -> list of (item, future, t_arrival); OrderedDict keeps the arrival order of each key's oldest request
         self._pending: "OrderedDict[Hashable, List[Tuple[Any, Future, float]]]" = OrderedDict()
@@ -55,7 +63,9 @@ class SessionBatcher:
         with self._cv:
             if self._closed:
                 raise RuntimeError("SessionBatcher is closed")
-            self._pending.setdefault(key, []).append((item, fut, time.monotonic()))
+            now = time.monotonic()
+            self._pending.setdefault(key, []).append((item, fut, now))
+            self._last_arrival = now
             self._cv.notify_all()
         return fut
 
@@ -70,6 +80,8 @@ class SessionBatcher:
                 if self._pending:
                     key, items = next(iter(self._pending.items()))
                     due = items[0][2] + self.max_wait_s
+                    if self.idle_gap_s is not None:       # the burst of resubmissions is over: nothing new for idle_gap_s
+                        due = min(due, max(items[-1][2], self._last_arrival) + self.idle_gap_s)
                     now = time.monotonic()
                     if len(items) >= self.max_batch or now >= due or self._closed:
                         batch = items[: self.max_batch]

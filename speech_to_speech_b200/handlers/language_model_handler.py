@@ -128,14 +128,15 @@ class _LlamaBundle:
     """One engine shared by the handler instances of a process: KV-cache slots handed out per handler, prefill serialised
     by a lock, decode chunks of concurrent sessions merged into one launch by the SessionBatcher."""
 
-    def __init__(self, engine: Any, tokenizer: Any, eos_ids: list, max_sessions: int, batch_wait_s: float, lane: int = 0, lanes: int = 1):
+    def __init__(self, engine: Any, tokenizer: Any, eos_ids: list, max_sessions: int, batch_wait_s: float, lane: int = 0, lanes: int = 1,
+                 batch_gap_s: Optional[float] = None):
         self.engine, self.tokenizer, self.eos_ids = engine, tokenizer, eos_ids
         self.lane, self.lanes = lane, lanes
         self.lock = threading.Lock()
         self._free = list(range(max_sessions))
         mb = max(1, min(int(engine.max_decode_batch()), max_sessions))
         self.batcher = SessionBatcher(self._run_batch, mb, batch_wait_s, "s2s-llm-batcher",
-                                      thread_context=self.lane_context) if max_sessions > 1 else None
+                                      thread_context=self.lane_context, idle_gap_s=batch_gap_s) if max_sessions > 1 else None
 
     def lane_context(self):
         """The lane's CUDA stream as the calling thread's current stream (engine.lane_context; a no-op for one lane)."""
@@ -284,7 +285,9 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
         self.stream_chunk_tokens = int(self.gen_kwargs.pop("stream_chunk_tokens", 8))
         max_pos = int(self.gen_kwargs.pop("max_positions", 4096))
         max_sessions = max(1, int(self.gen_kwargs.pop("max_sessions", 1)))
-        batch_wait_s = float(self.gen_kwargs.pop("batch_wait_ms", 2.0)) / 1000.0
+        batch_wait_s = float(self.gen_kwargs.pop("batch_wait_ms", 6.0)) / 1000.0   # upper bound of the batch window
+        gap_ms = float(self.gen_kwargs.pop("batch_gap_ms", 0.6))                     # a batch leaves once arrivals pause this long
+        batch_gap_s = gap_ms / 1000.0 if gap_ms > 0 else None
         # SM partition: the handler instances of lane i share lane i's engine (engine.get_context)
         lanes = max(1, int(self.gen_kwargs.pop("lanes", 1)))
         lane = int(self.gen_kwargs.pop("lane", 0)) % lanes
@@ -295,7 +298,7 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
                 geom = LLAMA_GEOMETRIES[parts[1]]
                 engine = E.LlamaEngine(geom, dtype=torch_dtype, max_sessions=max_sessions, max_positions=max_pos, max_prefill=512, device=dev, lane=lane, lanes=lanes)
                 engine.init_random(int(parts[2]) if len(parts) > 2 else 0)
-                return _LlamaBundle(engine, _IdTokenizer(geom["vocab"]), [geom["vocab"] - 1], max_sessions, batch_wait_s, lane, lanes)
+                return _LlamaBundle(engine, _IdTokenizer(geom["vocab"]), [geom["vocab"] - 1], max_sessions, batch_wait_s, lane, lanes, batch_gap_s)
             from transformers import AutoModelForCausalLM, AutoTokenizer
             tokenizer = AutoTokenizer.from_pretrained(model_name)
             hf = AutoModelForCausalLM.from_pretrained(model_name)
@@ -306,7 +309,7 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
             eos = hf.generation_config.eos_token_id
             eos_ids = list(eos) if isinstance(eos, (list, tuple)) else [int(eos)]
             del hf
-            return _LlamaBundle(engine, tokenizer, eos_ids, max_sessions, batch_wait_s, lane, lanes)
+            return _LlamaBundle(engine, tokenizer, eos_ids, max_sessions, batch_wait_s, lane, lanes, batch_gap_s)
 
         self._shared_key = ("llama", model_name, torch_dtype, dev, max_sessions, max_pos, lane, lanes) if max_sessions > 1 else None
         self.bundle = acquire_shared(self._shared_key, build, lambda b: b.close()) if self._shared_key else build()

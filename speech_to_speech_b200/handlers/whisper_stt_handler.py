@@ -69,12 +69,12 @@ class _EngineBundle:
     """An engine with what is needed to drive it; private to one handler or shared through the batcher."""
 
     def __init__(self, E: Any, engine: Any, tokens: "TokenTable", decode_text: Any, max_batch: int, batch_wait_s: float,
-                 lane: int = 0, lanes: int = 1):
+                 lane: int = 0, lanes: int = 1, batch_gap_s: Optional[float] = None):
         self.E, self.engine, self.tokens, self.decode_text = E, engine, tokens, decode_text
         self.lane, self.lanes = lane, lanes
         self.lock = threading.Lock()  # the engine handle is used by one thread at a time (INTEGRATION.md)
         self.batcher = SessionBatcher(self._run_batch, max_batch, batch_wait_s, "s2s-stt-batcher",
-                                      thread_context=self.lane_context) if max_batch > 1 else None
+                                      thread_context=self.lane_context, idle_gap_s=batch_gap_s) if max_batch > 1 else None
 
     def lane_context(self):
         """The lane's CUDA stream as the calling thread's current stream (engine.lane_context; a no-op for one lane)."""
@@ -141,7 +141,7 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
 
     def setup(self, model_name: str = "distil-whisper/distil-large-v3", device: str = "cuda", torch_dtype: str = "float16",
               compile_mode: Optional[str] = None, language: Optional[str] = None, gen_kwargs: dict[str, Any] = {},
-              max_batch: int = 1, batch_wait_ms: float = 4.0, lane: int = 0, lanes: int = 1) -> None:
+              max_batch: int = 1, batch_wait_ms: float = 6.0, lane: int = 0, lanes: int = 1, batch_gap_ms: float = 0.8) -> None:
         if not str(device).startswith("cuda"):
             raise ValueError(f"B200WhisperSTTHandler runs on CUDA (sm_100a) only, got device={device!r}; there is no CPU fallback")
         from .. import engine as E  # raises ImportError if libs2s_b200.so is not built
@@ -159,7 +159,8 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         self.processor = None
         # one persistent decode launch carries up to 16 sessions; more concurrent sessions queue in the batcher
         self.max_batch = max(1, min(int(max_batch), 16))
-        self.batch_wait_s = float(batch_wait_ms) / 1000.0
+        self.batch_wait_s = float(batch_wait_ms) / 1000.0      # upper bound; a batch leaves once arrivals pause for batch_gap_ms
+        self.batch_gap_s = float(batch_gap_ms) / 1000.0 if batch_gap_ms and batch_gap_ms > 0 else None
         # SM partition: the handler instances of lane i share lane i's engine (engine.get_context)
         self.lanes = max(1, int(lanes))
         self.lane = int(lane) % self.lanes
@@ -184,7 +185,7 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
                                      lane=self.lane, lanes=self.lanes)
             engine.init_random(seed)
             return _EngineBundle(E, engine, TokenTable.synthetic(geom["vocab"]), lambda ids: " ".join(f"<{i}>" for i in ids),
-                                 self.max_batch, self.batch_wait_s, self.lane, self.lanes)
+                                 self.max_batch, self.batch_wait_s, self.lane, self.lanes, self.batch_gap_s)
         from transformers import AutoModelForSpeechSeq2Seq, AutoProcessor
         processor = AutoProcessor.from_pretrained(model_name)
         hf = AutoModelForSpeechSeq2Seq.from_pretrained(model_name)
@@ -199,7 +200,7 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         del hf
         bundle = _EngineBundle(E, engine, tokens,
                                lambda ids: processor.batch_decode([ids], skip_special_tokens=True, decode_with_timestamps=False)[0],
-                               self.max_batch, self.batch_wait_s, self.lane, self.lanes)
+                               self.max_batch, self.batch_wait_s, self.lane, self.lanes, self.batch_gap_s)
         bundle.processor = processor   # every handler sharing the engine sees the processor, not only the one that loaded it
         return bundle
 

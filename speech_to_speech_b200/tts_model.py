@@ -96,7 +96,8 @@ def byte_tokenizer(text_vocab: int, reserved: int = 16) -> Callable[[str], list]
 
 class B200Qwen3TTS:
     def __init__(self, engine: Any, tokenize: Callable[[str], Sequence[int]], speakers: Mapping[str, int], max_sessions: int = 1,
-                 batch_wait_s: float = 0.002, tts_model_type: str = "custom_voice", lane: int = 0, lanes: int = 1):
+                 batch_wait_s: float = 0.006, tts_model_type: str = "custom_voice", lane: int = 0, lanes: int = 1,
+                 batch_gap_s: Optional[float] = 0.0006):
         self.engine = engine
         self.lane, self.lanes = int(lane), int(lanes)
         self.tokenize = tokenize
@@ -107,7 +108,7 @@ class B200Qwen3TTS:
         self._slot_cv = threading.Condition()
         mb = max(1, min(int(engine.max_batch()), max_sessions))
         self.batcher = SessionBatcher(self._run_frames, mb, batch_wait_s, "s2s-tts-batcher",
-                                      thread_context=self.lane_context) if max_sessions > 1 else None
+                                      thread_context=self.lane_context, idle_gap_s=batch_gap_s) if max_sessions > 1 else None
         # what the reference handler inspects: model.model.tts_model_type, get_supported_speakers (qwen3_tts_handler.py:574-593)
         inner = types.SimpleNamespace(tts_model_type=tts_model_type, get_supported_speakers=self.get_supported_speakers)
         self.model = types.SimpleNamespace(model=inner, get_supported_speakers=self.get_supported_speakers)

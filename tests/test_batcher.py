@@ -282,3 +282,26 @@ def test_thread_context_is_entered_by_the_engine_thread_and_failures_reach_the_c
     with pytest.raises(RuntimeError, match="could not enter"):
         b2.call("k", 1, timeout=5)
     b2.close()
+
+
+def test_idle_gap_dispatches_when_the_burst_is_over_not_after_the_whole_window():
+    """With idle_gap_s the window is an upper bound: a lone request leaves after one gap, a burst leaves together."""
+    import threading
+    import time
+    from speech_to_speech_b200.batcher import SessionBatcher
+    sizes = []
+    b = SessionBatcher(lambda k, it: (sizes.append(len(it)), list(it))[1], max_batch=16, max_wait_s=2.0, idle_gap_s=0.02)
+    t0 = time.monotonic()
+    assert b.call("k", 1, timeout=5) == 1
+    assert time.monotonic() - t0 < 1.0 and sizes == [1]          # did not sit out the 2 s window
+    futs = []
+
+    def burst():
+        for i in range(6):
+            futs.append(b.submit("k", i))
+            time.sleep(0.002)                                     # arrivals closer together than the gap: one batch
+    th = threading.Thread(target=burst)
+    th.start()
+    th.join()
+    assert [f.result(5) for f in futs] == list(range(6)) and sizes == [1, 6]
+    b.close()
