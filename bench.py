@@ -33,6 +33,7 @@ import os
 import statistics
 import subprocess
 import sys
+import queue
 import threading
 import time
 
@@ -401,8 +402,23 @@ def e2e_wave(handlers, auds, S) -> dict:
             vad = api.VADAudio(audio=auds[i], mode="final", turn_id=f"t{i}", turn_revision=0)
             out = list(stt.process(vad))
             tr = out[-1]
-            pieces, n_tok, first_audio, speech_s, t_tts0 = [], 0, None, 0.0, None
-            stream = llm.generate_text_stream(llm_prompt, max_new_tokens=MAX_NEW)
+            first_audio, speech_s, t_tts0 = None, 0.0, None
+            sentences: "queue.Queue" = queue.Queue()
+
+            def generate():
+                """The LLM stage of the unit: its own thread, like the reference's handler threads -- it keeps generating while
+                the TTS stage speaks the first sentence (sentences travel through a queue, LLM/language_model.py -> TTS)."""
+                try:
+                    sent_first = False
+                    for _piece in llm.generate_text_stream(llm_prompt, max_new_tokens=MAX_NEW):
+                        if not sent_first and len(llm.streamer.generated) >= FIRST_SENTENCE:
+                            sentences.put((FIRST_SENTENCE, F1))
+                            sent_first = True
+                    sentences.put((MAX_NEW - FIRST_SENTENCE, F2))
+                except BaseException as e:  # noqa: BLE001
+                    sentences.put(e)
+                finally:
+                    sentences.put(None)
 
             def speak(n_tokens, frames):
                 nonlocal first_audio, speech_s, t_tts0
@@ -415,13 +431,16 @@ def e2e_wave(handlers, auds, S) -> dict:
                     if first_audio is None:
                         first_audio = time.perf_counter()
                     speech_s += len(blk) / 16000.0
-            spoke_first = False
-            for piece in stream:
-                n_tok = len(llm.streamer.generated)
-                if not spoke_first and n_tok >= FIRST_SENTENCE:
-                    speak(FIRST_SENTENCE, F1)
-                    spoke_first = True
-            speak(MAX_NEW - FIRST_SENTENCE, F2)
+            gen_thread = threading.Thread(target=generate, daemon=True)
+            gen_thread.start()
+            while True:
+                it = sentences.get()
+                if it is None:
+                    break
+                if isinstance(it, BaseException):
+                    raise it
+                speak(*it)
+            gen_thread.join()
             t_end = time.perf_counter()
             lat[i] = 1e3 * (first_audio - vad.created_at_s)
             rtf[i] = speech_s / max(1e-9, t_end - t_tts0)
@@ -710,7 +729,8 @@ def main():
             line["e2e"] = {"value": e2e_val, "unit": "sessions", "h2d_bytes_per_step": S * N_SAMPLES * 4,
                            "d2h_bytes_per_step": S * int((F1 + F2) * 1920 * 2 / 3) * 2,
                            "wall_s_per_wave": e2e_wall_max, "path": "B200WhisperSTTHandler -> B200LanguageModelHandler -> B200Qwen3TTSHandler, "
-                           "one thread per session, shared engines + session batchers",
+                           "per session an LLM thread feeding a TTS thread through a queue (the reference's thread-per-stage shape), "
+                           "shared engines + session batchers per lane",
                            "tts_rtf_min": min(rtf_loaded) if rtf_loaded else None, "tts_rtf_p50": statistics.median(rtf_loaded) if rtf_loaded else None,
                            "real_time": realtime, "errors": [e for w in e2e["loaded"] for e in w["errors"]][:3],
                            "batching": e2e.get("batching")}

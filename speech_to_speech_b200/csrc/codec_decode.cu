@@ -235,6 +235,104 @@ __global__ void __launch_bounds__(TC_THREADS) conv1d_tc_kernel(const ConvArgs a,
       }
 }
 
+// The same contraction fed from fp16 ACTIVATIONS (a.x16): the producers whose output is consumed by a contraction only -- the
+// SnakeBeta activations in front of every convolution of the decoder blocks -- store fp16 directly, i.e. the rounding the
+// staging above applies moves into the producer (same values, same k order, same accumulation: bit-identical results), the
+// operand stream halves and both operands travel global -> shared through a 3-stage cp.async pipeline with no register staging.
+constexpr int TCH_STAGES = 3;
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_s, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_s), "l"(src), "r"(sz) : "memory");
+}
+__global__ void __launch_bounds__(TC_THREADS) conv1d_tc16_kernel(const ConvArgs a, const __half* __restrict__ x16, const __half2* __restrict__ wh,
+                                                                 int c_pairs) {
+  __shared__ __align__(16) __half As[TCH_STAGES][TC_BM][TC_BK + TC_APAD];
+  __shared__ __align__(16) uint32_t Bs[TCH_STAGES][TC_BK / 2][TC_BN + TC_BPAD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int m0 = blockIdx.y * TC_BM + a.t0, n0 = blockIdx.x * TC_BN, z = blockIdx.z;
+  const __half* X = x16 + (long long)z * a.x_bs;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+  const int kt_per_tap = (a.C_in + TC_BK - 1) / TC_BK;
+  const int n_kt = a.k * kt_per_tap;
+  // A: 128 rows x 4 chunks of 8 halves; thread -> rows a_row, a_row + 64, chunk a_ch.  B: 16 pair rows x 16 chunks of 4 words.
+  const int a_row = tid >> 2, a_ch = (tid & 3) * 8;
+  const int b_kp = tid >> 4, b_n = (tid & 15) * 4;
+  auto issue = [&](int kt, int buf) {
+    const int j = kt / kt_per_tap, c0 = (kt - j * kt_per_tap) * TC_BK;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int r = a_row + 64 * v;
+      const int xr = m0 + r + a.x_row0 + j * a.dil;
+      const bool ok = (m0 + r) < a.T_out && xr >= 0 && xr < a.T_in && (c0 + a_ch + 8) <= a.C_in;
+      const __half* src = ok ? X + (long long)xr * a.ldx + c0 + a_ch : X;
+      cp_async16_zfill(smem_u32(&As[buf][r][a_ch]), src, ok);
+    }
+    const bool kok = (c0 >> 1) + b_kp < c_pairs && (n0 + b_n + 4) <= a.N;
+    const __half2* wsrc = kok ? wh + (long long)(j * c_pairs + (c0 >> 1) + b_kp) * a.N + n0 + b_n : wh;
+    cp_async16_zfill(smem_u32(&Bs[buf][b_kp][b_n]), wsrc, kok);
+  };
+#pragma unroll
+  for (int s = 0; s < TCH_STAGES - 1; ++s) {
+    if (s < n_kt) issue(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < n_kt; ++kt) {
+    const int buf = kt % TCH_STAGES;
+    asm volatile("cp.async.wait_group %0;" ::"n"(TCH_STAGES - 2) : "memory");
+    __syncthreads();                                       // tile kt landed for every thread; tile kt-1's buffer is free
+    if (kt + TCH_STAGES - 1 < n_kt) issue(kt + TCH_STAGES - 1, (kt + TCH_STAGES - 1) % TCH_STAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+    for (int ks = 0; ks < TC_BK; ks += 16) {
+      uint32_t af[2][4], bf[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = wm * 32 + i * 16 + g;
+        af[i][0] = *reinterpret_cast<const uint32_t*>(&As[buf][r][ks + 2 * t]);
+        af[i][1] = *reinterpret_cast<const uint32_t*>(&As[buf][r + 8][ks + 2 * t]);
+        af[i][2] = *reinterpret_cast<const uint32_t*>(&As[buf][r][ks + 8 + 2 * t]);
+        af[i][3] = *reinterpret_cast<const uint32_t*>(&As[buf][r + 8][ks + 8 + 2 * t]);
+      }
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        const int n = wn * 32 + jn * 8 + g;
+        bf[jn][0] = Bs[buf][(ks >> 1) + t][n];
+        bf[jn][1] = Bs[buf][(ks >> 1) + 4 + t][n];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) mma_f16_16816(acc[i][jn], af[i][0], af[i][1], af[i][2], af[i][3], bf[jn][0], bf[jn][1]);
+    }
+  }
+  float* Y = a.y + (long long)z * a.y_bs;
+  const float* R = a.resid ? a.resid + (long long)z * a.r_bs : nullptr;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int tt = m0 + wm * 32 + i * 16 + g + (r >> 1) * 8;
+        const int n = n0 + wn * 32 + jn * 8 + 2 * t + (r & 1);
+        if (tt >= a.T_out || n >= a.N) continue;
+        float v = acc[i][jn][r];
+        if (a.bias) v += __ldg(a.bias + (n % a.bias_mod));
+        if (a.act == 1) v = gelu_erf(v);
+        else if (a.act == 2) v = v / (1.0f + expf(-v));
+        if (a.scale) v *= __ldg(a.scale + n);
+        if (R) v += R[(long long)tt * a.ldr + n];
+        Y[(long long)tt * a.ldy + n] = v;
+      }
+}
+
 // fp32 [k][C_in][N] -> half2 pairs [k][ceil(C_in / 2)][N]
 __global__ void pack_weight_pairs_kernel(const float* __restrict__ w, int k, int C_in, int N, __half2* __restrict__ out) {
   const int cp = (C_in + 1) >> 1;
@@ -356,6 +454,22 @@ __global__ void snake_beta_kernel(const float* __restrict__ x, const float* __re
   y[idx] = v + ib[c] * (s * s);
 }
 
+// the same, stored as fp16 for a tensor-core contraction (conv1d_tc16_kernel); 4 channels per thread (C % 4 == 0)
+__global__ void snake_beta_h_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ ib, int C,
+                                    int len, int first, long long n_per_seq, long long n, __half* __restrict__ y) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const long long b = i / n_per_seq, r = i - b * n_per_seq;
+  const long long idx = b * (long long)len * C + (long long)first * C + r;
+  const int c = (int)(r % C);
+  const float4 v = *reinterpret_cast<const float4*>(x + idx);
+  const float4 av = *reinterpret_cast<const float4*>(a + c), bv = *reinterpret_cast<const float4*>(ib + c);
+  const float s0 = sinf(v.x * av.x), s1 = sinf(v.y * av.y), s2 = sinf(v.z * av.z), s3 = sinf(v.w * av.w);
+  __half2* dst = reinterpret_cast<__half2*>(y + idx);
+  dst[0] = __floats2half2_rn(v.x + bv.x * (s0 * s0), v.y + bv.y * (s1 * s1));
+  dst[1] = __floats2half2_rn(v.z + bv.z * (s2 * s2), v.w + bv.w * (s3 * s3));
+}
+
 // ConvNeXt front: depthwise causal conv 7 + LayerNorm(eps) over channels; one CTA per time step
 __global__ void dwconv7_ln_kernel(const float* __restrict__ x, int T, int first, int C, const float* __restrict__ wd, const float* __restrict__ bd,
                                   const float* __restrict__ lw, const float* __restrict__ lb, float eps, float* __restrict__ y) {
@@ -428,6 +542,14 @@ int conv1d_tc_launch(const ConvArgs& a, const void* w_pairs, cudaStream_t st) {
   if (a.T_out - a.t0 <= 0 || a.N <= 0) return S2S_OK;
   const int batch = a.batch > 0 ? a.batch : 1;
   dim3 grid((a.N + TC_BN - 1) / TC_BN, (a.T_out - a.t0 + TC_BM - 1) / TC_BM, batch);
+  if (a.x16) {
+    S2S_REQUIRE(a.C_in % 8 == 0 && a.N % 4 == 0 && a.ldx % 8 == 0 && a.x_bs % 8 == 0, "conv1d_tc16: C_in %d / N %d / ldx %lld not 16-byte tileable",
+                a.C_in, a.N, a.ldx);
+    conv1d_tc16_kernel<<<grid, TC_THREADS, 0, st>>>(a, reinterpret_cast<const __half*>(a.x16), reinterpret_cast<const __half2*>(w_pairs),
+                                                    (a.C_in + 1) >> 1);
+    S2S_LAUNCH_CHECK();
+    return S2S_OK;
+  }
   conv1d_tc_kernel<<<grid, TC_THREADS, 0, st>>>(a, reinterpret_cast<const __half2*>(w_pairs), (a.C_in + 1) >> 1);
   S2S_LAUNCH_CHECK();
   return S2S_OK;
@@ -647,6 +769,22 @@ ConvArgs causal_conv_args(const float* x, int T, int C_in, const float* w, const
   a.x = x; a.ldx = C_in; a.T_in = T; a.x_row0 = -(k - 1) * dil; a.w = w; a.k = k; a.dil = dil; a.C_in = C_in; a.N = C_out;
   a.bias = b; a.bias_mod = C_out; a.y = y; a.ldy = C_out; a.T_out = T; a.batch = 1;
   return a;
+}
+
+// SnakeBeta whose only consumer is a tensor-core contraction: fp16 output (conv1d_tc16_kernel reads it with cp.async)
+int snake_launch_h(const float* x, const float* a, const float* ib, int C, int B, int len, int first, void* y16, cudaStream_t st) {
+  const long long per = (long long)(len - first) * C, n = per * B;
+  if (n <= 0) return S2S_OK;
+  snake_beta_h_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(x, a, ib, C, len, first, per, n, reinterpret_cast<__half*>(y16));
+  S2S_LAUNCH_CHECK();
+  return S2S_OK;
+}
+// may the contraction with weights w (C_in = C, N outputs) take an fp16 operand?  (tensor-core mode, packed weights, 16-byte tiles)
+bool fp16_operand_ok(const CodecDecoder* m, const float* w, int C, int N) {
+  if (m->cfg.precision == 0 || C % 8 != 0 || N % 4 != 0) return false;
+  if (const char* e = getenv("S2S_CODEC_FP16_OPERANDS")) { if (e[0] == '0') return false; }   // A/B switch (tests: bit-identical)
+  auto it = m->tc_w.find(w);
+  return it != m->tc_w.end() && it->second.packed != nullptr;
 }
 
 int snake_launch(const float* x, const float* a, const float* ib, int C, int B, int len, int first, float* y, cudaStream_t st) {
@@ -908,10 +1046,12 @@ int codec_decode_batch(CodecDecoder* m, const int32_t* const* codes_d, int B, in
   for (int i = 0; i < n_blk; ++i) {
     const CodecBlock& Bk = m->blocks[i];
     const int t_first = need_blk_in[i];                               // first input row (= first transposed-conv "row")
-    S2S_CHECK(snake_launch(X, Bk.a0, Bk.b0, Bk.cin, B, len, t_first, A, st));
+    const bool h0 = fp16_operand_ok(m, Bk.tc_w, Bk.cin, Bk.rate * Bk.cout);
+    if (h0) S2S_CHECK(snake_launch_h(X, Bk.a0, Bk.b0, Bk.cin, B, len, t_first, A, st));
+    else S2S_CHECK(snake_launch(X, Bk.a0, Bk.b0, Bk.cin, B, len, t_first, A, st));
     {
       ConvArgs a{};
-      a.x = A; a.ldx = Bk.cin; a.T_in = len; a.x_row0 = 0; a.w = Bk.tc_w; a.k = 2; a.dil = 1; a.C_in = Bk.cin; a.N = Bk.rate * Bk.cout;
+      a.x = A; a.x16 = h0 ? A : nullptr; a.ldx = Bk.cin; a.T_in = len; a.x_row0 = 0; a.w = Bk.tc_w; a.k = 2; a.dil = 1; a.C_in = Bk.cin; a.N = Bk.rate * Bk.cout;
       a.bias = Bk.tc_b; a.bias_mod = Bk.cout; a.y = X; a.ldy = (long long)Bk.rate * Bk.cout; a.T_out = len - 1;
       S2S_CHECK(contract(m, batched(a, Bk.cin, Bk.rate * Bk.cout, len, len - 1, t_first), st));
     }
@@ -920,10 +1060,18 @@ int codec_decode_batch(CodecDecoder* m, const int32_t* const* codes_d, int B, in
     for (int u = 0; u < 3; ++u) {
       const CodecResUnit& Ru = Bk.u[u];
       const int f_u = need_unit[i * 3 + u];                            // rows this unit must produce (reads f_u - 6 d >= have)
-      S2S_CHECK(snake_launch(X, Ru.a1, Ru.b1, Bk.cout, B, len, have, A, st));
-      S2S_CHECK(contract(m, batched(causal_conv_args(A, len, Bk.cout, Ru.c1_w, Ru.c1_b, 7, dil[u], Bk.cout, Hb), Bk.cout, Bk.cout, len, len, f_u), st));
-      S2S_CHECK(snake_launch(Hb, Ru.a2, Ru.b2, Bk.cout, B, len, f_u, A, st));
+      const bool h1 = fp16_operand_ok(m, Ru.c1_w, Bk.cout, Bk.cout), h2 = fp16_operand_ok(m, Ru.c2_w, Bk.cout, Bk.cout);
+      if (h1) S2S_CHECK(snake_launch_h(X, Ru.a1, Ru.b1, Bk.cout, B, len, have, A, st));
+      else S2S_CHECK(snake_launch(X, Ru.a1, Ru.b1, Bk.cout, B, len, have, A, st));
+      {
+        ConvArgs a1 = causal_conv_args(A, len, Bk.cout, Ru.c1_w, Ru.c1_b, 7, dil[u], Bk.cout, Hb);
+        a1.x16 = h1 ? A : nullptr;
+        S2S_CHECK(contract(m, batched(a1, Bk.cout, Bk.cout, len, len, f_u), st));
+      }
+      if (h2) S2S_CHECK(snake_launch_h(Hb, Ru.a2, Ru.b2, Bk.cout, B, len, f_u, A, st));
+      else S2S_CHECK(snake_launch(Hb, Ru.a2, Ru.b2, Bk.cout, B, len, f_u, A, st));
       ConvArgs a = linear_args(A, len, Bk.cout, Ru.c2_w, Bk.cout, X);
+      a.x16 = h2 ? A : nullptr;
       a.bias = Ru.c2_b; a.resid = X; a.ldr = Bk.cout;
       S2S_CHECK(contract(m, batched(a, Bk.cout, Bk.cout, len, len, f_u), st));
       have = f_u;

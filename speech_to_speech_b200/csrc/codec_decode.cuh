@@ -7,6 +7,7 @@
 // stride s is the same contraction with N = s * C_out and the output read as [(T - 1) * s, C_out] (see codec_decode.cu).
 struct ConvArgs {
   const float* x; long long ldx; int T_in; int x_row0;
+  const void* x16;                          // optional fp16 copy of x (same shape / strides in elements): tensor-core mode only
   const float* w; int k, dil, C_in, N;
   const float* bias; int bias_mod;
   int act;                                  // 0 none, 1 exact GELU, 2 SiLU

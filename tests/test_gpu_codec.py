@@ -76,7 +76,7 @@ def test_lengths_and_values_vs_oracle(model, T):
 
 
 @pytest.mark.parametrize("precision", [0, 1])
-def test_real_geometry_slice_vs_oracle(E, precision):
+def test_real_geometry_slice_vs_oracle(E, precision, monkeypatch):
     """The published 12 Hz geometry (hidden 1024, 16 heads, window 72, decoder 1536, x1920) with 2 transformer layers:
     tile shapes, channel counts and the sliding window of the real model; 3 frames so the numpy oracle stays fast."""
     g0 = C.GEOMETRIES["qwen3-12hz"]
@@ -113,3 +113,27 @@ def test_real_geometry_slice_vs_oracle(E, precision):
     print(msg)
     assert he16 < inherent_h and med16 < 3e-3 and we16 < inherent_w, msg
     assert he < 2 * inherent_h + 1e-3 and we < 2 * inherent_w + 1e-2, msg
+    # the fp16-activation path (SnakeBeta stores fp16, cp.async pipeline) against the converting path: bit-identical
+    monkeypatch.setenv("S2S_CODEC_FP16_OPERANDS", "0")
+    wav0 = eng.decode(_codes_dev(codes), 0)
+    assert torch.equal(wav0, wav)
+
+
+def test_fp16_activation_operands_are_bit_identical_to_the_converting_path(E, monkeypatch):
+    """Tensor-core mode: SnakeBeta stores fp16 and conv1d_tc16_kernel streams it with cp.async -- the rounding moved from the
+    consumer's staging into the producer, nothing else: the waveform must equal the converting path's bit for bit (full
+    decode and a trimmed chunk behind left context, two sequences per launch sequence)."""
+    g = C.GEOMETRIES["micro"]
+    w = C.make_weights(g, 0)
+    eng = E.CodecEngine(g.to_dict(), max_frames=40, precision=1)
+    eng.load_state_dict(w)
+    codes = np.random.default_rng(9).integers(0, g.codebook_size, (g.quantizers, 20))
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("S2S_CODEC_FP16_OPERANDS", flag)
+        full = eng.decode(_codes_dev(codes), 0)
+        chunk = eng.decode(_codes_dev(codes[:, 4:18]), 6)
+        torch.cuda.synchronize()
+        outs[flag] = (full.clone(), chunk.clone())
+    assert torch.equal(outs["1"][0], outs["0"][0]) and torch.equal(outs["1"][1], outs["0"][1])
+    assert float(outs["1"][0].abs().max()) > 0
