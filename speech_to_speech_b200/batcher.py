@@ -44,6 +44,7 @@ class SessionBatcher:
         self.max_wait_s = float(max_wait_s)
         self.idle_gap_s = None if idle_gap_s is None else float(idle_gap_s)
         self._last_arrival = 0.0
+        self._free_at = 0.0          # when the engine thread finished its last launch
         self._cv = threading.Condition()
         # key -> list of (item, future, t_arrival); OrderedDict keeps the arrival order of each key's oldest request
         self._pending: "OrderedDict[Hashable, List[Tuple[Any, Future, float]]]" = OrderedDict()
@@ -79,9 +80,12 @@ class SessionBatcher:
             while True:
                 if self._pending:
                     key, items = next(iter(self._pending.items()))
-                    due = items[0][2] + self.max_wait_s
+                    # both clocks run only while the engine is free: requests that queued up behind a running launch must not
+                    # leave the instant it ends -- the sessions of THAT launch are about to resubmit, and taking the queue
+                    # as it stands locks two groups of sessions into alternating half-full launches
+                    due = max(items[0][2], self._free_at) + self.max_wait_s
                     if self.idle_gap_s is not None:       # the burst of resubmissions is over: nothing new for idle_gap_s
-                        due = min(due, max(items[-1][2], self._last_arrival) + self.idle_gap_s)
+                        due = min(due, max(items[-1][2], self._last_arrival, self._free_at) + self.idle_gap_s)
                     now = time.monotonic()
                     if len(items) >= self.max_batch or now >= due or self._closed:
                         batch = items[: self.max_batch]
@@ -128,12 +132,14 @@ class SessionBatcher:
             except BaseException as exc:  # delivered to the waiting handler threads, never swallowed
                 for _, fut in live:
                     fut.set_exception(exc)
+                self._free_at = time.monotonic()
                 continue
             self.batches_run += 1
             self.items_run += len(live)
             self.largest_batch = max(self.largest_batch, len(live))
             for (_, fut), res in zip(live, results):
                 fut.set_result(res)
+            self._free_at = time.monotonic()
 
     def close(self, timeout: float = 5.0) -> None:
         """Serve what is queued, then stop the thread."""

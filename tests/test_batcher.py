@@ -305,3 +305,29 @@ def test_idle_gap_dispatches_when_the_burst_is_over_not_after_the_whole_window()
     th.join()
     assert [f.result(5) for f in futs] == list(range(6)) and sizes == [1, 6]
     b.close()
+
+
+def test_two_groups_merge_instead_of_alternating_half_full_launches():
+    """Two groups of sessions out of phase by one launch: the group that queued up behind the running launch must wait one idle
+    gap after it ends, so that the sessions of that launch (which resubmit immediately) ride along -- launches fill up to
+    max_batch instead of alternating between the groups forever."""
+    import threading
+    import time
+    from speech_to_speech_b200.batcher import SessionBatcher
+    sizes = []
+
+    def run(key, items):
+        sizes.append(len(items))
+        time.sleep(0.03)                       # a launch
+        return list(items)
+    b = SessionBatcher(run, max_batch=8, max_wait_s=0.5, idle_gap_s=0.01)
+
+    def session(i, delay):
+        time.sleep(delay)
+        for _ in range(6):
+            b.call("k", i, timeout=10)
+    ths = [threading.Thread(target=session, args=(i, 0.0 if i < 4 else 0.015)) for i in range(8)]   # group B starts mid-launch
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    b.close()
+    assert sizes[0] == 4 and sizes.count(8) >= 4, sizes    # after the first launches the groups travel together
