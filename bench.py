@@ -306,7 +306,31 @@ class Stack:
         self.torch = torch
 
 
-def wave_device(st: Stack, pcm_dev, ev) -> None:
+class TtsProfileWindow:
+    """cudaProfilerStart/Stop around chunks [first, first + n) of the second utterance's frame loop (all lanes): an ncu launch
+    list of the whole region is ~42k launches at ~0.2 s each, the per-chunk kernel mix is what the list is for."""
+
+    def __init__(self, torch, lanes: int, n: int, first: int = 2):
+        self.torch, self.lanes, self.n, self.first = torch, lanes, n, first
+        self.lock, self.started, self.stopped = threading.Lock(), 0, 0
+
+    def chunk_begin(self, ci: int) -> None:
+        if ci == self.first:
+            with self.lock:
+                self.started += 1
+                if self.started == 1:
+                    self.torch.cuda.cudart().cudaProfilerStart()
+
+    def chunk_end(self, ci: int) -> None:
+        if ci == self.first + self.n - 1:
+            self.torch.cuda.current_stream().synchronize()
+            with self.lock:
+                self.stopped += 1
+                if self.stopped == self.lanes:
+                    self.torch.cuda.cudart().cudaProfilerStop()
+
+
+def wave_device(st: Stack, pcm_dev, ev, tts_prof: "TtsProfileWindow | None" = None) -> None:
     """One wave of S full turns as an engine-level launch sequence; stage boundaries marked with CUDA events."""
     torch, S = st.torch, st.S
     dev = f"cuda:{st.dev}"
@@ -338,9 +362,11 @@ def wave_device(st: Stack, pcm_dev, ev) -> None:
     for text, frames in ((text1, F1), (text2, F2)):                       # ---- TTS: two utterances per turn
         for s in range(S):
             eng.prefill(s, text, 2301)
-        done = 0
+        done, ci = 0, 0
         while done < frames:
             n = min(CHUNK, frames - done)
+            if tts_prof is not None and text is text2:
+                tts_prof.chunk_begin(ci)
             for b0 in range(0, S, st.tts_b):
                 eng.decode_frames(list(range(b0, min(S, b0 + st.tts_b))), n)
             ev["frames_mark"].append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
@@ -350,11 +376,14 @@ def wave_device(st: Stack, pcm_dev, ev) -> None:
                 for wav in eng.decode_audio_batch(list(range(b0, min(S, b0 + st.tts_b))), n, LEFT_CTX):
                     st.post.to_int16_device(wav)
             b.record()
+            if tts_prof is not None and text is text2:
+                tts_prof.chunk_end(ci)
             done += n
+            ci += 1
     ev["tts"].record()
 
 
-def run_wave(stacks, pcm_dev, evs):
+def run_wave(stacks, pcm_dev, evs, tts_prof=None):
     """One wave on every lane at once: a host thread per lane issues the lane's launch sequence on the lane's stream; the step is
     timed on the calling stream, from an event every lane waits for to an event that waits for every lane."""
     torch = stacks[0].torch
@@ -362,7 +391,7 @@ def run_wave(stacks, pcm_dev, evs):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(cur)
     if len(stacks) == 1:
-        wave_device(stacks[0], pcm_dev, evs[0])
+        wave_device(stacks[0], pcm_dev, evs[0], tts_prof)
     else:
         errs, Sl = [], stacks[0].S
 
@@ -372,7 +401,7 @@ def run_wave(stacks, pcm_dev, evs):
                 torch.cuda.set_device(st.dev)
                 with st.E.lane_context(st.dev, st.lane, st.lanes):
                     torch.cuda.current_stream().wait_event(start)
-                    wave_device(st, pcm_dev[i * Sl:(i + 1) * Sl], evs[i])
+                    wave_device(st, pcm_dev[i * Sl:(i + 1) * Sl], evs[i], tts_prof)
                     evs[i]["done"].record()
             except BaseException as e:  # noqa: BLE001
                 errs.append(e)
@@ -389,8 +418,9 @@ def run_wave(stacks, pcm_dev, evs):
     return start, end
 
 
-def e2e_wave(handlers, auds, S) -> dict:
-    """The wave through the three handler classes, one thread per session (the reference's thread-per-unit shape)."""
+def e2e_wave(handlers, auds, S, offsets=None) -> dict:
+    """The wave through the three handler classes, one thread per session (the reference's thread-per-unit shape).  offsets[i]:
+    seconds after the start of the wave at which session i stops speaking (default: all at once, the worst case)."""
     from speech_to_speech_b200.host import resolve
     api = resolve()
     lat, rtf, t_done = [None] * S, [None] * S, [None] * S
@@ -399,6 +429,8 @@ def e2e_wave(handlers, auds, S) -> dict:
     def session(i):
         try:
             stt, llm, tts = handlers[i]
+            if offsets is not None:
+                time.sleep(offsets[i])
             vad = api.VADAudio(audio=auds[i], mode="final", turn_id=f"t{i}", turn_revision=0)
             out = list(stt.process(vad))
             tr = out[-1]
@@ -508,6 +540,8 @@ def main():
     ap.add_argument("--cpu-baseline-turns", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-tts-chunks", type=int, default=0,
+                    help="cudaProfilerStart/Stop around this many 8-frame chunks (frames + codec + post-processing) of the TTS stage only")
     ap.add_argument("--profile-region", action="store_true",
                     help="cudaProfilerStart/Stop around the device-timed region (use with ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -580,7 +614,8 @@ def main():
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                 # L2 flush between timed steps (not timed)
         ev = new_events()
-        spans.append(run_wave(stacks, pcm_dev, ev))
+        prof = TtsProfileWindow(torch, L, args.profile_tts_chunks) if args.profile_tts_chunks > 0 and i == 0 else None
+        spans.append(run_wave(stacks, pcm_dev, ev, prof))
         evs.append(ev[0])                     # stage boundaries: lane 0's (the lanes run the same sequence side by side)
     barrier()
     if args.profile_region:
@@ -635,7 +670,12 @@ def main():
             loaded = [e2e_wave(handlers, auds, S) for _ in range(2 if args.steps >= 4 else 1)]
             bs1 = batcher_stats()
             barrier()
-            e2e = {"single": single, "loaded": loaded,
+            # latency under a steady load: the sessions' turns end evenly spread, at 70 % of the arrival rate the loaded wave sustained
+            spacing = statistics.mean(w["wall_s"] for w in loaded) / S / 0.7
+            order = np.random.default_rng(3).permutation(S)          # lanes interleaved, not lane 0 first
+            staggered = e2e_wave(handlers, auds, S, offsets=[float(spacing * int(np.where(order == i)[0][0])) for i in range(S)])
+            log(f"staggered wave (one turn end every {1e3 * spacing:.0f} ms): p50 latency {statistics.median(staggered['latency_ms']) if staggered['latency_ms'] else None}")
+            e2e = {"single": single, "loaded": loaded, "staggered": staggered, "staggered_spacing_s": spacing,
                    "batching": {k: {"launch_groups": bs1[k][0] - bs0[k][0], "requests": bs1[k][1] - bs0[k][1],
                                     "mean_batch": round((bs1[k][1] - bs0[k][1]) / max(1, bs1[k][0] - bs0[k][0]), 2)} for k in bs1}}
             log(f"loaded e2e waves: {[round(w['wall_s'], 2) for w in loaded]} s")
@@ -736,8 +776,14 @@ def main():
                            "batching": e2e.get("batching")}
             line["latency_ms_p50"] = statistics.median(lat_loaded) if lat_loaded else None
             line["latency_ms_p50_single_session"] = statistics.median(lat_single) if lat_single else None
+            lat_st = sorted(e2e.get("staggered", {}).get("latency_ms", []))
+            if lat_st:
+                line["latency_ms_at_70pct_load"] = {"p50": statistics.median(lat_st), "p90": lat_st[min(len(lat_st) - 1, int(0.9 * len(lat_st)))],
+                                                    "turn_end_every_ms": 1e3 * e2e["staggered_spacing_s"], "sessions": len(lat_st),
+                                                    "errors": e2e["staggered"]["errors"]}
             line["latency_note"] = ("audio-in (VADAudio.created_at_s) -> first int16 block out of the TTS handler; 'single' = one session on an "
-                                    "idle GPU, 'latency_ms_p50' = the S sessions of a wave that all stop speaking at the same instant (worst case)")
+                                    "idle GPU (on its lane's SM partition), 'latency_ms_p50' = the S sessions of a wave that all stop speaking at the same instant (worst case), "
+                                    "'latency_ms_at_70pct_load' = turn ends evenly spread at 70 % of the rate the loaded wave sustains")
         elif e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -55,8 +55,12 @@ def _handler_module(use_reference: bool):
     else:
         if had:
             sys.path.remove(REF_SRC)
+    # the mirror base is only chosen when `speech_to_speech` cannot be imported: hide the already-imported modules for the
+    # duration of the import and PUT THEM BACK, so that other test modules keep seeing the class objects they imported
+    hidden = {}
+    if not use_reference:
         for m in [k for k in sys.modules if k == "speech_to_speech" or k.startswith("speech_to_speech.")]:
-            del sys.modules[m]
+            hidden[m] = sys.modules.pop(m)
     try:
         mod = importlib.import_module("speech_to_speech_b200.handlers.qwen3_tts_handler")
     finally:
@@ -64,6 +68,9 @@ def _handler_module(use_reference: bool):
             sys.path.remove(REF_SRC)
         if not use_reference and had:
             sys.path.insert(0, REF_SRC)
+        for m in [k for k in sys.modules if (k == "speech_to_speech" or k.startswith("speech_to_speech.")) and k in hidden]:
+            del sys.modules[m]
+        sys.modules.update(hidden)
     want = "speech_to_speech.TTS.qwen3_tts_handler" if use_reference else "speech_to_speech_b200.host.mirror_tts"
     if mod._Base.__module__ != want:
         pytest.skip(f"base class resolved to {mod._Base.__module__}")
