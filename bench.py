@@ -496,6 +496,10 @@ def e2e_wave(handlers, auds, S, offsets=None) -> dict:
     return {"wall_s": wall, "latency_ms": ok, "rtf": [x for x in rtf if x is not None], "errors": errs[:3]}
 
 
+LLM_STREAM_CHUNK = 4     # tokens per decode launch in the handler path: the TTS stage sees a sentence at most 4 steps late, and a
+                         # first-sentence TTS request waits behind at most 4 LLM steps on the lane's stream
+
+
 def make_handlers(S: int, dev: int, lanes: int = 1):
     """S pipeline units' worth of handler instances; the units of a lane share one engine per stage (gen_kwargs / kwargs of the
     reference slots)."""
@@ -517,7 +521,7 @@ def make_handlers(S: int, dev: int, lanes: int = 1):
         llm.device = f"cuda:{dev}"
         B200LanguageModelHandler._load_model(llm, "random:llama-3-8b:7", f"cuda:{dev}", "bfloat16",
                                              {"max_new_tokens": MAX_NEW, "max_sessions": Sl, "max_positions": LLM_PROMPT + MAX_NEW + 8,
-                                              "stream_chunk_tokens": 8, "lane": lane, "lanes": lanes})
+                                              "stream_chunk_tokens": LLM_STREAM_CHUNK, "lane": lane, "lanes": lanes})
         llm.eos_ids = []                      # random-init weights: never stop early, every reply has 128 tokens
         llm.streamer.eos_ids = set()
         tts = B200Qwen3TTSHandler(Event(), queue_in=Queue(), queue_out=Queue(), setup_args=(Event(),),
@@ -574,6 +578,10 @@ def main():
     full = None
     if rank == 0:
         full = torch.stack([torch.from_numpy(W.synthetic_audio(sid, N_SAMPLES)) for r in range(world) for sid in layout[r]]).to(dev)
+    if world > 1:   # the first collective of a process group builds the NCCL communicator: keep that out of the exchange timing
+        shard.scatter_from_ingest(full, S, (N_SAMPLES,), torch.float32, dev)
+        shard.gather_to_ingest(torch.zeros((S, 64), dtype=torch.int32, device=dev))
+        torch.cuda.synchronize()
     xe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     xe[0].record()
     pcm_dev = shard.scatter_from_ingest(full, S, (N_SAMPLES,), torch.float32, dev)
@@ -650,6 +658,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
+            # ~70 Python threads (two per session + the batchers' engine threads) hand work to each other through the GIL: the
+            # default 5 ms switch interval is longer than a whole batch window
+            sys.setswitchinterval(0.0005)
             handlers = make_handlers(S, local_rank, L)
             log("handler instances built and warmed up")
             auds = [pcm_dev[i].cpu().numpy() for i in range(S)]
