@@ -97,12 +97,13 @@ def byte_tokenizer(text_vocab: int, reserved: int = 16) -> Callable[[str], list]
 class B200Qwen3TTS:
     def __init__(self, engine: Any, tokenize: Callable[[str], Sequence[int]], speakers: Mapping[str, int], max_sessions: int = 1,
                  batch_wait_s: float = 0.012, tts_model_type: str = "custom_voice", lane: int = 0, lanes: int = 1,
-                 batch_gap_s: Optional[float] = 0.003):
+                 batch_gap_s: Optional[float] = 0.003, prefetch_chunks: bool = True):
         # batch_gap_s: a session needs a few ms of host work between two chunk requests (resample + int16 + D2H of the chunk it
         # just received); the gap must cover it, or the sessions of the launch that just ended miss the next one and two groups
         # alternate in half-full launches (measured: mean batch 7.8 of 16 with a 0.6 ms gap)
         self.engine = engine
         self.lane, self.lanes = int(lane), int(lanes)
+        self.prefetch_chunks = bool(prefetch_chunks)   # False: request chunk k + 1 only after the consumer took chunk k (A/B, tests)
         self.tokenize = tokenize
         self.speakers = {str(k).lower(): int(v) for k, v in speakers.items()}
         self.sample_rate = SAMPLE_RATE
@@ -244,19 +245,43 @@ class B200Qwen3TTS:
         ids = list(text_ids)[: eng.cfg.max_text] or [0]
         slot = self._acquire_slot()
         t0 = perf_counter()
+        pending = None
         try:
             with self._lock:
                 eng.prefill(slot, ids, speaker_id)
             done = 0
-            while done < budget:
-                n = min(chunk, budget - done)
-                valid, finished, wav = self.batcher.call(n, slot) if self.batcher is not None else self._run_frames(n, [slot])[0]
+            if self.batcher is None:
+                while done < budget:
+                    valid, finished, wav = self._run_frames(min(chunk, budget - done), [slot])[0]
+                    done += valid
+                    if wav is not None and wav.numel() > 0:
+                        yield DeviceAudio(wav), SAMPLE_RATE, {"frames": done, "elapsed_s": perf_counter() - t0}
+                    if finished:
+                        break
+                return
+            # Shared engine: the request for chunk k + 1 leaves BEFORE chunk k is handed to the consumer.  The consumer's work on a
+            # chunk (wait for its codec kernels, resample, int16, D2H: ~10 ms) would otherwise delay this session's next request
+            # past the batch window, and two groups of sessions lock into alternating half-full launches (measured: mean batch
+            # 7.8 of 16); with the request already queued, every session of the launch that just ended rides the next one, and the
+            # engine computes chunk k + 1 while the handler threads post-process chunk k.
+            pending = self.batcher.submit(min(chunk, budget), slot)
+            while pending is not None:
+                valid, finished, wav = pending.result()
+                pending = None
                 done += valid
+                more = not finished and done < budget
+                if more and self.prefetch_chunks:
+                    pending = self.batcher.submit(min(chunk, budget - done), slot)
                 if wav is not None and wav.numel() > 0:
                     yield DeviceAudio(wav), SAMPLE_RATE, {"frames": done, "elapsed_s": perf_counter() - t0}
-                if finished:
-                    break
+                if more and not self.prefetch_chunks:
+                    pending = self.batcher.submit(min(chunk, budget - done), slot)
         finally:
+            if pending is not None and not pending.cancel():     # consumer stopped early: the slot is in use until the launch ends
+                try:
+                    pending.result()
+                except Exception:  # noqa: BLE001
+                    pass
             self._release_slot(slot)
 
     def close(self) -> None:

@@ -1,0 +1,100 @@
+"""Host logic of tts_model.B200Qwen3TTS on the CPU with a fake engine: chunk requests of concurrent sessions through the
+SessionBatcher.  The case that matters is two groups of sessions out of phase by half a launch whose consumers need longer
+than the batch gap to digest a chunk (on the GPU: waiting for the chunk's codec kernels + resample + D2H, ~10 ms): without the
+prefetched request they lock into alternating half-full launches, with it they merge into full ones."""
+import threading
+import time
+import types
+
+import pytest
+import torch
+
+from speech_to_speech_b200.tts_model import B200Qwen3TTS
+
+LAUNCH_S, DIGEST_S, CHUNKS = 0.02, 0.012, 14
+
+
+class FakeEngine:
+    device, codec_eos = 0, -1
+    cfg = types.SimpleNamespace(max_positions=4096, max_text=128)
+
+    def __init__(self):
+        self.n, self.launches = {}, []
+        self.stream = threading.Lock()     # the lane's CUDA stream: launches and the consumers' small kernels run one after another
+
+    def max_batch(self):
+        return 16
+
+    def prefill(self, slot, ids, spk):
+        self.n[slot] = 0
+
+    def frames(self, s):
+        return self.n[s]
+
+    def set_frames(self, s, n):
+        self.n[s] = n
+
+    def decode_frames(self, slots, n):
+        self.launches.append(len(slots))
+        with self.stream:
+            time.sleep(LAUNCH_S)
+        for s in slots:
+            self.n[s] += n
+        return torch.zeros((len(slots), n, 16), dtype=torch.int32)
+
+    def history_context(self, s, valid, left):
+        return min(left, self.n[s] - valid)
+
+    def decode_audio_batch(self, slots, valid, left):
+        return [torch.full((valid * 10,), float(self.n[s])) for s in slots]
+
+    def close(self):
+        pass
+
+
+def _run(prefetch: bool):
+    eng = FakeEngine()
+    tts = B200Qwen3TTS(eng, lambda text: [1, 2, 3], {"a": 0}, max_sessions=16, batch_wait_s=0.06, batch_gap_s=0.004, prefetch_chunks=prefetch)
+    got = {}
+
+    def session(i, delay):
+        time.sleep(delay)
+        chunks = []
+        for audio, sr, info in tts.generate_custom_voice_streaming("x", "a", chunk_size=8, max_new_tokens=8 * CHUNKS):
+            chunks.append((info["frames"], float(audio.tensor[0])))
+            time.sleep(DIGEST_S)                     # the consumer's host work on the chunk it just received ...
+            with eng.stream:                         # ... and its resample kernel + D2H, queued on the lane's stream behind whatever
+                time.sleep(0.0005)                   # launch got there first (the other group's frames, if it did not wait)
+        got[i] = chunks
+    ths = [threading.Thread(target=session, args=(i, 0.0 if i < 8 else LAUNCH_S / 2)) for i in range(16)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    tts.close()
+    return eng, got
+
+
+def test_prefetched_requests_merge_two_groups_into_full_launches():
+    eng, got = _run(prefetch=True)
+    for i in range(16):   # every session got its chunks in order, each decoded from its own frame counter
+        assert [f for f, _ in got[i]] == [8 * (k + 1) for k in range(CHUNKS)]
+        assert [v for _, v in got[i]] == [float(8 * (k + 1)) for k in range(CHUNKS)]
+    assert eng.launches.count(16) >= CHUNKS - 6, eng.launches          # the groups travel together after the first launches
+    assert len(eng.launches) <= CHUNKS + 8, eng.launches               # (28 launches of 8 without the prefetch)
+
+
+def test_without_prefetch_the_groups_alternate_in_half_full_launches():
+    """The behaviour the prefetch removes (kept as a regression reference: it is what the handler wave measured on the GPU)."""
+    eng, got = _run(prefetch=False)
+    assert all(len(got[i]) == CHUNKS for i in range(16))
+    assert eng.launches.count(8) >= CHUNKS, eng.launches
+
+
+def test_consumer_that_stops_early_releases_the_slot_after_the_prefetched_launch():
+    eng = FakeEngine()
+    tts = B200Qwen3TTS(eng, lambda text: [1], {"a": 0}, max_sessions=2, batch_wait_s=0.01, batch_gap_s=0.002)
+    gen = tts.generate_custom_voice_streaming("x", "a", chunk_size=8, max_new_tokens=80)
+    next(gen)
+    gen.close()                                    # GeneratorExit at the yield: the prefetched request is cancelled or awaited
+    assert sorted(tts._free) == [0, 1]
+    assert eng.n[0] in (8, 16)                     # at most one chunk ahead of the consumer
+    tts.close()
