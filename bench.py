@@ -749,7 +749,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "sessions", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 (Whisper) / bf16 (Llama, talker) operands, f32 accumulate; codec decoder f32", "data": "synthetic",
+            "dtype": "f16 (Whisper, codec-decoder contractions) / bf16 (Llama, talker, code predictor) operands, f32 accumulate and residual streams", "data": "synthetic",
             "config": workload_config(world, S),
             "l2": "flushed between timed steps (256 MiB write); every stage streams > 126 MB of weights per launch",
             "lanes": {"per_gpu": L, "ctas_per_lane": lane_ctas, "sessions_per_lane": Sl,

@@ -47,6 +47,7 @@ extern "C" int s2s_tts_postproc(s2s_ctx* ctx, const float* wav24k_d, int32_t n, 
   const int n_out = (n * 2 + 2) / 3;  // ceil(n * up / down)
   *n_out_h = n_out;
   if (n_out == 0) return S2S_OK;
+  S2S_CHECK_CUDA(cudaSetDevice(ctx->device));   // handler threads start on device 0 whatever GPU their session lives on
   tts_post_kernel<<<(n_out + 255) / 256, 256, n_taps * sizeof(float), (cudaStream_t)stream>>>(
       wav24k_d, n, taps_d, n_taps, (n_taps - 1) / 2, reinterpret_cast<short*>(out16k_d), n_out);
   S2S_LAUNCH_CHECK();
