@@ -257,7 +257,7 @@ def reference_arm(args, rank, world):
         return
     threads = host_threads()
     line = {"metric": METRIC, "unit": "sessions", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (STT) / bf16 (LLM)", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference", "config": workload_config(world, args.sessions)}
     try:
         cb = cpu_turn(max(1, args.steps), threads)
