@@ -201,3 +201,78 @@ def test_device_audio_satisfies_the_numpy_tuple_contract():
     tok = byte_tokenizer(512)
     ids = tok("Hello, wörld")
     assert ids and all(0 <= i < 496 for i in ids)
+
+
+@pytest.mark.parametrize("use_reference", [True, False])
+def test_concurrent_handlers_on_the_real_model_object_with_a_fake_engine(monkeypatch, use_reference):
+    """The handler slot on top of tts_model.B200Qwen3TTS itself (session batcher, prefetched chunk requests, DeviceAudio) with a
+    fake engine and a fake device post-processor: 4 handler threads speak at once, every one of them receives its own audio in
+    order, and the engine saw merged launches."""
+    import threading
+    import time
+    import types
+    import torch
+    mod = _handler_module(use_reference)
+    from speech_to_speech_b200.tts_model import B200Qwen3TTS
+
+    class Eng:
+        device, codec_eos = 0, -1
+        cfg = types.SimpleNamespace(max_positions=4096, max_text=128)
+
+        def __init__(self):
+            self.n, self.launches = {}, []
+
+        def max_batch(self):
+            return 16
+
+        def prefill(self, slot, ids, spk):
+            self.n[slot] = 0
+
+        def frames(self, s):
+            return self.n[s]
+
+        def set_frames(self, s, n):
+            self.n[s] = n
+
+        def decode_frames(self, slots, n):
+            self.launches.append(len(slots))
+            time.sleep(0.01)
+            for s in slots:
+                self.n[s] += n
+            return torch.zeros((len(slots), n, 16), dtype=torch.int32)
+
+        def history_context(self, s, valid, left):
+            return min(left, self.n[s] - valid)
+
+        def decode_audio_batch(self, slots, valid, left):   # 1920 samples per frame; the value names the slot
+            return [torch.full((valid * 1920,), 0.1 * (s + 1)) for s in slots]
+
+        def close(self):
+            pass
+
+    eng = Eng()
+    model = B200Qwen3TTS(eng, lambda text: [1, 2, 3], {"aiden": 0}, max_sessions=4, batch_wait_s=0.05, batch_gap_s=0.004)
+    monkeypatch.setattr(mod.B200Qwen3TTSHandler, "_b200_post",
+                        types.SimpleNamespace(from_device=lambda t: (t.numpy()[::3].repeat(2)[: (2 * t.numel() + 2) // 3] * 32767).astype(np.int16)))
+    hs = [_make(mod, model, monkeypatch, speaker="Aiden", blocksize=512, max_sessions=4) for _ in range(4)]
+    eng.launches.clear()
+    outs = {}
+
+    def speak(i):
+        hs[i].max_new_tokens = 40                     # 5 chunks of 8 frames
+        outs[i] = list(hs[i].process(_tts_input(mod, "Hello there.")))
+    ths = [threading.Thread(target=speak, args=(i,)) for i in range(4)]
+    [t.start() for t in ths]
+    [t.join(60) for t in ths]
+    assert sorted(model._free) == [0, 1, 2, 3]                     # every slot came back
+    levels = set()
+    for i in range(4):
+        blocks = outs[i]
+        assert blocks and all(b.dtype == np.int16 and b.shape == (512,) for b in blocks)
+        vals = {int(v) for v in np.unique(np.concatenate(blocks)) if v != 0}
+        assert len(vals) == 1, vals                                # one session's audio only, never another slot's
+        levels |= vals
+        assert 40 * 1280 // 512 - 2 <= len(blocks) <= 40 * 1280 // 512 + 1
+    assert len(levels) == 4
+    assert max(eng.launches) >= 2 and len(eng.launches) < 4 * 5   # chunk requests of concurrent sessions shared launches
+    model.close()
