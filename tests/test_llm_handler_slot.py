@@ -250,3 +250,46 @@ def test_concurrent_prompts_share_one_batched_prefill_pass():
     assert out == [200, 201, 102, 103, 104]
     assert [c[1] for c in eng.calls if c[0] == "reset"] == [0, 1, 2, 3, 4]
     assert b.prefill(1, [1, 2]) == 101          # no batcher (one session): straight through
+
+
+def test_lanes_select_their_own_shared_engine_and_do_not_leak_into_gen_kwargs(monkeypatch):
+    """`lane` / `lanes` in gen_kwargs: the units of a lane share that lane's engine (built on the lane's context), units of
+    different lanes get different engines, and the keys are consumed (they are not generation options)."""
+    import types
+    from speech_to_speech_b200 import engine as E
+    from speech_to_speech_b200.handlers import language_model_handler as LH
+    built = []
+
+    class FakeLlamaEngine:
+        cfg = types.SimpleNamespace(max_prefill=512)
+        device = 0
+
+        def __init__(self, geom, dtype="bfloat16", max_sessions=1, max_positions=2048, max_prefill=512, device=0, lane=0, lanes=1):
+            self.lane, self.lanes, self.max_positions = lane, lanes, max_positions
+            built.append((lane, lanes, max_sessions))
+
+        def init_random(self, seed):
+            pass
+
+        def max_decode_batch(self):
+            return 4
+
+        def close(self):
+            pass
+    monkeypatch.setattr(E, "LlamaEngine", FakeLlamaEngine)
+
+    def unit(lane):
+        h = object.__new__(LH.B200LanguageModelHandler)
+        h._load_model("random:micro:1", "cuda:0", "bfloat16", {"max_new_tokens": 8, "max_sessions": 2, "lane": lane, "lanes": 2})
+        return h
+    a0, a1, b0 = unit(0), unit(0), unit(1)
+    try:
+        assert a0.bundle is a1.bundle and a0.bundle is not b0.bundle
+        assert sorted(built) == [(0, 2, 2), (1, 2, 2)]
+        assert a0.bundle.lane == 0 and b0.bundle.lane == 1 and b0.bundle.lanes == 2
+        assert {a0.slot, a1.slot} == {0, 1} and b0.slot == 0
+        for h in (a0, a1, b0):
+            assert "lane" not in h.gen_kwargs and "lanes" not in h.gen_kwargs and "max_sessions" not in h.gen_kwargs
+    finally:
+        for h in (a0, a1, b0):
+            h.cleanup()
