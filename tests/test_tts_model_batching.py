@@ -2,12 +2,16 @@
 SessionBatcher.  The case that matters is two groups of sessions out of phase by half a launch whose consumers need longer
 than the batch gap to digest a chunk (on the GPU: waiting for the chunk's codec kernels + resample + D2H, ~10 ms): without the
 prefetched request they lock into alternating half-full launches, with it they merge into full ones."""
+import os
+import sys
 import threading
 import time
 import types
 
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # `python tests/test_tts_model_batching.py`
 
 from speech_to_speech_b200.tts_model import B200Qwen3TTS
 
@@ -82,11 +86,9 @@ def test_prefetched_requests_merge_two_groups_into_full_launches():
     assert len(eng.launches) <= CHUNKS + 8, eng.launches               # (28 launches of 8 without the prefetch)
 
 
-def test_without_prefetch_the_groups_alternate_in_half_full_launches():
-    """The behaviour the prefetch removes (kept as a regression reference: it is what the handler wave measured on the GPU)."""
-    eng, got = _run(prefetch=False)
-    assert all(len(got[i]) == CHUNKS for i in range(16))
-    assert eng.launches.count(8) >= CHUNKS, eng.launches
+# Without the prefetch the two groups alternate in half-full launches (what the handler wave measured on the GPU: mean batch 7.8
+# of 16): `python tests/test_tts_model_batching.py` prints both launch sequences.  Not a test: the alternation is an unstable
+# equilibrium under host-thread jitter, on a busy CPU box the groups sometimes fall into step by chance.
 
 
 def test_consumer_that_stops_early_releases_the_slot_after_the_prefetched_launch():
@@ -98,3 +100,8 @@ def test_consumer_that_stops_early_releases_the_slot_after_the_prefetched_launch
     assert sorted(tts._free) == [0, 1]
     assert eng.n[0] in (8, 16)                     # at most one chunk ahead of the consumer
     tts.close()
+
+
+if __name__ == "__main__":
+    for pf in (False, True):
+        print("prefetch" if pf else "no prefetch", _run(pf)[0].launches)
