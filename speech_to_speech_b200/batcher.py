@@ -149,6 +149,22 @@ class SessionBatcher:
         self._thread.join(timeout)
 
 
+# ---- lanes: which SM partition a new pipeline unit joins --------------------------------------------------------
+_lane_counters: dict = {}
+
+
+def assign_lane(group: Hashable, lanes: int) -> int:
+    """Round-robin lane of the next handler of `group` (slot kind, model, device): unit k of a `--num_pipelines N` process lands
+    on lane k mod lanes for each of its three handlers (they are constructed in unit order), so `max_sessions = ceil(N / lanes)`
+    slots per lane suffice.  lanes <= 1 -> 0."""
+    if lanes <= 1:
+        return 0
+    with _registry_lock:
+        k = _lane_counters.get(group, 0)
+        _lane_counters[group] = k + 1
+    return k % lanes
+
+
 # ---- engines shared between handler instances ------------------------------------------------------------------
 class _Shared:
     def __init__(self, value: Any, closer: Callable[[Any], None]):

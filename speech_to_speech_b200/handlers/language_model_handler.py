@@ -19,7 +19,7 @@ import logging
 import threading
 from typing import Any, Callable, Iterator, Optional, Sequence
 
-from ..batcher import SessionBatcher, acquire_shared, release_shared
+from ..batcher import SessionBatcher, acquire_shared, assign_lane, release_shared
 from ..host import _stub_optional
 
 logger = logging.getLogger(__name__)
@@ -290,7 +290,10 @@ class B200LanguageModelHandler(_Base if _Base is not None else _StandaloneBase):
         batch_gap_s = gap_ms / 1000.0 if gap_ms > 0 else None
         # SM partition: the handler instances of lane i share lane i's engine (engine.get_context)
         lanes = max(1, int(self.gen_kwargs.pop("lanes", 1)))
-        lane = int(self.gen_kwargs.pop("lane", 0)) % lanes
+        lane = self.gen_kwargs.pop("lane", None)
+        if lane is None:   # not pinned by the caller: units join the lanes round-robin in construction order
+            lane = assign_lane(("llama", model_name, dev), lanes)
+        lane = int(lane) % lanes
 
         def build() -> _LlamaBundle:
             if model_name.startswith("random:"):

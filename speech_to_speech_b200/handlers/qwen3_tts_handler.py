@@ -25,7 +25,7 @@ from typing import Any, Optional
 
 import numpy as np
 
-from ..batcher import acquire_shared, release_shared
+from ..batcher import acquire_shared, assign_lane, release_shared
 from ..tts_model import B200Qwen3TTS, DeviceAudio
 
 logger = logging.getLogger(__name__)
@@ -53,7 +53,10 @@ class B200Qwen3TTSHandler(_Base):  # type: ignore[misc, valid-type]
         self._b200_max_sessions = int(max_sessions if max_sessions is not None else gk.pop("max_sessions", 1))
         # SM partition: the handler instances of lane i share lane i's engine (engine.get_context); see INTEGRATION.md section 4
         self._b200_lanes = max(1, int(lanes if lanes is not None else gk.pop("lanes", 1)))
-        self._b200_lane = int(lane if lane is not None else gk.pop("lane", 0)) % self._b200_lanes
+        lane = lane if lane is not None else gk.pop("lane", None)
+        if lane is None:   # not pinned by the caller: units join the lanes round-robin in construction order
+            lane = assign_lane(("qwen3tts", str(kwargs.get("model_name", "")), str(kwargs.get("device", "cuda"))), self._b200_lanes)
+        self._b200_lane = int(lane) % self._b200_lanes
         self._b200_seed = int(gk.pop("seed", 0))
         kwargs["gen_kwargs"] = gk
         if "backend" in kwargs and kwargs["backend"] == "ggml":

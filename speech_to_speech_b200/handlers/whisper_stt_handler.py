@@ -21,7 +21,7 @@ from typing import Any, Iterator, Optional
 import numpy as np
 
 from ..host import resolve
-from ..batcher import SessionBatcher, acquire_shared, release_shared
+from ..batcher import SessionBatcher, acquire_shared, assign_lane, release_shared
 
 logger = logging.getLogger(__name__)
 _api = resolve()
@@ -141,7 +141,7 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
 
     def setup(self, model_name: str = "distil-whisper/distil-large-v3", device: str = "cuda", torch_dtype: str = "float16",
               compile_mode: Optional[str] = None, language: Optional[str] = None, gen_kwargs: dict[str, Any] = {},
-              max_batch: int = 1, batch_wait_ms: float = 6.0, lane: int = 0, lanes: int = 1, batch_gap_ms: float = 0.8) -> None:
+              max_batch: int = 1, batch_wait_ms: float = 6.0, lane: Optional[int] = None, lanes: int = 1, batch_gap_ms: float = 0.8) -> None:
         if not str(device).startswith("cuda"):
             raise ValueError(f"B200WhisperSTTHandler runs on CUDA (sm_100a) only, got device={device!r}; there is no CPU fallback")
         from .. import engine as E  # raises ImportError if libs2s_b200.so is not built
@@ -163,6 +163,8 @@ class B200WhisperSTTHandler(_api.BaseSTTHandler):
         self.batch_gap_s = float(batch_gap_ms) / 1000.0 if batch_gap_ms and batch_gap_ms > 0 else None
         # SM partition: the handler instances of lane i share lane i's engine (engine.get_context)
         self.lanes = max(1, int(lanes))
+        if lane is None:   # not pinned by the caller: units join the lanes round-robin in construction order
+            lane = assign_lane(("whisper", model_name, self.device_index), self.lanes)
         self.lane = int(lane) % self.lanes
         self._shared_key = None
         if self.max_batch > 1:

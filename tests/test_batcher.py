@@ -331,3 +331,11 @@ def test_two_groups_merge_instead_of_alternating_half_full_launches():
     [t.join() for t in ths]
     b.close()
     assert sizes[0] == 4 and sizes.count(8) >= 4, sizes    # after the first launches the groups travel together
+
+
+def test_units_join_the_lanes_round_robin_when_the_caller_does_not_pin_one():
+    from speech_to_speech_b200.batcher import assign_lane
+    g = ("kind", "model-%d" % id(object()), 0)
+    assert [assign_lane(g, 2) for _ in range(5)] == [0, 1, 0, 1, 0]
+    assert [assign_lane(("other",) + g, 3) for _ in range(4)] == [0, 1, 2, 0]      # counters are per (kind, model, device)
+    assert assign_lane(g, 1) == 0 and assign_lane(g, 2) == 1                       # one lane does not advance the counter
