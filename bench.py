@@ -686,7 +686,13 @@ def main():
             order = np.random.default_rng(3).permutation(S)          # lanes interleaved, not lane 0 first
             staggered = e2e_wave(handlers, auds, S, offsets=[float(spacing * int(np.where(order == i)[0][0])) for i in range(S)])
             log(f"staggered wave (one turn end every {1e3 * spacing:.0f} ms): p50 latency {statistics.median(staggered['latency_ms']) if staggered['latency_ms'] else None}")
+            # and at 30 %: the other end of the latency-vs-load curve (half the sessions keep the run short)
+            spacing30 = statistics.mean(w["wall_s"] for w in loaded) / S / 0.3
+            half = [int(i) for i in order[: max(2, S // 2)]]
+            light = e2e_wave([handlers[i] for i in half], [auds[i] for i in half], len(half), offsets=[float(spacing30 * k) for k in range(len(half))])
+            log(f"staggered wave (one turn end every {1e3 * spacing30:.0f} ms): p50 latency {statistics.median(light['latency_ms']) if light['latency_ms'] else None}")
             e2e = {"single": single, "loaded": loaded, "staggered": staggered, "staggered_spacing_s": spacing,
+                   "light": light, "light_spacing_s": spacing30,
                    "batching": {k: {"launch_groups": bs1[k][0] - bs0[k][0], "requests": bs1[k][1] - bs0[k][1],
                                     "mean_batch": round((bs1[k][1] - bs0[k][1]) / max(1, bs1[k][0] - bs0[k][0]), 2)} for k in bs1}}
             log(f"loaded e2e waves: {[round(w['wall_s'], 2) for w in loaded]} s")
@@ -792,9 +798,14 @@ def main():
                 line["latency_ms_at_70pct_load"] = {"p50": statistics.median(lat_st), "p90": lat_st[min(len(lat_st) - 1, int(0.9 * len(lat_st)))],
                                                     "turn_end_every_ms": 1e3 * e2e["staggered_spacing_s"], "sessions": len(lat_st),
                                                     "errors": e2e["staggered"]["errors"]}
+            lat_30 = sorted(e2e.get("light", {}).get("latency_ms", []))
+            if lat_30:
+                line["latency_ms_at_30pct_load"] = {"p50": statistics.median(lat_30), "p90": lat_30[min(len(lat_30) - 1, int(0.9 * len(lat_30)))],
+                                                    "turn_end_every_ms": 1e3 * e2e["light_spacing_s"], "sessions": len(lat_30),
+                                                    "errors": e2e["light"]["errors"]}
             line["latency_note"] = ("audio-in (VADAudio.created_at_s) -> first int16 block out of the TTS handler; 'single' = one session on an "
                                     "idle GPU (on its lane's SM partition), 'latency_ms_p50' = the S sessions of a wave that all stop speaking at the same instant (worst case), "
-                                    "'latency_ms_at_70pct_load' = turn ends evenly spread at 70 % of the rate the loaded wave sustains")
+                                    "'latency_ms_at_70pct_load' / 'latency_ms_at_30pct_load' = turn ends evenly spread at 70 % / 30 % of the rate the loaded wave sustains")
         elif e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
