@@ -61,3 +61,54 @@ def test_tts_profile_window_brackets_the_chosen_chunks_of_all_lanes(bench):
     [t.join() for t in ths]
     assert events.count("start") == 1 and events.count("stop") == 1 and events.count("sync") == 2
     assert events[0] == "start" and events[-1] == "stop"
+
+
+def test_e2e_wave_runs_the_stages_in_their_own_threads_and_honours_offsets(bench):
+    """bench.e2e_wave with fake handlers: STT -> LLM thread -> queue -> TTS thread per session; a sentence is spoken as soon as the
+    LLM has produced it (the LLM keeps generating meanwhile); offsets stagger the turn ends; a failing session is reported."""
+    import time
+    import numpy as np
+    t_wave = time.perf_counter()
+    started = {}
+
+    class STT:
+        def __init__(self, i):
+            self.i = i
+
+        def process(self, vad):
+            started[self.i] = time.perf_counter() - t_wave
+            yield types.SimpleNamespace(text="hi", speech_stopped_at_s=getattr(vad, "created_at_s", None))
+
+    class LLM:
+        def __init__(self, fail=False):
+            self.streamer = types.SimpleNamespace(generated=[])
+            self.fail = fail
+
+        def generate_text_stream(self, prompt, max_new_tokens=128):
+            self.streamer.generated = []
+            for k in range(max_new_tokens // 4):
+                time.sleep(0.001)
+                self.streamer.generated += [1, 2, 3, 4]
+                if self.fail and k == 3:
+                    raise RuntimeError("boom")
+                yield "x"
+
+    class TTS:
+        def __init__(self):
+            self.spoken = []
+
+        def process(self, item):
+            self.spoken.append((len(item.text), self.max_new_tokens))
+            for _ in range(3):
+                time.sleep(0.002)
+                yield np.zeros(512, np.int16)
+
+    hs = [(STT(i), LLM(fail=(i == 2)), TTS()) for i in range(3)]
+    auds = [np.zeros(1600, np.float32)] * 3
+    r = bench.e2e_wave(hs, auds, 3, offsets=[0.0, 0.05, 0.1])
+    assert len(r["latency_ms"]) == 2 and all(0 < x < 2000 for x in r["latency_ms"])        # sessions 0 and 1; session 2 failed
+    assert len(r["errors"]) == 1 and "boom" in r["errors"][0]
+    assert started[1] >= 0.045 and started[2] >= 0.09                                         # the offsets were slept before the turn end
+    for i in (0, 1):
+        assert hs[i][2].spoken == [(bench.FIRST_SENTENCE, bench.F1), (bench.MAX_NEW - bench.FIRST_SENTENCE, bench.F2)]
+    assert all(x > 0 for x in r["rtf"])
